@@ -1,0 +1,325 @@
+"""ctypes binding of libpwmscan.so (include/pwmscan.h) — the only compute path of this package.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present every
+compute entry point raises `PwmScanError` (loudly), it never silently degrades.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpwmscan.so")
+
+SEQ_UPPERCASE = 1
+SEQ_KEEP_ASCII = 2
+
+OK, EINVAL, ECUDA, ENUCL, ERANGE, EDOMAIN = 0, -1, -2, -3, -4, -5
+
+PENAL = {"linear": 0, "quadratic": 1, "cubic": 2, "exp": 3}
+COMB = {"l1": 0, "l2": 1, "l3": 2, "max": 3}
+
+
+class PwmScanError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pwmscan error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+class InvalidNucleotide(PwmScanError, ValueError):
+    """The reference's `error "... invalid nucleotide"` (Motif/Search.hs:157, Motif.hs:185)."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_vp = C.c_void_p
+_dp = C.POINTER(C.c_double)
+
+
+def build(verbose=False):
+    """Compile libpwmscan.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")] + ([] if verbose else ["-s"]))
+
+
+def load():
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise PwmScanError(ECUDA, "libpwmscan.so is not built (%s); run bioinformatics_toolkit_b200._lib.build() — "
+                                      "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.pwmscan_last_error.restype = C.c_char_p
+        L.pwmscan_last_error.argtypes = [_vp]
+        L.pwmscan_seq_length.restype = C.c_int64
+        L.pwmscan_hits_count.restype = C.c_int64
+        L.pwmscan_hits_count.argtypes = [_vp]
+        L.pwmscan_ctx_destroy.argtypes = [_vp]
+        L.pwmscan_seq_free.argtypes = [_vp]
+        L.pwmscan_motifs_free.argtypes = [_vp]
+        L.pwmscan_plan_free.argtypes = [_vp]
+        L.pwmscan_hits_free.argtypes = [_vp]
+        L.pwmscan_free.argtypes = [_vp]
+        _lib = L
+        return L
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class Context:
+    """One per device (pwmscan_ctx)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        self.h = _vp()
+        rc = self.L.pwmscan_ctx_create(C.c_int(device), C.byref(self.h))
+        if rc != 0:
+            raise PwmScanError(rc, (self.L.pwmscan_last_error(None) or b"").decode())
+        self.device = device
+
+    def check(self, rc):
+        if rc == 0:
+            return
+        msg = (self.L.pwmscan_last_error(self.h) or b"").decode()
+        if rc == ENUCL:
+            raise InvalidNucleotide(rc, msg)
+        raise PwmScanError(rc, msg)
+
+    def timing(self):
+        out = np.zeros(8)
+        self.L.pwmscan_last_timing(self.h, _ptr(out), C.c_int(8))
+        return {"prefilter_ms": out[0], "rescore_ms": out[1], "sort_ms": out[2], "device_ms": out[3],
+                "h2d_bytes": out[4], "d2h_bytes": out[5], "candidates": out[6], "prefilter_launches": out[7]}
+
+    def close(self):
+        if self.h:
+            self.L.pwmscan_ctx_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context for `device` (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("PWMSCAN_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceSeq:
+    """A DNA sequence (or several segments) packed in HBM (pwmscan_seq)."""
+
+    def __init__(self, ctx, data, seg_off=None, uppercase=False, keep_ascii=False):
+        self.ctx = ctx
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(bytes(data), dtype=np.uint8)
+        data = _arr(data, np.uint8)
+        flags = (SEQ_UPPERCASE if uppercase else 0) | (SEQ_KEEP_ASCII if keep_ascii else 0)
+        self.h = _vp()
+        self.length = int(data.size)
+        self.keep_ascii = keep_ascii
+        if seg_off is None:
+            self.nseg = 1
+            self.seg_off = np.array([0, data.size], dtype=np.int64)
+            rc = ctx.L.pwmscan_seq_upload(ctx.h, _ptr(data), C.c_int64(data.size), C.c_int(flags), C.byref(self.h))
+        else:
+            so = _arr(seg_off, np.int64)
+            self.nseg = int(so.size - 1)
+            self.seg_off = so
+            rc = ctx.L.pwmscan_seq_upload_segments(ctx.h, _ptr(data), _ptr(so), C.c_int32(self.nseg), C.c_int(flags), C.byref(self.h))
+        ctx.check(rc)
+
+    def first_invalid(self, alphabet="IUPAC"):
+        pos = C.c_int64(-1)
+        self.ctx.check(self.ctx.L.pwmscan_seq_first_invalid(self.ctx.h, self.h, C.c_int(0 if alphabet == "Basic" else 1), C.byref(pos)))
+        return pos.value
+
+    def free(self):
+        if self.h:
+            self.ctx.L.pwmscan_seq_free(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceMotifs:
+    """A set of PWMs + background with their device tables (pwmscan_motifs)."""
+
+    def __init__(self, ctx, mats, bg=(0.25, 0.25, 0.25, 0.25)):
+        self.ctx = ctx
+        self.mats = [_arr(m, np.float64).reshape(-1, 4) for m in mats]
+        self.M = len(self.mats)
+        self.ncol = np.array([m.shape[0] for m in self.mats], dtype=np.int32)
+        flat = np.concatenate([m.reshape(-1) for m in self.mats]) if self.mats else np.zeros(0)
+        self.bg = _arr(bg, np.float64)
+        self.h = _vp()
+        ctx.check(ctx.L.pwmscan_motifs_create(ctx.h, C.c_int32(self.M), _ptr(self.ncol), _ptr(flat), _ptr(self.bg), C.byref(self.h)))
+
+    def set_sigma(self, m, strand, sigma):
+        s = _arr(sigma, np.float64)
+        if s.size != self.ncol[m]:
+            raise ValueError("sigma must have one entry per PWM column")
+        self.ctx.check(self.ctx.L.pwmscan_motifs_set_sigma(self.h, C.c_int32(m), C.c_int(strand), _ptr(s)))
+
+    def get_sigma(self, m, strand=0):
+        out = np.empty(int(self.ncol[m]))
+        self.ctx.check(self.ctx.L.pwmscan_motifs_get_sigma(self.h, C.c_int32(m), C.c_int(strand), _ptr(out)))
+        return out
+
+    # -- scoreCDF / pValueToScore -------------------------------------------------------------
+    def score_cdf(self, m):
+        x = _dp()
+        p = _dp()
+        n = C.c_int64(0)
+        self.ctx.check(self.ctx.L.pwmscan_score_cdf(self.ctx.h, self.h, C.c_int32(m), C.byref(x), C.byref(p), C.byref(n)))
+        xs = np.ctypeslib.as_array(x, shape=(n.value,)).copy()
+        ps = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        self.ctx.L.pwmscan_free(C.cast(x, _vp))
+        self.ctx.L.pwmscan_free(C.cast(p, _vp))
+        return xs, ps
+
+    def pvalue_to_score(self, p):
+        out = np.empty(self.M)
+        self.ctx.check(self.ctx.L.pwmscan_pvalue_to_score(self.ctx.h, self.h, C.c_double(p), _ptr(out)))
+        return out
+
+    # -- alignment ------------------------------------------------------------------------------
+    def align_all_pairs(self, penal="exp", gap=0.05, comb="l1"):
+        npair = self.M * (self.M - 1) // 2
+        d = np.empty(npair)
+        sd = np.empty(npair, dtype=np.uint8)
+        pos = np.empty(npair, dtype=np.int32)
+        self.ctx.check(self.ctx.L.pwmscan_align_all_pairs(self.ctx.h, self.h, C.c_int(PENAL[penal]), C.c_double(gap),
+                                                          C.c_int(COMB[comb]), _ptr(d), _ptr(sd), _ptr(pos)))
+        return d, sd, pos
+
+    def align_pairs(self, a, b, penal="exp", gap=0.05, comb="l1"):
+        a = _arr(a, np.int32)
+        b = _arr(b, np.int32)
+        d = np.empty(a.size)
+        sd = np.empty(a.size, dtype=np.uint8)
+        pos = np.empty(a.size, dtype=np.int32)
+        self.ctx.check(self.ctx.L.pwmscan_align_pairs(self.ctx.h, self.h, C.c_int64(a.size), _ptr(a), _ptr(b), C.c_int(PENAL[penal]),
+                                                      C.c_double(gap), C.c_int(COMB[comb]), _ptr(d), _ptr(sd), _ptr(pos)))
+        return d, sd, pos
+
+    def free(self):
+        if self.h:
+            self.ctx.L.pwmscan_motifs_free(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Hits:
+    """Columns of a hit list sorted by (segment, motif, strand, pos)."""
+
+    __slots__ = ("motif", "strand", "segment", "pos", "score")
+
+    def __init__(self, motif, strand, segment, pos, score):
+        self.motif, self.strand, self.segment, self.pos, self.score = motif, strand, segment, pos, score
+
+    def __len__(self):
+        return int(self.pos.size)
+
+    def select(self, motif=None, strand=None, segment=None):
+        k = np.ones(self.pos.size, dtype=bool)
+        if motif is not None:
+            k &= self.motif == motif
+        if strand is not None:
+            k &= self.strand == strand
+        if segment is not None:
+            k &= self.segment == segment
+        return Hits(self.motif[k], self.strand[k], self.segment[k], self.pos[k], self.score[k])
+
+
+class Plan:
+    """Device-side analogue of [CutoffMotif] (pwmscan_plan): tables for fixed (motifs, cutoffs)."""
+
+    def __init__(self, motifs, thres, strands=2, skip_ambiguous=True):
+        self.ctx = motifs.ctx
+        self.motifs = motifs
+        th = _arr(thres, np.float64)
+        if th.size != motifs.M:
+            raise ValueError("one cutoff per motif expected")
+        self.h = _vp()
+        self.ctx.check(self.ctx.L.pwmscan_plan_create(self.ctx.h, motifs.h, _ptr(th), C.c_int(strands),
+                                                      C.c_int(1 if skip_ambiguous else 0), C.byref(self.h)))
+
+    def scan(self, seq):
+        L = self.ctx.L
+        hh = _vp()
+        self.ctx.check(L.pwmscan_scan(self.ctx.h, seq.h, self.h, C.byref(hh)))
+        try:
+            n = L.pwmscan_hits_count(hh)
+            pm, ps, pg, pp, pc = (C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)(),
+                                  C.POINTER(C.c_int64)(), C.POINTER(C.c_double)())
+            L.pwmscan_hits_columns(hh, C.byref(pm), C.byref(ps), C.byref(pg), C.byref(pp), C.byref(pc))
+            if n == 0:
+                return Hits(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0))
+            return Hits(np.ctypeslib.as_array(pm, shape=(n,)).copy(), np.ctypeslib.as_array(ps, shape=(n,)).copy(),
+                        np.ctypeslib.as_array(pg, shape=(n,)).copy(), np.ctypeslib.as_array(pp, shape=(n,)).copy(),
+                        np.ctypeslib.as_array(pc, shape=(n,)).copy())
+        finally:
+            L.pwmscan_hits_free(hh)
+
+    def free(self):
+        if self.h:
+            self.ctx.L.pwmscan_plan_free(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def scores(seq, motifs, m, strand=0):
+    n = int(motifs.ncol[m])
+    nwin = max(0, seq.length - n + 1)
+    out = np.empty(nwin)
+    seq.ctx.check(seq.ctx.L.pwmscan_scores(seq.ctx.h, seq.h, motifs.h, C.c_int32(m), C.c_int(strand), _ptr(out), C.c_int64(nwin)))
+    return out
+
+
+def max_match_sc(seq, motifs):
+    out = np.empty(motifs.M)
+    seq.ctx.check(seq.ctx.L.pwmscan_max_match_sc(seq.ctx.h, seq.h, motifs.h, _ptr(out)))
+    return out
+
+
+def exported_symbols():
+    """Names declared in include/pwmscan.h (used by the CPU test that checks the .so exports them all)."""
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "pwmscan.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(pwmscan_[a-z0-9_]+)\s*\(", txt)))

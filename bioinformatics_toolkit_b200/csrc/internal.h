@@ -1,0 +1,110 @@
+// internal.h — handle layouts shared by the translation units of libpwmscan.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pwmscan.h"
+#include "plan.h"
+
+struct pwmscan_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int sm_count = 148;
+    // grow-only device scratch
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // pinned host staging (grow-only)
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes[2] = {0, 0};
+    unsigned long long* d_counters = nullptr;   // [0] candidates [1] hits [2] error flag [3] work counter (32-bit view)
+    unsigned long long* h_counters = nullptr;   // pinned mirror
+};
+
+struct pwmscan_seq {
+    pwmscan_ctx* ctx = nullptr;
+    int64_t len = 0;                 // concatenated length
+    int32_t nseg = 1;
+    std::vector<int64_t> seg_off;    // nseg+1
+    int64_t* d_seg_off = nullptr;
+    uint32_t* d_seq2_alloc = nullptr;   // 1 front word + words + tail
+    uint32_t* d_seq2 = nullptr;         // = alloc + 1; stored base u at word u>>4
+    uint32_t* d_mask = nullptr;         // stored base u at bit u&31 of word u>>5 (1 = not ACGT)
+    uint8_t* d_ascii = nullptr;         // optional (KEEP_ASCII): upper-cased bytes, position p at [p]
+    int64_t nwords2 = 0, nwords_mask = 0;
+    int64_t first_non_acgt = -1, first_non_iupac = -1;
+    int flags = 0;
+};
+
+struct pwmscan_motifs {
+    pwmscan_ctx* ctx = nullptr;
+    int32_t M = 0;
+    double bg[4] = {0.25, 0.25, 0.25, 0.25};
+    std::vector<pwmscan::MotifHost> mh;
+    std::vector<int64_t> tab_off;       // offset of (motif, strand) in d_tab16 (doubles): tab_off[2m+s]
+    std::vector<int64_t> col_off;       // offset of (motif, strand) in per-column arrays: col_off[2m+s]
+    double* d_tab16 = nullptr;          // all IUPAC tables
+    double* d_mats = nullptr;           // all probability matrices (strand 0 and 1), n x 4, same order as col_off*4
+    int64_t total_cols2 = 0;            // sum over (motif,strand) of n
+};
+
+struct DevCombo {
+    int32_t motif;      // caller's motif index, -1 = empty
+    int32_t strand;
+    int32_t n;
+    int32_t c;          // anchor column
+    int64_t tab_off;    // doubles into d_tab16
+    int64_t th_off;     // doubles into d_th
+};
+
+struct DevBlock {
+    int32_t s1, nl, nslot, pad;
+    int64_t table_off;  // 32-bit words into d_tables
+};
+
+struct pwmscan_plan {
+    pwmscan_ctx* ctx = nullptr;
+    const pwmscan_motifs* motifs = nullptr;
+    int strands = 2, skip = 1;
+    int nblocks = 0;                   // prefilter blocks
+    int max_nslot = 0;
+    std::vector<pwmscan::BlockPlan> blocks;
+    std::vector<DevCombo> generic;     // combos handled by the exact kernel only
+    DevBlock* d_blocks = nullptr;
+    DevCombo* d_combos = nullptr;      // nblocks * 128
+    DevCombo* d_generic = nullptr;
+    uint32_t* d_tables = nullptr;
+    double* d_th = nullptr;            // th[k] = thres - sigma[k] per (motif,strand)
+    double cand_rate = 0;              // expected candidates per sequence position
+    int max_n = 0;
+};
+
+struct pwmscan_hits {
+    int64_t count = 0;
+    std::vector<int32_t> motif, segment;
+    std::vector<uint8_t> strand;
+    std::vector<int64_t> pos;
+    std::vector<double> score;
+};
+
+namespace pwmscan {
+
+int set_err(pwmscan_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(pwmscan_ctx* ctx, cudaError_t e, const char* what);
+// grow-only scratch; returns nullptr on failure (error already recorded)
+void* scratch_get(pwmscan_ctx* ctx, int slot, size_t bytes);
+void* pinned_get(pwmscan_ctx* ctx, int slot, size_t bytes);
+
+#define PWM_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return pwmscan::cuda_fail(ctx, e__, #call);     \
+    } while (0)
+
+}  // namespace pwmscan

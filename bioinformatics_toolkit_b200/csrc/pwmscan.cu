@@ -1,0 +1,708 @@
+// pwmscan.cu — context, sequence packing, motif tables, plans, and the thresholded scan
+// (findTFBS / findTFBSWith / scanMotif body) of libpwmscan.so.  sm_100a only.
+//
+// Data layout in HBM:
+//   seq2   2 bits/base, 16 bases per 32-bit word, stored base index u = position + 32
+//   mask   1 bit/base, 1 = not one of ACGT (or padding)
+//   ascii  optional upper-cased copy (IUPAC-aware entry points only)
+//   tables per 64-motif block: nslot x 256 x 32 words, staged into shared memory by the kernel
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+#include "scan_core.cuh"
+
+using namespace pwmscan;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+namespace pwmscan {
+
+int set_err(pwmscan_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(pwmscan_ctx* ctx, cudaError_t e, const char* what) {
+    std::string m = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    cudaGetLastError();
+    return set_err(ctx, PWMSCAN_ECUDA, m);
+}
+
+void* scratch_get(pwmscan_ctx* ctx, int slot, size_t bytes) {
+    if (ctx->scratch_bytes[slot] >= bytes && ctx->scratch[slot]) return ctx->scratch[slot];
+    if (ctx->scratch[slot]) { cudaFree(ctx->scratch[slot]); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMalloc(scratch)"); return nullptr; }
+    ctx->scratch[slot] = p; ctx->scratch_bytes[slot] = want;
+    return p;
+}
+
+void* pinned_get(pwmscan_ctx* ctx, int slot, size_t bytes) {
+    if (ctx->pinned_bytes[slot] >= bytes && ctx->pinned[slot]) return ctx->pinned[slot];
+    if (ctx->pinned[slot]) { cudaFreeHost(ctx->pinned[slot]); ctx->pinned[slot] = nullptr; ctx->pinned_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMallocHost"); return nullptr; }
+    ctx->pinned[slot] = p; ctx->pinned_bytes[slot] = want;
+    return p;
+}
+
+}  // namespace pwmscan
+
+extern "C" int pwmscan_abi_version(void) { return PWMSCAN_ABI_VERSION; }
+
+extern "C" const char* pwmscan_last_error(pwmscan_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int pwmscan_ctx_create(int device, pwmscan_ctx** out) {
+    if (!out) return set_err(nullptr, PWMSCAN_EINVAL, "pwmscan_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(nullptr, PWMSCAN_ECUDA,
+                       std::string("pwmscan_ctx_create: no CUDA device available (") +
+                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                           "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return set_err(nullptr, PWMSCAN_EINVAL, "pwmscan_ctx_create: bad device index");
+    pwmscan_ctx* ctx = new (std::nothrow) pwmscan_ctx();
+    if (!ctx) return set_err(nullptr, PWMSCAN_EINVAL, "out of host memory");
+    ctx->device = device;
+    auto fail = [&](cudaError_t err, const char* what) { int rc = cuda_fail(nullptr, err, what); delete ctx; return rc; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) { delete ctx; return set_err(nullptr, PWMSCAN_ECUDA, "pwmscan: device is not sm_100 (Blackwell B200) class"); }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
+    if ((e = cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMallocHost(counters)");
+    *out = ctx;
+    return PWMSCAN_OK;
+}
+
+extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& p : ctx->scratch) if (p) cudaFree(p);
+    for (auto& p : ctx->pinned) if (p) cudaFreeHost(p);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int pwmscan_last_timing(pwmscan_ctx* ctx, double* out, int n) {
+    if (!ctx || !out) return PWMSCAN_EINVAL;
+    for (int i = 0; i < n && i < 8; ++i) out[i] = ctx->timing[i];
+    return PWMSCAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequence upload + packing
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kThreads = 512;                          // prefilter CTA: 16 warps, 1 CTA per SM
+constexpr int kWarps = kThreads / 32;
+constexpr int kIters = 32;                             // x 32 anchors per warp per work item
+constexpr int64_t kChunk = (int64_t)kWarps * 32 * kIters;   // anchors per work item (16384)
+
+__constant__ unsigned char c_iupac_lut[256];
+
+// One thread per 32 stored bases: two packed words + one mask word.
+__global__ void pack_kernel(const uint8_t* ascii, int64_t len, int uppercase, uint32_t* __restrict__ seq2,
+                            uint32_t* __restrict__ mask, uint8_t* ascii_out /* may alias ascii */, int64_t nmask_words,
+                            unsigned long long* first_bad /* [0] non-ACGT, [1] non-IUPAC */) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nmask_words) return;
+    const int64_t u0 = t * 32;
+    uint32_t w0 = 0, w1 = 0, mk = 0;
+    unsigned long long bad_acgt = ~0ull, bad_iupac = ~0ull;
+    const int64_t p0 = u0 - kPadFront;
+    __align__(16) uint8_t buf[32];
+    const bool interior = (p0 >= 0) && (p0 + 32 <= len) && ((((uintptr_t)(ascii + p0)) & 15) == 0);
+    if (interior) {
+        const uint4 a = *reinterpret_cast<const uint4*>(ascii + p0);
+        const uint4 b = *reinterpret_cast<const uint4*>(ascii + p0 + 16);
+        *reinterpret_cast<uint4*>(buf) = a;
+        *reinterpret_cast<uint4*>(buf + 16) = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const int64_t p = p0 + k; buf[k] = (p >= 0 && p < len) ? ascii[p] : 0; }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int64_t p = p0 + k;
+        unsigned char ch = buf[k];
+        if (uppercase && ch >= 'a' && ch <= 'z') ch = (unsigned char)(ch - 32);
+        buf[k] = ch;
+        const bool inside = (p >= 0 && p < len);
+        const unsigned code = inside ? c_iupac_lut[ch] : 15u;
+        uint32_t c2;
+        if (code < 4) c2 = code;
+        else {
+            c2 = pad_hash(u0 + k);
+            mk |= 1u << k;
+            if (inside) {
+                if (bad_acgt == ~0ull) bad_acgt = (unsigned long long)p;
+                if (code == 15 && bad_iupac == ~0ull) bad_iupac = (unsigned long long)p;
+            }
+        }
+        if (k < 16) w0 |= c2 << (2 * k); else w1 |= c2 << (2 * (k - 16));
+    }
+    seq2[2 * t] = w0;
+    seq2[2 * t + 1] = w1;
+    mask[t] = mk;
+    if (ascii_out) {
+        if (interior) {
+            *reinterpret_cast<uint4*>(ascii_out + p0) = *reinterpret_cast<uint4*>(buf);
+            *reinterpret_cast<uint4*>(ascii_out + p0 + 16) = *reinterpret_cast<uint4*>(buf + 16);
+        } else {
+            for (int k = 0; k < 32; ++k) { const int64_t p = p0 + k; if (p >= 0 && p < len) ascii_out[p] = buf[k]; }
+        }
+    }
+    if (bad_acgt != ~0ull) atomicMin(&first_bad[0], bad_acgt);
+    if (bad_iupac != ~0ull) atomicMin(&first_bad[1], bad_iupac);
+}
+
+bool g_lut_ready[64] = {false};
+
+int ensure_lut(pwmscan_ctx* ctx) {
+    if (g_lut_ready[ctx->device & 63]) return PWMSCAN_OK;
+    unsigned char lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = (unsigned char)iupac_code((unsigned char)i);
+    PWM_CUDA(cudaMemcpyToSymbol(c_iupac_lut, lut, 256));
+    g_lut_ready[ctx->device & 63] = true;
+    return PWMSCAN_OK;
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg, int flags,
+                           pwmscan_seq** out) {
+    if (!ctx || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: NULL argument");
+    *out = nullptr;
+    if (nseg < 1 || nseg > PWMSCAN_MAX_SEGMENTS) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_seq_upload: segment count out of range");
+    const int64_t len = seg_off[nseg];
+    if (len < 0 || (len > 0 && !ascii)) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: bad length / NULL data");
+    if (len >= ((int64_t)1 << 39)) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_seq_upload: sequence too long");
+    for (int32_t i = 0; i < nseg; ++i) {
+        if (seg_off[i + 1] < seg_off[i] || seg_off[0] != 0) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: seg_off must be ascending from 0");
+        if (seg_off[i + 1] - seg_off[i] >= ((int64_t)1 << 32)) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_seq_upload: segment longer than 2^32");
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_lut(ctx);
+    if (rc) return rc;
+    pwmscan_seq* s = new (std::nothrow) pwmscan_seq();
+    if (!s) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
+    s->ctx = ctx; s->len = len; s->nseg = nseg; s->flags = flags;
+    s->seg_off.assign(seg_off, seg_off + nseg + 1);
+    const int64_t n_anchor = round_up(len + kPadFront + 64, kChunk);
+    s->nwords2 = n_anchor / 16 + 8;
+    s->nwords_mask = n_anchor / 32 + 4;
+    auto bail = [&](int code) { pwmscan_seq_free(s); return code; };
+    cudaError_t e;
+    if ((e = cudaMalloc(&s->d_seq2_alloc, (size_t)(s->nwords2 + 1) * 4)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(seq2)"));
+    s->d_seq2 = s->d_seq2_alloc + 1;
+    if ((e = cudaMalloc(&s->d_mask, (size_t)s->nwords_mask * 4)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(mask)"));
+    if ((e = cudaMalloc(&s->d_seg_off, (size_t)(nseg + 1) * 8)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(seg_off)"));
+    if ((e = cudaMemcpyAsync(s->d_seg_off, seg_off, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(seg_off)"));
+    // the raw bytes: either kept (upper-cased in place by the pack kernel) or a scratch buffer
+    uint8_t* d_raw = nullptr;
+    if (flags & PWMSCAN_SEQ_KEEP_ASCII) {
+        if ((e = cudaMalloc(&s->d_ascii, (size_t)len + 64)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(ascii)"));
+        d_raw = s->d_ascii;
+    } else {
+        d_raw = (uint8_t*)scratch_get(ctx, 0, (size_t)len + 64);
+        if (!d_raw) return bail(PWMSCAN_ECUDA);
+    }
+    if (len > 0 && (e = cudaMemcpyAsync(d_raw, ascii, (size_t)len, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(ascii)"));
+    if ((e = cudaMemsetAsync(s->d_seq2_alloc, 0, (size_t)(s->nwords2 + 1) * 4, ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
+    if ((e = cudaMemsetAsync(ctx->d_counters + 4, 0xFF, 16, ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
+    {
+        const int64_t nt = s->nwords_mask;
+        const int bs = 256;
+        pack_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(
+            d_raw, len, (flags & PWMSCAN_SEQ_UPPERCASE) ? 1 : 0, s->d_seq2, s->d_mask,
+            (flags & PWMSCAN_SEQ_KEEP_ASCII) ? s->d_ascii : nullptr, nt, ctx->d_counters + 4);
+        if ((e = cudaGetLastError()) != cudaSuccess) return bail(cuda_fail(ctx, e, "pack_kernel launch"));
+    }
+    if ((e = cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(first_bad)"));
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "pack_kernel"));
+    s->first_non_acgt = ctx->h_counters[4] == ~0ull ? -1 : (int64_t)ctx->h_counters[4];
+    s->first_non_iupac = ctx->h_counters[5] == ~0ull ? -1 : (int64_t)ctx->h_counters[5];
+    ctx->timing[4] = (double)len + (double)(nseg + 1) * 8;
+    *out = s;
+    return PWMSCAN_OK;
+}
+
+extern "C" int pwmscan_seq_upload(pwmscan_ctx* ctx, const uint8_t* ascii, int64_t len, int flags, pwmscan_seq** out) {
+    const int64_t off[2] = {0, len};
+    return seq_upload_impl(ctx, ascii, off, 1, flags, out);
+}
+
+extern "C" int pwmscan_seq_upload_segments(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg,
+                                           int flags, pwmscan_seq** out) {
+    if (!seg_off) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload_segments: seg_off is NULL");
+    return seq_upload_impl(ctx, ascii, seg_off, nseg, flags, out);
+}
+
+extern "C" int64_t pwmscan_seq_length(const pwmscan_seq* seq) { return seq ? seq->len : -1; }
+
+extern "C" int pwmscan_seq_first_invalid(pwmscan_ctx* ctx, const pwmscan_seq* seq, int alphabet, int64_t* pos_out) {
+    if (!seq || !pos_out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_first_invalid: NULL argument");
+    *pos_out = alphabet == 0 ? seq->first_non_acgt : seq->first_non_iupac;
+    return PWMSCAN_OK;
+}
+
+extern "C" void pwmscan_seq_free(pwmscan_seq* s) {
+    if (!s) return;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    if (s->d_seq2_alloc) cudaFree(s->d_seq2_alloc);
+    if (s->d_mask) cudaFree(s->d_mask);
+    if (s->d_ascii) cudaFree(s->d_ascii);
+    if (s->d_seg_off) cudaFree(s->d_seg_off);
+    delete s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// motifs
+// ------------------------------------------------------------------------------------------------
+extern "C" int pwmscan_motifs_create(pwmscan_ctx* ctx, int32_t M, const int32_t* ncol, const double* mats,
+                                     const double bg[4], pwmscan_motifs** out) {
+    if (!ctx || !out || !ncol || !mats || !bg) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_motifs_create: NULL argument");
+    *out = nullptr;
+    if (M < 1 || M > PWMSCAN_MAX_MOTIFS) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_motifs_create: motif count out of range");
+    for (int m = 0; m < M; ++m)
+        if (ncol[m] < 1 || ncol[m] > PWMSCAN_MAX_COLS) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_motifs_create: PWM must have 1..64 columns");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    pwmscan_motifs* mo = new (std::nothrow) pwmscan_motifs();
+    if (!mo) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
+    mo->ctx = ctx; mo->M = M;
+    for (int b = 0; b < 4; ++b) mo->bg[b] = bg[b];
+    mo->mh.resize(M);
+    mo->tab_off.resize(2 * (size_t)M);
+    mo->col_off.resize(2 * (size_t)M);
+    int64_t off = 0, cols = 0;
+    const double* p = mats;
+    for (int m = 0; m < M; ++m) {
+        motif_prepare(mo->mh[m], ncol[m], p, bg);
+        p += 4 * ncol[m];
+        for (int s = 0; s < 2; ++s) { mo->tab_off[2 * m + s] = off; off += 16 * (int64_t)ncol[m]; mo->col_off[2 * m + s] = cols; cols += ncol[m]; }
+    }
+    mo->total_cols2 = cols;
+    std::vector<double> h_tab((size_t)off), h_mat((size_t)cols * 4);
+    for (int m = 0; m < M; ++m)
+        for (int s = 0; s < 2; ++s) {
+            std::memcpy(h_tab.data() + mo->tab_off[2 * m + s], mo->mh[m].tab16[s].data(), sizeof(double) * 16 * ncol[m]);
+            std::memcpy(h_mat.data() + 4 * mo->col_off[2 * m + s], mo->mh[m].mat[s].data(), sizeof(double) * 4 * ncol[m]);
+        }
+    cudaError_t e;
+    auto bail = [&](int code) { pwmscan_motifs_free(mo); return code; };
+    if ((e = cudaMalloc(&mo->d_tab16, h_tab.size() * 8)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(tab16)"));
+    if ((e = cudaMalloc(&mo->d_mats, h_mat.size() * 8)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(mats)"));
+    if ((e = cudaMemcpy(mo->d_tab16, h_tab.data(), h_tab.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemcpy(tab16)"));
+    if ((e = cudaMemcpy(mo->d_mats, h_mat.data(), h_mat.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemcpy(mats)"));
+    *out = mo;
+    return PWMSCAN_OK;
+}
+
+extern "C" int pwmscan_motifs_set_sigma(pwmscan_motifs* mo, int32_t m, int strand, const double* sigma) {
+    if (!mo || !sigma || m < 0 || m >= mo->M || strand < 0 || strand > 1) return set_err(mo ? mo->ctx : nullptr, PWMSCAN_EINVAL, "pwmscan_motifs_set_sigma: bad argument");
+    mo->mh[m].sigma[strand].assign(sigma, sigma + mo->mh[m].n);
+    return PWMSCAN_OK;
+}
+
+extern "C" int pwmscan_motifs_get_sigma(const pwmscan_motifs* mo, int32_t m, int strand, double* sigma_out) {
+    if (!mo || !sigma_out || m < 0 || m >= mo->M || strand < 0 || strand > 1) return set_err(mo ? mo->ctx : nullptr, PWMSCAN_EINVAL, "pwmscan_motifs_get_sigma: bad argument");
+    std::memcpy(sigma_out, mo->mh[m].sigma[strand].data(), sizeof(double) * mo->mh[m].n);
+    return PWMSCAN_OK;
+}
+
+extern "C" int32_t pwmscan_motifs_count(const pwmscan_motifs* mo) { return mo ? mo->M : -1; }
+
+extern "C" void pwmscan_motifs_free(pwmscan_motifs* mo) {
+    if (!mo) return;
+    if (mo->ctx) cudaSetDevice(mo->ctx->device);
+    if (mo->d_tab16) cudaFree(mo->d_tab16);
+    if (mo->d_mats) cudaFree(mo->d_mats);
+    delete mo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+extern "C" void pwmscan_plan_free(pwmscan_plan* pl) {
+    if (!pl) return;
+    if (pl->ctx) cudaSetDevice(pl->ctx->device);
+    if (pl->d_blocks) cudaFree(pl->d_blocks);
+    if (pl->d_combos) cudaFree(pl->d_combos);
+    if (pl->d_generic) cudaFree(pl->d_generic);
+    if (pl->d_tables) cudaFree(pl->d_tables);
+    if (pl->d_th) cudaFree(pl->d_th);
+    delete pl;
+}
+
+extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, const double* thres, int strands,
+                                   int skip_ambiguous, pwmscan_plan** out) {
+    if (!ctx || !mo || !thres || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_plan_create: NULL argument");
+    *out = nullptr;
+    if (strands != 1 && strands != 2) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_plan_create: strands must be 1 or 2");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    pwmscan_plan* pl = new (std::nothrow) pwmscan_plan();
+    if (!pl) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
+    pl->ctx = ctx; pl->motifs = mo; pl->strands = strands; pl->skip = skip_ambiguous ? 1 : 0;
+    HostPlan hp;
+    if (!build_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, hp)) {
+        pwmscan_plan_free(pl);
+        return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_plan_create: internal: block cannot be placed");
+    }
+    auto dev_combo = [&](int m, int s) {
+        DevCombo dc;
+        dc.motif = m; dc.strand = s; dc.n = mo->mh[m].n; dc.c = 0;
+        dc.tab_off = mo->tab_off[2 * m + s]; dc.th_off = mo->col_off[2 * m + s];
+        return dc;
+    };
+    std::vector<double>& h_th = hp.th;
+    pl->max_n = hp.max_n; pl->max_nslot = hp.max_nslot;
+    for (auto& g : hp.generic) pl->generic.push_back(dev_combo(g.first, g.second));
+    pl->blocks = std::move(hp.blocks);
+    pl->nblocks = (int)pl->blocks.size();
+    std::vector<DevBlock> h_blocks(pl->nblocks);
+    std::vector<DevCombo> h_combos((size_t)pl->nblocks * kCombosPerBlock);
+    std::vector<uint32_t> h_tables;
+    const double cand_rate = hp.cand_rate;
+    for (int b = 0; b < pl->nblocks; ++b) {
+        const BlockPlan& bp = pl->blocks[b];
+        h_blocks[b].s1 = bp.s1; h_blocks[b].nl = bp.nl; h_blocks[b].nslot = bp.nslot; h_blocks[b].pad = 0;
+        h_blocks[b].table_off = (int64_t)h_tables.size();
+        h_tables.insert(h_tables.end(), bp.table.begin(), bp.table.end());
+        for (int ci = 0; ci < kCombosPerBlock; ++ci) {
+            DevCombo dc;
+            const ComboPlan& cp = bp.combo[ci];
+            if (cp.motif >= 0) { dc = dev_combo(cp.motif, cp.strand); dc.c = cp.c; }
+            else { dc.motif = -1; dc.strand = 0; dc.n = 0; dc.c = 0; dc.tab_off = 0; dc.th_off = 0; }
+            h_combos[(size_t)b * kCombosPerBlock + ci] = dc;
+        }
+    }
+    pl->cand_rate = cand_rate;
+    cudaError_t e;
+    auto bail = [&](int code) { pwmscan_plan_free(pl); return code; };
+    auto up = [&](void** dst, const void* src, size_t bytes, const char* what) -> int {
+        if (bytes == 0) return 0;
+        if ((e = cudaMalloc(dst, bytes)) != cudaSuccess) return cuda_fail(ctx, e, what);
+        if ((e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(ctx, e, what);
+        return 0;
+    };
+    int rc;
+    if ((rc = up((void**)&pl->d_th, h_th.data(), h_th.size() * 8, "upload th"))) return bail(rc);
+    if ((rc = up((void**)&pl->d_blocks, h_blocks.data(), h_blocks.size() * sizeof(DevBlock), "upload blocks"))) return bail(rc);
+    if ((rc = up((void**)&pl->d_combos, h_combos.data(), h_combos.size() * sizeof(DevCombo), "upload combos"))) return bail(rc);
+    if ((rc = up((void**)&pl->d_tables, h_tables.data(), h_tables.size() * 4, "upload tables"))) return bail(rc);
+    if ((rc = up((void**)&pl->d_generic, pl->generic.data(), pl->generic.size() * sizeof(DevCombo), "upload generic"))) return bail(rc);
+    *out = pl;
+    return PWMSCAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels of the thresholded scan
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// counters: [0] candidates, [1] hits, [2] error flag, [3] work counter
+__global__ void __launch_bounds__(kThreads, 1)
+prefilter_kernel(const uint32_t* __restrict__ seq2, long long chunks_per_block, long long total_items,
+                 const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ tables,
+                 unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ long long s_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cur_blk = -1;
+    int s1 = 2, nl = 0, nslot = 2;
+    for (;;) {
+        if (tid == 0) s_item = (long long)atomicAdd(&counters[3], 1ull);
+        __syncthreads();
+        const long long item = s_item;
+        if (item >= total_items) break;
+        const int blk = (int)(item / chunks_per_block);
+        const long long chunk = item % chunks_per_block;
+        if (blk != cur_blk) {
+            const DevBlock db = blocks[blk];
+            s1 = db.s1; nl = db.nl; nslot = db.nslot;
+            const uint4* src = reinterpret_cast<const uint4*>(tables + db.table_off);
+            uint4* dst = reinterpret_cast<uint4*>(smem);
+            const int n16 = nslot * (kSlotBytes / 16);
+            for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+            cur_blk = blk;
+        }
+        __syncthreads();   // tables ready; also protects s_item against the next iteration's write
+        const long long U0 = chunk * kChunk + (long long)warp * (32 * kIters);
+        const uint32_t* w = seq2 + (U0 >> 4);
+        uint32_t x0 = __ldg(w - 1), x1 = __ldg(w), x2 = __ldg(w + 1), x3 = __ldg(w + 2), x4 = __ldg(w + 3);
+        const unsigned long long combo_base = (unsigned long long)blk * kCombosPerBlock + (unsigned)lane * 4u;
+        auto emit = [&](int q, long long u) {
+            const unsigned long long slot = atomicAdd(&counters[0], 1ull);
+            if (slot < cand_cap) cand[slot] = ((combo_base + (unsigned)q) << 40) | (unsigned long long)u;
+        };
+        if (s1 == 2) {
+#pragma unroll 1
+            for (int it = 0; it < kIters; ++it) {
+                const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);
+                process32<2>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem, nl, nslot, emit);
+                x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;
+            }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < kIters; ++it) {
+                const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);
+                process32<3>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem, nl, nslot, emit);
+                x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;
+            }
+        }
+        __syncthreads();   // every warp is done with the tables before a possible reload
+    }
+}
+
+__device__ __forceinline__ int find_segment(const int64_t* __restrict__ seg_off, int nseg, int64_t i) {
+    int lo = 0, hi = nseg;           // last seg with seg_off[seg] <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__device__ __forceinline__ unsigned long long hit_key(int seg, int motif, int strand, int64_t pos_in_seg) {
+    return ((unsigned long long)seg << 48) | ((unsigned long long)motif << 33) | ((unsigned long long)strand << 32) |
+           (unsigned long long)pos_in_seg;
+}
+
+__global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsigned long long cand_cap,
+                               const DevCombo* __restrict__ combos, const uint32_t* __restrict__ seq2,
+                               const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
+                               const double* __restrict__ tab16, const double* __restrict__ th,
+                               unsigned long long* __restrict__ hit_keys, double* __restrict__ hit_sc,
+                               unsigned long long hit_cap, unsigned long long* counters) {
+    unsigned long long ncand = counters[0];
+    if (ncand > cand_cap) ncand = cand_cap;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < ncand;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long cd = cand[k];
+        const DevCombo cb = combos[cd >> 40];
+        const int64_t u = (int64_t)(cd & ((1ull << 40) - 1));
+        const int64_t i = u - kPadFront - cb.c;
+        if (cb.motif < 0 || i < 0 || i + cb.n > len) continue;
+        const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
+        if (i + cb.n > seg_off[seg + 1]) continue;
+        double sc;
+        if (replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
+            const unsigned long long slot = atomicAdd(&counters[1], 1ull);
+            if (slot < hit_cap) { hit_keys[slot] = hit_key(seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+        }
+    }
+}
+
+// Exact kernel: every window of every listed combo replayed in fp64 (IUPAC-aware when skip == 0).
+// Used for combos the prefilter cannot take (skip == 0, > 28 columns, non-finite cutoffs/tables).
+__global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, int skip, const uint32_t* __restrict__ seq2,
+                             const uint32_t* __restrict__ mask, const uint8_t* __restrict__ ascii,
+                             const int64_t* __restrict__ seg_off, int nseg, int64_t len, const double* __restrict__ tab16,
+                             const double* __restrict__ th, unsigned long long* __restrict__ hit_keys,
+                             double* __restrict__ hit_sc, unsigned long long hit_cap, unsigned long long* counters) {
+  for (int ci = blockIdx.y; ci < ncombo; ci += gridDim.y) {
+    const DevCombo cb = combos[ci];
+    const double* tb = tab16 + cb.tab_off;
+    const double* tk = th + cb.th_off;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + cb.n <= len; i += (int64_t)gridDim.x * blockDim.x) {
+        const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
+        if (i + cb.n > seg_off[seg + 1]) continue;
+        double sc = 0.0;
+        bool hit;
+        if (skip) {
+            hit = replay_skip(seq2, mask, i + kPadFront, cb.n, tb, tk, &sc);
+        } else {
+            hit = true;
+            for (int k = 0; k < cb.n; ++k) {          // lookAheadSearch, Search.hs:133-157
+                const unsigned code = c_iupac_lut[ascii[i + k]];
+                if (code == 15u) { atomicOr(&counters[2], 1ull); hit = false; break; }
+                sc = __dadd_rn(sc, tb[16 * k + code]);
+                if (sc < tk[k]) { hit = false; break; }
+            }
+        }
+        if (hit) {
+            const unsigned long long slot = atomicAdd(&counters[1], 1ull);
+            if (slot < hit_cap) { hit_keys[slot] = hit_key(seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+        }
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// scan driver
+// ------------------------------------------------------------------------------------------------
+extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* pl, pwmscan_hits** out) {
+    if (!ctx || !seq || !pl || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: NULL argument");
+    *out = nullptr;
+    if (seq->ctx != ctx || pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: handles belong to another context");
+    if (!pl->skip && !seq->d_ascii) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: skip_ambiguous = 0 needs a sequence uploaded with PWMSCAN_SEQ_KEEP_ASCII");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_lut(ctx);
+    if (rc) return rc;
+    const pwmscan_motifs* mo = pl->motifs;
+    const int64_t len = seq->len;
+    const int64_t n_anchor = round_up(len + kPadFront + 64, kChunk);
+    const long long chunks_per_block = n_anchor / kChunk;
+    const long long total_items = chunks_per_block * pl->nblocks;
+    const size_t smem_bytes = (size_t)pl->max_nslot * kSlotBytes;
+    if (pl->nblocks > 0) {
+        static bool attr_set[64] = {false};
+        if (!attr_set[ctx->device & 63]) {
+            PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
+            attr_set[ctx->device & 63] = true;
+        }
+    }
+    // capacities: expected + slack, grown and re-run on overflow
+    unsigned long long cand_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
+    unsigned long long hit_cap = cand_cap;
+    if (!pl->generic.empty() && hit_cap < (1ull << 22)) hit_cap = 1ull << 22;
+    unsigned long long nhits = 0, ncand = 0;
+    unsigned long long *d_cand = nullptr, *d_keys = nullptr;
+    double* d_sc = nullptr;
+    float ms_pre = 0, ms_res = 0, ms_sort = 0, ms_tot = 0;
+    int launches = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        d_cand = (unsigned long long*)scratch_get(ctx, 1, cand_cap * 8);
+        d_keys = (unsigned long long*)scratch_get(ctx, 2, hit_cap * 8);
+        d_sc = (double*)scratch_get(ctx, 3, hit_cap * 8);
+        if (!d_cand || !d_keys || !d_sc) return PWMSCAN_ECUDA;
+        PWM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        PWM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        if (pl->nblocks > 0) {
+            const int grid = (int)std::min<long long>(ctx->sm_count, total_items);
+            prefilter_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, chunks_per_block, total_items, pl->d_blocks,
+                                                                         pl->d_tables, d_cand, cand_cap, ctx->d_counters);
+            PWM_CUDA(cudaGetLastError());
+            ++launches;
+        }
+        PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (pl->nblocks > 0) {
+            rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, pl->d_combos, seq->d_seq2, seq->d_mask,
+                                                                      seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
+                                                                      d_sc, hit_cap, ctx->d_counters);
+            PWM_CUDA(cudaGetLastError());
+        }
+        if (!pl->generic.empty() && len > 0) {
+            const int bs = 256;
+            const long long gx = std::min<long long>((len + bs - 1) / bs, 65535LL * 16);
+            dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(pl->generic.size(), 65535));
+            exact_kernel<<<grid, bs, 0, ctx->stream>>>(pl->d_generic, (int)pl->generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
+                                                      seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, hit_cap, ctx->d_counters);
+            PWM_CUDA(cudaGetLastError());
+        }
+        PWM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+        PWM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PWM_CUDA(cudaStreamSynchronize(ctx->stream));
+        ncand = ctx->h_counters[0]; nhits = ctx->h_counters[1];
+        if (ctx->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.Search.lookAheadSearch: invalid nucleotide");
+        if (ncand <= cand_cap && nhits <= hit_cap) break;
+        if (attempt == 3) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit buffers kept overflowing");
+        cand_cap = std::max(cand_cap, ncand + (ncand >> 3) + 1024);
+        hit_cap = std::max(hit_cap, std::max(nhits, ncand) + (nhits >> 3) + 1024);
+    }
+    pwmscan_hits* h = new (std::nothrow) pwmscan_hits();
+    if (!h) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
+    h->count = (int64_t)nhits;
+    if (nhits > 0) {
+        unsigned long long* d_keys2 = (unsigned long long*)scratch_get(ctx, 4, nhits * 8);
+        double* d_sc2 = (double*)scratch_get(ctx, 5, nhits * 8);
+        if (!d_keys2 || !d_sc2) { delete h; return PWMSCAN_ECUDA; }
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, 64, ctx->stream);
+        void* d_tmp = scratch_get(ctx, 6, tmp_bytes);
+        if (!d_tmp) { delete h; return PWMSCAN_ECUDA; }
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, 64, ctx->stream);
+        if (e != cudaSuccess) { delete h; return cuda_fail(ctx, e, "cub::DeviceRadixSort"); }
+        cudaEventRecord(ctx->ev[3], ctx->stream);
+        unsigned long long* hk = (unsigned long long*)pinned_get(ctx, 0, nhits * 8);
+        double* hs = (double*)pinned_get(ctx, 1, nhits * 8);
+        if (!hk || !hs) { delete h; return PWMSCAN_ECUDA; }
+        if ((e = cudaMemcpyAsync(hk, d_keys2, nhits * 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "D2H keys"); }
+        if ((e = cudaMemcpyAsync(hs, d_sc2, nhits * 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "D2H scores"); }
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "scan sync"); }
+        h->motif.resize(nhits); h->segment.resize(nhits); h->strand.resize(nhits); h->pos.resize(nhits); h->score.resize(nhits);
+        for (unsigned long long k = 0; k < nhits; ++k) {
+            const unsigned long long key = hk[k];
+            h->segment[k] = (int32_t)(key >> 48);
+            h->motif[k] = (int32_t)((key >> 33) & 0x7FFF);
+            h->strand[k] = (uint8_t)((key >> 32) & 1);
+            h->pos[k] = (int64_t)(key & 0xFFFFFFFFull);
+        }
+        std::memcpy(h->score.data(), hs, nhits * 8);
+        cudaEventElapsedTime(&ms_sort, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&ms_tot, ctx->ev[0], ctx->ev[3]);
+    } else {
+        cudaEventElapsedTime(&ms_tot, ctx->ev[0], ctx->ev[2]);
+    }
+    cudaEventElapsedTime(&ms_pre, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ms_res, ctx->ev[1], ctx->ev[2]);
+    ctx->timing[0] = ms_pre; ctx->timing[1] = ms_res; ctx->timing[2] = ms_sort; ctx->timing[3] = ms_tot;
+    ctx->timing[5] = (double)nhits * 16 + 32;
+    ctx->timing[6] = (double)ncand;
+    ctx->timing[7] = (double)launches;
+    *out = h;
+    return PWMSCAN_OK;
+}
+
+extern "C" int pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs, const double* thres,
+                                 int strands, int skip_ambiguous, pwmscan_hits** out) {
+    pwmscan_plan* pl = nullptr;
+    int rc = pwmscan_plan_create(ctx, motifs, thres, strands, skip_ambiguous, &pl);
+    if (rc) return rc;
+    rc = pwmscan_scan(ctx, seq, pl, out);
+    pwmscan_plan_free(pl);
+    return rc;
+}
+
+extern "C" int64_t pwmscan_hits_count(const pwmscan_hits* h) { return h ? h->count : -1; }
+
+extern "C" int pwmscan_hits_columns(const pwmscan_hits* h, const int32_t** motif, const uint8_t** strand, const int32_t** segment,
+                                    const int64_t** pos, const double** score) {
+    if (!h) return PWMSCAN_EINVAL;
+    if (motif) *motif = h->motif.data();
+    if (strand) *strand = h->strand.data();
+    if (segment) *segment = h->segment.data();
+    if (pos) *pos = h->pos.data();
+    if (score) *score = h->score.data();
+    return PWMSCAN_OK;
+}
+
+extern "C" void pwmscan_hits_free(pwmscan_hits* h) { delete h; }
+
+extern "C" void pwmscan_free(void* p) { std::free(p); }

@@ -1,0 +1,127 @@
+// scan_core.cuh — per-lane body of the prefilter kernel and the exact fp64 replay, written as
+// __host__ __device__ code so that the CPU unit test (tests/emul) can run the very same index
+// arithmetic lane by lane.  On the device `tab` is the shared-memory table base; on the host it is
+// a plain array with the same layout [slot][kmer][lane] of 32-bit words (4 combos, one byte each).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PWM_HD __host__ __device__ __forceinline__
+#else
+#define PWM_HD inline
+#endif
+
+namespace pwmscan {
+
+PWM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s == 0 ? lo : ((lo >> s) | (hi << (32 - s)));
+#endif
+}
+
+PWM_HD uint32_t lds32(const unsigned char* tab, uint32_t byte_off) {
+    return *reinterpret_cast<const uint32_t*>(tab + byte_off);
+}
+
+// byte `b` (0..15) of the 16-byte window Y[0..3]
+PWM_HD uint32_t window_byte(uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, int b) {
+    const uint32_t w = b < 8 ? (b < 4 ? y0 : y1) : (b < 12 ? y2 : y3);
+    return (w >> (8 * (b & 3))) & 0xFFu;
+}
+
+// Survivor of the first stage: add the remaining slots one by one (dead byte lanes are parked at
+// 0x80 so nothing ever carries into a neighbour), then report the byte lanes still alive.
+// Returns the alive mask (bit 8q+7 set <=> combo 4*lane+q is a candidate).
+PWM_HD uint32_t second_stage(uint32_t acc, uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, int byte0 /* 4+j-nl */,
+                             int nl, int s1, int nslot, const unsigned char* tab, uint32_t lane_off) {
+    for (int s = 0; s < nslot; ++s) {
+        if (s >= nl && s < nl + s1) continue;
+        const uint32_t m = acc & 0x80808080u;
+        if (m == 0x80808080u) return 0u;
+        acc &= ~(m - (m >> 7));
+        const uint32_t kmer = window_byte(y0, y1, y2, y3, byte0 + s);
+        acc += lds32(tab, (uint32_t)s * 32768u + kmer * 128u + lane_off);
+    }
+    return ~acc & 0x80808080u;
+}
+
+// 32 consecutive anchors u = U .. U+31 (U a multiple of 16) for one lane.
+// X[q] = packed word (U/16 - 1 + q), q = 0..4 (16 bases per word, base t at bits 2t..2t+1).
+// emit(q, u) is called for every candidate byte lane q at anchor u.
+template <int S1, class Emit>
+PWM_HD void process32(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, int64_t U, int lane,
+                      const unsigned char* tab, int nl, int nslot, Emit&& emit) {
+    const uint32_t lane_off = (uint32_t)lane * 4u;
+    const uint32_t base1 = (uint32_t)nl * 32768u + lane_off;     // first-stage slot 0
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        // Y covers the bases U-16+r .. U+47+r; byte b holds the 4 bases from U-16+r+4b
+        const uint32_t y0 = funnel_r(x0, x1, 2 * r), y1 = funnel_r(x1, x2, 2 * r);
+        const uint32_t y2 = funnel_r(x2, x3, 2 * r), y3 = funnel_r(x3, x4, 2 * r);
+        uint32_t idx[8 + S1 - 1];                                 // bytes 4 .. 4+7+S1-1
+#pragma unroll
+        for (int b = 0; b < 8 + S1 - 1; ++b) {
+            const int bb = 4 + b;
+            const uint32_t w = bb < 8 ? y1 : (bb < 12 ? y2 : y3);
+            idx[b] = ((w >> (8 * (bb & 3))) & 0xFFu) * 128u + base1;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t acc = lds32(tab, idx[j]) + lds32(tab, idx[j + 1] + 32768u);
+            if (S1 == 3) acc += lds32(tab, idx[j + 2] + 65536u);
+            if ((~acc & 0x80808080u) != 0u) {
+                uint32_t alive = second_stage(acc, y0, y1, y2, y3, 4 + j - nl, nl, S1, nslot, tab, lane_off);
+                while (alive) {
+#if defined(__CUDA_ARCH__)
+                    const int bit = __ffs((int)alive) - 1;
+#else
+                    const int bit = __builtin_ctz(alive);
+#endif
+                    alive &= alive - 1;
+                    emit(bit >> 3, U + 4 * j + r);
+                }
+            }
+        }
+    }
+}
+
+// 2-bit code stored for a base that is not A/C/G/T (or for padding): a position hash, so that long
+// N runs look like random sequence to the prefilter instead of a poly-A tract.  The invalid-base
+// bit plane is what makes such windows non-hits (exact replay).
+PWM_HD uint32_t pad_hash(int64_t u) {
+    uint32_t x = (uint32_t)u * 0x9E3779B1u + (uint32_t)((uint64_t)u >> 32) * 0x85EBCA77u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    return x & 3u;
+}
+
+// 2-bit base code / invalid flag of stored base index u
+PWM_HD uint32_t packed_base(const uint32_t* seq2, int64_t u) { return (seq2[u >> 4] >> (2 * (int)(u & 15))) & 3u; }
+PWM_HD uint32_t invalid_bit(const uint32_t* mask, int64_t u) { return (mask[u >> 5] >> (int)(u & 31)) & 1u; }
+
+#if defined(__CUDA_ARCH__)
+#define PWM_DADD(a, b) __dadd_rn((a), (b))
+#define PWM_NEG_INF __longlong_as_double((long long)0xFFF0000000000000ull)
+#else
+#define PWM_DADD(a, b) ((a) + (b))
+#define PWM_NEG_INF (-__builtin_huge_val())
+#endif
+
+// lookAheadSearch' replayed exactly (Motif/Search.hs:176-189): acc_k = acc_{k-1} + s[k][base]
+// (-inf for a non-ACGT base), window rejected as soon as acc_k < th[k] (th[k] = thres - sigma[k]).
+// tab16: n x 16 doubles, first four codes A,C,G,T.
+PWM_HD bool replay_skip(const uint32_t* seq2, const uint32_t* mask, int64_t u0, int n, const double* tab16,
+                        const double* th, double* score) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const int64_t u = u0 + k;
+        const double sc = invalid_bit(mask, u) ? PWM_NEG_INF : tab16[16 * k + packed_base(seq2, u)];
+        acc = PWM_DADD(acc, sc);
+        if (acc < th[k]) return false;
+    }
+    *score = acc;
+    return true;
+}
+
+}  // namespace pwmscan

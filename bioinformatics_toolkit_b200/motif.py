@@ -1,0 +1,290 @@
+"""Bio.Motif mirror (bioinformatics-toolkit/src/Bio/Motif.hs), same names and argument meaning.
+
+Types: PWM (Motif.hs:59-62), Motif (94-97), Bkgd (101-104).  Compute entry points go to the CUDA
+library through `_lib` (no CPU fallback): scores / scores' / score (127-149), scoreCDF (282-326),
+pValueToScore (213-214).  Host-side glue kept here exactly where the Haskell drop-in keeps it in
+Haskell: rcPWM (77-78), optimalScore (152-162), cdf / cdf' / truncateCDF on an already-computed CDF
+(236-274), MEME / motif-fasta parsing and printing (329-386).
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+from .seq import DNA
+
+
+class Bkgd:
+    """newtype Bkgd = BG (a, c, g, t); `def` = uniform 0.25 (Motif.hs:101-104)."""
+
+    def __init__(self, a=0.25, c=0.25, g=0.25, t=0.25):
+        self.freqs = (float(a), float(c), float(g), float(t))
+
+    def __iter__(self):
+        return iter(self.freqs)
+
+
+BG = Bkgd
+default_bkgd = Bkgd()
+
+
+class PWM:
+    """k x 4 position weight matrix (Motif.hs:59-62)."""
+
+    def __init__(self, nSites, mat):
+        self._nSites = nSites
+        self._mat = np.ascontiguousarray(mat, dtype=np.float64).reshape(-1, 4)
+
+
+class Motif:
+    def __init__(self, name, pwm):
+        self._name = name
+        self._pwm = pwm
+
+
+def size(pwm):
+    return pwm._mat.shape[0]
+
+
+def subPWM(i, l, pwm):
+    """M.subMatrix (i,0) (i+l,3): rows i..i+l inclusive, as the reference passes them (Motif.hs:72-73)."""
+    return PWM(pwm._nSites, pwm._mat[i:i + l + 1])
+
+
+def rcPWM(pwm):
+    """Reverse of the row-major flattening (Motif.hs:77-78)."""
+    return PWM(pwm._nSites, pwm._mat.reshape(-1)[::-1].reshape(-1, 4).copy())
+
+
+def gcContentPWM(pwm):
+    acc = 0.0
+    for i in range(size(pwm)):
+        acc = acc + pwm._mat[i, 1] + pwm._mat[i, 2]
+    return acc / size(pwm)
+
+
+def toPWM(lines):
+    """Motif.hs:329-330: lines of 4 numbers."""
+    return PWM(None, [[float(x) for x in (l.decode() if isinstance(l, bytes) else l).split()] for l in lines])
+
+
+def _argmax_last(row):
+    bi, bs = 0, row[0]
+    for i in range(1, 4):
+        if not (row[i] < bs):
+            bs, bi = row[i], i
+    return bi
+
+
+def optimalScore(bg, pwm):
+    """Motif.hs:152-162 (libm log on the host, like GHC)."""
+    f = bg.freqs
+    acc = 0.0
+    for row in pwm._mat:
+        j = _argmax_last(row)
+        acc = acc + math.log(row[j] / f[j])
+    return acc
+
+
+# ---- device handles ------------------------------------------------------------------------
+def _dev_seq(dna, keep_ascii=False, ctx=None):
+    if isinstance(dna, _lib.DeviceSeq):
+        return dna
+    ctx = ctx or _lib.default_context()
+    bs = dna.bs if isinstance(dna, DNA) else bytes(dna)
+    return _lib.DeviceSeq(ctx, bs, keep_ascii=keep_ascii)
+
+
+def _dev_motifs(bg, pwms, ctx=None):
+    ctx = ctx or _lib.default_context()
+    return _lib.DeviceMotifs(ctx, [p._mat for p in pwms], bg.freqs)
+
+
+def scores(bg, pwm, dna):
+    """Scores of a long sequence at each position (Motif.hs:127-133), IUPAC aware."""
+    seq = _dev_seq(dna, keep_ascii=True)
+    return _lib.scores(seq, _dev_motifs(bg, [pwm], seq.ctx), 0, 0)
+
+
+def scores_(bg, pwm, dna):
+    """scores' — the streaming version (Motif.hs:136-145); here an iterator over the same array."""
+    return iter(scores(bg, pwm, dna))
+
+
+def score(bg, pwm, dna):
+    """Motif.hs:147-149: scoreHelp over the whole of `dna` (its length should be size pwm)."""
+    bs = dna.bs if isinstance(dna, DNA) else bytes(dna)
+    n = size(pwm)
+    if len(bs) == n:
+        return float(scores(bg, pwm, DNA(bs))[0])
+    # B.foldl over every byte with M.unsafeIndex: only len == n is meaningful in the reference
+    raise ValueError("score: sequence length must equal the PWM size")
+
+
+# ---- CDF ----------------------------------------------------------------------------------------
+class CDF:
+    """newtype CDF = CDF (Vector (x, P(X <= x))) (Motif.hs:233)."""
+
+    def __init__(self, xs, ps):
+        self.xs = np.ascontiguousarray(xs, dtype=np.float64)
+        self.ps = np.ascontiguousarray(ps, dtype=np.float64)
+
+    def __len__(self):
+        return int(self.xs.size)
+
+
+def scoreCDF(bg, pwm):
+    """Motif.hs:282-326, computed on the device."""
+    xs, ps = _dev_motifs(bg, [pwm]).score_cdf(0)
+    return CDF(xs, ps)
+
+
+def _lower_bound(keys, q):
+    # binarySearchBy (Utils/Functions.hs:136-152) returns the first index whose key is >= q
+    return int(np.searchsorted(keys, q, side="left"))
+
+
+def cdf(c, x):
+    """P(X <= x) (Motif.hs:236-249)."""
+    n = len(c)
+    i = _lower_bound(c.xs, x)
+    if i >= n:
+        return float(c.ps[-1])
+    if i == 0:
+        return float(c.ps[0]) if x == c.xs[0] else 0.0
+    a, a1, b, b1 = float(c.xs[i - 1]), float(c.ps[i - 1]), float(c.xs[i]), float(c.ps[i])
+    al = (b - x) / (b - a)
+    be = (x - a) / (b - a)
+    return al * a1 + be * b1
+
+
+def cdf_(c, p):
+    """cdf' — the inverse of cdf (Motif.hs:252-270)."""
+    if p > 1 or p < 0:
+        raise ValueError("p must be in [0,1]")
+    n = len(c)
+    i = _lower_bound(c.ps, p)
+    if i >= n:
+        return math.inf
+    if i == 0:
+        if p == c.ps[0]:
+            return float(c.xs[0])
+        raise ValueError("cdf': impossible!")
+    a, a1, b, b1 = float(c.xs[i - 1]), float(c.ps[i - 1]), float(c.xs[i]), float(c.ps[i])
+    al = (b1 - p) / (b1 - a1)
+    be = (p - a1) / (b1 - a1)
+    return al * a + be * b
+
+
+def truncateCDF(x, c):
+    """Motif.hs:273-274."""
+    k = c.ps >= x
+    return CDF(c.xs[k], c.ps[k])
+
+
+def pValueToScore(p, bg, pwm):
+    """Motif.hs:213-214: cdf' (scoreCDF bg pwm) (1 - p), evaluated on the device."""
+    return float(_dev_motifs(bg, [pwm]).pvalue_to_score(p)[0])
+
+
+def pValueToScores(p, bg, pwms):
+    """Batched pValueToScore for a list of PWMs (one launch per DP column for all motifs)."""
+    return _dev_motifs(bg, pwms).pvalue_to_score(p)
+
+
+def toIUPAC(pwm):
+    """Consensus sequence (Motif.hs:107-124)."""
+    out = []
+    for row in pwm._mat:
+        order = sorted(zip("ACGT", row), key=lambda t: -t[1])   # sortBy (flip (comparing snd)): stable
+        (a, pa), (b, pb) = order[0], order[1]
+        if pa > 0.5 and pa > 2 * pb:
+            out.append(a)
+        elif pa + pb > 0.75:
+            x, y = (a, b) if a <= b else (b, a)
+            out.append({("A", "C"): "M", ("G", "T"): "K", ("A", "T"): "W", ("C", "G"): "S", ("C", "T"): "Y", ("A", "G"): "R"}[(x, y)])
+        else:
+            out.append("N")
+    return DNA("".join(out).encode(), "IUPAC")
+
+
+# ---- motif files -----------------------------------------------------------------------------
+def fromMEME(meme):
+    """Motif.hs:361-386 (state machine over the lines of a MEME file)."""
+    if isinstance(meme, bytes):
+        meme = meme.decode("latin1")
+    out, st, cur = [], 0, None
+    for x in meme.split("\n"):
+        if x.startswith("MOTIF"):
+            st, cur = 1, [x[6:]]
+            continue
+        if st == 1:
+            if x.startswith("letter-probability matrix:"):
+                cur.append(x.split()[7])
+                st = 2
+        elif st == 2:
+            y = x.lstrip(" ")
+            if y == "" or y.startswith("URL"):
+                out.append(_to_motif(cur))
+                st, cur = 0, None
+            else:
+                cur.append(y)
+    if st == 2:
+        out.append(_to_motif(cur))
+    return out
+
+
+def _to_motif(parts):
+    name, n, rows = parts[0], parts[1], parts[2:]
+    return Motif(name.encode("latin1"), PWM(int(n), [[float(v) for v in r.split()] for r in rows]))
+
+
+def readMEME(path):
+    with open(path, "rb") as f:
+        return fromMEME(f.read())
+
+
+def _shortest(x):
+    r = repr(float(x))
+    return r[:-2] if r.endswith(".0") else r   # double-conversion toShortest prints 1 not 1.0
+
+
+def toMEME(motifs, bg=default_bkgd):
+    a, c, g, t = bg.freqs
+    s = "MEME version 4\n\nALPHABET= ACGT\n\nstrands: + -\n\nBackground letter frequencies\nA %f C %f G %f T %f\n\n" % (a, c, g, t)
+    for m in motifs:
+        sites = 1 if m._pwm._nSites is None else m._pwm._nSites
+        s += "MOTIF " + m._name.decode("latin1") + "\n"
+        s += "letter-probability matrix: alength= 4 w= %d nsites= %d E= 0\n" % (size(m._pwm), sites)
+        s += "".join(" " + " ".join(_shortest(v) for v in row) + "\n" for row in m._pwm._mat) + "\n"
+    return s.encode("latin1")
+
+
+def writeMEME(path, motifs, bg=default_bkgd):
+    with open(path, "wb") as f:
+        f.write(toMEME(motifs, bg))
+
+
+def readFasta_(path):
+    """readFasta' for Motif records (Data/Fasta.hs:33-51): '>name' then rows of 4 numbers."""
+    out, cur = [], None
+    with open(path, "rb") as f:
+        for l in f.read().split(b"\n"):
+            if l == b"":
+                continue
+            if l[:1] == b">":
+                if cur is not None:
+                    out.append(Motif(cur[0], toPWM(cur[1])))
+                cur = (l[1:], [])
+            elif cur is not None:
+                cur[1].append(l)
+    if cur is not None:
+        out.append(Motif(cur[0], toPWM(cur[1])))
+    return out
+
+
+def writeFasta(path, motifs):
+    with open(path, "wb") as f:
+        for m in motifs:
+            f.write(b">" + m._name + b"\n")
+            f.write("".join(" ".join(_shortest(v) for v in row) + "\n" for row in m._pwm._mat).encode() + b"\n")

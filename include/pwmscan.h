@@ -1,0 +1,156 @@
+/* pwmscan.h — C ABI of libpwmscan.so, the B200 (sm_100a) implementation of the
+ * position-weight-matrix motif-scan path of kaizhang/bioinformatics-toolkit.
+ *
+ * The reference is pure Haskell and has no FFI; the boundary it exposes for this path is a set of
+ * exported Haskell functions.  Each entry point below names the reference function(s) it replaces
+ * (paths relative to bioinformatics-toolkit/src/Bio/).  INTEGRATION.md shows the
+ * `foreign import ccall` stubs a maintainer adds to keep those Haskell signatures unchanged.
+ *
+ * Conventions
+ *  - every call returns 0 on success or a negative PWMSCAN_E* code; the message is available from
+ *    pwmscan_last_error(ctx) (ctx may be NULL for failures of pwmscan_ctx_create);
+ *  - handles are opaque; inputs are borrowed for the duration of the call only; outputs are
+ *    library-owned buffers released by the matching *_free;
+ *  - one ctx per device; calls on one ctx are serialised by an internal mutex; different ctxs may
+ *    be used concurrently from different OS threads (import as `ccall safe`);
+ *  - results are deterministic: same inputs => bit-identical outputs, in the reference's order;
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with PWMSCAN_ECUDA.
+ */
+#ifndef PWMSCAN_H
+#define PWMSCAN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWMSCAN_ABI_VERSION 1
+
+/* error codes */
+#define PWMSCAN_OK        0
+#define PWMSCAN_EINVAL   -1   /* bad argument */
+#define PWMSCAN_ECUDA    -2   /* CUDA runtime failure (no device, OOM, launch failure) */
+#define PWMSCAN_ENUCL    -3   /* invalid nucleotide met where the reference calls `error`
+                                 (Motif/Search.hs:157, Motif.hs:185) */
+#define PWMSCAN_ERANGE   -4   /* a size exceeds what the library supports (see limits below) */
+#define PWMSCAN_EDOMAIN  -5   /* "p must be in [0,1]" / "cdf': impossible!" (Motif.hs:254,261) */
+
+/* limits */
+#define PWMSCAN_MAX_COLS      64      /* PWM columns */
+#define PWMSCAN_MAX_MOTIFS    32768   /* motifs per pwmscan_motifs */
+#define PWMSCAN_MAX_SEGMENTS  65536   /* sequences per pwmscan_seq */
+
+typedef struct pwmscan_ctx    pwmscan_ctx;
+typedef struct pwmscan_seq    pwmscan_seq;
+typedef struct pwmscan_motifs pwmscan_motifs;
+typedef struct pwmscan_plan   pwmscan_plan;
+typedef struct pwmscan_hits   pwmscan_hits;
+
+int pwmscan_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  pwmscan_ctx_create(int device, pwmscan_ctx** out);
+void pwmscan_ctx_destroy(pwmscan_ctx* ctx);
+const char* pwmscan_last_error(pwmscan_ctx* ctx);
+/* Device time (ms, CUDA events on the library's stream) of the phases of the last scan call:
+ * out[0] prefilter kernel, out[1] exact re-score kernel, out[2] sort, out[3] total device span,
+ * out[4] host->device bytes, out[5] device->host bytes, out[6] prefilter candidates,
+ * out[7] prefilter kernel launches. n = number of doubles available in out. */
+int  pwmscan_last_timing(pwmscan_ctx* ctx, double* out, int n);
+
+/* ---- sequences: Bio.Seq `DNA a` (Seq.hs:41,59-67,86-95) ------------------------------------- */
+#define PWMSCAN_SEQ_UPPERCASE  1   /* apply toUpper first, as fromBS does (Seq.hs:86-95) */
+#define PWMSCAN_SEQ_KEEP_ASCII 2   /* keep the (upper-cased) bytes on the device: needed by the
+                                      IUPAC-aware entry points (skip_ambiguous = 0, scores, maxMatchSc) */
+/* One sequence (a `DNA a` ByteString via unsafeUseAsCStringLen).  Packs 2 bits/base + an
+ * invalid-base bit plane in HBM. */
+int  pwmscan_seq_upload(pwmscan_ctx* ctx, const uint8_t* ascii, int64_t len, int flags, pwmscan_seq** out);
+/* nseg sequences laid end to end in `ascii`; seg_off has nseg+1 entries (seg_off[0] = 0).
+ * Windows never span two segments.  Used by scanMotif to batch BED regions. */
+int  pwmscan_seq_upload_segments(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t* seg_off,
+                                 int32_t nseg, int flags, pwmscan_seq** out);
+int64_t pwmscan_seq_length(const pwmscan_seq* seq);
+/* fromBS validation (Seq.hs:86-95): position of the first byte (after optional upper-casing)
+ * outside "ACGT" (alphabet 0, `DNA Basic`) or "ACGTNVHDBMKWSYR" (alphabet 1, `DNA IUPAC`); -1 if none. */
+int  pwmscan_seq_first_invalid(pwmscan_ctx* ctx, const pwmscan_seq* seq, int alphabet, int64_t* pos_out);
+void pwmscan_seq_free(pwmscan_seq* seq);
+
+/* ---- motifs: PWM / Bkgd (Motif.hs:59-62,101-104), rcPWM (77-78), optimalScoresSuffix
+ *      (Motif/Search.hs:111-124) -------------------------------------------------------------- */
+/* mats: the M matrices row-major (ncol[m] rows x 4 columns A,C,G,T), concatenated.  The library
+ * derives the reverse-complement PWM, both fp64 log-odds tables (host libm `log`, pseudocount
+ * 0.0001: Search.hs:185-196) and both sigma vectors. */
+int  pwmscan_motifs_create(pwmscan_ctx* ctx, int32_t M, const int32_t* ncol, const double* mats,
+                           const double bg[4], pwmscan_motifs** out);
+/* findTFBSWith (Search.hs:38-58) lets the caller pass its own sigma; override motif m's vector
+ * for strand 0 (the PWM) or 1 (its rcPWM). */
+int  pwmscan_motifs_set_sigma(pwmscan_motifs* motifs, int32_t m, int strand, const double* sigma);
+int  pwmscan_motifs_get_sigma(const pwmscan_motifs* motifs, int32_t m, int strand, double* sigma_out);
+int32_t pwmscan_motifs_count(const pwmscan_motifs* motifs);
+void pwmscan_motifs_free(pwmscan_motifs* motifs);
+
+/* ---- thresholded scan: findTFBS / findTFBSWith (Search.hs:25-58), the per-region body of
+ *      scanMotif (Data/Bed/Utils.hs:112-118) ---------------------------------------------------- */
+/* A plan is the device-side analogue of CutoffMotif (Data/Bed/Utils.hs:78-98): everything that
+ * depends on (motifs, cutoffs) and not on the sequence.  thres[m] is the cutoff of motif m and is
+ * used for both strands (Utils.hs:91-98).  strands: 1 = the PWMs only (findTFBS), 2 = PWMs and
+ * their rcPWMs (scanMotif).  skip_ambiguous: the reference's `skip` flag — 1 = lookAheadSearch'
+ * (non-ACGT => -inf), 0 = IUPAC-aware lookAheadSearch (needs PWMSCAN_SEQ_KEEP_ASCII). */
+int  pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, const double* thres,
+                         int strands, int skip_ambiguous, pwmscan_plan** out);
+void pwmscan_plan_free(pwmscan_plan* plan);
+/* Hit list sorted by (segment, motif, strand, position); position is the 0-based window start
+ * within its segment on the forward sequence (also for strand 1: Utils.hs:109-111); score is the
+ * reference's fp64 accumulator, bit-identical. */
+int  pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* plan, pwmscan_hits** out);
+/* Convenience: plan_create + scan + plan_free. */
+int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
+                       const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);
+int64_t pwmscan_hits_count(const pwmscan_hits* hits);
+/* Column views (host memory owned by `hits`); any pointer argument may be NULL. */
+int  pwmscan_hits_columns(const pwmscan_hits* hits, const int32_t** motif, const uint8_t** strand,
+                          const int32_t** segment, const int64_t** pos, const double** score);
+void pwmscan_hits_free(pwmscan_hits* hits);
+
+/* ---- dense scoring: scores / scores' / score (Motif.hs:127-149), maxMatchSc (Search.hs:98-109) */
+/* out[i] = scoreHelp of the window at i, i in [0, len-n]; IUPAC-aware ('N' scores 0); needs
+ * PWMSCAN_SEQ_KEEP_ASCII and a single-segment seq.  PWMSCAN_ENUCL on any other byte. */
+int  pwmscan_scores(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs, int32_t m,
+                    int strand, double* out, int64_t out_len);
+/* out[m] = maximum window score of motif m (strand 0) over the sequence; -inf if len < n. */
+int  pwmscan_max_match_sc(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs, double* out);
+
+/* ---- score distribution: scoreCDF (Motif.hs:282-326), cdf' (252-270), pValueToScore (213-214) */
+/* Compressed CDF points of motif m (strand 0) under the motifs' background; *x and *P are
+ * library-owned (release with pwmscan_free). */
+int  pwmscan_score_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int32_t m, double** x, double** P, int64_t* npts);
+/* thres_out[m] = cdf' (scoreCDF bg pwm_m) (1 - p) for every motif. */
+int  pwmscan_pvalue_to_score(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, double p, double* thres_out);
+void pwmscan_free(void* p);
+
+/* ---- PWM-PWM alignment: alignmentBy jsd pFn combFn (Motif/Alignment.hs:83-132), the all-pairs
+ *      initialisation and row refresh of iterativeMerge (Motif/Merge.hs:138-145,161-165) -------- */
+#define PWMSCAN_PENAL_LINEAR 0
+#define PWMSCAN_PENAL_QUAD   1
+#define PWMSCAN_PENAL_CUBIC  2
+#define PWMSCAN_PENAL_EXP    3
+#define PWMSCAN_COMB_L1   0
+#define PWMSCAN_COMB_L2   1
+#define PWMSCAN_COMB_L3   2
+#define PWMSCAN_COMB_LINF 3
+/* All pairs i<j, packed upper triangle in row-major order (pair (i,j) at
+ * i*M - i*(i+1)/2 + (j-i-1)): dist, same_dir (1 = True) and pos as alignmentBy returns them for
+ * `align pwm_i pwm_j`. */
+int  pwmscan_align_all_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int penalty_kind, double gap,
+                             int combine_kind, double* dist, uint8_t* same_dir, int32_t* pos);
+/* Explicit pair list: result k is `align pwm_{a[k]} pwm_{b[k]}` (argument order preserved —
+ * Merge.hs:142-143 relies on it). */
+int  pwmscan_align_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int64_t npairs, const int32_t* a,
+                         const int32_t* b, int penalty_kind, double gap, int combine_kind,
+                         double* dist, uint8_t* same_dir, int32_t* pos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWMSCAN_H */

@@ -1,0 +1,95 @@
+// emul_scan.cpp — CPU emulation of the device scan pipeline, TEST ONLY.
+//
+// Runs the very same planning code (csrc/plan.h) and the very same per-lane kernel body
+// (csrc/scan_core.cuh: process32 / second_stage / replay_skip) the CUDA kernels run, with the 32
+// lanes of a warp executed one after another on the host.  It lets the CPU test-suite check the
+// quantised prefilter for false negatives against the oracle without a GPU.  It is never loaded
+// by the product package.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../bioinformatics_toolkit_b200/csrc/plan.h"
+#include "../../bioinformatics_toolkit_b200/csrc/scan_core.cuh"
+
+using namespace pwmscan;
+
+extern "C" __attribute__((visibility("default")))
+int64_t emul_scan(int M, const int* ncol, const double* mats, const double* bg, const double* thres, int strands,
+                  const unsigned char* ascii, int64_t len, int force_s1,
+                  int32_t* out_motif, unsigned char* out_strand, int64_t* out_pos, double* out_sc, int64_t cap,
+                  int64_t* stats /* [0] candidates [1] first-stage survivors(lane level) [2] nblocks [3] generic combos */) {
+    std::vector<MotifHost> mh(M);
+    std::vector<int64_t> col_off(2 * (size_t)M);
+    int64_t cols = 0;
+    const double* p = mats;
+    for (int m = 0; m < M; ++m) {
+        motif_prepare(mh[m], ncol[m], p, bg);
+        p += 4 * ncol[m];
+        for (int s = 0; s < 2; ++s) { col_off[2 * m + s] = cols; cols += ncol[m]; }
+    }
+    HostPlan hp;
+    if (!build_host_plan(mh, col_off, cols, thres, strands, 1, hp, force_s1)) return -1;
+    // pack (restates pack_kernel)
+    const int64_t kChunk = 16384;
+    const int64_t n_anchor = (len + kPadFront + 64 + kChunk - 1) / kChunk * kChunk;
+    std::vector<uint32_t> seq2_alloc((size_t)(n_anchor / 16 + 9), 0u), mask((size_t)(n_anchor / 32 + 4), 0u);
+    uint32_t* seq2 = seq2_alloc.data() + 1;
+    for (int64_t u = 0; u < (int64_t)mask.size() * 32; ++u) {
+        const int64_t pos = u - kPadFront;
+        const int code = (pos >= 0 && pos < len) ? iupac_code(ascii[pos]) : 15;
+        uint32_t c2;
+        if (code < 4) c2 = (uint32_t)code; else { c2 = pad_hash(u); mask[u >> 5] |= 1u << (u & 31); }
+        seq2[u >> 4] |= c2 << (2 * (u & 15));
+    }
+    struct Hit { int32_t motif; unsigned char strand; int64_t pos; double sc; };
+    std::vector<Hit> hits;
+    int64_t ncand = 0;
+    for (size_t b = 0; b < hp.blocks.size(); ++b) {
+        const BlockPlan& bp = hp.blocks[b];
+        const unsigned char* tab = reinterpret_cast<const unsigned char*>(bp.table.data());
+        for (int64_t U = 0; U < n_anchor; U += 32) {
+            const uint32_t* w = seq2 + (U >> 4);
+            for (int lane = 0; lane < 32; ++lane) {
+                auto emit = [&](int q, int64_t u) {
+                    ++ncand;
+                    const ComboPlan& cp = bp.combo[lane * 4 + q];
+                    if (cp.motif < 0) return;
+                    const int64_t i = u - kPadFront - cp.c;
+                    if (i < 0 || i + cp.n > len) return;
+                    double sc;
+                    if (replay_skip(seq2, mask.data(), i + kPadFront, cp.n, mh[cp.motif].tab16[cp.strand].data(),
+                                    hp.th.data() + col_off[2 * cp.motif + cp.strand], &sc))
+                        hits.push_back({cp.motif, (unsigned char)cp.strand, i, sc});
+                };
+                if (bp.s1 == 2) process32<2>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
+                else            process32<3>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
+            }
+        }
+    }
+    // combos the prefilter cannot take: exact replay of every window
+    for (auto& g : hp.generic) {
+        const int m = g.first, s = g.second, n = mh[m].n;
+        for (int64_t i = 0; i + n <= len; ++i) {
+            double sc;
+            if (replay_skip(seq2, mask.data(), i + kPadFront, n, mh[m].tab16[s].data(), hp.th.data() + col_off[2 * m + s], &sc))
+                hits.push_back({m, (unsigned char)s, i, sc});
+        }
+    }
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) {
+        if (a.motif != b.motif) return a.motif < b.motif;
+        if (a.strand != b.strand) return a.strand < b.strand;
+        return a.pos < b.pos;
+    });
+    for (size_t k = 0; k < hits.size() && (int64_t)k < cap; ++k) {
+        out_motif[k] = hits[k].motif; out_strand[k] = hits[k].strand; out_pos[k] = hits[k].pos; out_sc[k] = hits[k].sc;
+    }
+    if (stats) {
+        stats[0] = ncand; stats[1] = 0; stats[2] = (int64_t)hp.blocks.size(); stats[3] = (int64_t)hp.generic.size();
+        double pw = 0; for (auto& bp : hp.blocks) pw += bp.p_warp;
+        stats[1] = (int64_t)(1e6 * (hp.blocks.empty() ? 0 : pw / hp.blocks.size()));
+        stats[4] = hp.blocks.empty() ? 0 : hp.blocks[0].s1 * 100 + hp.blocks[0].nl * 10 + hp.blocks[0].nr;
+    }
+    return (int64_t)hits.size();
+}

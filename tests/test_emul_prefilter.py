@@ -1,0 +1,106 @@
+"""CPU check of the device pipeline's host-visible logic: the planning code (csrc/plan.h) and the
+per-lane kernel body (csrc/scan_core.cuh) are compiled with g++ and run lane by lane
+(tests/emul/emul_scan.cpp); the hit list must equal the oracle's bit for bit — in particular the
+quantised prefilter must never lose a hit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bioinformatics_toolkit_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BG = (0.25, 0.25, 0.25, 0.25)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(HERE, "emul", "libemul.so")
+    src = os.path.join(HERE, "emul", "emul_scan.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    L.emul_scan.restype = C.c_int64
+
+    def run(mats, thres, dna, strands=2, force_s1=0, bg=BG):
+        ncol = np.array([m.shape[0] for m in mats], dtype=np.int32)
+        flat = np.concatenate([np.ascontiguousarray(m, dtype=np.float64).reshape(-1) for m in mats])
+        cap = 1 << 21
+        om, os_, op, osc = np.empty(cap, np.int32), np.empty(cap, np.uint8), np.empty(cap, np.int64), np.empty(cap)
+        st = np.zeros(8, np.int64)
+        bga, th = np.array(bg, float), np.array(thres, float)
+        d = np.ascontiguousarray(np.frombuffer(bytes(dna), dtype=np.uint8))
+        vp = C.c_void_p
+        n = L.emul_scan(C.c_int(len(mats)), ncol.ctypes.data_as(vp), flat.ctypes.data_as(vp), bga.ctypes.data_as(vp),
+                        th.ctypes.data_as(vp), C.c_int(strands), d.ctypes.data_as(vp), C.c_int64(d.size), C.c_int(force_s1),
+                        om.ctypes.data_as(vp), os_.ctypes.data_as(vp), op.ctypes.data_as(vp), osc.ctypes.data_as(vp),
+                        C.c_int64(cap), st.ctypes.data_as(vp))
+        assert 0 <= n <= cap
+        return (om[:n].copy(), os_[:n].copy(), op[:n].copy(), osc[:n].copy()), st
+    return run
+
+
+def _same(h, o):
+    return all(np.array_equal(a, b) for a, b in zip(h, o))
+
+
+@pytest.mark.parametrize("force_s1", [0, 2, 3])
+def test_mixed_lengths_both_strands(emul, oracle, force_s1):
+    mats = synth.synth_pwms(70, 21, nmin=6, nmax=24)
+    dna = synth.synth_dna(60000, 9, gc=0.45, n_runs=[(0, 40), (30000, 700), (59990, 10)])
+    thres = [0.55 * oracle.optimal_score(BG, m) for m in mats]
+    h, st = emul(mats, thres, dna, force_s1=force_s1)
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=1, nthreads=4, cap=1 << 21)
+    assert cnt == len(o[0]) and cnt > 100
+    assert _same(h, o)
+    assert st[2] == 2 and st[3] == 0
+
+
+def test_pvalue_thresholds_and_reference_fixtures(emul, oracle, ref_motifs, ref_motifs_meme):
+    mats = [m for _, m in ref_motifs] + [m for _, m in ref_motifs_meme]
+    dna = synth.synth_dna(200000, 3)
+    thres = [oracle.pvalue_to_score(1e-4, BG, m) for m in mats]
+    h, st = emul(mats, thres, dna)
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=0, nthreads=4, cap=1 << 20)
+    assert cnt > 50 and _same(h, o)
+    assert st[0] < 4 * cnt + 100          # the prefilter is tight: few false candidates
+
+
+def test_long_motifs_go_to_the_exact_path(emul, oracle):
+    mats = synth.synth_pwms(3, 5, nmin=29, nmax=40) + synth.synth_pwms(3, 6, nmin=25, nmax=28)
+    dna = synth.synth_dna(20000, 4)
+    thres = [0.35 * oracle.optimal_score(BG, m) for m in mats]
+    h, st = emul(mats, thres, dna)
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=1, nthreads=2, cap=1 << 20)
+    assert st[3] == 6 and _same(h, o)
+
+
+def test_forward_only_nonuniform_background_and_edge_cutoffs(emul, oracle):
+    bg = (0.3, 0.2, 0.2, 0.3)
+    mats = synth.synth_pwms(9, 8, nmin=5, nmax=16)
+    dna = synth.synth_dna(50000, 6, gc=0.4)
+    opt = [max(oracle.optimal_score(bg, m), 1.0) for m in mats]
+    thres = [0.5 * opt[0], 0.9 * opt[1], 1.5 * opt[2], -1e9, 0.0, 0.7 * opt[5], float("inf"), 0.6 * opt[7], 0.3 * opt[8]]
+    mats[3] = mats[3][:5]
+    h, st = emul(mats, thres, dna[:3000], strands=1, bg=bg)
+    ref = []
+    for m, (mat, th) in enumerate(zip(mats, thres)):
+        pos, sc = oracle.find_tfbs(bg, mat, dna[:3000], th, True)
+        ref.append((np.full(pos.size, m, np.int32), np.zeros(pos.size, np.uint8), pos, sc))
+    o = tuple(np.concatenate([r[k] for r in ref]) for k in range(4))
+    assert _same(h, o)
+    assert (h[0] == 3).sum() == 3000 - 5 + 1          # cutoff -1e9: every window is a hit
+    assert (h[0] == 2).sum() == 0 and (h[0] == 6).sum() == 0
+
+
+def test_tiny_and_empty_sequences(emul, oracle, ref_motifs):
+    mats = [m for _, m in ref_motifs]
+    thres = [0.0] * len(mats)
+    for dna in (b"", b"ACGT", b"ACGTACGTAC", bytes(synth.synth_dna(11, 1)), bytes(synth.synth_dna(33, 1))):
+        h, _ = emul(mats, thres, dna)
+        cnt, o = oracle.scan_mt(BG, mats, thres, np.frombuffer(dna, dtype=np.uint8), mode=1, cap=1 << 16)
+        if cnt == 0:
+            assert h[0].size == 0
+        else:
+            assert _same(h, o)

@@ -1,0 +1,199 @@
+"""Parity of the CUDA scan (through the C ABI) with the oracle: bit-identical hit sets
+(motif, strand, position) AND bit-identical fp64 scores."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from bioinformatics_toolkit_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+BG = (0.25, 0.25, 0.25, 0.25)
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_scan(ctx, mats, thres, dna, strands=2, skip=True, bg=BG, seg_off=None, keep_ascii=False):
+    seq = _lib.DeviceSeq(ctx, dna, seg_off=seg_off, keep_ascii=keep_ascii or not skip)
+    mo = _lib.DeviceMotifs(ctx, mats, bg)
+    return _lib.Plan(mo, thres, strands=strands, skip_ambiguous=skip).scan(seq)
+
+
+def oracle_scan(oracle, mats, thres, dna, strands=2, bg=BG, skip=True):
+    cols = []
+    for m, (mat, th) in enumerate(zip(mats, thres)):
+        for s in range(strands):
+            mm = mat if s == 0 else oracle.rc_pwm(mat)
+            pos, sc = oracle.find_tfbs(bg, mm, dna, th, skip, mode=1)
+            cols.append((np.full(pos.size, m, np.int32), np.full(pos.size, s, np.uint8), pos, sc))
+    return tuple(np.concatenate([c[k] for c in cols]) for k in range(4))
+
+
+def assert_same(h, o):
+    assert len(h) == o[0].size
+    assert np.array_equal(h.motif, o[0]) and np.array_equal(h.strand, o[1]) and np.array_equal(h.pos, o[2])
+    assert np.array_equal(h.score.view(np.uint64), o[3].view(np.uint64))     # bit-identical fp64
+
+
+def test_mixed_lengths_both_strands(ctx, oracle):
+    mats = synth.synth_pwms(150, 21, nmin=6, nmax=24)
+    dna = synth.synth_dna(400000, 9, gc=0.45, n_runs=[(0, 40), (30000, 700), (399990, 10)])
+    thres = [0.55 * oracle.optimal_score(BG, m) for m in mats]
+    h = gpu_scan(ctx, mats, thres, dna)
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=1, nthreads=8, cap=1 << 23)
+    assert cnt > 1000
+    assert_same(h, o)
+
+
+def test_reference_fixture_goldens(ctx, oracle, ref_motifs):
+    g = json.load(open(os.path.join(GOLDEN, "oracle_goldens.json")))
+    dna = synth.synth_dna(5000, 2)
+    mats = [m for _, m in ref_motifs]
+    thres = [0.6 * oracle.optimal_score(BG, m) for m in mats]
+    h = gpu_scan(ctx, mats, thres, dna, strands=1)
+    for m, e in enumerate(g["fasta"]):
+        hm = h.select(motif=m)
+        assert hm.pos.tolist() == e["tfbs_pos"]
+        assert [float(v).hex() for v in hm.score] == e["tfbs_sc"]
+
+
+def test_long_motifs_and_edge_cutoffs(ctx, oracle):
+    bg = (0.3, 0.2, 0.2, 0.3)
+    mats = synth.synth_pwms(6, 5, nmin=29, nmax=60) + synth.synth_pwms(9, 8, nmin=5, nmax=16)
+    dna = synth.synth_dna(30000, 6, gc=0.4, n_runs=[(5000, 64)])
+    opt = [max(oracle.optimal_score(bg, m), 1.0) for m in mats]
+    thres = [0.3 * o for o in opt]
+    thres[7] = 1.5 * opt[7]
+    thres[8] = -1e9
+    thres[9] = float("inf")
+    thres[10] = float("-inf")
+    thres[11] = 0.0
+    h = gpu_scan(ctx, mats, thres, dna[:4000], bg=bg)
+    o = oracle_scan(oracle, mats, thres, dna[:4000], bg=bg)
+    assert_same(h, o)
+    assert len(h.select(motif=7)) == 0 and len(h.select(motif=9)) == 0
+    assert len(h.select(motif=8, strand=0)) == 4000 - mats[8].shape[0] + 1
+
+
+def test_segments_never_span(ctx, oracle):
+    mats = synth.synth_pwms(20, 33, nmin=6, nmax=20)
+    lens = [0, 5, 500, 37, 1200, 19, 20, 3000, 1]
+    segs = [synth.synth_dna(L, 50 + i, n_runs=[(L // 3, 3)] if L > 100 else ()) for i, L in enumerate(lens)]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    thres = [0.45 * oracle.optimal_score(BG, m) for m in mats]
+    h = gpu_scan(ctx, mats, thres, np.concatenate(segs), seg_off=off)
+    tot = 0
+    for s, d in enumerate(segs):
+        o = oracle_scan(oracle, mats, thres, d)
+        hs = h.select(segment=s)
+        assert_same(hs, o)
+        tot += o[0].size
+    assert tot == len(h) and tot > 100
+    assert np.all(np.diff(h.segment) >= 0)
+
+
+def test_iupac_aware_search(ctx, oracle, ref_motifs):
+    mats = [m for _, m in ref_motifs]
+    d = bytearray(bytes(synth.synth_dna(20000, 5)))
+    for i, ch in enumerate(b"NVHDBMKWSYR"):
+        d[1000 + 37 * i] = ch
+    d[5000:5040] = b"N" * 40
+    thres = [0.4 * oracle.optimal_score(BG, m) for m in mats]
+    h = gpu_scan(ctx, mats, thres, bytes(d), skip=False)
+    o = oracle_scan(oracle, mats, thres, bytes(d), skip=False)
+    assert_same(h, o)
+    d[777] = ord("X")
+    with pytest.raises(_lib.InvalidNucleotide):
+        gpu_scan(ctx, mats, [-1e9] * len(mats), bytes(d), skip=False)
+
+
+def test_lowercase_and_uppercase_flag(ctx, oracle, ref_motifs):
+    mats = [m for _, m in ref_motifs]
+    raw = synth.synth_dna(50000, 12, lower_frac=0.3)
+    thres = [0.5 * oracle.optimal_score(BG, m) for m in mats]
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    plan = _lib.Plan(mo, thres)
+    # raw bytes: lower case is not ACGT (lookAheadSearch' scores it -inf)
+    assert_same(plan.scan(_lib.DeviceSeq(ctx, raw)), oracle_scan(oracle, mats, thres, raw))
+    # fromBS semantics: upper-cased first
+    up = np.frombuffer(bytes(raw).upper(), dtype=np.uint8)
+    s = _lib.DeviceSeq(ctx, raw, uppercase=True)
+    assert_same(plan.scan(s), oracle_scan(oracle, mats, thres, up))
+    assert s.first_invalid("Basic") == -1
+    assert _lib.DeviceSeq(ctx, raw).first_invalid("Basic") == int(np.nonzero(raw >= 97)[0][0])
+
+
+def test_tiny_and_empty(ctx, oracle, ref_motifs):
+    mats = [m for _, m in ref_motifs]
+    for dna in (b"", b"ACGT", b"ACGTACGTAC", bytes(synth.synth_dna(11, 1)), bytes(synth.synth_dna(33, 1))):
+        h = gpu_scan(ctx, mats, [0.0] * len(mats), dna)
+        o = oracle_scan(oracle, mats, [0.0] * len(mats), np.frombuffer(dna, dtype=np.uint8))
+        assert_same(h, o)
+
+
+def test_dense_scores_and_max(ctx, oracle, ref_motifs, ref_motifs_meme):
+    mats = [m for _, m in ref_motifs] + [m for _, m in ref_motifs_meme]
+    d = bytearray(bytes(synth.synth_dna(70000, 15)))
+    for i, ch in enumerate(b"NVHDBMKWSYR"):
+        d[2000 + 41 * i] = ch
+    seq = _lib.DeviceSeq(ctx, bytes(d), keep_ascii=True)
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    mx = _lib.max_match_sc(seq, mo)
+    for m, mat in enumerate(mats):
+        for s in (0, 1):
+            ref = oracle.scores(BG, mat if s == 0 else oracle.rc_pwm(mat), bytes(d))
+            got = _lib.scores(seq, mo, m, s)
+            assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+        assert mx[m] == oracle.max_match_sc(BG, mat, bytes(d))
+    d[100] = ord("!")
+    with pytest.raises(_lib.InvalidNucleotide):
+        _lib.scores(_lib.DeviceSeq(ctx, bytes(d), keep_ascii=True), mo, 0, 0)
+    short = _lib.DeviceSeq(ctx, b"ACG", keep_ascii=True)
+    assert _lib.scores(short, mo, 0, 0).size == 0 and np.all(np.isneginf(_lib.max_match_sc(short, mo)))
+
+
+def test_config_c1_full_size(ctx, oracle):
+    """BASELINE config 1: one CTCF-like 19-bp PWM over 10 Mbp, both strands, vs the oracle."""
+    dna, mats = synth.config_c1()
+    th = [json.load(open(os.path.join(GOLDEN, "config_thresholds.json")))["c1"][0]]
+    th = [float.fromhex(th[0])]
+    up = np.frombuffer(bytes(dna).upper(), dtype=np.uint8)
+    h = _lib.Plan(_lib.DeviceMotifs(ctx, mats, BG), th).scan(_lib.DeviceSeq(ctx, dna, uppercase=True))
+    cnt, o = oracle.scan_mt(BG, mats, th, up, mode=1, nthreads=8, cap=1 << 20)
+    assert 20 < cnt < 5000
+    assert_same(h, o)
+
+
+def test_config_c2_full_size_properties(ctx, oracle):
+    """BASELINE config 2 (100 PWMs x 248 956 422 bp): size-independent properties + an oracle slice."""
+    dna, mats = synth.config_c2()
+    th = [float.fromhex(v) for v in json.load(open(os.path.join(GOLDEN, "config_thresholds.json")))["c2"]]
+    seq = _lib.DeviceSeq(ctx, dna)
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    h = _lib.Plan(mo, th).scan(seq)
+    assert 100000 < len(h) < 3000000
+    # sorted (motif, strand, pos), no duplicates
+    key = (h.motif.astype(np.int64) << 40) | (h.strand.astype(np.int64) << 39) | h.pos
+    assert np.all(np.diff(key) > 0)
+    # idempotence / determinism
+    h2 = _lib.Plan(mo, th).scan(seq)
+    assert np.array_equal(h.pos, h2.pos) and np.array_equal(h.score.view(np.uint64), h2.score.view(np.uint64))
+    # strand symmetry: strand-1 hits of motif m == strand-0 hits of rcPWM(m), same cutoff
+    rcs = [oracle.rc_pwm(m) for m in mats[:8]]
+    hr = _lib.Plan(_lib.DeviceMotifs(ctx, rcs, BG), th[:8], strands=1).scan(seq)
+    for m in range(8):
+        a, b = h.select(motif=m, strand=1), hr.select(motif=m)
+        assert np.array_equal(a.pos, b.pos) and np.array_equal(a.score.view(np.uint64), b.score.view(np.uint64))
+    # no hit inside the N blocks
+    for (p, ln) in synth.chr1_n_runs():
+        inside = (h.pos + 7 >= p) & (h.pos < p + ln - 30)
+        assert not inside.any()
+    # oracle on two slices (one straddling the 18 Mbp N block's end)
+    for lo in (5_000_000, 139_699_000):
+        hi = lo + 1_000_000
+        cnt, o = oracle.scan_mt(BG, mats, th, dna[lo:hi], mode=1, nthreads=8, cap=1 << 22)
+        nlen = np.array([m.shape[0] for m in mats])[h.motif]
+        k = (h.pos >= lo) & (h.pos + nlen <= hi)
+        assert k.sum() == cnt
+        assert np.array_equal(h.motif[k], o[0]) and np.array_equal(h.strand[k], o[1]) and np.array_equal(h.pos[k] - lo, o[2])
+        assert np.array_equal(h.score[k].view(np.uint64), o[3].view(np.uint64))

@@ -9,6 +9,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -399,6 +400,16 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
     std::vector<DevCombo> h_combos((size_t)pl->nblocks * kCombosPerBlock);
     std::vector<uint32_t> h_tables;
     const double cand_rate = hp.cand_rate;
+    if (std::getenv("PWMSCAN_VERBOSE")) {
+        for (int b = 0; b < pl->nblocks; ++b) {
+            const BlockPlan& bp = pl->blocks[b];
+            int nmin = 999, nmax = 0, nen = 0;
+            for (int ci = 0; ci < kCombosPerBlock; ++ci) if (bp.combo[ci].motif >= 0) { nmin = std::min(nmin, bp.combo[ci].n); nmax = std::max(nmax, bp.combo[ci].n); nen += bp.combo[ci].enabled; }
+            std::fprintf(stderr, "[pwmscan] block %d: s1=%d nl=%d nr=%d nslot=%d Q=%d cols %d..%d enabled=%d p_warp=%.4f cost=%.3f\n",
+                         b, bp.s1, bp.nl, bp.nr, bp.nslot, bp.Q, nmin, nmax, nen, bp.p_warp, bp.cost);
+        }
+        std::fprintf(stderr, "[pwmscan] generic combos=%zu cand_rate=%.3e\n", pl->generic.size(), cand_rate);
+    }
     for (int b = 0; b < pl->nblocks; ++b) {
         const BlockPlan& bp = pl->blocks[b];
         h_blocks[b].s1 = bp.s1; h_blocks[b].nl = bp.nl; h_blocks[b].nslot = bp.nslot; h_blocks[b].pad = 0;

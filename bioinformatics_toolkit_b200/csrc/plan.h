@@ -28,6 +28,8 @@ constexpr int kSlotBytes = 256 * kLanes * 4;            // 32768
 constexpr int kPadFront = 32;                           // stored base index u = position + kPadFront
 constexpr int kQ2 = 120;                                // quantisation levels, 2-slot first stage
 constexpr int kQ3 = 60;                                 // quantisation levels, 3-slot first stage
+constexpr int kQ4 = 41;                                 // quantisation levels, 4-slot first stage
+// (bias 127-Q plus S1 saturated entries Q+1 must stay below 256: Q <= (128 - S1) / (S1 - 1))
 constexpr int kIupacCodes = 16;                         // ACGTNVHDBMKWSYR + invalid(15)
 
 inline double add_some(double x) { return x == 0 ? 0.0001 : x; }
@@ -210,7 +212,7 @@ inline bool place_block(const std::vector<ComboDef>& defs, int s1, int nl, int n
 inline void build_block_tables(const std::vector<ComboInput>& in, const std::vector<ComboDef>& defs, int s1, int nl,
                                int nr, const int* c_in, BlockPlan& bp) {
     const int nslot = nl + s1 + nr;
-    const int Q = (s1 == 2) ? kQ2 : kQ3;
+    const int Q = (s1 == 2) ? kQ2 : (s1 == 3 ? kQ3 : kQ4);
     bp.s1 = s1; bp.nl = nl; bp.nr = nr; bp.nslot = nslot; bp.Q = Q;
     bp.table.assign((size_t)nslot * 256 * kLanes, 0u);
     std::vector<int> qtab((size_t)nslot * 256);
@@ -265,7 +267,10 @@ inline void build_block_tables(const std::vector<ComboInput>& in, const std::vec
     }
     // a warp's 32 lanes see the same anchor: it takes the slow path if any combo survives
     bp.p_warp = 1.0 - std::exp(log_nosurv);
-    bp.cost = (double)s1 + bp.p_warp * 6.0;
+    // cost model in shared-memory-load slots per anchor: s1 loads, the per-phase handler (8 anchors
+    // share one branch) and the second stage of the survivors
+    const double p_phase = 1.0 - std::pow(1.0 - bp.p_warp, 8.0);
+    bp.cost = (double)s1 + 0.5 + p_phase * 5.0 + bp.p_warp * 5.0;
 }
 
 // Chooses (s1, nl, nr) for a block.  Returns false if the block cannot use the prefilter
@@ -278,7 +283,7 @@ inline bool build_block(const std::vector<ComboInput>& in, BlockPlan& best, int 
     if (nmax > 4 * kMaxSlots) return false;
     bool have = false;
     int cbuf[kCombosPerBlock], cbest[kCombosPerBlock];
-    for (int s1 = 2; s1 <= 3; ++s1) {
+    for (int s1 = 2; s1 <= 4; ++s1) {
         if (force_s1 && s1 != force_s1) continue;
         const int nslot = std::max(s1, std::min(kMaxSlots, (nmax + 3) / 4 + 1));
         int best_nl = -1; double best_tot = -1;

@@ -122,9 +122,9 @@ extern "C" int pwmscan_last_timing(pwmscan_ctx* ctx, double* out, int n) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kThreads = 512;                          // prefilter CTA: 16 warps, 1 CTA per SM
+constexpr int kThreads = 1024;                         // prefilter CTA: 32 warps, 1 CTA per SM
 constexpr int kWarps = kThreads / 32;
-constexpr int kIters = 32;                             // x 32 anchors per warp per work item
+constexpr int kIters = 16;                             // x 32 anchors per warp per work item
 constexpr int64_t kChunk = (int64_t)kWarps * 32 * kIters;   // anchors per work item (16384)
 
 __constant__ unsigned char c_iupac_lut[256];
@@ -381,7 +381,8 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
     if (!pl) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
     pl->ctx = ctx; pl->motifs = mo; pl->strands = strands; pl->skip = skip_ambiguous ? 1 : 0;
     HostPlan hp;
-    if (!build_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, hp)) {
+    const char* fs1 = std::getenv("PWMSCAN_FORCE_S1");
+    if (!build_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, hp, fs1 ? std::atoi(fs1) : 0)) {
         pwmscan_plan_free(pl);
         return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_plan_create: internal: block cannot be placed");
     }
@@ -455,6 +456,7 @@ prefilter_kernel(const uint32_t* __restrict__ seq2, long long chunks_per_block, 
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
     int cur_blk = -1;
     int s1 = 2, nl = 0, nslot = 2;
     for (;;) {
@@ -482,21 +484,14 @@ prefilter_kernel(const uint32_t* __restrict__ seq2, long long chunks_per_block, 
             const unsigned long long slot = atomicAdd(&counters[0], 1ull);
             if (slot < cand_cap) cand[slot] = ((combo_base + (unsigned)q) << 40) | (unsigned long long)u;
         };
-        if (s1 == 2) {
-#pragma unroll 1
-            for (int it = 0; it < kIters; ++it) {
-                const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);
-                process32<2>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem, nl, nslot, emit);
-                x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;
-            }
-        } else {
-#pragma unroll 1
-            for (int it = 0; it < kIters; ++it) {
-                const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);
-                process32<3>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem, nl, nslot, emit);
-                x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;
-            }
+#define PWM_RUN(S1)                                                                                   \
+        _Pragma("unroll 1") for (int it = 0; it < kIters; ++it) {                                     \
+            const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);                    \
+            process32<S1>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem_addr, nl, nslot, emit);             \
+            x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;                                              \
         }
+        if (s1 == 2) { PWM_RUN(2) } else if (s1 == 3) { PWM_RUN(3) } else { PWM_RUN(4) }
+#undef PWM_RUN
         __syncthreads();   // every warp is done with the tables before a possible reload
     }
 }

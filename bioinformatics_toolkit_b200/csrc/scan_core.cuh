@@ -21,8 +21,22 @@ PWM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s) {
 #endif
 }
 
-PWM_HD uint32_t lds32(const unsigned char* tab, uint32_t byte_off) {
-    return *reinterpret_cast<const uint32_t*>(tab + byte_off);
+// Table handle (template parameter Tab): on the device a 32-bit address in the shared window (the
+// per-lane base is one register and a table read is `LDS R, [R + imm]`), on the host a pointer.
+PWM_HD uint32_t lds32(const unsigned char* p) { return *reinterpret_cast<const uint32_t*>(p); }
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+#endif
+PWM_HD uint32_t byte_of(uint32_t w, int q) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x4440u + (uint32_t)q);
+#else
+    return (w >> (8 * q)) & 0xFFu;
+#endif
 }
 
 // byte `b` (0..15) of the 16-byte window Y[0..3]
@@ -34,15 +48,23 @@ PWM_HD uint32_t window_byte(uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, 
 // Survivor of the first stage: add the remaining slots one by one (dead byte lanes are parked at
 // 0x80 so nothing ever carries into a neighbour), then report the byte lanes still alive.
 // Returns the alive mask (bit 8q+7 set <=> combo 4*lane+q is a candidate).
+// tab_lane = table base + 4*lane.
+template <class Tab>
 PWM_HD uint32_t second_stage(uint32_t acc, uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, int byte0 /* 4+j-nl */,
-                             int nl, int s1, int nslot, const unsigned char* tab, uint32_t lane_off) {
-    for (int s = 0; s < nslot; ++s) {
-        if (s >= nl && s < nl + s1) continue;
+                             int nl, int s1, int nslot, Tab tab_lane) {
+    for (int s = nl - 1; s >= 0; --s) {                    // slots left of the first stage
         const uint32_t m = acc & 0x80808080u;
         if (m == 0x80808080u) return 0u;
         acc &= ~(m - (m >> 7));
         const uint32_t kmer = window_byte(y0, y1, y2, y3, byte0 + s);
-        acc += lds32(tab, (uint32_t)s * 32768u + kmer * 128u + lane_off);
+        acc += lds32(tab_lane + ((uint32_t)s * 32768u + kmer * 128u));
+    }
+    for (int s = nl + s1; s < nslot; ++s) {                // slots right of it
+        const uint32_t m = acc & 0x80808080u;
+        if (m == 0x80808080u) return 0u;
+        acc &= ~(m - (m >> 7));
+        const uint32_t kmer = window_byte(y0, y1, y2, y3, byte0 + s);
+        acc += lds32(tab_lane + ((uint32_t)s * 32768u + kmer * 128u));
     }
     return ~acc & 0x80808080u;
 }
@@ -50,37 +72,53 @@ PWM_HD uint32_t second_stage(uint32_t acc, uint32_t y0, uint32_t y1, uint32_t y2
 // 32 consecutive anchors u = U .. U+31 (U a multiple of 16) for one lane.
 // X[q] = packed word (U/16 - 1 + q), q = 0..4 (16 bases per word, base t at bits 2t..2t+1).
 // emit(q, u) is called for every candidate byte lane q at anchor u.
-template <int S1, class Emit>
+//
+// The first stage is straight-line code: for each of the 4 phases r (anchors U+4j+r, j = 0..7) the
+// 16-byte window Y is the sequence shifted by r bases, so the 4-mer of slot t at anchor j is the
+// plain byte 4+j+t of Y; each table address is computed once (byte extract + multiply-add) and
+// shared by S1 anchors.  The 8 accumulators of a phase are tested together (one branch per 8
+// anchors); only phases in which some byte lane is still below 128 enter the per-anchor handler.
+template <int S1, class Tab, class Emit>
 PWM_HD void process32(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, int64_t U, int lane,
-                      const unsigned char* tab, int nl, int nslot, Emit&& emit) {
-    const uint32_t lane_off = (uint32_t)lane * 4u;
-    const uint32_t base1 = (uint32_t)nl * 32768u + lane_off;     // first-stage slot 0
+                      Tab tab, int nl, int nslot, Emit&& emit) {
+    const Tab tab_lane = tab + (uint32_t)lane * 4u;
+    const Tab tab1 = tab_lane + (uint32_t)nl * 32768u;          // first-stage slot 0, this lane's bank
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         // Y covers the bases U-16+r .. U+47+r; byte b holds the 4 bases from U-16+r+4b
         const uint32_t y0 = funnel_r(x0, x1, 2 * r), y1 = funnel_r(x1, x2, 2 * r);
         const uint32_t y2 = funnel_r(x2, x3, 2 * r), y3 = funnel_r(x3, x4, 2 * r);
-        uint32_t idx[8 + S1 - 1];                                 // bytes 4 .. 4+7+S1-1
+        Tab idx[8 + S1 - 1];                                    // bytes 4 .. 4+7+S1-1
 #pragma unroll
         for (int b = 0; b < 8 + S1 - 1; ++b) {
             const int bb = 4 + b;
             const uint32_t w = bb < 8 ? y1 : (bb < 12 ? y2 : y3);
-            idx[b] = ((w >> (8 * (bb & 3))) & 0xFFu) * 128u + base1;
+            idx[b] = tab1 + byte_of(w, bb & 3) * 128u;
         }
+        uint32_t acc[8];
+        uint32_t any = 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            uint32_t acc = lds32(tab, idx[j]) + lds32(tab, idx[j + 1] + 32768u);
-            if (S1 == 3) acc += lds32(tab, idx[j + 2] + 65536u);
-            if ((~acc & 0x80808080u) != 0u) {
-                uint32_t alive = second_stage(acc, y0, y1, y2, y3, 4 + j - nl, nl, S1, nslot, tab, lane_off);
-                while (alive) {
+            uint32_t a = lds32(idx[j]) + lds32(idx[j + 1] + 32768u);
+            if (S1 >= 3) a += lds32(idx[j + 2] + 65536u);
+            if (S1 >= 4) a += lds32(idx[j + 3] + 98304u);
+            acc[j] = a;
+            any |= ~a;
+        }
+        if ((any & 0x80808080u) != 0u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if ((~acc[j] & 0x80808080u) != 0u) {
+                    uint32_t alive = second_stage(acc[j], y0, y1, y2, y3, 4 + j - nl, nl, S1, nslot, tab_lane);
+                    while (alive) {
 #if defined(__CUDA_ARCH__)
-                    const int bit = __ffs((int)alive) - 1;
+                        const int bit = __ffs((int)alive) - 1;
 #else
-                    const int bit = __builtin_ctz(alive);
+                        const int bit = __builtin_ctz(alive);
 #endif
-                    alive &= alive - 1;
-                    emit(bit >> 3, U + 4 * j + r);
+                        alive &= alive - 1;
+                        emit(bit >> 3, U + 4 * j + r);
+                    }
                 }
             }
         }

@@ -45,7 +45,7 @@ def _same(h, o):
     return all(np.array_equal(a, b) for a, b in zip(h, o))
 
 
-@pytest.mark.parametrize("force_s1", [0, 2, 3])
+@pytest.mark.parametrize("force_s1", [0, 2, 3, 4])
 def test_mixed_lengths_both_strands(emul, oracle, force_s1):
     mats = synth.synth_pwms(70, 21, nmin=6, nmax=24)
     dna = synth.synth_dna(60000, 9, gc=0.45, n_runs=[(0, 40), (30000, 700), (59990, 10)])

@@ -204,12 +204,16 @@ def main():
     dev_seqs = [_lib.DeviceSeq(ctx, p.numpy()) for p in pinned]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    last_timing = {}
+
     def step_resident():
         nh, pre_ms = 0, 0.0
         for s in dev_seqs:
             h = plan.scan(s)
             nh += len(h)
-            pre_ms += ctx.timing()["prefilter_ms"]
+            t = ctx.timing()
+            pre_ms += t["prefilter_ms"]
+            last_timing.update(t)
         return nh, pre_ms
 
     def step_e2e():
@@ -302,7 +306,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
             "vs_baseline": None, "dtype": "u8 prefilter + f64 re-score", "data": "synthetic",
             "config": {"workload": desc, "l2": "256 MiB flush write between steps", "thresholds": th_src,
-                       "hits_per_step_rank0": int(nh)},
+                       "hits_per_step_rank0": int(nh),
+                       "device_ms_breakdown_last_scan": {k: round(float(v), 4) for k, v in last_timing.items()}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(args.steps * len(dev_seqs) * 2), "clocks": clocks,
             "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu}), flush=True)

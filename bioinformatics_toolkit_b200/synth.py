@@ -125,3 +125,21 @@ def config_c2(length=248956422):
 
 def config_c4_motifs(count=800):
     return synth_pwms(count, 13, lengths=jaspar_like_lengths(count, 13))
+
+
+def config_c5_motifs(count=2000, seed=15):
+    """C5: PWMs with n ~ U{6..20}; 5 % exact palindromes and 5 % duplicates / reverse-complement
+    duplicates of earlier motifs, to exercise the tie rules of alignmentBy."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mats = []
+    for i in range(count):
+        u = rng.random()
+        if i > 10 and u < 0.05:
+            half = synth_pwm(int(rng.integers(3, 11)), rng, 0.3, 0.1)
+            mats.append(np.ascontiguousarray(np.vstack([half, half.reshape(-1)[::-1].reshape(-1, 4)])))
+        elif i > 10 and u < 0.10:
+            src = mats[int(rng.integers(0, i))]
+            mats.append(src.copy() if rng.random() < 0.5 else np.ascontiguousarray(src.reshape(-1)[::-1].reshape(-1, 4)))
+        else:
+            mats.append(synth_pwm(int(rng.integers(6, 21)), rng, 0.3, 0.1))
+    return mats

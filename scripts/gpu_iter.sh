@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; rc=$?
 tail -5 gpurun_out/pytest.log
 [ $rc -eq 0 ] || { echo PYTEST FAILED; tail -40 gpurun_out/pytest.log; exit 2; }
-for v in "" 3 4; do
+for v in ""; do
   echo "== FORCE_S1=$v"
   PWMSCAN_FORCE_S1=$v PWMSCAN_VERBOSE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$v.log 2> gpurun_out/bench_$v.err || { echo BENCH FAILED; tail -20 gpurun_out/bench_$v.err; }
   grep pwmscan gpurun_out/bench_$v.err | sort | uniq | head -5

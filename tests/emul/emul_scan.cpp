@@ -93,3 +93,21 @@ int64_t emul_scan(int M, const int* ncol, const double* mats, const double* bg, 
     }
     return (int64_t)hits.size();
 }
+
+// ---- alignment: the host build of csrc/align_core.h (the function the CUDA kernel runs) -----------
+#include "../../bioinformatics_toolkit_b200/csrc/align_core.h"
+
+extern "C" __attribute__((visibility("default")))
+void emul_align(int n1, const double* m1, int n2, const double* m2, int penal_kind, double gap, int comb_kind,
+                double* d_out, int* same_dir, int* pos, int* ambiguous) {
+    AlignCfg cfg;
+    cfg.penal_kind = penal_kind; cfg.comb_kind = comb_kind; cfg.gap = gap; cfg.ln2 = std::log(2.0);
+    std::vector<double> m2r(4 * n2), l1(4 * n1), l2(4 * n2), l2r(4 * n2), o1(64), o2(64);
+    for (int i = 0; i < 4 * n2; ++i) m2r[i] = m2[4 * n2 - 1 - i];
+    for (int i = 0; i < 4 * n1; ++i) l1[i] = std::log(m1[i]) / cfg.ln2;
+    for (int i = 0; i < 4 * n2; ++i) { l2[i] = std::log(m2[i]) / cfg.ln2; l2r[i] = std::log(m2r[i]) / cfg.ln2; }
+    aln_optimal_sc(cfg, n1, n2, o1.data());
+    aln_optimal_sc(cfg, n2, n1, o2.data());
+    *ambiguous = 0;
+    align_pair(cfg, m1, l1.data(), n1, m2, l2.data(), m2r.data(), l2r.data(), n2, o1.data(), o2.data(), d_out, same_dir, pos, ambiguous);
+}

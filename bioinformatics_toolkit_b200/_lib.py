@@ -207,6 +207,20 @@ class DeviceMotifs:
         self.ctx.check(self.ctx.L.pwmscan_pvalue_to_score(self.ctx.h, self.h, C.c_double(p), _ptr(out)))
         return out
 
+    def cutoff_cdfs(self, p):
+        """mkCutoffMotif for all motifs: (cutoffs[M], [(xs, ps) of truncateCDF (1 - 10p) cdf_m])."""
+        th = np.empty(self.M)
+        off = np.zeros(self.M + 1, dtype=np.int64)
+        x = _dp()
+        P = _dp()
+        self.ctx.check(self.ctx.L.pwmscan_cutoff_cdfs(self.ctx.h, self.h, C.c_double(p), _ptr(th), C.byref(x), C.byref(P), _ptr(off)))
+        tot = int(off[-1])
+        xs = np.ctypeslib.as_array(x, shape=(max(tot, 1),))[:tot].copy()
+        ps = np.ctypeslib.as_array(P, shape=(max(tot, 1),))[:tot].copy()
+        self.ctx.L.pwmscan_free(C.cast(x, _vp))
+        self.ctx.L.pwmscan_free(C.cast(P, _vp))
+        return th, [(xs[off[m]:off[m + 1]], ps[off[m]:off[m + 1]]) for m in range(self.M)]
+
     # -- alignment ------------------------------------------------------------------------------
     def align_all_pairs(self, penal="exp", gap=0.05, comb="l1"):
         npair = self.M * (self.M - 1) // 2

@@ -1,0 +1,162 @@
+"""Bio.Data.Bed.Utils motif part (bioinformatics-toolkit/src/Bio/Data/Bed/Utils.hs:76-124).
+
+CutoffMotif (78-86), mkCutoffMotif (88-98), scanMotif (101-124).  scanMotif batches the BED
+regions: the region bytes are gathered from the genome file, laid end to end (one segment per
+region), packed and scanned on the device in one launch per batch for all motifs and both strands;
+hits come back in the reference's order (region, motif, forward hits ascending, reverse hits
+ascending).  The per-hit BED score (toAffinity of 1 - cdf) is host-side formatting, as in Haskell.
+"""
+import math
+import sys
+
+import numpy as np
+
+from . import _lib
+from .motif import CDF, rcPWM, size
+from .seq import ALPHABET, _UPPER
+from .seq_io import raw_bytes
+
+
+class CutoffMotif:
+    __slots__ = ("_motif_name", "_motif_pwm", "_motif_sigma", "_motif_pwm_rc", "_motif_sigma_rc", "_background", "_cutoff", "_cdf")
+
+    def __init__(self, name, pwm, sigma, pwm_rc, sigma_rc, bg, cutoff, cdf):
+        self._motif_name, self._motif_pwm, self._motif_sigma = name, pwm, sigma
+        self._motif_pwm_rc, self._motif_sigma_rc, self._background, self._cutoff, self._cdf = pwm_rc, sigma_rc, bg, cutoff, cdf
+
+
+def mkCutoffMotifs(bg, p, motifs, ctx=None):
+    """[mkCutoffMotif bg p m | m <- motifs], with all score CDFs computed in batched launches."""
+    ctx = ctx or _lib.default_context()
+    mo = _lib.DeviceMotifs(ctx, [m._pwm._mat for m in motifs], bg.freqs)
+    cut, cdfs = mo.cutoff_cdfs(p)
+    out = []
+    for i, m in enumerate(motifs):
+        out.append(CutoffMotif(m._name, m._pwm, mo.get_sigma(i, 0), rcPWM(m._pwm), mo.get_sigma(i, 1), bg, float(cut[i]), CDF(*cdfs[i])))
+    return out
+
+
+def mkCutoffMotif(bg, p, motif):
+    return mkCutoffMotifs(bg, p, [motif])[0]
+
+
+def _cdf_vec(c, x):
+    """cdf (Motif.hs:236-249) for an array of scores; elementwise IEEE arithmetic, no transcendentals."""
+    xs, ps = c.xs, c.ps
+    n = xs.size
+    i = np.searchsorted(xs, x, side="left")
+    out = np.empty(x.size)
+    hi = i >= n
+    lo = (i == 0) & ~hi
+    mid = ~hi & ~lo
+    out[hi] = ps[-1] if n else 0.0
+    out[lo] = np.where(x[lo] == (xs[0] if n else 0.0), ps[0] if n else 0.0, 0.0)
+    im = i[mid]
+    a, a1, b, b1 = xs[im - 1], ps[im - 1], xs[im], ps[im]
+    al = (b - x[mid]) / (b - a)
+    be = (x[mid] - a) / (b - a)
+    out[mid] = al * a1 + be * b1
+    return out
+
+
+def toAffinity(x1):
+    """round (1000 / (1 + exp (-(-log10 (max 1e-20 x') - 5)))), half-even, libm (Utils.hs:120-123)."""
+    x = -(math.log(max(1e-20, x1)) / math.log(10.0))
+    sc = 1 / (1 + math.exp(-(x - 5)))
+    return int(round(sc * 1000))       # Python round() on a float is round-half-even, like Haskell's
+
+
+def _affinity_vec(pv):
+    x = -(np.log(np.maximum(1e-20, pv)) / math.log(10.0))
+    v = 1 / (1 + np.exp(-(x - 5))) * 1000
+    out = np.rint(v).astype(np.int64)
+    # numpy's SIMD log/exp may differ from libm in the last ulp: settle anything near a rounding tie with libm
+    near = np.nonzero(np.abs(np.abs(v - np.floor(v)) - 0.5) < 1e-6)[0]
+    for k in near:
+        out[k] = toAffinity(float(pv[k]))
+    return out
+
+
+def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.stderr, ctx=None):
+    """beds: iterable of (chrom, start, end).  Yields BED6 tuples
+    (chrom, start, end, name, score, strand) — or, if `out` is a binary file object, writes the
+    reference's `toLine` text (Data/Bed/Types.hs:139-149) to it and returns the hit count."""
+    ctx = ctx or _lib.default_context()
+    if not motifs:
+        return 0 if out is not None else []
+    bg = motifs[0]._background
+    mo = _lib.DeviceMotifs(ctx, [m._motif_pwm._mat for m in motifs], bg.freqs)
+    for i, m in enumerate(motifs):                                 # findTFBSWith takes the stored sigmas
+        mo.set_sigma(i, 0, m._motif_sigma)
+        mo.set_sigma(i, 1, m._motif_sigma_rc)
+    plan = _lib.Plan(mo, [m._cutoff for m in motifs], strands=2, skip_ambiguous=True)
+    nlen = np.array([size(m._motif_pwm) for m in motifs], dtype=np.int64)
+    names = [m._motif_name for m in motifs]
+    valid = np.zeros(256, dtype=bool)
+    valid[np.frombuffer(ALPHABET["IUPAC"], dtype=np.uint8)] = True
+    results = [] if out is None else None
+    total = 0
+
+    def flush(regs, chunks):
+        nonlocal total
+        if not regs:
+            return
+        lens = np.array([c.size for c in chunks], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        data = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+        seq = _lib.DeviceSeq(ctx, data, seg_off=off, uppercase=True)
+        h = plan.scan(seq)
+        seq.free()
+        if len(h) == 0:
+            return
+        score = np.empty(len(h), dtype=np.int64)
+        for m in np.unique(h.motif):
+            k = h.motif == m
+            score[k] = _affinity_vec(1 - _cdf_vec(motifs[m]._cdf, h.score[k]))
+        starts = np.array([r[1] for r in regs], dtype=np.int64)[h.segment] + h.pos
+        ends = starts + nlen[h.motif]
+        total += len(h)
+        if out is None:
+            for k in range(len(h)):
+                results.append((regs[h.segment[k]][0], int(starts[k]), int(ends[k]), names[h.motif[k]], int(score[k]), h.strand[k] == 0))
+        else:
+            lines = []
+            for k in range(len(h)):
+                lines.append(b"\t".join((regs[h.segment[k]][0], b"%d" % starts[k], b"%d" % ends[k], names[h.motif[k]],
+                                         b"%d" % score[k], b"+" if h.strand[k] == 0 else b"-")))
+            out.write(b"\n".join(lines) + b"\n")
+
+    regs, chunks, nb = [], [], 0
+    for (chr_, start, end) in beds:
+        if isinstance(chr_, str):
+            chr_ = chr_.encode()
+        ok, r = raw_bytes(genome, (chr_, start, end))
+        if ok:
+            r = np.asarray(r)
+            if not valid[_UPPER[r]].all():                         # fromBS: unknown character => Left
+                ok = False
+        if not ok:
+            if warn is not None:
+                print("Warning: no sequence for region: " + repr((chr_.decode("latin1"), start, end)), file=warn)
+            continue
+        regs.append((chr_, start, end))
+        chunks.append(r)
+        nb += r.size
+        if nb >= batch_bases or len(regs) >= 65000:
+            flush(regs, chunks)
+            regs, chunks, nb = [], [], 0
+    flush(regs, chunks)
+    return total if out is not None else results
+
+
+def streamBed3(path):
+    """streamBed ... :: BED3 (Data/Bed.hs:307-309, Types.hs:175-177): first three tab-separated fields."""
+    with open(path, "rb") as f:
+        for l in f:
+            l = l.rstrip(b"\n")
+            if not l:
+                continue
+            w = l.split(b"\t")
+            if len(w) < 3:
+                raise ValueError("Read BED fail: Incorrect number of fields")
+            yield w[0], int(w[1]), int(w[2])

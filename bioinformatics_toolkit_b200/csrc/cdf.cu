@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kCdfThreads, 1)
 cdf_kernel(int M, int m0, const int32_t* __restrict__ ncol, const int64_t* __restrict__ xat_off,
            const double* __restrict__ xat /* [col][4] = log' p - log bg */, const double* __restrict__ bg4,
            unsigned char* work, double q, int mode, double* __restrict__ thres_out, int* __restrict__ status_out,
-           double* out_x, double* out_p, long long* out_n) {
+           double* out_x, double* out_p, long long* out_n, double trunc) {
     __shared__ int s_warp[33];
     __shared__ double s_chunk[kScanChunk];
     __shared__ int s_K, s_nbin, s_skip, s_plen;
@@ -225,6 +225,16 @@ cdf_kernel(int M, int m0, const int32_t* __restrict__ ncol, const int64_t* __res
             for (int i = tid; i < nc; i += kCdfThreads) { out_x[i] = cx[i]; out_p[i] = cp[i]; }
             if (tid == 0) *out_n = nc;
         }
+        if (mode == 2) {
+            // truncateCDF trunc (Motif.hs:273-274): points with P >= trunc; P is non-decreasing, so a suffix
+            int lo_i = 0, hi_i = nc;
+            while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (cp[mid] >= trunc) hi_i = mid; else lo_i = mid + 1; }
+            const int first = lo_i;
+            double* ox = out_x + (size_t)(m - m0) * kMaxBin;
+            double* op = out_p + (size_t)(m - m0) * kMaxBin;
+            for (int i = first + tid; i < nc; i += kCdfThreads) { ox[i - first] = cx[i]; op[i - first] = cp[i]; }
+            if (tid == 0) out_n[m - m0] = nc - first;
+        }
         // ---- cdf' (Motif.hs:252-270)
         if (tid == 0) {
             int st = 0;
@@ -251,7 +261,7 @@ cdf_kernel(int M, int m0, const int32_t* __restrict__ ncol, const int64_t* __res
 }
 
 int run_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int m0, int mcount, double q, int mode, double* thres_out,
-            double** x_out, double** p_out, int64_t* n_out) {
+            double** x_out, double** p_out, int64_t* n_out, double trunc = 0.0) {
     PWM_CUDA(cudaSetDevice(ctx->device));
     const int M = mo->M;
     // host: x_at = log' p - log bg   (Motif.hs:311-314,324-325), libm
@@ -277,13 +287,15 @@ int run_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int m0, int mcount, doub
     int64_t* d_off = (int64_t*)(d_small + b_xat);
     double* d_th = (double*)(d_small + b_xat + b_off);
     double* d_bg = (double*)(d_small + b_xat + b_off + b_th);
-    long long* d_nout = (long long*)(d_small + b_xat + b_off + b_th + 32);
     int32_t* d_n = (int32_t*)(d_small + b_xat + b_off + b_th + 32 + 8);
     int* d_st = (int*)(d_small + b_xat + b_off + b_th + 32 + 8 + b_n);
+    long long* d_nout = (long long*)scratch_get(ctx, 5, (size_t)(mode == 2 ? mcount : 1) * 8);
+    if (!d_nout) return PWMSCAN_ECUDA;
     double *d_ox = nullptr, *d_op = nullptr;
-    if (mode == 1) {
-        d_ox = (double*)scratch_get(ctx, 3, (size_t)kMaxBin * 8);
-        d_op = (double*)scratch_get(ctx, 4, (size_t)kMaxBin * 8);
+    if (mode >= 1) {
+        const size_t cnt = mode == 2 ? (size_t)mcount : 1;
+        d_ox = (double*)scratch_get(ctx, 3, cnt * kMaxBin * 8);
+        d_op = (double*)scratch_get(ctx, 4, cnt * kMaxBin * 8);
         if (!d_ox || !d_op) return PWMSCAN_ECUDA;
     }
     PWM_CUDA(cudaMemcpyAsync(d_xat, h_xat.data(), b_xat, cudaMemcpyHostToDevice, ctx->stream));
@@ -291,7 +303,7 @@ int run_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int m0, int mcount, doub
     PWM_CUDA(cudaMemcpyAsync(d_n, h_n.data(), b_n, cudaMemcpyHostToDevice, ctx->stream));
     PWM_CUDA(cudaMemcpyAsync(d_bg, mo->bg, 32, cudaMemcpyHostToDevice, ctx->stream));
     PWM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    cdf_kernel<<<grid, kCdfThreads, 0, ctx->stream>>>(m0 + mcount, m0, d_n, d_off, d_xat, d_bg, d_work, q, mode, d_th, d_st, d_ox, d_op, d_nout);
+    cdf_kernel<<<grid, kCdfThreads, 0, ctx->stream>>>(m0 + mcount, m0, d_n, d_off, d_xat, d_bg, d_work, q, mode, d_th, d_st, d_ox, d_op, d_nout, trunc);
     PWM_CUDA(cudaGetLastError());
     PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     std::vector<double> h_th(M);
@@ -319,6 +331,27 @@ int run_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int m0, int mcount, doub
         if (h_st[m] == 2) return set_err(ctx, PWMSCAN_EDOMAIN, "cdf': impossible!");
         thres_out[m] = h_th[m];
     }
+    if (mode == 2) {
+        // gather the truncated CDFs of this batch: n_out[0..mcount) counts, *x_out/*p_out appended by the caller
+        std::vector<long long> cnt(mcount);
+        PWM_CUDA(cudaMemcpy(cnt.data(), d_nout, (size_t)mcount * 8, cudaMemcpyDeviceToHost));
+        long long tot = 0;
+        for (int k = 0; k < mcount; ++k) { n_out[k] = cnt[k]; tot += cnt[k]; }
+        double* hx = (double*)std::malloc((size_t)std::max<long long>(tot, 1) * 8);
+        double* hp = (double*)std::malloc((size_t)std::max<long long>(tot, 1) * 8);
+        if (!hx || !hp) { std::free(hx); std::free(hp); return set_err(ctx, PWMSCAN_EINVAL, "out of host memory"); }
+        long long o = 0;
+        for (int k = 0; k < mcount; ++k) {
+            if (cnt[k] > 0) {
+                cudaMemcpyAsync(hx + o, d_ox + (size_t)k * kMaxBin, (size_t)cnt[k] * 8, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(hp + o, d_op + (size_t)k * kMaxBin, (size_t)cnt[k] * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            }
+            o += cnt[k];
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { std::free(hx); std::free(hp); return cuda_fail(ctx, e, "D2H truncated cdf"); }
+        *x_out = hx; *p_out = hp;
+    }
     return PWMSCAN_OK;
 }
 
@@ -335,4 +368,35 @@ extern "C" int pwmscan_pvalue_to_score(pwmscan_ctx* ctx, const pwmscan_motifs* m
     if (!ctx || !mo || !thres_out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_pvalue_to_score: NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     return run_cdf(ctx, mo, 0, mo->M, 1 - p, 0, thres_out, nullptr, nullptr, nullptr);
+}
+
+// mkCutoffMotif for a whole motif set (Data/Bed/Utils.hs:88-98): cutoff = cdf' cdf (1 - p) on the
+// full CDF, plus truncateCDF (1 - 10 p) cdf for the per-hit p-values of scanMotif.
+extern "C" int pwmscan_cutoff_cdfs(pwmscan_ctx* ctx, const pwmscan_motifs* mo, double p, double* thres_out, double** x, double** P,
+                                   int64_t* offsets /* M+1 */) {
+    if (!ctx || !mo || !thres_out || !x || !P || !offsets) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_cutoff_cdfs: NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int M = mo->M, batch = 128;
+    std::vector<double> ax, ap;
+    std::vector<int64_t> cnt(M);
+    offsets[0] = 0;
+    for (int m0 = 0; m0 < M; m0 += batch) {
+        const int mc = std::min(batch, M - m0);
+        double *bx = nullptr, *bp = nullptr;
+        int rc = run_cdf(ctx, mo, m0, mc, 1 - p, 2, thres_out, &bx, &bp, cnt.data() + m0, 1 - p * 10);
+        if (rc) return rc;
+        int64_t tot = 0;
+        for (int k = 0; k < mc; ++k) tot += cnt[m0 + k];
+        ax.insert(ax.end(), bx, bx + tot);
+        ap.insert(ap.end(), bp, bp + tot);
+        std::free(bx); std::free(bp);
+    }
+    for (int m = 0; m < M; ++m) offsets[m + 1] = offsets[m] + cnt[m];
+    double* hx = (double*)std::malloc(std::max<size_t>(ax.size(), 1) * 8);
+    double* hp = (double*)std::malloc(std::max<size_t>(ap.size(), 1) * 8);
+    if (!hx || !hp) { std::free(hx); std::free(hp); return set_err(ctx, PWMSCAN_EINVAL, "out of host memory"); }
+    std::memcpy(hx, ax.data(), ax.size() * 8);
+    std::memcpy(hp, ap.data(), ap.size() * 8);
+    *x = hx; *P = hp;
+    return PWMSCAN_OK;
 }

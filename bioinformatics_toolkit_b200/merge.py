@@ -1,0 +1,207 @@
+"""Bio.Motif.Merge mirror (bioinformatics-toolkit/src/Bio/Motif/Merge.hs).
+
+mergePWM (32-46), mergePWMWeighted (48-71), dilute (74-81), trim (83-90), mergeTree(Weighted)
+(92-111), iterativeMerge (113-170), buildTree (173-176), cutTreeBy (178-186).  The all-pairs
+alignment matrix and every row refresh of iterativeMerge run on the device (one launch each); the
+greedy argmin / bookkeeping stays on the host, in the reference's scan order.
+"""
+import math
+
+import numpy as np
+
+from .alignment import pair_index
+from .motif import PWM, rcPWM, size
+
+
+def mergePWM(m1, m2, shift):
+    a, b, s = (m1._mat, m2._mat, shift) if shift >= 0 else (m2._mat, m1._mat, -shift)
+    n1, n2 = a.shape[0], b.shape[0]
+    rows, i = [], 0
+    while True:
+        i2 = i - s
+        if i2 < 0 or (i < n1 and i2 >= n2):
+            rows.append(a[i].copy())
+        elif i < n1 and i2 < n2:
+            rows.append((a[i] + b[i2]) / 2)
+        elif i >= n1 and i2 < n2:
+            rows.append(b[i2].copy())
+        else:
+            break
+        i += 1
+    return PWM(None, np.array(rows))
+
+
+def mergePWMWeighted(m1, m2, shift):
+    """m1, m2 = (PWM, weights); Merge.hs:48-71."""
+    (p1, w1), (p2, w2), s = (m1, m2, shift) if shift >= 0 else (m2, m1, -shift)
+    a, b = p1._mat, p2._mat
+    n1, n2 = a.shape[0], b.shape[0]
+    rows, ws, i = [], [], 0
+    while True:
+        i2 = i - s
+        if i2 < 0 or (i < n1 and i2 >= n2):
+            rows.append(a[i].copy()); ws.append(w1[i])
+        elif i < n1 and i2 < n2:
+            wx, wy = w1[i], w2[i2]
+            rows.append((float(wx) * a[i] + float(wy) * b[i2]) / float(wx + wy)); ws.append(wx + wy)
+        elif i >= n1 and i2 < n2:
+            rows.append(b[i2].copy()); ws.append(w2[i2])
+        else:
+            break
+        i += 1
+    return PWM(None, np.array(rows)), ws
+
+
+def dilute(pwm_ws):
+    pwm, ws = pwm_ws
+    n = max(ws)
+    rows = []
+    for w, r in zip(ws, pwm._mat):
+        if w < n:
+            d = float(n - w)
+            rows.append((float(w) * r + 0.25 * d) / float(n))
+        else:
+            rows.append(r.copy())
+    return PWM(None, np.array(rows))
+
+
+def _kld(xs, ys):
+    acc = 0.0
+    for x, y in zip(xs, ys):
+        if x == 0:
+            continue
+        acc = acc + x * (math.log(x) / math.log(2) - math.log(y) / math.log(2))
+    return acc
+
+
+def trim(bg, cutoff, pwm):
+    rs = list(pwm._mat)
+    f = [_kld(r, bg.freqs) < cutoff for r in rs]
+    lo = 0
+    while lo < len(rs) and f[lo]:
+        lo += 1
+    hi = len(rs)
+    while hi > lo and f[hi - 1]:
+        hi -= 1
+    return PWM(None, np.array(rs[lo:hi]).reshape(-1, 4))
+
+
+class Leaf:
+    def __init__(self, a):
+        self.a = a
+
+
+class Branch:
+    def __init__(self, size_, dist, left, right):
+        self.size, self.dist, self.left, self.right = size_, dist, left, right
+
+
+def flatten(t):
+    return [t.a] if isinstance(t, Leaf) else flatten(t.left) + flatten(t.right)
+
+
+def mergeTree(align, t):
+    if isinstance(t, Leaf):
+        return t.a._pwm
+    a, b = mergeTree(align, t.left), mergeTree(align, t.right)
+    _, (same, i) = align(a, b)
+    return mergePWM(a, b, i) if same else mergePWM(a, rcPWM(b), i)
+
+
+def mergeTreeWeighted(align, t):
+    if isinstance(t, Leaf):
+        return t.a._pwm, [1] * size(t.a._pwm)
+    (a, w1), (b, w2) = mergeTreeWeighted(align, t.left), mergeTreeWeighted(align, t.right)
+    _, (same, i) = align(a, b)
+    return mergePWMWeighted((a, w1), (b, w2), i) if same else mergePWMWeighted((a, w1), (rcPWM(b), w2[::-1]), i)
+
+
+def iterativeMerge(align, th, motifs):
+    """Merge.hs:113-170.  Returns [([names], PWM, weights)]."""
+    n = len(motifs)
+    items = [([m._name], m._pwm, [1] * size(m._pwm)) for m in motifs]
+    if n < 2:
+        return items
+    d, sd, pos = align.all_pairs([m._pwm for m in motifs])         # initialisation, Merge.hs:161-165
+    D = np.full((n, n), np.inf)
+    S = np.zeros((n, n), dtype=bool)
+    P = np.zeros((n, n), dtype=np.int64)
+    iu = np.triu_indices(n, 1)                                     # row-major order == packed order
+    D[iu], S[iu], P[iu] = d, sd.astype(bool), pos
+    alive = [True] * n
+    while True:
+        # first minimum in the scan order i ascending, j ascending (strict <, Merge.hs:149-158)
+        k = int(np.argmin(D))
+        i, j = divmod(k, n)
+        if not (D[i, j] < th):
+            break
+        same, p = bool(S[i, j]), int(P[i, j])
+        nm1, pwm1, w1 = items[i]
+        nm2, pwm2, w2 = items[j]
+        pwm_, w_ = mergePWMWeighted((pwm1, w1), (pwm2, w2), p) if same else mergePWMWeighted((pwm1, w1), (rcPWM(pwm2), w2[::-1]), p)
+        D[:, j] = np.inf                                           # Merge.hs:135 (column j; row j becomes unreachable too)
+        D[j, :] = np.inf
+        items[i] = (nm1 + nm2, pwm_, w_)
+        items[j] = None
+        alive[j] = False
+        others = [q for q in range(n) if q != i and alive[q]]
+        if others:                                                 # row refresh, Merge.hs:138-145, argument order kept
+            pw = [pwm_] + [items[q][1] for q in others]
+            a = [0 if i < q else k2 + 1 for k2, q in enumerate(others)]
+            b = [k2 + 1 if i < q else 0 for k2, q in enumerate(others)]
+            dd, ss, pp = align.pairs(pw, a, b)
+            for k2, q in enumerate(others):
+                r, c = (i, q) if i < q else (q, i)
+                D[r, c], S[r, c], P[r, c] = dd[k2], bool(ss[k2]), int(pp[k2])
+    return [it for it in items if it is not None]
+
+
+def buildTree(align, motifs):
+    """hclust Average motifs (fst . align) (Merge.hs:173-176).  `clustering`'s hclust is a
+    third-party package the reference does not pin; this is plain average linkage (UPGMA) merging
+    the closest pair first (ties: lowest indices)."""
+    n = len(motifs)
+    if n == 1:
+        return Leaf(motifs[0])
+    d, _, _ = align.all_pairs([m._pwm for m in motifs])
+    D = np.full((n, n), np.inf)
+    iu = np.triu_indices(n, 1)
+    D[iu] = d
+    D = np.minimum(D, D.T)
+    nodes = {i: Leaf(motifs[i]) for i in range(n)}
+    sizes = {i: 1 for i in range(n)}
+    active = list(range(n))
+    while len(active) > 1:
+        sub = D[np.ix_(active, active)]
+        k = int(np.argmin(sub))
+        ai, bi = divmod(k, len(active))
+        a, b = active[ai], active[bi]
+        if a > b:
+            a, b = b, a
+        dist = float(D[a, b])
+        na, nb = sizes[a], sizes[b]
+        for c in active:
+            if c != a and c != b:
+                v = (na * D[a, c] + nb * D[b, c]) / (na + nb)
+                D[a, c] = D[c, a] = v
+        D[b, :] = np.inf
+        D[:, b] = np.inf
+        nodes[a] = Branch(na + nb, dist, nodes[a], nodes[b])
+        sizes[a] = na + nb
+        active.remove(b)
+    return nodes[active[0]]
+
+
+def cutAt(tree, h):
+    if isinstance(tree, Leaf) or tree.dist <= h:
+        return [tree]
+    return cutAt(tree.left, h) + cutAt(tree.right, h)
+
+
+def cutTreeBy(start, step, fn, tree):
+    x = start
+    while True:
+        clusters = cutAt(tree, x)
+        if fn(clusters) or not (x - step > 0):
+            return clusters
+        x = x - step

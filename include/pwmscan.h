@@ -127,6 +127,11 @@ int  pwmscan_max_match_sc(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmsca
 int  pwmscan_score_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int32_t m, double** x, double** P, int64_t* npts);
 /* thres_out[m] = cdf' (scoreCDF bg pwm_m) (1 - p) for every motif. */
 int  pwmscan_pvalue_to_score(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, double p, double* thres_out);
+/* mkCutoffMotif for every motif (Data/Bed/Utils.hs:88-98): thres_out[m] = cdf' cdf_m (1 - p) on the
+ * full CDF, and the points of truncateCDF (1 - 10 p) cdf_m concatenated in *x / *P (library-owned,
+ * release with pwmscan_free); motif m owns [offsets[m], offsets[m+1]).  offsets has M+1 entries. */
+int  pwmscan_cutoff_cdfs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, double p, double* thres_out,
+                         double** x, double** P, int64_t* offsets);
 void pwmscan_free(void* p);
 
 /* ---- PWM-PWM alignment: alignmentBy jsd pFn combFn (Motif/Alignment.hs:83-132), the all-pairs

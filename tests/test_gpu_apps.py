@@ -1,0 +1,104 @@
+"""scan_motif / merge path through the Python mirror of the reference API (device compute) against
+the oracle-side restatement of the host logic (oracle/app_oracle.py)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from bioinformatics_toolkit_b200 import merge as M
+from bioinformatics_toolkit_b200 import motif as Mo
+from bioinformatics_toolkit_b200 import synth
+from bioinformatics_toolkit_b200.alignment import AlignFn, alignment
+from bioinformatics_toolkit_b200.bed_utils import mkCutoffMotifs, scanMotif, streamBed3
+from bioinformatics_toolkit_b200.seq_io import getChrSizes, getSeq, openGenome, write_genome
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_genome(tmp_path_factory):
+    d = tmp_path_factory.mktemp("genome")
+    chroms = [(b"chr1", synth.synth_dna(60000, 31, gc=0.45, n_runs=[(20000, 900)], lower_frac=0.2)),
+              (b"chr2", synth.synth_dna(25000, 32, gc=0.40)),
+              (b"chrW", np.frombuffer(b"ACGTRYKMACGTNNNNACGTXACGT" * 40, dtype=np.uint8))]
+    path = os.path.join(d, "genome.idx")
+    write_genome(chroms, path)
+    return path, dict(chroms)
+
+
+def test_genome_index_roundtrip(small_genome):
+    path, chroms = small_genome
+    g = openGenome(path)
+    assert getChrSizes(g) == [(b"chr1", 60000), (b"chr2", 25000), (b"chrW", 1000)]
+    ok, dna = getSeq(g, (b"chr2", 100, 160))
+    assert ok and dna.bs == bytes(chroms[b"chr2"][100:160]).upper()
+    assert getSeq(g, (b"chr2", 100, 25001))[0] is False and getSeq(g, (b"chrQ", 0, 1))[0] is False
+    assert getSeq(g, (b"chrW", 0, 30))[0] is False          # 'X' is not in the IUPAC alphabet
+
+
+def test_scan_motif_app_lines(small_genome, tmp_path):
+    from oracle import app_oracle
+    path, chroms = small_genome
+    rng = np.random.default_rng(5)
+    mats = synth.synth_pwms(12, 44, nmin=6, nmax=18)
+    names = [b"M%03d some name" % i for i in range(len(mats))]
+    motifs = [Mo.Motif(nm, Mo.PWM(None, m)) for nm, m in zip(names, mats)]
+    beds = []
+    for _ in range(60):
+        c = [b"chr1", b"chr2", b"chrW", b"chrMissing"][int(rng.integers(0, 4))]
+        L = len(chroms.get(c, b"x" * 30000))
+        s = int(rng.integers(0, max(1, L - 600)))
+        beds.append((c, s, s + int(rng.integers(5, 700))))
+    beds.append((b"chr2", 24900, 25100))                      # beyond the end: skipped
+    bedfile = os.path.join(tmp_path, "in.bed")
+    with open(bedfile, "wb") as f:
+        for c, s, e in beds:
+            f.write(b"%s\t%d\t%d\textra\t0\t+\n" % (c, s, e))
+    p = 1e-3
+    cms = mkCutoffMotifs(Mo.default_bkgd, p, motifs)
+    out = io.BytesIO()
+    n = scanMotif(openGenome(path), cms, streamBed3(bedfile), out=out, warn=None)
+    got = out.getvalue().split(b"\n")[:-1] if n else []
+    exp = app_oracle.scan_motif_lines(chroms, names, mats, beds, p=p)
+    assert len(exp) > 50
+    assert got == exp
+
+
+def test_iterative_merge_and_tree(oracle):
+    from oracle import app_oracle
+    mats = synth.synth_pwms(14, 71, nmin=6, nmax=14)
+    mats += [oracle.rc_pwm(mats[2]), mats[4].copy(), 0.5 * (mats[6] + 0.25)]
+    names = [b"m%d" % i for i in range(len(mats))]
+    motifs = [Mo.Motif(nm, Mo.PWM(None, m)) for nm, m in zip(names, mats)]
+    got = M.iterativeMerge(alignment, 0.2, motifs)
+    exp = app_oracle.iterative_merge(0.2, names, mats)
+    assert [g[0] for g in got] == [e[0] for e in exp]
+    assert len(got) < len(mats)
+    for g, e in zip(got, exp):
+        assert g[2] == e[2] and np.allclose(g[1]._mat, e[1], rtol=0, atol=1e-15)
+    tree = M.buildTree(AlignFn("exp", 0.05, "l1"), motifs)
+    assert sorted(m._name for m in M.flatten(tree)) == sorted(names)
+    cl = M.cutAt(tree, 0.2)
+    assert 1 < len(cl) < len(mats)
+    merged = M.dilute(M.mergeTreeWeighted(alignment, cl[0]))
+    assert merged._mat.shape[1] == 4 and np.allclose(merged._mat.sum(axis=1), 1.0, atol=1e-9)
+
+
+def test_reference_api_invariants(ref_motifs):
+    """The five invariants of the reference's own test-suite (Tests/Motif.hs:58-97), through the
+    drop-in API with the device doing the work."""
+    from bioinformatics_toolkit_b200 import search as S
+    from bioinformatics_toolkit_b200.seq import DNA, rc
+    bg = Mo.default_bkgd
+    dna = DNA(bytes(synth.synth_dna(5000, 2)), "Basic")
+    pwms = [Mo.PWM(None, m) for _, m in ref_motifs]
+    th = 0.6 * Mo.optimalScore(bg, pwms[0])
+    assert S.findTFBS(bg, pwms[0], dna, th, True) == S.findTFBSSlow(bg, pwms[0], dna, th)
+    for p in pwms:
+        assert S.maxMatchSc(bg, p, dna) == Mo.scores(bg, p, dna).max()
+        c = Mo.scoreCDF(bg, p)
+        assert Mo.cdf_(c, 1 - 1e-4) == Mo.cdf_(Mo.truncateCDF(0.999, c), 1 - 1e-4) == Mo.pValueToScore(1e-4, bg, p)
+        a = np.round(1e5 * Mo.scores(bg, p, dna))
+        b = np.round(1e5 * Mo.scores(bg, Mo.rcPWM(p), rc(dna))[::-1])
+        assert np.array_equal(a, b)

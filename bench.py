@@ -164,7 +164,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
@@ -228,11 +228,11 @@ def main():
         return nh, h2d, d2h
 
     # ---- device-resident arm -------------------------------------------------------------------
+    sampler = ClockSampler(local)          # started before the warm-up: nvidia-smi needs ~100 ms to produce its first row
+    sampler.start()
     for _ in range(args.warmup):
         flush.fill_(1)
         nh, _ = step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
     pre_ms_tot = 0.0
     barrier()
     t0 = time.perf_counter()
@@ -264,6 +264,17 @@ def main():
     if world > 1:
         dist.all_reduce(el2, op=dist.ReduceOp.MAX)
     e2e_val = un.item() / (el2.item() / args.steps) / 1e9
+
+    # ---- plain pinned->device copy of the same bytes, to read the e2e number against the PCIe link ----
+    dst = torch.empty(pinned[0].numel(), dtype=torch.uint8, device="cuda")
+    dst.copy_(pinned[0], non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(pinned[0], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * pinned[0].numel() / (time.perf_counter() - t0) / 1e9
+    del dst
 
     # ---- roofline of the dominant kernel (prefilter) ------------------------------------------------
     peaks = load_peaks()
@@ -308,7 +319,8 @@ def main():
             "config": {"workload": desc, "l2": "256 MiB flush write between steps", "thresholds": th_src,
                        "hits_per_step_rank0": int(nh),
                        "device_ms_breakdown_last_scan": {k: round(float(v), 4) for k, v in last_timing.items()}},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * el2.item() / args.steps, "pinned_h2d_gbs_this_box": h2d_gbs},
             "gpu_launches": int(args.steps * len(dev_seqs) * 2), "clocks": clocks,
             "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu}), flush=True)
     if world > 1:

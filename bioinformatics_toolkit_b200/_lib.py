@@ -253,8 +253,37 @@ class DeviceMotifs:
             pass
 
 
+class _HitsHandle:
+    """Owns a pwmscan_hits (pinned host columns); released when the last array view dies."""
+
+    def __init__(self, L, h):
+        self.L, self.h = L, h
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.pwmscan_hits_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class _OwnedArray(np.ndarray):
+    """ndarray view over library-owned memory that keeps its owner alive (also through slices)."""
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+def _view(ptr, n, owner):
+    a = np.ctypeslib.as_array(ptr, shape=(n,)).view(_OwnedArray)
+    a._owner = owner
+    return a
+
+
 class Hits:
-    """Columns of a hit list sorted by (segment, motif, strand, pos)."""
+    """Columns of a hit list sorted by (segment, motif, strand, pos).  The arrays are zero-copy
+    views of the library's pinned host buffer."""
 
     __slots__ = ("motif", "strand", "segment", "pos", "score")
 
@@ -292,18 +321,14 @@ class Plan:
         L = self.ctx.L
         hh = _vp()
         self.ctx.check(L.pwmscan_scan(self.ctx.h, seq.h, self.h, C.byref(hh)))
-        try:
-            n = L.pwmscan_hits_count(hh)
-            pm, ps, pg, pp, pc = (C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)(),
-                                  C.POINTER(C.c_int64)(), C.POINTER(C.c_double)())
-            L.pwmscan_hits_columns(hh, C.byref(pm), C.byref(ps), C.byref(pg), C.byref(pp), C.byref(pc))
-            if n == 0:
-                return Hits(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0))
-            return Hits(np.ctypeslib.as_array(pm, shape=(n,)).copy(), np.ctypeslib.as_array(ps, shape=(n,)).copy(),
-                        np.ctypeslib.as_array(pg, shape=(n,)).copy(), np.ctypeslib.as_array(pp, shape=(n,)).copy(),
-                        np.ctypeslib.as_array(pc, shape=(n,)).copy())
-        finally:
-            L.pwmscan_hits_free(hh)
+        owner = _HitsHandle(L, hh)
+        n = L.pwmscan_hits_count(hh)
+        if n == 0:
+            return Hits(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0))
+        pm, ps, pg, pp, pc = (C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)(),
+                              C.POINTER(C.c_int64)(), C.POINTER(C.c_double)())
+        L.pwmscan_hits_columns(hh, C.byref(pm), C.byref(ps), C.byref(pg), C.byref(pp), C.byref(pc))
+        return Hits(_view(pm, n, owner), _view(ps, n, owner), _view(pg, n, owner), _view(pp, n, owner), _view(pc, n, owner))
 
     def free(self):
         if self.h:

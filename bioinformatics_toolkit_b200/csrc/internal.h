@@ -23,6 +23,11 @@ struct pwmscan_ctx {
     // pinned host staging (grow-only)
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes[2] = {0, 0};
+    // small caches of freed device / pinned buffers (sequence planes, hit lists): cudaMalloc,
+    // cudaFree and cudaMallocHost cost milliseconds and would dominate a scan of a few ms
+    struct PoolBuf { void* p; size_t bytes; };
+    std::vector<PoolBuf> dev_pool, pin_pool;
+    std::mutex pool_mu;
     unsigned long long* d_counters = nullptr;   // [0] candidates [1] hits [2] error flag [3] work counter (32-bit view)
     unsigned long long* h_counters = nullptr;   // pinned mirror
 };
@@ -33,6 +38,7 @@ struct pwmscan_seq {
     int32_t nseg = 1;
     std::vector<int64_t> seg_off;    // nseg+1
     int64_t* d_seg_off = nullptr;
+    size_t cap_seq2 = 0, cap_mask = 0, cap_ascii = 0, cap_seg = 0;   // allocation sizes (for the pool)
     uint32_t* d_seq2_alloc = nullptr;   // 1 front word + words + tail
     uint32_t* d_seq2 = nullptr;         // = alloc + 1; stored base u at word u>>4
     uint32_t* d_mask = nullptr;         // stored base u at bit u&31 of word u>>5 (1 = not ACGT)
@@ -86,11 +92,15 @@ struct pwmscan_plan {
 };
 
 struct pwmscan_hits {
+    pwmscan_ctx* ctx = nullptr;
     int64_t count = 0;
-    std::vector<int32_t> motif, segment;
-    std::vector<uint8_t> strand;
-    std::vector<int64_t> pos;
-    std::vector<double> score;
+    void* buf = nullptr;          // pinned: [pos i64 x n][score f64 x n][motif i32 x n][segment i32 x n][strand u8 x n]
+    size_t buf_bytes = 0;
+    const int64_t* pos = nullptr;
+    const double* score = nullptr;
+    const int32_t* motif = nullptr;
+    const int32_t* segment = nullptr;
+    const uint8_t* strand = nullptr;
 };
 
 namespace pwmscan {
@@ -100,6 +110,11 @@ int cuda_fail(pwmscan_ctx* ctx, cudaError_t e, const char* what);
 // grow-only scratch; returns nullptr on failure (error already recorded)
 void* scratch_get(pwmscan_ctx* ctx, int slot, size_t bytes);
 void* pinned_get(pwmscan_ctx* ctx, int slot, size_t bytes);
+// pooled allocations: *bytes_out receives the real capacity to hand back to pool_put
+void* dev_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
+void dev_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
+void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
+void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 
 #define PWM_CUDA(call)                                                          \
     do {                                                                        \

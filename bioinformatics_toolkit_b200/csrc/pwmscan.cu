@@ -59,6 +59,64 @@ void* pinned_get(pwmscan_ctx* ctx, int slot, size_t bytes) {
     return p;
 }
 
+static void* pool_take(std::vector<pwmscan_ctx::PoolBuf>& pool, size_t bytes, size_t* bytes_out) {
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); ++i)
+        if (pool[i].bytes >= bytes && pool[i].bytes <= 2 * bytes + (1 << 20) && (best < 0 || pool[i].bytes < pool[best].bytes)) best = (int)i;
+    if (best < 0) return nullptr;
+    void* p = pool[best].p;
+    *bytes_out = pool[best].bytes;
+    pool.erase(pool.begin() + best);
+    return p;
+}
+
+void* dev_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        if (void* p = pool_take(ctx->dev_pool, bytes, bytes_out)) return p;
+    }
+    void* p = nullptr;
+    const size_t want = bytes + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {                       // release the cache and retry once
+        std::vector<pwmscan_ctx::PoolBuf> drop;
+        { std::lock_guard<std::mutex> lk(ctx->pool_mu); drop.swap(ctx->dev_pool); }
+        for (auto& b : drop) cudaFree(b.p);
+        cudaGetLastError();
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMalloc"); return nullptr; }
+    *bytes_out = want;
+    return p;
+}
+
+void dev_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    if (ctx->dev_pool.size() >= 12) { cudaFree(ctx->dev_pool.front().p); ctx->dev_pool.erase(ctx->dev_pool.begin()); }
+    ctx->dev_pool.push_back({p, bytes});
+}
+
+void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        if (void* p = pool_take(ctx->pin_pool, bytes, bytes_out)) return p;
+    }
+    void* p = nullptr;
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMallocHost"); return nullptr; }
+    *bytes_out = want;
+    return p;
+}
+
+void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    if (ctx->pin_pool.size() >= 6) { cudaFreeHost(ctx->pin_pool.front().p); ctx->pin_pool.erase(ctx->pin_pool.begin()); }
+    ctx->pin_pool.push_back({p, bytes});
+}
+
 }  // namespace pwmscan
 
 extern "C" int pwmscan_abi_version(void) { return PWMSCAN_ABI_VERSION; }
@@ -104,6 +162,8 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& p : ctx->scratch) if (p) cudaFree(p);
     for (auto& p : ctx->pinned) if (p) cudaFreeHost(p);
+    for (auto& b : ctx->dev_pool) cudaFree(b.p);
+    for (auto& b : ctx->pin_pool) cudaFreeHost(b.p);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -225,16 +285,16 @@ static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t
     s->nwords_mask = n_anchor / 32 + 4;
     auto bail = [&](int code) { pwmscan_seq_free(s); return code; };
     cudaError_t e;
-    if ((e = cudaMalloc(&s->d_seq2_alloc, (size_t)(s->nwords2 + 1) * 4)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(seq2)"));
+    if (!(s->d_seq2_alloc = (uint32_t*)dev_pool_get(ctx, (size_t)(s->nwords2 + 1) * 4, &s->cap_seq2))) return bail(PWMSCAN_ECUDA);
     s->d_seq2 = s->d_seq2_alloc + 1;
-    if ((e = cudaMalloc(&s->d_mask, (size_t)s->nwords_mask * 4)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(mask)"));
-    if ((e = cudaMalloc(&s->d_seg_off, (size_t)(nseg + 1) * 8)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(seg_off)"));
+    if (!(s->d_mask = (uint32_t*)dev_pool_get(ctx, (size_t)s->nwords_mask * 4, &s->cap_mask))) return bail(PWMSCAN_ECUDA);
+    if (!(s->d_seg_off = (int64_t*)dev_pool_get(ctx, (size_t)(nseg + 1) * 8, &s->cap_seg))) return bail(PWMSCAN_ECUDA);
     if ((e = cudaMemcpyAsync(s->d_seg_off, seg_off, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(seg_off)"));
     // the raw bytes: either kept (upper-cased in place by the pack kernel) or a scratch buffer
     uint8_t* d_raw = nullptr;
     if (flags & PWMSCAN_SEQ_KEEP_ASCII) {
-        if ((e = cudaMalloc(&s->d_ascii, (size_t)len + 64)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(ascii)"));
+        if (!(s->d_ascii = (uint8_t*)dev_pool_get(ctx, (size_t)len + 64, &s->cap_ascii))) return bail(PWMSCAN_ECUDA);
         d_raw = s->d_ascii;
     } else {
         d_raw = (uint8_t*)scratch_get(ctx, 0, (size_t)len + 64);
@@ -283,11 +343,12 @@ extern "C" int pwmscan_seq_first_invalid(pwmscan_ctx* ctx, const pwmscan_seq* se
 
 extern "C" void pwmscan_seq_free(pwmscan_seq* s) {
     if (!s) return;
-    if (s->ctx) cudaSetDevice(s->ctx->device);
-    if (s->d_seq2_alloc) cudaFree(s->d_seq2_alloc);
-    if (s->d_mask) cudaFree(s->d_mask);
-    if (s->d_ascii) cudaFree(s->d_ascii);
-    if (s->d_seg_off) cudaFree(s->d_seg_off);
+    if (s->ctx) {
+        dev_pool_put(s->ctx, s->d_seq2_alloc, s->cap_seq2);
+        dev_pool_put(s->ctx, s->d_mask, s->cap_mask);
+        dev_pool_put(s->ctx, s->d_ascii, s->cap_ascii);
+        dev_pool_put(s->ctx, s->d_seg_off, s->cap_seg);
+    }
     delete s;
 }
 
@@ -532,6 +593,20 @@ __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsi
     }
 }
 
+// Sorted (key, score) pairs -> the column layout handed to the caller (one D2H copy).
+__global__ void decode_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, long long n,
+                              long long* __restrict__ pos, double* __restrict__ score, int32_t* __restrict__ motif,
+                              int32_t* __restrict__ segment, uint8_t* __restrict__ strand) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[k];
+        pos[k] = (long long)(key & 0xFFFFFFFFull);
+        score[k] = sc[k];
+        motif[k] = (int32_t)((key >> 33) & 0x7FFF);
+        segment[k] = (int32_t)(key >> 48);
+        strand[k] = (uint8_t)((key >> 32) & 1);
+    }
+}
+
 // Exact kernel: every window of every listed combo replayed in fp64 (IUPAC-aware when skip == 0).
 // Used for combos the prefilter cannot take (skip == 0, > 28 columns, non-finite cutoffs/tables).
 __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, int skip, const uint32_t* __restrict__ seq2,
@@ -644,6 +719,7 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
     }
     pwmscan_hits* h = new (std::nothrow) pwmscan_hits();
     if (!h) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
+    h->ctx = ctx;
     h->count = (int64_t)nhits;
     if (nhits > 0) {
         unsigned long long* d_keys2 = (unsigned long long*)scratch_get(ctx, 4, nhits * 8);
@@ -651,26 +727,28 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
         if (!d_keys2 || !d_sc2) { delete h; return PWMSCAN_ECUDA; }
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, 64, ctx->stream);
-        void* d_tmp = scratch_get(ctx, 6, tmp_bytes);
+        const size_t n8 = (nhits + 7) & ~7ull;                       // keeps every column 8-byte aligned
+        const size_t col_bytes = n8 * 25;
+        unsigned char* d_tmp = (unsigned char*)scratch_get(ctx, 6, tmp_bytes + 256 + col_bytes);
         if (!d_tmp) { delete h; return PWMSCAN_ECUDA; }
         cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, 64, ctx->stream);
         if (e != cudaSuccess) { delete h; return cuda_fail(ctx, e, "cub::DeviceRadixSort"); }
+        unsigned char* d_cols = d_tmp + ((tmp_bytes + 255) & ~(size_t)255);
+        long long* c_pos = (long long*)d_cols;
+        double* c_sc = (double*)(d_cols + n8 * 8);
+        int32_t* c_mo = (int32_t*)(d_cols + n8 * 16);
+        int32_t* c_sg = (int32_t*)(d_cols + n8 * 20);
+        uint8_t* c_st = (uint8_t*)(d_cols + n8 * 24);
+        decode_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_keys2, d_sc2, (long long)nhits, c_pos, c_sc, c_mo, c_sg, c_st);
+        if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "decode_kernel"); }
         cudaEventRecord(ctx->ev[3], ctx->stream);
-        unsigned long long* hk = (unsigned long long*)pinned_get(ctx, 0, nhits * 8);
-        double* hs = (double*)pinned_get(ctx, 1, nhits * 8);
-        if (!hk || !hs) { delete h; return PWMSCAN_ECUDA; }
-        if ((e = cudaMemcpyAsync(hk, d_keys2, nhits * 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "D2H keys"); }
-        if ((e = cudaMemcpyAsync(hs, d_sc2, nhits * 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "D2H scores"); }
-        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "scan sync"); }
-        h->motif.resize(nhits); h->segment.resize(nhits); h->strand.resize(nhits); h->pos.resize(nhits); h->score.resize(nhits);
-        for (unsigned long long k = 0; k < nhits; ++k) {
-            const unsigned long long key = hk[k];
-            h->segment[k] = (int32_t)(key >> 48);
-            h->motif[k] = (int32_t)((key >> 33) & 0x7FFF);
-            h->strand[k] = (uint8_t)((key >> 32) & 1);
-            h->pos[k] = (int64_t)(key & 0xFFFFFFFFull);
-        }
-        std::memcpy(h->score.data(), hs, nhits * 8);
+        h->buf = pin_pool_get(ctx, col_bytes, &h->buf_bytes);
+        if (!h->buf) { delete h; return PWMSCAN_ECUDA; }
+        if ((e = cudaMemcpyAsync(h->buf, d_cols, col_bytes, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { pwmscan_hits_free(h); return cuda_fail(ctx, e, "D2H hits"); }
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { pwmscan_hits_free(h); return cuda_fail(ctx, e, "scan sync"); }
+        unsigned char* hb = (unsigned char*)h->buf;
+        h->pos = (const int64_t*)hb; h->score = (const double*)(hb + n8 * 8); h->motif = (const int32_t*)(hb + n8 * 16);
+        h->segment = (const int32_t*)(hb + n8 * 20); h->strand = (const uint8_t*)(hb + n8 * 24);
         cudaEventElapsedTime(&ms_sort, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&ms_tot, ctx->ev[0], ctx->ev[3]);
     } else {
@@ -679,7 +757,7 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
     cudaEventElapsedTime(&ms_pre, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ms_res, ctx->ev[1], ctx->ev[2]);
     ctx->timing[0] = ms_pre; ctx->timing[1] = ms_res; ctx->timing[2] = ms_sort; ctx->timing[3] = ms_tot;
-    ctx->timing[5] = (double)nhits * 16 + 32;
+    ctx->timing[5] = (double)nhits * 25 + 32;
     ctx->timing[6] = (double)ncand;
     ctx->timing[7] = (double)launches;
     *out = h;
@@ -701,14 +779,18 @@ extern "C" int64_t pwmscan_hits_count(const pwmscan_hits* h) { return h ? h->cou
 extern "C" int pwmscan_hits_columns(const pwmscan_hits* h, const int32_t** motif, const uint8_t** strand, const int32_t** segment,
                                     const int64_t** pos, const double** score) {
     if (!h) return PWMSCAN_EINVAL;
-    if (motif) *motif = h->motif.data();
-    if (strand) *strand = h->strand.data();
-    if (segment) *segment = h->segment.data();
-    if (pos) *pos = h->pos.data();
-    if (score) *score = h->score.data();
+    if (motif) *motif = h->motif;
+    if (strand) *strand = h->strand;
+    if (segment) *segment = h->segment;
+    if (pos) *pos = h->pos;
+    if (score) *score = h->score;
     return PWMSCAN_OK;
 }
 
-extern "C" void pwmscan_hits_free(pwmscan_hits* h) { delete h; }
+extern "C" void pwmscan_hits_free(pwmscan_hits* h) {
+    if (!h) return;
+    if (h->buf && h->ctx) pin_pool_put(h->ctx, h->buf, h->buf_bytes);
+    delete h;
+}
 
 extern "C" void pwmscan_free(void* p) { std::free(p); }

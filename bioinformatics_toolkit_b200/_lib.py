@@ -317,10 +317,24 @@ class Plan:
         self.ctx.check(self.ctx.L.pwmscan_plan_create(self.ctx.h, motifs.h, _ptr(th), C.c_int(strands),
                                                       C.c_int(1 if skip_ambiguous else 0), C.byref(self.h)))
 
-    def scan(self, seq):
-        L = self.ctx.L
+    def scan_host(self, data, seg_off=None, uppercase=False):
+        """One-shot scan of host bytes (pwmscan_scan_host): upload, packing and scan are pipelined."""
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(bytes(data), dtype=np.uint8)
+        data = _arr(data, np.uint8)
+        so = _arr(seg_off if seg_off is not None else [0, data.size], np.int64)
         hh = _vp()
-        self.ctx.check(L.pwmscan_scan(self.ctx.h, seq.h, self.h, C.byref(hh)))
+        self.ctx.check(self.ctx.L.pwmscan_scan_host(self.ctx.h, self.h, _ptr(data), _ptr(so), C.c_int32(so.size - 1),
+                                                   C.c_int(SEQ_UPPERCASE if uppercase else 0), C.byref(hh)))
+        return self._hits(hh)
+
+    def scan(self, seq):
+        hh = _vp()
+        self.ctx.check(self.ctx.L.pwmscan_scan(self.ctx.h, seq.h, self.h, C.byref(hh)))
+        return self._hits(hh)
+
+    def _hits(self, hh):
+        L = self.ctx.L
         owner = _HitsHandle(L, hh)
         n = L.pwmscan_hits_count(hh)
         if n == 0:

@@ -12,6 +12,8 @@
 struct pwmscan_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host->device chunks of pwmscan_scan_host
+    std::vector<cudaEvent_t> chunk_ev;           // one per in-flight chunk (created on demand)
     std::mutex mu;
     std::string err;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -70,8 +72,9 @@ struct DevCombo {
 };
 
 struct DevBlock {
-    int32_t s1, nl, nslot, pad;
-    int64_t table_off;  // 32-bit words into d_tables
+    int32_t s1, nl, nslot;
+    int32_t rep_log2;    // log2 of the lane replication factor (0 = 64 motifs across the 32 lanes)
+    int64_t table_off;   // 32-bit words into d_tables
 };
 
 struct pwmscan_plan {

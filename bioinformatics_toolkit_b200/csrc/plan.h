@@ -126,6 +126,9 @@ struct ComboPlan {
 
 struct BlockPlan {
     int s1 = 2, nl = 0, nr = 0, nslot = 2, Q = kQ2;
+    // Few motifs: only lanes 0..groups-1 carry motifs; their table columns are replicated rep =
+    // 32/groups times and every replica scans its own stretch of the sequence (position-parallel).
+    int rep = 1, groups = kLanes;
     ComboPlan combo[kCombosPerBlock];
     std::vector<uint32_t> table;   // nslot * 256 * 32 words: [slot][kmer][lane]
     double p_warp = 0;             // P(some lane of a warp survives the first stage)
@@ -265,8 +268,17 @@ inline void build_block_tables(const std::vector<ComboInput>& in, const std::vec
         cp.sigma_all = sa;
         log_nosurv += std::log1p(-std::min(s1p, 0.999999));
     }
+    // replicate the used lanes' columns
+    int used = 0;
+    for (int ci = 0; ci < kCombosPerBlock; ++ci) if (bp.combo[ci].motif >= 0) used = ci / kCombosPerLane + 1;
+    int groups = 1;
+    while (groups < used) groups <<= 1;
+    bp.groups = groups; bp.rep = kLanes / groups;
+    if (bp.rep > 1)
+        for (size_t row = 0; row < (size_t)nslot * 256; ++row)
+            for (int lane = groups; lane < kLanes; ++lane) bp.table[row * kLanes + lane] = bp.table[row * kLanes + (lane % groups)];
     // a warp's 32 lanes see the same anchor: it takes the slow path if any combo survives
-    bp.p_warp = 1.0 - std::exp(log_nosurv);
+    bp.p_warp = 1.0 - std::exp(log_nosurv * bp.rep);
     // cost model in shared-memory-load slots per anchor: s1 loads, the per-phase handler (8 anchors
     // share one branch) and the second stage of the survivors
     const double p_phase = 1.0 - std::pow(1.0 - bp.p_warp, 8.0);

@@ -22,6 +22,8 @@ using namespace pwmscan;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+constexpr int kMaxChunks = 120;                      // host->device chunks of one pipelined scan
+constexpr int kCounterWords = 8 + kMaxChunks + 8;    // [0..7] scalars, [8..] one work counter per launch
 
 namespace pwmscan {
 
@@ -145,12 +147,13 @@ extern "C" int pwmscan_ctx_create(int device, pwmscan_ctx** out) {
     auto fail = [&](cudaError_t err, const char* what) { int rc = cuda_fail(nullptr, err, what); delete ctx; return rc; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "cudaEventCreate");
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     if (prop.major < 10) { delete ctx; return set_err(nullptr, PWMSCAN_ECUDA, "pwmscan: device is not sm_100 (Blackwell B200) class"); }
     ctx->sm_count = prop.multiProcessorCount;
-    if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
+    if ((e = cudaMalloc(&ctx->d_counters, kCounterWords * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
     if ((e = cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMallocHost(counters)");
     *out = ctx;
     return PWMSCAN_OK;
@@ -167,6 +170,8 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->chunk_ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -185,16 +190,17 @@ namespace {
 constexpr int kThreads = 1024;                         // prefilter CTA: 32 warps, 1 CTA per SM
 constexpr int kWarps = kThreads / 32;
 constexpr int kIters = 16;                             // x 32 anchors per warp per work item
-constexpr int64_t kChunk = (int64_t)kWarps * 32 * kIters;   // anchors per work item (16384)
+constexpr int64_t kChunk = (int64_t)kWarps * 32 * kIters;   // anchors per work item (16384) x replication
+constexpr int64_t kAnchorRound = kChunk * 32;               // anchor ranges are rounded to the largest work item
 
 __constant__ unsigned char c_iupac_lut[256];
 
 // One thread per 32 stored bases: two packed words + one mask word.
 __global__ void pack_kernel(const uint8_t* ascii, int64_t len, int uppercase, uint32_t* __restrict__ seq2,
-                            uint32_t* __restrict__ mask, uint8_t* ascii_out /* may alias ascii */, int64_t nmask_words,
+                            uint32_t* __restrict__ mask, uint8_t* ascii_out /* may alias ascii */, int64_t t0, int64_t t1,
                             unsigned long long* first_bad /* [0] non-ACGT, [1] non-IUPAC */) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nmask_words) return;
+    const int64_t t = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
     const int64_t u0 = t * 32;
     uint32_t w0 = 0, w1 = 0, mk = 0;
     unsigned long long bad_acgt = ~0ull, bad_iupac = ~0ull;
@@ -260,10 +266,7 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg, int flags,
-                           pwmscan_seq** out) {
-    if (!ctx || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: NULL argument");
-    *out = nullptr;
+static int seq_check_args(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg) {
     if (nseg < 1 || nseg > PWMSCAN_MAX_SEGMENTS) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_seq_upload: segment count out of range");
     const int64_t len = seg_off[nseg];
     if (len < 0 || (len > 0 && !ascii)) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: bad length / NULL data");
@@ -272,15 +275,18 @@ static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t
         if (seg_off[i + 1] < seg_off[i] || seg_off[0] != 0) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: seg_off must be ascending from 0");
         if (seg_off[i + 1] - seg_off[i] >= ((int64_t)1 << 32)) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_seq_upload: segment longer than 2^32");
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PWM_CUDA(cudaSetDevice(ctx->device));
-    int rc = ensure_lut(ctx);
-    if (rc) return rc;
+    return PWMSCAN_OK;
+}
+
+// Allocates the device planes of a sequence (from the pool) and uploads the segment table.
+// *d_raw_out is where the ASCII bytes must land (the kept copy, or scratch slot 0).  ctx->mu held.
+static int seq_alloc(pwmscan_ctx* ctx, const int64_t* seg_off, int32_t nseg, int flags, pwmscan_seq** out, uint8_t** d_raw_out) {
+    const int64_t len = seg_off[nseg];
     pwmscan_seq* s = new (std::nothrow) pwmscan_seq();
     if (!s) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
     s->ctx = ctx; s->len = len; s->nseg = nseg; s->flags = flags;
     s->seg_off.assign(seg_off, seg_off + nseg + 1);
-    const int64_t n_anchor = round_up(len + kPadFront + 64, kChunk);
+    const int64_t n_anchor = round_up(len + kPadFront + 64, kAnchorRound);
     s->nwords2 = n_anchor / 16 + 8;
     s->nwords_mask = n_anchor / 32 + 4;
     auto bail = [&](int code) { pwmscan_seq_free(s); return code; };
@@ -289,34 +295,59 @@ static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t
     s->d_seq2 = s->d_seq2_alloc + 1;
     if (!(s->d_mask = (uint32_t*)dev_pool_get(ctx, (size_t)s->nwords_mask * 4, &s->cap_mask))) return bail(PWMSCAN_ECUDA);
     if (!(s->d_seg_off = (int64_t*)dev_pool_get(ctx, (size_t)(nseg + 1) * 8, &s->cap_seg))) return bail(PWMSCAN_ECUDA);
-    if ((e = cudaMemcpyAsync(s->d_seg_off, seg_off, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(s->d_seg_off, s->seg_off.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(seg_off)"));
     // the raw bytes: either kept (upper-cased in place by the pack kernel) or a scratch buffer
-    uint8_t* d_raw = nullptr;
     if (flags & PWMSCAN_SEQ_KEEP_ASCII) {
         if (!(s->d_ascii = (uint8_t*)dev_pool_get(ctx, (size_t)len + 64, &s->cap_ascii))) return bail(PWMSCAN_ECUDA);
-        d_raw = s->d_ascii;
+        *d_raw_out = s->d_ascii;
     } else {
-        d_raw = (uint8_t*)scratch_get(ctx, 0, (size_t)len + 64);
-        if (!d_raw) return bail(PWMSCAN_ECUDA);
+        *d_raw_out = (uint8_t*)scratch_get(ctx, 0, (size_t)len + 64);
+        if (!*d_raw_out) return bail(PWMSCAN_ECUDA);
     }
+    if ((e = cudaMemsetAsync(ctx->d_counters + 4, 0xFF, 16, ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
+    *out = s;
+    return PWMSCAN_OK;
+}
+
+static int seq_launch_pack(pwmscan_ctx* ctx, pwmscan_seq* s, const uint8_t* d_raw, int64_t t0, int64_t t1) {
+    if (t1 <= t0) return PWMSCAN_OK;
+    const int bs = 256;
+    pack_kernel<<<(unsigned)((t1 - t0 + bs - 1) / bs), bs, 0, ctx->stream>>>(
+        d_raw, s->len, (s->flags & PWMSCAN_SEQ_UPPERCASE) ? 1 : 0, s->d_seq2, s->d_mask,
+        (s->flags & PWMSCAN_SEQ_KEEP_ASCII) ? s->d_ascii : nullptr, t0, t1, ctx->d_counters + 4);
+    PWM_CUDA(cudaGetLastError());
+    return PWMSCAN_OK;
+}
+
+static int seq_finish(pwmscan_ctx* ctx, pwmscan_seq* s) {   // after a stream sync: fetch the fromBS validation result
+    s->first_non_acgt = ctx->h_counters[4] == ~0ull ? -1 : (int64_t)ctx->h_counters[4];
+    s->first_non_iupac = ctx->h_counters[5] == ~0ull ? -1 : (int64_t)ctx->h_counters[5];
+    return PWMSCAN_OK;
+}
+
+static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg, int flags,
+                           pwmscan_seq** out) {
+    if (!ctx || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_seq_upload: NULL argument");
+    *out = nullptr;
+    int rc = seq_check_args(ctx, ascii, seg_off, nseg);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ensure_lut(ctx))) return rc;
+    pwmscan_seq* s = nullptr;
+    uint8_t* d_raw = nullptr;
+    if ((rc = seq_alloc(ctx, seg_off, nseg, flags, &s, &d_raw))) return rc;
+    auto bail = [&](int code) { pwmscan_seq_free(s); return code; };
+    const int64_t len = s->len;
+    cudaError_t e;
     if (len > 0 && (e = cudaMemcpyAsync(d_raw, ascii, (size_t)len, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(ascii)"));
-    if ((e = cudaMemsetAsync(s->d_seq2_alloc, 0, (size_t)(s->nwords2 + 1) * 4, ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
-    if ((e = cudaMemsetAsync(ctx->d_counters + 4, 0xFF, 16, ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
-    {
-        const int64_t nt = s->nwords_mask;
-        const int bs = 256;
-        pack_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(
-            d_raw, len, (flags & PWMSCAN_SEQ_UPPERCASE) ? 1 : 0, s->d_seq2, s->d_mask,
-            (flags & PWMSCAN_SEQ_KEEP_ASCII) ? s->d_ascii : nullptr, nt, ctx->d_counters + 4);
-        if ((e = cudaGetLastError()) != cudaSuccess) return bail(cuda_fail(ctx, e, "pack_kernel launch"));
-    }
+    if ((rc = seq_launch_pack(ctx, s, d_raw, 0, s->nwords_mask))) return bail(rc);
     if ((e = cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(first_bad)"));
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "pack_kernel"));
-    s->first_non_acgt = ctx->h_counters[4] == ~0ull ? -1 : (int64_t)ctx->h_counters[4];
-    s->first_non_iupac = ctx->h_counters[5] == ~0ull ? -1 : (int64_t)ctx->h_counters[5];
+    seq_finish(ctx, s);
     ctx->timing[4] = (double)len + (double)(nseg + 1) * 8;
     *out = s;
     return PWMSCAN_OK;
@@ -467,14 +498,16 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
             const BlockPlan& bp = pl->blocks[b];
             int nmin = 999, nmax = 0, nen = 0;
             for (int ci = 0; ci < kCombosPerBlock; ++ci) if (bp.combo[ci].motif >= 0) { nmin = std::min(nmin, bp.combo[ci].n); nmax = std::max(nmax, bp.combo[ci].n); nen += bp.combo[ci].enabled; }
-            std::fprintf(stderr, "[pwmscan] block %d: s1=%d nl=%d nr=%d nslot=%d Q=%d cols %d..%d enabled=%d p_warp=%.4f cost=%.3f\n",
-                         b, bp.s1, bp.nl, bp.nr, bp.nslot, bp.Q, nmin, nmax, nen, bp.p_warp, bp.cost);
+            std::fprintf(stderr, "[pwmscan] block %d: s1=%d nl=%d nr=%d nslot=%d Q=%d cols %d..%d enabled=%d rep=%d p_warp=%.4f cost=%.3f\n",
+                         b, bp.s1, bp.nl, bp.nr, bp.nslot, bp.Q, nmin, nmax, nen, bp.rep, bp.p_warp, bp.cost);
         }
         std::fprintf(stderr, "[pwmscan] generic combos=%zu cand_rate=%.3e\n", pl->generic.size(), cand_rate);
     }
     for (int b = 0; b < pl->nblocks; ++b) {
         const BlockPlan& bp = pl->blocks[b];
-        h_blocks[b].s1 = bp.s1; h_blocks[b].nl = bp.nl; h_blocks[b].nslot = bp.nslot; h_blocks[b].pad = 0;
+        h_blocks[b].s1 = bp.s1; h_blocks[b].nl = bp.nl; h_blocks[b].nslot = bp.nslot;
+        h_blocks[b].rep_log2 = 0;
+        while ((1 << h_blocks[b].rep_log2) < bp.rep) ++h_blocks[b].rep_log2;
         h_blocks[b].table_off = (int64_t)h_tables.size();
         h_tables.insert(h_tables.end(), bp.table.begin(), bp.table.end());
         for (int ci = 0; ci < kCombosPerBlock; ++ci) {
@@ -510,26 +543,39 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
 namespace {
 
 // counters: [0] candidates, [1] hits, [2] error flag, [3] work counter
+//
+// Persistent CTAs (one per SM, 32 warps) pull work items (block, chunk of anchors) from an atomic
+// counter; items are block-major so a CTA reloads its shared-memory tables only when it moves to
+// the next motif block.  Item b,c covers the anchors [c, c+1) * kChunk * rep_b; warp w takes a
+// stretch of 512 * rep_b of them and, when the block is replicated (few motifs), lane replica r
+// the r-th 512-anchor part of that stretch.
 __global__ void __launch_bounds__(kThreads, 1)
-prefilter_kernel(const uint32_t* __restrict__ seq2, long long chunks_per_block, long long total_items,
-                 const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ tables,
-                 unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor /* of this launch */, long long total_items,
+                 int iters /* x 32 anchors per lane per item: 16 normally, less for short inputs */, int nblocks, const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ tables,
+                 unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters,
+                 unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
-    int cur_blk = -1;
-    int s1 = 2, nl = 0, nslot = 2;
+    int cur_blk = -1, blk = 0;
+    const long long item_anchors = (long long)kWarps * 32 * iters;            // x replication
+    long long blk_first = 0, blk_items = (n_anchor / item_anchors) >> blocks[0].rep_log2;
+    int s1 = 2, nl = 0, nslot = 2, rep_log2 = 0;
     for (;;) {
-        if (tid == 0) s_item = (long long)atomicAdd(&counters[3], 1ull);
+        if (tid == 0) s_item = (long long)atomicAdd(work_counter, 1ull);
         __syncthreads();
         const long long item = s_item;
         if (item >= total_items) break;
-        const int blk = (int)(item / chunks_per_block);
-        const long long chunk = item % chunks_per_block;
+        while (item >= blk_first + blk_items) {                 // items are handed out in increasing order
+            blk_first += blk_items;
+            ++blk;
+            blk_items = (n_anchor / item_anchors) >> blocks[blk].rep_log2;
+        }
+        const long long chunk = item - blk_first;
         if (blk != cur_blk) {
             const DevBlock db = blocks[blk];
-            s1 = db.s1; nl = db.nl; nslot = db.nslot;
+            s1 = db.s1; nl = db.nl; nslot = db.nslot; rep_log2 = db.rep_log2;
             const uint4* src = reinterpret_cast<const uint4*>(tables + db.table_off);
             uint4* dst = reinterpret_cast<uint4*>(smem);
             const int n16 = nslot * (kSlotBytes / 16);
@@ -537,18 +583,20 @@ prefilter_kernel(const uint32_t* __restrict__ seq2, long long chunks_per_block, 
             cur_blk = blk;
         }
         __syncthreads();   // tables ready; also protects s_item against the next iteration's write
-        const long long U0 = chunk * kChunk + (long long)warp * (32 * kIters);
+        const int group_lanes = 32 >> rep_log2;                  // lanes that carry distinct motifs
+        const int replica = lane >> (5 - rep_log2);
+        const long long U0 = anchor0 + ((chunk * item_anchors + (long long)warp * (32 * iters)) << rep_log2) + (long long)replica * (32 * iters);
         const uint32_t* w = seq2 + (U0 >> 4);
         uint32_t x0 = __ldg(w - 1), x1 = __ldg(w), x2 = __ldg(w + 1), x3 = __ldg(w + 2), x4 = __ldg(w + 3);
-        const unsigned long long combo_base = (unsigned long long)blk * kCombosPerBlock + (unsigned)lane * 4u;
+        const unsigned long long combo_base = (unsigned long long)blk * kCombosPerBlock + (unsigned)(lane & (group_lanes - 1)) * 4u;
         auto emit = [&](int q, long long u) {
             const unsigned long long slot = atomicAdd(&counters[0], 1ull);
             if (slot < cand_cap) cand[slot] = ((combo_base + (unsigned)q) << 40) | (unsigned long long)u;
         };
 #define PWM_RUN(S1)                                                                                   \
-        _Pragma("unroll 1") for (int it = 0; it < kIters; ++it) {                                     \
+        _Pragma("unroll 1") for (int it = 0; it < iters; ++it) {                                      \
             const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);                    \
-            process32<S1>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem_addr, nl, nslot, emit);             \
+            process32<S1>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem_addr, nl, nslot, emit);        \
             x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;                                              \
         }
         if (s1 == 2) { PWM_RUN(2) } else if (s1 == 3) { PWM_RUN(3) } else { PWM_RUN(4) }
@@ -647,20 +695,26 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
 // ------------------------------------------------------------------------------------------------
 // scan driver
 // ------------------------------------------------------------------------------------------------
-extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* pl, pwmscan_hits** out) {
-    if (!ctx || !seq || !pl || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: NULL argument");
-    *out = nullptr;
-    if (seq->ctx != ctx || pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: handles belong to another context");
-    if (!pl->skip && !seq->d_ascii) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: skip_ambiguous = 0 needs a sequence uploaded with PWMSCAN_SEQ_KEEP_ASCII");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PWM_CUDA(cudaSetDevice(ctx->device));
+// Host->device job of a pipelined scan (pwmscan_scan_host): the ASCII bytes go up in chunks on the
+// copy stream; each chunk is packed and scanned on the compute stream as soon as it has landed, so
+// the PCIe transfer hides behind the prefilter kernel of the previous chunks.
+struct UploadJob {
+    const uint8_t* ascii;
+    uint8_t* d_raw;
+    pwmscan_seq* seq;      // mutable view of the sequence being filled
+};
+
+static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* pl, pwmscan_hits** out, const UploadJob* job) {
     int rc = ensure_lut(ctx);
     if (rc) return rc;
     const pwmscan_motifs* mo = pl->motifs;
     const int64_t len = seq->len;
-    const int64_t n_anchor = round_up(len + kPadFront + 64, kChunk);
-    const long long chunks_per_block = n_anchor / kChunk;
-    const long long total_items = chunks_per_block * pl->nblocks;
+    const int64_t n_anchor = round_up(len + kPadFront + 64, kAnchorRound);
+    auto items_of = [&](long long anchors, int iters) {
+        long long t = 0;
+        for (int b = 0; b < pl->nblocks; ++b) t += (anchors / ((long long)kWarps * 32 * iters)) / pl->blocks[b].rep;
+        return t;
+    };
     const size_t smem_bytes = (size_t)pl->max_nslot * kSlotBytes;
     if (pl->nblocks > 0) {
         static bool attr_set[64] = {false};
@@ -678,19 +732,58 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
     double* d_sc = nullptr;
     float ms_pre = 0, ms_res = 0, ms_sort = 0, ms_tot = 0;
     int launches = 0;
+    auto launch_prefilter = [&](long long a0, long long a1, int slot) -> int {
+        if (pl->nblocks == 0) return PWMSCAN_OK;
+        int iters = kIters;                                   // short inputs: smaller items so that every SM gets work
+        while (iters > 1 && items_of(a1 - a0, iters) < 4LL * ctx->sm_count) iters >>= 1;
+        const long long items = items_of(a1 - a0, iters);
+        if (items == 0) return PWMSCAN_OK;
+        const int grid = (int)std::min<long long>(ctx->sm_count, items);
+        prefilter_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+                                                                     d_cand, cand_cap, ctx->d_counters, ctx->d_counters + 8 + slot);
+        PWM_CUDA(cudaGetLastError());
+        ++launches;
+        return PWMSCAN_OK;
+    };
     for (int attempt = 0; attempt < 4; ++attempt) {
         d_cand = (unsigned long long*)scratch_get(ctx, 1, cand_cap * 8);
         d_keys = (unsigned long long*)scratch_get(ctx, 2, hit_cap * 8);
         d_sc = (double*)scratch_get(ctx, 3, hit_cap * 8);
         if (!d_cand || !d_keys || !d_sc) return PWMSCAN_ECUDA;
         PWM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        PWM_CUDA(cudaMemsetAsync(ctx->d_counters + 8, 0, (kCounterWords - 8) * sizeof(unsigned long long), ctx->stream));
         PWM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-        if (pl->nblocks > 0) {
-            const int grid = (int)std::min<long long>(ctx->sm_count, total_items);
-            prefilter_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, chunks_per_block, total_items, pl->d_blocks,
-                                                                         pl->d_tables, d_cand, cand_cap, ctx->d_counters);
-            PWM_CUDA(cudaGetLastError());
-            ++launches;
+        if (job && attempt == 0) {
+            // chunk boundaries are multiples of the anchor rounding unit, so every launch covers whole work items
+            int64_t cb = 32 * kAnchorRound;                                   // 16 Mi bases per chunk
+            while ((len + cb - 1) / cb > kMaxChunks) cb *= 2;
+            const int nch = (int)std::max<int64_t>(1, (len + cb - 1) / cb);
+            while ((int)ctx->chunk_ev.size() < nch) {
+                cudaEvent_t ev;
+                PWM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                ctx->chunk_ev.push_back(ev);
+            }
+            PWM_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));               // copies must not overtake the previous use of d_raw
+            PWM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[4], 0));
+            for (int l = 0; l < nch; ++l) {
+                const int64_t b0 = (int64_t)l * cb, b1 = std::min<int64_t>(len, b0 + cb);
+                if (b1 > b0) PWM_CUDA(cudaMemcpyAsync(job->d_raw + b0, job->ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, ctx->copy_stream));
+                PWM_CUDA(cudaEventRecord(ctx->chunk_ev[l], ctx->copy_stream));
+            }
+            long long scanned = 0;
+            for (int l = 0; l < nch; ++l) {
+                const bool last = (l == nch - 1);
+                const int64_t b0 = (int64_t)l * cb, b1 = std::min<int64_t>(len, b0 + cb);
+                PWM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[l], 0));
+                // pack threads own 32 stored bases: positions [32t-32, 32t)
+                const int64_t t0 = l == 0 ? 0 : b0 / 32 + 1, t1 = last ? job->seq->nwords_mask : b1 / 32 + 1;
+                if ((rc = seq_launch_pack(ctx, job->seq, job->d_raw, t0, t1))) return rc;
+                // anchors whose windows (and the prefetch of the next words) lie inside what is packed so far
+                const long long a1 = last ? n_anchor : std::max<long long>(scanned, b1 - kAnchorRound);
+                if (a1 > scanned) { if ((rc = launch_prefilter(scanned, a1, l))) return rc; scanned = a1; }
+            }
+        } else {
+            if ((rc = launch_prefilter(0, n_anchor, 0))) return rc;
         }
         PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
         if (pl->nblocks > 0) {
@@ -708,8 +801,9 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
             PWM_CUDA(cudaGetLastError());
         }
         PWM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-        PWM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PWM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         PWM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (job && attempt == 0) seq_finish(ctx, job->seq);
         ncand = ctx->h_counters[0]; nhits = ctx->h_counters[1];
         if (ctx->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.Search.lookAheadSearch: invalid nucleotide");
         if (ncand <= cand_cap && nhits <= hit_cap) break;
@@ -762,6 +856,38 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
     ctx->timing[7] = (double)launches;
     *out = h;
     return PWMSCAN_OK;
+}
+
+extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* pl, pwmscan_hits** out) {
+    if (!ctx || !seq || !pl || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: NULL argument");
+    *out = nullptr;
+    if (seq->ctx != ctx || pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: handles belong to another context");
+    if (!pl->skip && !seq->d_ascii) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: skip_ambiguous = 0 needs a sequence uploaded with PWMSCAN_SEQ_KEEP_ASCII");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    return scan_impl(ctx, seq, pl, out, nullptr);
+}
+
+extern "C" int pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* pl, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg,
+                                 int flags, pwmscan_hits** out) {
+    if (!ctx || !pl || !out || !seg_off) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_host: NULL argument");
+    *out = nullptr;
+    if (pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_host: plan belongs to another context");
+    int rc = seq_check_args(ctx, ascii, seg_off, nseg);
+    if (rc) return rc;
+    if (!pl->skip) flags |= PWMSCAN_SEQ_KEEP_ASCII;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ensure_lut(ctx))) return rc;
+    pwmscan_seq* s = nullptr;
+    uint8_t* d_raw = nullptr;
+    if ((rc = seq_alloc(ctx, seg_off, nseg, flags, &s, &d_raw))) return rc;
+    UploadJob job{ascii, d_raw, s};
+    rc = scan_impl(ctx, s, pl, out, &job);
+    if (rc) cudaDeviceSynchronize();          // no copy may still read the caller's buffer after we return
+    ctx->timing[4] = (double)s->len + (double)(nseg + 1) * 8;
+    pwmscan_seq_free(s);
+    return rc;
 }
 
 extern "C" int pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs, const double* thres,

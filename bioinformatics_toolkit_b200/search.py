@@ -16,11 +16,17 @@ def optimalScoresSuffix(bg, pwm):
 
 def findTFBSWith(sigma, bg, pwm, dna, thres, skip=True):
     """[(i, score)] of the windows passing the look-ahead search with the caller's sigma."""
-    seq = _dev_seq(dna, keep_ascii=not skip)
-    mo = _dev_motifs(bg, [pwm], seq.ctx)
+    if isinstance(dna, _lib.DeviceSeq):
+        mo = _dev_motifs(bg, [pwm], dna.ctx)
+    else:
+        mo = _dev_motifs(bg, [pwm])
     if sigma is not None:
         mo.set_sigma(0, 0, sigma)
-    hits = _lib.Plan(mo, [thres], strands=1, skip_ambiguous=skip).scan(seq)
+    plan = _lib.Plan(mo, [thres], strands=1, skip_ambiguous=skip)
+    if isinstance(dna, _lib.DeviceSeq):
+        hits = plan.scan(dna)
+    else:
+        hits = plan.scan_host(dna.bs if hasattr(dna, "bs") else bytes(dna))
     return list(zip(hits.pos.tolist(), hits.score.tolist()))
 
 

@@ -104,6 +104,12 @@ void pwmscan_plan_free(pwmscan_plan* plan);
  * within its segment on the forward sequence (also for strand 1: Utils.hs:109-111); score is the
  * reference's fp64 accumulator, bit-identical. */
 int  pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* plan, pwmscan_hits** out);
+/* One-shot scan of HOST bytes (what `findTFBS bg pwm dna thres` / one scanMotif batch call): the
+ * ASCII goes to the device in chunks and each chunk is packed and scanned while the next one is in
+ * flight, so the PCIe transfer overlaps the scan.  seg_off/nseg/flags as pwmscan_seq_upload_segments
+ * (pass {0,len}, 1 for a single sequence).  Same result as seq_upload + scan. */
+int  pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* plan, const uint8_t* ascii, const int64_t* seg_off,
+                       int32_t nseg, int flags, pwmscan_hits** out);
 /* Convenience: plan_create + scan + plan_free. */
 int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
                        const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);

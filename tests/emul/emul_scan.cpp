@@ -32,7 +32,7 @@ int64_t emul_scan(int M, const int* ncol, const double* mats, const double* bg, 
     HostPlan hp;
     if (!build_host_plan(mh, col_off, cols, thres, strands, 1, hp, force_s1)) return -1;
     // pack (restates pack_kernel)
-    const int64_t kChunk = 16384;
+    const int64_t kChunk = 16384 * 32;    // kAnchorRound of the library
     const int64_t n_anchor = (len + kPadFront + 64 + kChunk - 1) / kChunk * kChunk;
     std::vector<uint32_t> seq2_alloc((size_t)(n_anchor / 16 + 9), 0u), mask((size_t)(n_anchor / 32 + 4), 0u);
     uint32_t* seq2 = seq2_alloc.data() + 1;
@@ -49,22 +49,29 @@ int64_t emul_scan(int M, const int* ncol, const double* mats, const double* bg, 
     for (size_t b = 0; b < hp.blocks.size(); ++b) {
         const BlockPlan& bp = hp.blocks[b];
         const unsigned char* tab = reinterpret_cast<const unsigned char*>(bp.table.data());
-        for (int64_t U = 0; U < n_anchor; U += 32) {
-            const uint32_t* w = seq2 + (U >> 4);
+        // like the kernel: a warp owns a stretch of 512 * rep anchors; lane replica r scans the r-th 512 of it
+        const int64_t stretch = 512 * (int64_t)bp.rep;
+        for (int64_t W0 = 0; W0 < n_anchor; W0 += stretch) {
             for (int lane = 0; lane < 32; ++lane) {
-                auto emit = [&](int q, int64_t u) {
-                    ++ncand;
-                    const ComboPlan& cp = bp.combo[lane * 4 + q];
-                    if (cp.motif < 0) return;
-                    const int64_t i = u - kPadFront - cp.c;
-                    if (i < 0 || i + cp.n > len) return;
-                    double sc;
-                    if (replay_skip(seq2, mask.data(), i + kPadFront, cp.n, mh[cp.motif].tab16[cp.strand].data(),
-                                    hp.th.data() + col_off[2 * cp.motif + cp.strand], &sc))
-                        hits.push_back({cp.motif, (unsigned char)cp.strand, i, sc});
-                };
-                if (bp.s1 == 2) process32<2>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
-                else            process32<3>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
+                const int replica = lane / bp.groups;
+                for (int it = 0; it < 16; ++it) {
+                    const int64_t U = W0 + (int64_t)replica * 512 + 32 * it;
+                    const uint32_t* w = seq2 + (U >> 4);
+                    auto emit = [&](int q, int64_t u) {
+                        ++ncand;
+                        const ComboPlan& cp = bp.combo[(lane % bp.groups) * 4 + q];
+                        if (cp.motif < 0) return;
+                        const int64_t i = u - kPadFront - cp.c;
+                        if (i < 0 || i + cp.n > len) return;
+                        double sc;
+                        if (replay_skip(seq2, mask.data(), i + kPadFront, cp.n, mh[cp.motif].tab16[cp.strand].data(),
+                                        hp.th.data() + col_off[2 * cp.motif + cp.strand], &sc))
+                            hits.push_back({cp.motif, (unsigned char)cp.strand, i, sc});
+                    };
+                    if (bp.s1 == 2)      process32<2>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
+                    else if (bp.s1 == 3) process32<3>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
+                    else                 process32<4>(w[-1], w[0], w[1], w[2], w[3], U, lane, tab, bp.nl, bp.nslot, emit);
+                }
             }
         }
     }

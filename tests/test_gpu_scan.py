@@ -197,3 +197,43 @@ def test_config_c2_full_size_properties(ctx, oracle):
         assert k.sum() == cnt
         assert np.array_equal(h.motif[k], o[0]) and np.array_equal(h.strand[k], o[1]) and np.array_equal(h.pos[k] - lo, o[2])
         assert np.array_equal(h.score[k].view(np.uint64), o[3].view(np.uint64))
+
+
+def test_scan_host_pipeline_equals_resident_scan(ctx, oracle):
+    """pwmscan_scan_host (chunked upload overlapped with the scan) == seq_upload + scan, including
+    sequences spanning several 16 Mi-base chunks, segments and the IUPAC-aware path."""
+    mats = synth.synth_pwms(70, 3, nmin=6, nmax=22)
+    thres = [0.62 * oracle.optimal_score(BG, m) for m in mats]
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    plan = _lib.Plan(mo, thres)
+    for L in (1000, 16_777_216 - 5, 40_000_000):
+        dna = synth.synth_dna(L, 77, gc=0.45, n_runs=[(L // 2, 2000)], lower_frac=0.05)
+        a = plan.scan_host(dna, uppercase=True)
+        b = plan.scan(_lib.DeviceSeq(ctx, dna, uppercase=True))
+        assert len(a) == len(b) and len(a) > 0
+        for x, y in ((a.motif, b.motif), (a.strand, b.strand), (a.pos, b.pos), (a.score.view(np.uint64), b.score.view(np.uint64))):
+            assert np.array_equal(x, y)
+    lens = [300, 0, 5000, 17]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    dna = synth.synth_dna(int(off[-1]), 5)
+    a = plan.scan_host(dna, seg_off=off)
+    b = plan.scan(_lib.DeviceSeq(ctx, dna, seg_off=off))
+    assert np.array_equal(a.pos, b.pos) and np.array_equal(a.segment, b.segment)
+    p2 = _lib.Plan(mo, thres, skip_ambiguous=False)
+    d = bytearray(bytes(synth.synth_dna(3000, 8)))
+    d[100] = ord("N")
+    o = oracle_scan(oracle, mats, thres, bytes(d), skip=False)
+    assert_same(p2.scan_host(bytes(d)), o)
+
+
+def test_single_motif_replicated_lanes(ctx, oracle):
+    """Few motifs: the block's table columns are replicated and every lane replica scans its own
+    stretch of the sequence; result must not change."""
+    for count in (1, 2, 3, 9, 17):
+        mats = synth.synth_pwms(count, 100 + count, nmin=6, nmax=20)
+        dna = synth.synth_dna(2_000_000, 31 + count, gc=0.5, n_runs=[(1_000_000, 777)])
+        thres = [0.6 * oracle.optimal_score(BG, m) for m in mats]
+        h = gpu_scan(ctx, mats, thres, dna)
+        cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=1, nthreads=8, cap=1 << 22)
+        assert cnt > 0
+        assert_same(h, o)

@@ -276,21 +276,32 @@ def main():
 
     # ---- roofline of the dominant kernel (prefilter) ------------------------------------------------
     peaks = load_peaks()
+    info = plan.info()
     pre_ms_launch = pre_ms_tot / args.steps / max(1, len(dev_seqs))
     bp_launch = sum(int(a.size) for _, a in seqs_host) / max(1, len(dev_seqs))
-    nblocks = (M + 63) // 64
-    alg_bytes = 0.25 * bp_launch * nblocks                   # 2-bit genome read once per 64-motif block pass
-    hbm_ach = alg_bytes / (pre_ms_launch / 1e3) / 1e9
+    clk = peaks["sm_max_mhz"] * 1e6
+    # governing roof: shared-memory crossbar, one 128-B wavefront per clock per SM (B300_MICROARCH.md; not a
+    # MEASURED_PEAKS.json entry).  Algorithmic bytes: first-stage look-up rows, S1_b x 128 B per position per block.
+    smem_bytes = info["smem_wavefronts_per_position"] * 128.0 * bp_launch
+    smem_peak = 148 * 128 * clk / 1e9
+    smem_ach = smem_bytes / (pre_ms_launch / 1e3) / 1e9
+    hbm_bytes = 0.25 * bp_launch * info["genome_passes"]          # 2-bit genome read once per block pass
+    hbm_ach = hbm_bytes / (pre_ms_launch / 1e3) / 1e9
     ncol_mean = float(np.mean([m.shape[0] for m in mats]))
-    lane_ops = 2.0 * ncol_mean * bp_launch * M                # brute-force lookups+adds, both strands
-    issue_peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                "traffic": None, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch, "peak_source": peaks["source"],
-                "note": "issue/LDS-bound kernel: HBM is not the governing roof at 100 motifs; see issue_roofline"}
-    issue = {"bound": "int/fp32 issue (governing for many motifs)", "achieved": lane_ops / (pre_ms_launch / 1e3) / 1e12,
-             "peak": issue_peak, "unit": "T lane-ops/s (brute-force 2*n per bp*motif)",
+    lane_ops = 2.0 * ncol_mean * bp_launch * M                     # brute-force look-ups + adds, both strands
+    issue_peak = 148 * 128 * clk / 1e12
+    roofline = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
+                "traffic": None, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
+                "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md) x sm_max_mhz (%s)" % peaks["source"],
+                "algorithmic_bytes_per_launch": smem_bytes,
+                "note": "shared-memory-bandwidth bound look-up kernel; ncu (profiles/) reports the LSU/shared pipe at the same fraction"}
+    roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                    "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peaks["source"],
+                    "note": "HBM is not the governing roof at >= 64 motifs (0.25 B/base per 64-motif block pass)"}
+    issue = {"bound": "int/fp32 issue of the brute-force algorithm", "achieved": lane_ops / (pre_ms_launch / 1e3) / 1e12,
+             "peak": issue_peak, "unit": "T lane-ops/s (2*n per bp*motif)",
              "frac": lane_ops / (pre_ms_launch / 1e3) / 1e12 / issue_peak,
-             "lds_bound_gbp_motifs_s": 148 * peaks["sm_max_mhz"] * 1e6 * 64 / 2.0 / 1e9}
+             "note": "> 1 means the 4-mer/SIMD-byte restructuring does fewer operations than the brute-force count"}
 
     # ---- CPU baseline (oracle port, bounded sample), rank 0 at N=1 only ---------------------------------
     cpu = None
@@ -320,7 +331,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * el2.item() / args.steps, "pinned_h2d_gbs_this_box": h2d_gbs},
             "gpu_launches": int(args.steps * len(dev_seqs) * 2), "clocks": clocks,
-            "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu}), flush=True)
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "issue_roofline": issue, "plan": info, "cpu_baseline": cpu}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -317,6 +317,12 @@ class Plan:
         self.ctx.check(self.ctx.L.pwmscan_plan_create(self.ctx.h, motifs.h, _ptr(th), C.c_int(strands),
                                                       C.c_int(1 if skip_ambiguous else 0), C.byref(self.h)))
 
+    def info(self):
+        out = np.zeros(8)
+        self.ctx.L.pwmscan_plan_info(self.h, _ptr(out), C.c_int(8))
+        return {"blocks": int(out[0]), "smem_wavefronts_per_position": out[1], "exact_combos": int(out[2]),
+                "candidates_per_position": out[3], "table_bytes": out[4], "genome_passes": out[5], "p_second_stage_sum": out[6]}
+
     def scan_host(self, data, seg_off=None, uppercase=False):
         """One-shot scan of host bytes (pwmscan_scan_host): upload, packing and scan are pipelined."""
         if isinstance(data, (bytes, bytearray, memoryview)):

@@ -451,6 +451,22 @@ extern "C" void pwmscan_motifs_free(pwmscan_motifs* mo) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+extern "C" int pwmscan_plan_info(const pwmscan_plan* pl, double* out, int n) {
+    if (!pl || !out) return PWMSCAN_EINVAL;
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    v[0] = pl->nblocks;
+    for (const auto& b : pl->blocks) {
+        v[1] += (double)b.s1 / b.rep;          // first-stage shared-memory wavefronts (128 B) per sequence position
+        v[4] += (double)b.nslot * kSlotBytes;  // shared-memory table bytes
+        v[5] += 1.0 / b.rep;                   // passes over the packed genome
+        v[6] += b.p_warp;
+    }
+    v[2] = (double)pl->generic.size();
+    v[3] = pl->cand_rate;
+    for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    return PWMSCAN_OK;
+}
+
 extern "C" void pwmscan_plan_free(pwmscan_plan* pl) {
     if (!pl) return;
     if (pl->ctx) cudaSetDevice(pl->ctx->device);

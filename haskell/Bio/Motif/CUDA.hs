@@ -1,0 +1,168 @@
+{-# LANGUAGE ForeignFunctionInterface #-}
+{-# LANGUAGE BangPatterns             #-}
+-- | Thin FFI shim over libpwmscan.so (include/pwmscan.h).
+--
+-- NOT COMPILED IN THIS REPOSITORY'S ENVIRONMENT (no GHC in the build image): it is the binding a
+-- maintainer of kaizhang/bioinformatics-toolkit adds so that Bio.Motif.Search / Bio.Motif /
+-- Bio.Data.Bed.Utils keep their exported signatures while the work runs on a B200.  It is mirrored
+-- 1:1 by the ctypes layer bioinformatics_toolkit_b200/_lib.py, which IS exercised by the tests.
+module Bio.Motif.CUDA
+    ( withDevice
+    , findTFBSWithGPU
+    , scoresGPU
+    , maxMatchScGPU
+    , pValueToScoreGPU
+    , scoreCDFGPU
+    , scanRegionsGPU
+    , alignAllPairsGPU
+    ) where
+
+import           Control.Exception        (bracket)
+import           Control.Monad            (when)
+import qualified Data.ByteString          as B
+import qualified Data.ByteString.Unsafe   as BU
+import           Data.Int
+import qualified Data.Matrix.Unboxed      as M
+import qualified Data.Vector.Storable     as S
+import qualified Data.Vector.Unboxed      as U
+import           Data.Word
+import           Foreign
+import           Foreign.C.String
+import           Foreign.C.Types
+import           System.IO.Unsafe         (unsafePerformIO)
+
+import           Bio.Motif                (Bkgd (..), CDF (..), PWM (..), size)
+import           Bio.Seq                  (DNA, toBS)
+
+data Ctx; data Seq; data Motifs; data Plan; data Hits
+
+-- `safe` so that a long scan does not block the GHC runtime.
+foreign import ccall safe "pwmscan_ctx_create"       c_ctx_create   :: CInt -> Ptr (Ptr Ctx) -> IO CInt
+foreign import ccall safe "pwmscan_ctx_destroy"      c_ctx_destroy  :: Ptr Ctx -> IO ()
+foreign import ccall safe "pwmscan_last_error"       c_last_error   :: Ptr Ctx -> IO CString
+foreign import ccall safe "pwmscan_motifs_create"    c_motifs_create :: Ptr Ctx -> Int32 -> Ptr Int32 -> Ptr Double -> Ptr Double -> Ptr (Ptr Motifs) -> IO CInt
+foreign import ccall safe "pwmscan_motifs_set_sigma" c_set_sigma    :: Ptr Motifs -> Int32 -> CInt -> Ptr Double -> IO CInt
+foreign import ccall safe "pwmscan_motifs_free"      c_motifs_free  :: Ptr Motifs -> IO ()
+foreign import ccall safe "pwmscan_plan_create"      c_plan_create  :: Ptr Ctx -> Ptr Motifs -> Ptr Double -> CInt -> CInt -> Ptr (Ptr Plan) -> IO CInt
+foreign import ccall safe "pwmscan_plan_free"        c_plan_free    :: Ptr Plan -> IO ()
+foreign import ccall safe "pwmscan_scan_host"        c_scan_host    :: Ptr Ctx -> Ptr Plan -> Ptr Word8 -> Ptr Int64 -> Int32 -> CInt -> Ptr (Ptr Hits) -> IO CInt
+foreign import ccall safe "pwmscan_hits_count"       c_hits_count   :: Ptr Hits -> IO Int64
+foreign import ccall safe "pwmscan_hits_columns"     c_hits_columns :: Ptr Hits -> Ptr (Ptr Int32) -> Ptr (Ptr Word8) -> Ptr (Ptr Int32) -> Ptr (Ptr Int64) -> Ptr (Ptr Double) -> IO CInt
+foreign import ccall safe "pwmscan_hits_free"        c_hits_free    :: Ptr Hits -> IO ()
+foreign import ccall safe "pwmscan_seq_upload"       c_seq_upload   :: Ptr Ctx -> Ptr Word8 -> Int64 -> CInt -> Ptr (Ptr Seq) -> IO CInt
+foreign import ccall safe "pwmscan_seq_free"         c_seq_free     :: Ptr Seq -> IO ()
+foreign import ccall safe "pwmscan_scores"           c_scores       :: Ptr Ctx -> Ptr Seq -> Ptr Motifs -> Int32 -> CInt -> Ptr Double -> Int64 -> IO CInt
+foreign import ccall safe "pwmscan_max_match_sc"     c_max_match    :: Ptr Ctx -> Ptr Seq -> Ptr Motifs -> Ptr Double -> IO CInt
+foreign import ccall safe "pwmscan_pvalue_to_score"  c_pvalue       :: Ptr Ctx -> Ptr Motifs -> Double -> Ptr Double -> IO CInt
+foreign import ccall safe "pwmscan_score_cdf"        c_score_cdf    :: Ptr Ctx -> Ptr Motifs -> Int32 -> Ptr (Ptr Double) -> Ptr (Ptr Double) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "pwmscan_free"             c_free         :: Ptr a -> IO ()
+foreign import ccall safe "pwmscan_align_all_pairs"  c_align_all    :: Ptr Ctx -> Ptr Motifs -> CInt -> Double -> CInt -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
+
+-- | The reference signals failure with `error` (pure code) — so do we.
+check :: Ptr Ctx -> CInt -> IO ()
+check ctx rc = when (rc /= 0) $ c_last_error ctx >>= peekCString >>= error
+
+withDevice :: Int -> (Ptr Ctx -> IO a) -> IO a
+withDevice dev = bracket open c_ctx_destroy
+  where open = alloca $ \p -> do { rc <- c_ctx_create (fromIntegral dev) p; check nullPtr rc; peek p }
+
+-- | One process-wide context (device 0, or PWMSCAN_DEVICE).  The pure entry points below go
+-- through it with unsafePerformIO; every call is deterministic, so this is referentially transparent.
+{-# NOINLINE theCtx #-}
+theCtx :: Ptr Ctx
+theCtx = unsafePerformIO $ alloca $ \p -> do { rc <- c_ctx_create 0 p; check nullPtr rc; peek p }
+
+-- U.Vector / M.Matrix are unpinned: copy to Storable before the call.
+withMotifs :: Bkgd -> [PWM] -> (Ptr Motifs -> IO a) -> IO a
+withMotifs (BG (a, c, g, t)) pwms act =
+    S.unsafeWith ncol $ \pn -> S.unsafeWith flat $ \pm -> S.unsafeWith bg $ \pb ->
+    bracket (alloca $ \pp -> do { rc <- c_motifs_create theCtx (fromIntegral $ length pwms) pn pm pb pp; check theCtx rc; peek pp })
+            c_motifs_free act
+  where
+    ncol = S.fromList $ map (fromIntegral . size) pwms :: S.Vector Int32
+    flat = S.concat $ map (S.convert . M.flatten . _mat) pwms :: S.Vector Double
+    bg   = S.fromList [a, c, g, t]
+
+-- | Body of findTFBS / findTFBSWith (Bio/Motif/Search.hs:25-58): hits (position, score), ascending.
+findTFBSWithGPU :: Maybe (U.Vector Double) -> Bkgd -> PWM -> DNA a -> Double -> Bool -> [(Int, Double)]
+findTFBSWithGPU sigma bg pwm dna thres skip = unsafePerformIO $
+    withMotifs bg [pwm] $ \mo -> do
+        case sigma of
+            Just sg -> S.unsafeWith (S.convert sg) $ \ps -> c_set_sigma mo 0 0 ps >>= check theCtx
+            Nothing -> return ()
+        bracket (with thres $ \pt -> alloca $ \pp -> do
+                    rc <- c_plan_create theCtx mo pt 1 (if skip then 1 else 0) pp
+                    check theCtx rc >> peek pp) c_plan_free $ \plan ->
+          BU.unsafeUseAsCStringLen (toBS dna) $ \(p, n) ->
+          withArray [0, fromIntegral n] $ \poff ->
+          bracket (alloca $ \ph -> do
+                      rc <- c_scan_host theCtx plan (castPtr p) poff 1 0 ph
+                      check theCtx rc >> peek ph) c_hits_free $ \h -> do
+              cnt <- fromIntegral <$> c_hits_count h
+              alloca $ \ppos -> alloca $ \psc -> do
+                  _ <- c_hits_columns h nullPtr nullPtr nullPtr ppos psc
+                  pos <- peek ppos >>= peekArray cnt
+                  sc  <- peek psc  >>= peekArray cnt
+                  return $! zip (map fromIntegral pos) sc
+
+-- | scores (Bio/Motif.hs:127-145).
+scoresGPU :: Bkgd -> PWM -> DNA a -> [Double]
+scoresGPU bg pwm dna = unsafePerformIO $ withMotifs bg [pwm] $ \mo ->
+    BU.unsafeUseAsCStringLen (toBS dna) $ \(p, n) ->
+    bracket (alloca $ \ps -> do { rc <- c_seq_upload theCtx (castPtr p) (fromIntegral n) 2 ps; check theCtx rc; peek ps }) c_seq_free $ \sq -> do
+        let nwin = max 0 (n - size pwm + 1)
+        allocaArray (max 1 nwin) $ \out -> do
+            c_scores theCtx sq mo 0 0 out (fromIntegral nwin) >>= check theCtx
+            peekArray nwin out
+
+-- | maxMatchSc (Bio/Motif/Search.hs:98-109).
+maxMatchScGPU :: Bkgd -> PWM -> DNA a -> Double
+maxMatchScGPU bg pwm dna = unsafePerformIO $ withMotifs bg [pwm] $ \mo ->
+    BU.unsafeUseAsCStringLen (toBS dna) $ \(p, n) ->
+    bracket (alloca $ \ps -> do { rc <- c_seq_upload theCtx (castPtr p) (fromIntegral n) 2 ps; check theCtx rc; peek ps }) c_seq_free $ \sq ->
+    alloca $ \out -> c_max_match theCtx sq mo out >>= check theCtx >> peek out
+
+-- | pValueToScore (Bio/Motif.hs:213-214), batched.
+pValueToScoreGPU :: Double -> Bkgd -> [PWM] -> [Double]
+pValueToScoreGPU p bg pwms = unsafePerformIO $ withMotifs bg pwms $ \mo ->
+    allocaArray (length pwms) $ \out -> c_pvalue theCtx mo p out >>= check theCtx >> peekArray (length pwms) out
+
+-- | scoreCDF (Bio/Motif.hs:282-326).
+scoreCDFGPU :: Bkgd -> PWM -> CDF
+scoreCDFGPU bg pwm = unsafePerformIO $ withMotifs bg [pwm] $ \mo ->
+    alloca $ \px -> alloca $ \pp -> alloca $ \pn -> do
+        c_score_cdf theCtx mo 0 px pp pn >>= check theCtx
+        n <- fromIntegral <$> peek pn
+        x <- peek px; q <- peek pp
+        xs <- peekArray n x; ps <- peekArray n q
+        c_free x >> c_free q
+        return $ CDF $ U.fromList $ zip xs ps
+
+-- | Per-batch body of scanMotif (Bio/Data/Bed/Utils.hs:101-118): regions laid end to end, one
+-- segment each; returns (region index, motif index, isForward, position in region, score) in the
+-- reference's order (region, motif, forward hits ascending, reverse hits ascending).
+scanRegionsGPU :: Ptr Plan -> B.ByteString -> [Int] -> IO [(Int, Int, Bool, Int, Double)]
+scanRegionsGPU plan bytes lens =
+    BU.unsafeUseAsCStringLen bytes $ \(p, _) ->
+    withArray (map fromIntegral $ scanl (+) 0 lens) $ \poff ->
+    bracket (alloca $ \ph -> do
+                rc <- c_scan_host theCtx plan (castPtr p) poff (fromIntegral $ length lens) 1 ph   -- 1 = upper-case like fromBS
+                check theCtx rc >> peek ph) c_hits_free $ \h -> do
+        cnt <- fromIntegral <$> c_hits_count h
+        alloca $ \pm -> alloca $ \pst -> alloca $ \psg -> alloca $ \ppos -> alloca $ \psc -> do
+            _ <- c_hits_columns h pm pst psg ppos psc
+            ms <- peek pm >>= peekArray cnt; st <- peek pst >>= peekArray cnt; sg <- peek psg >>= peekArray cnt
+            ps <- peek ppos >>= peekArray cnt; sc <- peek psc >>= peekArray cnt
+            return [ (fromIntegral g, fromIntegral m, s == 0, fromIntegral q, v) | (g, m, s, q, v) <- zip5' sg ms st ps sc ]
+  where zip5' (a:as) (b:bs) (c:cs) (d:ds) (e:es) = (a, b, c, d, e) : zip5' as bs cs ds es
+        zip5' _ _ _ _ _ = []
+
+-- | All i<j alignments for `alignmentBy jsd (pFn gap) combFn` (Bio/Motif/Alignment.hs:83-132),
+-- packed upper triangle in the order iterativeMerge initialises its matrix (Bio/Motif/Merge.hs:161-165).
+alignAllPairsGPU :: Int -> Double -> Int -> [PWM] -> [(Double, (Bool, Int))]
+alignAllPairsGPU penalKind gap combKind pwms = unsafePerformIO $ withMotifs (BG (0.25, 0.25, 0.25, 0.25)) pwms $ \mo ->
+    let n = length pwms; np = n * (n - 1) `div` 2 in
+    allocaArray (max 1 np) $ \pd -> allocaArray (max 1 np) $ \ps -> allocaArray (max 1 np) $ \pp -> do
+        c_align_all theCtx mo (fromIntegral penalKind) gap (fromIntegral combKind) pd ps pp >>= check theCtx
+        d <- peekArray np pd; s <- peekArray np ps; q <- peekArray np pp
+        return [ (x, (y /= 0, fromIntegral z)) | (x, y, z) <- zip3 d s (q :: [Int32]) ]

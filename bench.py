@@ -208,12 +208,14 @@ def main():
 
     def step_resident():
         nh, pre_ms = 0, 0.0
+        last_timing.clear()
         for s in dev_seqs:
             h = plan.scan(s)
             nh += len(h)
             t = ctx.timing()
             pre_ms += t["prefilter_ms"]
-            last_timing.update(t)
+            for k, v in t.items():
+                last_timing[k] = last_timing.get(k, 0.0) + float(v)
         return nh, pre_ms
 
     def step_e2e():
@@ -327,7 +329,7 @@ def main():
             "vs_baseline": None, "dtype": "u8 prefilter + f64 re-score", "data": "synthetic",
             "config": {"workload": desc, "l2": "256 MiB flush write between steps", "thresholds": th_src,
                        "hits_per_step_rank0": int(nh),
-                       "device_ms_breakdown_last_scan": {k: round(float(v), 4) for k, v in last_timing.items()}},
+                       "device_ms_breakdown_last_step": {k: round(float(v), 4) for k, v in last_timing.items()}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * el2.item() / args.steps, "pinned_h2d_gbs_this_box": h2d_gbs},
             "gpu_launches": int(args.steps * len(dev_seqs) * 2), "clocks": clocks,

@@ -565,6 +565,7 @@ namespace {
 // the next motif block.  Item b,c covers the anchors [c, c+1) * kChunk * rep_b; warp w takes a
 // stretch of 512 * rep_b of them and, when the block is replicated (few motifs), lane replica r
 // the r-th 512-anchor part of that stretch.
+template <bool USE_TMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor /* of this launch */, long long total_items,
                  int iters /* x 32 anchors per lane per item: 16 normally, less for short inputs */, int nblocks, const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ tables,
@@ -572,8 +573,20 @@ prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long
                  unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ long long s_item;
+    __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
+    uint32_t tq = 0;                                             // TMEM address of this warp's 32-lane quarter, column 0
+    if (USE_TMEM) {
+        if (warp == 0) {                                         // all 512 columns: 2 first-stage slots x 256 k-mers
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        tq = s_tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    }
     int cur_blk = -1, blk = 0;
     const long long item_anchors = (long long)kWarps * 32 * iters;            // x replication
     long long blk_first = 0, blk_items = (n_anchor / item_anchors) >> blocks[0].rep_log2;
@@ -596,9 +609,17 @@ prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long
             uint4* dst = reinterpret_cast<uint4*>(smem);
             const int n16 = nslot * (kSlotBytes / 16);
             for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+            if (USE_TMEM && rep_log2 == 0 && warp < 4) {
+                // first-stage slots nl, nl+1 -> TMEM columns [0,256) and [256,512) of this warp's lane quarter
+                const uint32_t* t0 = tables + db.table_off + (size_t)nl * 256 * 32 + lane;
+                for (int c = 0; c < 512; ++c) tmem_st32(tq + (uint32_t)c, __ldg(t0 + (size_t)c * 32));
+                tmem_wait_st();
+            }
+            if (USE_TMEM) asm volatile("tcgen05.fence::before_thread_sync;");
             cur_blk = blk;
         }
         __syncthreads();   // tables ready; also protects s_item against the next iteration's write
+        if (USE_TMEM) asm volatile("tcgen05.fence::after_thread_sync;");
         const int group_lanes = 32 >> rep_log2;                  // lanes that carry distinct motifs
         const int replica = lane >> (5 - rep_log2);
         const long long U0 = anchor0 + ((chunk * item_anchors + (long long)warp * (32 * iters)) << rep_log2) + (long long)replica * (32 * iters);
@@ -615,9 +636,25 @@ prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long
             process32<S1>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem_addr, nl, nslot, emit);        \
             x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;                                              \
         }
-        if (s1 == 2) { PWM_RUN(2) } else if (s1 == 3) { PWM_RUN(3) } else { PWM_RUN(4) }
+#define PWM_RUN_T(S1)                                                                                 \
+        _Pragma("unroll 1") for (int it = 0; it < iters; ++it) {                                      \
+            const uint32_t n3 = __ldg(w + 4 + 2 * it), n4 = __ldg(w + 5 + 2 * it);                    \
+            process32_tmem<S1>(x0, x1, x2, x3, x4, U0 + 32 * it, lane, smem_addr, tq, nl, nslot, emit); \
+            x0 = x2; x1 = x3; x2 = x4; x3 = n3; x4 = n4;                                              \
+        }
+        if (USE_TMEM && rep_log2 == 0) {
+            if (s1 == 2) { PWM_RUN_T(2) } else if (s1 == 3) { PWM_RUN_T(3) } else { PWM_RUN_T(4) }
+        } else {
+            if (s1 == 2) { PWM_RUN(2) } else if (s1 == 3) { PWM_RUN(3) } else { PWM_RUN(4) }
+        }
 #undef PWM_RUN
+#undef PWM_RUN_T
         __syncthreads();   // every warp is done with the tables before a possible reload
+    }
+    if (USE_TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(512));
     }
 }
 
@@ -735,7 +772,8 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     if (pl->nblocks > 0) {
         static bool attr_set[64] = {false};
         if (!attr_set[ctx->device & 63]) {
-            PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
+            PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
+            PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
             attr_set[ctx->device & 63] = true;
         }
     }
@@ -755,8 +793,18 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         const long long items = items_of(a1 - a0, iters);
         if (items == 0) return PWMSCAN_OK;
         const int grid = (int)std::min<long long>(ctx->sm_count, items);
-        prefilter_kernel<<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
-                                                                     d_cand, cand_cap, ctx->d_counters, ctx->d_counters + 8 + slot);
+        // Experimental variant (off by default): first-stage slots 0/1 read through TMEM (tcgen05.ld) next to the
+        // shared-memory port.  Correct (same parity tests) but measured slower on C2 (9.7 vs 7.6 ms): the extra
+        // R2UR / address instructions cost more issue slots than the second port saves.
+        static const bool use_tmem = std::getenv("PWMSCAN_TMEM") != nullptr;
+        bool any_full = false;                                        // TMEM serves blocks whose 32 lanes carry distinct motifs
+        for (const auto& b : pl->blocks) any_full |= (b.rep == 1);
+        if (any_full && use_tmem)
+            prefilter_kernel<true><<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+                                                                               d_cand, cand_cap, ctx->d_counters, ctx->d_counters + 8 + slot);
+        else
+            prefilter_kernel<false><<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+                                                                                d_cand, cand_cap, ctx->d_counters, ctx->d_counters + 8 + slot);
         PWM_CUDA(cudaGetLastError());
         ++launches;
         return PWMSCAN_OK;

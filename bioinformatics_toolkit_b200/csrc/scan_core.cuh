@@ -125,6 +125,91 @@ PWM_HD void process32(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32
     }
 }
 
+#if defined(__CUDACC__)
+// ---- Blackwell tensor memory (TMEM) as a second look-up port ---------------------------------------
+// tcgen05.ld.32x32b.x1 hands thread l of a warp the 32-bit cell (lane 32*(warp%4)+l, column c) of
+// TMEM for a warp-uniform column c — exactly the access pattern of the first stage (all lanes of a
+// warp look at the same anchor, lane l wants row `kmer`, bank/column l of the table).  Measured on
+// B200 (scratch/tmem/tmem_bench.cu): LDTM 0.77 clk per warp-load per SM, LDS 1.00, interleaved 0.6,
+// i.e. the two ports run side by side.  The first two first-stage slots live in TMEM (512 columns =
+// 2 x 256 k-mers, every 32-lane quarter holds a copy), the others stay in shared memory.
+__device__ __forceinline__ uint32_t tmem_ld32(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    return v;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(v));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Same contract as process32, first-stage slots 0 and 1 read from TMEM (tq = TMEM address of this
+// warp's lane quarter, column 0; its low byte is 0 so one PRMT splices the k-mer byte in).
+template <int S1, class Emit>
+__device__ __forceinline__ void process32_tmem(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, int64_t U,
+                                               int lane, uint32_t tab, uint32_t tq, int nl, int nslot, Emit&& emit) {
+    const uint32_t tab_lane = tab + (uint32_t)lane * 4u;
+    const uint32_t tab1 = tab_lane + (uint32_t)nl * 32768u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t y0 = funnel_r(x0, x1, 2 * r), y1 = funnel_r(x1, x2, 2 * r);
+        const uint32_t y2 = funnel_r(x2, x3, 2 * r), y3 = funnel_r(x3, x4, 2 * r);
+        uint32_t tix[9];                                          // TMEM addresses of bytes 4..12 (slots 0 and 1)
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+            const int bb = 4 + b;
+            const uint32_t w = bb < 8 ? y1 : (bb < 12 ? y2 : y3);
+            tix[b] = __byte_perm(w, tq, 0x7650u + (uint32_t)(bb & 3));
+        }
+        uint32_t six[S1 >= 3 ? 8 + S1 - 3 : 1];                   // shared-memory addresses of bytes 6.. (slots 2, 3)
+        if (S1 >= 3) {
+#pragma unroll
+            for (int b = 0; b < 8 + S1 - 3; ++b) {
+                const int bb = 6 + b;
+                const uint32_t w = bb < 8 ? y1 : (bb < 12 ? y2 : y3);
+                six[b] = tab1 + byte_of(w, bb & 3) * 128u;
+            }
+        }
+        uint32_t acc[8];
+        uint32_t any = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                             // two half-phases of 4 anchors: 8 TMEM loads in flight
+            uint32_t t0[4], t1[4], sm[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t0[q] = tmem_ld32(tix[4 * h + q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t1[q] = tmem_ld32(tix[4 * h + q + 1] + 256u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sm[q] = 0u;
+                if (S1 >= 3) sm[q] = lds32(six[4 * h + q] + 65536u);
+                if (S1 >= 4) sm[q] += lds32(six[4 * h + q + 1] + 98304u);
+            }
+            // t0/t1 are valid only after the wait; tying them to it keeps the compiler from moving their uses above it
+            asm volatile("tcgen05.wait::ld.sync.aligned;"
+                         : "+r"(t0[0]), "+r"(t0[1]), "+r"(t0[2]), "+r"(t0[3]), "+r"(t1[0]), "+r"(t1[1]), "+r"(t1[2]), "+r"(t1[3])
+                         :: "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const uint32_t a = t0[q] + t1[q] + sm[q]; acc[4 * h + q] = a; any |= ~a; }
+        }
+        if ((any & 0x80808080u) != 0u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if ((~acc[j] & 0x80808080u) != 0u) {
+                    uint32_t alive = second_stage(acc[j], y0, y1, y2, y3, 4 + j - nl, nl, S1, nslot, tab_lane);
+                    while (alive) {
+                        const int bit = __ffs((int)alive) - 1;
+                        alive &= alive - 1;
+                        emit(bit >> 3, U + 4 * j + r);
+                    }
+                }
+            }
+        }
+    }
+}
+#endif
+
 // 2-bit code stored for a base that is not A/C/G/T (or for padding): a position hash, so that long
 // N runs look like random sequence to the prefilter instead of a poly-A tract.  The invalid-base
 // bit plane is what makes such windows non-hits (exact replay).

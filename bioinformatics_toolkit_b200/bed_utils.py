@@ -97,6 +97,12 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
     results = [] if out is None else None
     total = 0
 
+    import ctypes as C
+    L = ctx.L
+    mname_off = np.concatenate([[0], np.cumsum([len(x) for x in names])]).astype(np.int64)
+    mname_buf = b"".join(names)
+    mlen32 = nlen.astype(np.int32)
+
     def flush(regs, chunks):
         nonlocal total
         if not regs:
@@ -104,48 +110,83 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
         lens = np.array([c.size for c in chunks], dtype=np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         data = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
-        seq = _lib.DeviceSeq(ctx, data, seg_off=off, uppercase=True)
-        h = plan.scan(seq)
-        seq.free()
-        if len(h) == 0:
+        h = plan.scan_host(data, seg_off=off, uppercase=True)
+        n = len(h)
+        if n == 0:
             return
-        score = np.empty(len(h), dtype=np.int64)
-        for m in np.unique(h.motif):
-            k = h.motif == m
-            score[k] = _affinity_vec(1 - _cdf_vec(motifs[m]._cdf, h.score[k]))
-        starts = np.array([r[1] for r in regs], dtype=np.int64)[h.segment] + h.pos
-        ends = starts + nlen[h.motif]
-        total += len(h)
+        # per-hit p-value and affinity, motif by motif (hits grouped with one stable argsort)
+        score = np.empty(n, dtype=np.int64)
+        order = np.argsort(h.motif, kind="stable")
+        ms = h.motif[order]
+        cuts = np.flatnonzero(np.diff(ms)) + 1
+        for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [n]])):
+            idx = order[a:b]
+            score[idx] = _affinity_vec(1 - _cdf_vec(motifs[int(ms[a])]._cdf, h.score[idx]))
+        total += n
+        starts = np.array([r[1] for r in regs], dtype=np.int64)
         if out is None:
-            for k in range(len(h)):
-                results.append((regs[h.segment[k]][0], int(starts[k]), int(ends[k]), names[h.motif[k]], int(score[k]), h.strand[k] == 0))
-        else:
-            lines = []
-            for k in range(len(h)):
-                lines.append(b"\t".join((regs[h.segment[k]][0], b"%d" % starts[k], b"%d" % ends[k], names[h.motif[k]],
-                                         b"%d" % score[k], b"+" if h.strand[k] == 0 else b"-")))
-            out.write(b"\n".join(lines) + b"\n")
+            st = starts[h.segment] + h.pos
+            en = st + nlen[h.motif]
+            for k in range(n):
+                results.append((regs[h.segment[k]][0], int(st[k]), int(en[k]), names[h.motif[k]], int(score[k]), h.strand[k] == 0))
+            return
+        chroms = sorted(set(r[0] for r in regs))
+        cidx = {c: i for i, c in enumerate(chroms)}
+        rchrom = np.array([cidx[r[0]] for r in regs], dtype=np.int32)
+        coff = np.concatenate([[0], np.cumsum([len(c) for c in chroms])]).astype(np.int64)
+        cbuf = b"".join(chroms)
+        text = C.c_char_p()
+        tlen = C.c_int64(0)
+        p = _lib._ptr
+        rc = L.pwmscan_format_bed6(C.c_int64(n), p(np.ascontiguousarray(h.segment)), p(np.ascontiguousarray(h.motif)),
+                                   p(np.ascontiguousarray(h.strand)), p(np.ascontiguousarray(h.pos)), p(score), p(rchrom), p(starts),
+                                   C.c_char_p(cbuf), p(coff), C.c_char_p(mname_buf), p(mname_off), p(mlen32),
+                                   C.byref(text), C.byref(tlen))
+        if rc != 0:
+            raise _lib.PwmScanError(rc, "pwmscan_format_bed6 failed")
+        out.write(C.string_at(text, tlen.value))
+        L.pwmscan_free(text)
 
+    def submit(regs, chunks):
+        """fromBS per region (Seq.hs:86-95), vectorised over the batch: a region with a byte outside the
+        IUPAC alphabet is a Left (warning, skipped)."""
+        if not regs:
+            return
+        lens = np.array([c.size for c in chunks], dtype=np.int64)
+        data = np.concatenate(chunks)
+        if data.size:
+            bad = ~valid[_UPPER[data]]
+            if bad.any():
+                starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+                nz = lens > 0
+                nbad = np.zeros(len(regs), dtype=np.int64)
+                nbad[nz] = np.add.reduceat(bad.astype(np.int64), starts[nz])
+                keep = nbad == 0
+                for r, k in zip(regs, keep):
+                    if not k and warn is not None:
+                        print("Warning: no sequence for region: " + repr((r[0].decode("latin1"), r[1], r[2])), file=warn)
+                regs = [r for r, k in zip(regs, keep) if k]
+                chunks = [c for c, k in zip(chunks, keep) if k]
+        flush(regs, chunks)
+
+    index, hsize, gdata = genome.index, genome.header_size, genome.data
     regs, chunks, nb = [], [], 0
     for (chr_, start, end) in beds:
         if isinstance(chr_, str):
             chr_ = chr_.encode()
-        ok, r = raw_bytes(genome, (chr_, start, end))
-        if ok:
-            r = np.asarray(r)
-            if not valid[_UPPER[r]].all():                         # fromBS: unknown character => Left
-                ok = False
-        if not ok:
+        ent = index.get(chr_)
+        if ent is None or end > ent[1]:                            # getSeq: Left (SeqIO.hs:65-75)
             if warn is not None:
                 print("Warning: no sequence for region: " + repr((chr_.decode("latin1"), start, end)), file=warn)
             continue
+        o = hsize + ent[0] + start
         regs.append((chr_, start, end))
-        chunks.append(r)
-        nb += r.size
+        chunks.append(gdata[o:o + max(0, end - start)])
+        nb += max(0, end - start)
         if nb >= batch_bases or len(regs) >= 65000:
-            flush(regs, chunks)
+            submit(regs, chunks)
             regs, chunks, nb = [], [], 0
-    flush(regs, chunks)
+    submit(regs, chunks)
     return total if out is not None else results
 
 

@@ -14,14 +14,12 @@ using namespace pwmscan;
 namespace {
 
 __constant__ unsigned char c_lut[256];
-bool g_lut_ready[64] = {false};
-
-int ensure_lut(pwmscan_ctx* ctx) {
-    if (g_lut_ready[ctx->device & 63]) return PWMSCAN_OK;
+int ensure_lut(pwmscan_ctx* ctx) {      // ctx->mu held
+    if (ctx->dense_lut_ready) return PWMSCAN_OK;
     unsigned char lut[256];
     for (int i = 0; i < 256; ++i) lut[i] = (unsigned char)iupac_code((unsigned char)i);
     PWM_CUDA(cudaMemcpyToSymbol(c_lut, lut, 256));
-    g_lut_ready[ctx->device & 63] = true;
+    ctx->dense_lut_ready = true;
     return PWMSCAN_OK;
 }
 

@@ -19,6 +19,7 @@ struct pwmscan_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int sm_count = 148;
+    bool lut_ready = false, dense_lut_ready = false, smem_attr_set = false;   // per-context one-time device setup
     // grow-only device scratch
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -251,14 +251,12 @@ __global__ void pack_kernel(const uint8_t* ascii, int64_t len, int uppercase, ui
     if (bad_iupac != ~0ull) atomicMin(&first_bad[1], bad_iupac);
 }
 
-bool g_lut_ready[64] = {false};
-
-int ensure_lut(pwmscan_ctx* ctx) {
-    if (g_lut_ready[ctx->device & 63]) return PWMSCAN_OK;
+int ensure_lut(pwmscan_ctx* ctx) {      // ctx->mu held
+    if (ctx->lut_ready) return PWMSCAN_OK;
     unsigned char lut[256];
     for (int i = 0; i < 256; ++i) lut[i] = (unsigned char)iupac_code((unsigned char)i);
     PWM_CUDA(cudaMemcpyToSymbol(c_iupac_lut, lut, 256));
-    g_lut_ready[ctx->device & 63] = true;
+    ctx->lut_ready = true;
     return PWMSCAN_OK;
 }
 
@@ -770,11 +768,10 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     };
     const size_t smem_bytes = (size_t)pl->max_nslot * kSlotBytes;
     if (pl->nblocks > 0) {
-        static bool attr_set[64] = {false};
-        if (!attr_set[ctx->device & 63]) {
+        if (!ctx->smem_attr_set) {
             PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
             PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
-            attr_set[ctx->device & 63] = true;
+            ctx->smem_attr_set = true;
         }
     }
     // capacities: expected + slack, grown and re-run on overflow

@@ -166,6 +166,16 @@ int  pwmscan_align_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int64_t
                          const int32_t* b, int penalty_kind, double gap, int combine_kind,
                          double* dist, uint8_t* same_dir, int32_t* pos);
 
+/* ---- host-side helper: BED6 text of scanMotif hits (toLine, Data/Bed/Types.hs:139-149, of mkBed,
+ *      Data/Bed/Utils.hs:109-111).  Names are concatenated bytes with count+1 offsets; region r has
+ *      chromosome region_chrom[r] and start region_start[r]; one '\n'-terminated line per hit in *text
+ *      (release with pwmscan_free). ------------------------------------------------------------- */
+int  pwmscan_format_bed6(int64_t nhits, const int32_t* segment, const int32_t* motif, const uint8_t* strand,
+                         const int64_t* pos, const int64_t* score, const int32_t* region_chrom,
+                         const int64_t* region_start, const char* chrom_names, const int64_t* chrom_off,
+                         const char* motif_names, const int64_t* motif_off, const int32_t* motif_len,
+                         char** text, int64_t* text_len);
+
 #ifdef __cplusplus
 }
 #endif

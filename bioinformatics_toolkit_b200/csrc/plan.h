@@ -15,6 +15,8 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <thread>
+#include <atomic>
 
 namespace pwmscan {
 
@@ -213,7 +215,7 @@ inline bool place_block(const std::vector<ComboDef>& defs, int s1, int nl, int n
 
 // Quantised tables + survival estimates for a placed block.
 inline void build_block_tables(const std::vector<ComboInput>& in, const std::vector<ComboDef>& defs, int s1, int nl,
-                               int nr, const int* c_in, BlockPlan& bp) {
+                               int nr, const int* c_in, BlockPlan& bp, bool want_sigma_all) {
     const int nslot = nl + s1 + nr;
     const int Q = (s1 == 2) ? kQ2 : (s1 == 3 ? kQ3 : kQ4);
     bp.s1 = s1; bp.nl = nl; bp.nr = nr; bp.nslot = nslot; bp.Q = Q;
@@ -263,9 +265,11 @@ inline void build_block_tables(const std::vector<ComboInput>& in, const std::vec
         for (int s = nl + 1; s < nl + s1; ++s) { detail::slot_hist(&qtab[(size_t)s * 256], Q, h); detail::conv_sat(acc, h, Q, acc); }
         double s1p = 0; for (int i = 0; i <= Q; ++i) s1p += acc[i];
         cp.sigma1 = s1p;
-        for (int s = 0; s < nslot; ++s) if (s < nl || s >= nl + s1) { detail::slot_hist(&qtab[(size_t)s * 256], Q, h); detail::conv_sat(acc, h, Q, acc); }
-        double sa = 0; for (int i = 0; i <= Q; ++i) sa += acc[i];
-        cp.sigma_all = sa;
+        if (want_sigma_all) {
+            for (int s = 0; s < nslot; ++s) if (s < nl || s >= nl + s1) { detail::slot_hist(&qtab[(size_t)s * 256], Q, h); detail::conv_sat(acc, h, Q, acc); }
+            double sa = 0; for (int i = 0; i <= Q; ++i) sa += acc[i];
+            cp.sigma_all = sa;
+        } else cp.sigma_all = s1p;
         log_nosurv += std::log1p(-std::min(s1p, 0.999999));
     }
     // replicate the used lanes' columns
@@ -294,7 +298,7 @@ inline bool build_block(const std::vector<ComboInput>& in, BlockPlan& best, int 
         if (in[i].motif >= 0) { nmax = std::max(nmax, in[i].n); combo_deficits(in[i], defs[i]); }
     if (nmax > 4 * kMaxSlots) return false;
     bool have = false;
-    int cbuf[kCombosPerBlock], cbest[kCombosPerBlock];
+    int cbuf[kCombosPerBlock], cbest[kCombosPerBlock], cchosen[kCombosPerBlock];
     for (int s1 = 2; s1 <= 4; ++s1) {
         if (force_s1 && s1 != force_s1) continue;
         const int nslot = std::max(s1, std::min(kMaxSlots, (nmax + 3) / 4 + 1));
@@ -308,8 +312,13 @@ inline bool build_block(const std::vector<ComboInput>& in, BlockPlan& best, int 
         }
         if (best_nl < 0) continue;
         BlockPlan bp;
-        build_block_tables(in, defs, s1, best_nl, nslot - s1 - best_nl, cbest, bp);
-        if (!have || bp.cost < best.cost) { best = std::move(bp); have = true; }
+        build_block_tables(in, defs, s1, best_nl, nslot - s1 - best_nl, cbest, bp, false);
+        if (!have || bp.cost < best.cost) { best = std::move(bp); have = true; std::memcpy(cchosen, cbest, sizeof(cbest)); }
+        if (have && best.cost < (double)(s1 + 1) + 0.5) break;    // a larger first stage cannot be cheaper than its own loads
+    }
+    if (have) {                                                    // candidate probabilities only for the chosen configuration
+        const int s1 = best.s1, nl = best.nl, nr = best.nr;
+        build_block_tables(in, defs, s1, nl, nr, cchosen, best, true);
     }
     return have;
 }
@@ -347,7 +356,8 @@ inline bool build_host_plan(const std::vector<MotifHost>& mh, const std::vector<
     std::stable_sort(pre.begin(), pre.end(), [&](int a, int b) { return mh[a].n < mh[b].n; });
     const int nblocks = (int)((pre.size() + kMotifsPerBlock - 1) / kMotifsPerBlock);
     hp.blocks.resize(nblocks);
-    for (int b = 0; b < nblocks; ++b) {
+    std::vector<char> okb(nblocks, 1);
+    auto build_one = [&](int b) {
         std::vector<ComboInput> in(kCombosPerBlock);
         for (int ci = 0; ci < kCombosPerBlock; ++ci) {
             in[ci].motif = -1; in[ci].strand = 0; in[ci].n = 0; in[ci].tab16 = nullptr; in[ci].th_last = 0;
@@ -358,7 +368,17 @@ inline bool build_host_plan(const std::vector<MotifHost>& mh, const std::vector<
             in[ci].motif = m; in[ci].strand = s; in[ci].n = mh[m].n; in[ci].tab16 = mh[m].tab16[s].data();
             in[ci].th_last = hp.th[(size_t)col_off[2 * m + s] + mh[m].n - 1];
         }
-        if (!build_block(in, hp.blocks[b], force_s1)) return false;
+        if (!build_block(in, hp.blocks[b], force_s1)) okb[b] = 0;
+    };
+    {   // blocks are independent: build them on a few host threads
+        const int nth = std::max(1, std::min<int>(nblocks, (int)std::min<unsigned>(8u, std::thread::hardware_concurrency())));
+        std::atomic<int> next(0);
+        auto worker = [&]() { for (;;) { const int b = next.fetch_add(1); if (b >= nblocks) return; build_one(b); } };
+        if (nth <= 1) worker();
+        else { std::vector<std::thread> th; for (int t = 0; t < nth; ++t) th.emplace_back(worker); for (auto& t : th) t.join(); }
+    }
+    for (int b = 0; b < nblocks; ++b) {
+        if (!okb[b]) return false;
         hp.max_nslot = std::max(hp.max_nslot, hp.blocks[b].nslot);
         for (int ci = 0; ci < kCombosPerBlock; ++ci)
             if (hp.blocks[b].combo[ci].enabled) hp.cand_rate += hp.blocks[b].combo[ci].sigma_all;

@@ -33,10 +33,12 @@ class Genome:
             self.index[w[i]] = (int(w[i + 1]), int(w[i + 2]))
             self.order.append(w[i])
         self.header_size = len(sig) + len(header) + 2
-        self.data = np.memmap(path, dtype=np.uint8, mode="r")
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        self.data = self._mm.view(np.ndarray)          # plain ndarray view: slicing a np.memmap object is ~20x slower
 
     def close(self):
         self.data = None
+        self._mm = None
 
     def __enter__(self):
         return self

@@ -237,3 +237,51 @@ def test_single_motif_replicated_lanes(ctx, oracle):
         cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=1, nthreads=8, cap=1 << 22)
         assert cnt > 0
         assert_same(h, o)
+
+
+def test_repetitive_sequence_overflows_and_retries(ctx, oracle):
+    """Low-complexity DNA makes far more candidates than the plan's iid estimate: the scan must grow
+    its buffers and re-run (never truncate), resident and pipelined alike."""
+    unit = b"ACGTTGCAAC"
+    motif = np.full((10, 4), 0.01)
+    for k, ch in enumerate(unit):
+        motif[k, b"ACGT".index(ch)] = 0.97
+    mats = [motif] + synth.synth_pwms(5, 9, nmin=8, nmax=12)
+    L = 30_000_000
+    dna = np.frombuffer(unit * (L // len(unit)), dtype=np.uint8).copy()
+    dna[123_456:123_500] = ord("N")
+    thres = [0.9 * oracle.optimal_score(BG, m) for m in mats]
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    plan = _lib.Plan(mo, thres)
+    h = plan.scan(_lib.DeviceSeq(ctx, dna))
+    n0 = len(h.select(motif=0, strand=0))
+    assert n0 >= L // len(unit) - 20                       # one forward hit per repeat unit
+    assert len(h) > 2_500_000
+    # oracle on a slice
+    lo, hi = 100_000, 160_000
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna[lo:hi], mode=1, nthreads=4, cap=1 << 20)
+    nlen = np.array([m.shape[0] for m in mats])[h.motif]
+    k = (h.pos >= lo) & (h.pos + nlen <= hi)
+    assert k.sum() == cnt and np.array_equal(h.pos[k] - lo, o[2]) and np.array_equal(h.score[k].view(np.uint64), o[3].view(np.uint64))
+    h2 = plan.scan_host(dna)
+    assert len(h2) == len(h) and np.array_equal(h2.pos, h.pos) and np.array_equal(h2.motif, h.motif)
+
+
+def test_many_segments_and_many_motifs(ctx, oracle):
+    rng = np.random.default_rng(4)
+    lens = rng.integers(0, 60, size=40000)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    dna = synth.synth_dna(int(off[-1]), 19)
+    mats = synth.synth_pwms(200, 55, nmin=5, nmax=30)
+    thres = [0.7 * oracle.optimal_score(BG, m) for m in mats]
+    h = gpu_scan(ctx, mats, thres, dna, seg_off=off)
+    # reference: scan the concatenation, then drop windows that straddle a boundary
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna, mode=1, nthreads=8, cap=1 << 22)
+    nlen = np.array([m.shape[0] for m in mats])[o[0]]
+    seg = np.searchsorted(off, o[2], side="right") - 1
+    inside = o[2] + nlen <= off[seg + 1]
+    order = np.lexsort((o[2][inside], o[1][inside], o[0][inside], seg[inside]))
+    assert len(h) == inside.sum() and len(h) > 1000
+    assert np.array_equal(h.segment, seg[inside][order]) and np.array_equal(h.motif, o[0][inside][order])
+    assert np.array_equal(h.pos, (o[2] - off[seg])[inside][order])
+    assert np.array_equal(h.score.view(np.uint64), o[3][inside][order].view(np.uint64))

@@ -8,6 +8,7 @@
 
 #include "../../include/pwmscan.h"
 #include "plan.h"
+#include "plan_mma.h"
 
 struct pwmscan_ctx {
     int device = 0;
@@ -19,7 +20,7 @@ struct pwmscan_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int sm_count = 148;
-    bool lut_ready = false, dense_lut_ready = false, smem_attr_set = false;   // per-context one-time device setup
+    bool lut_ready = false, dense_lut_ready = false, smem_attr_set = false, mma_attr_set = false;   // per-context one-time device setup
     // grow-only device scratch
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -78,6 +79,12 @@ struct DevBlock {
     int64_t table_off;   // 32-bit words into d_tables
 };
 
+struct DevMmaBlock {
+    int32_t steps;       // MMAs (8 motif columns each) per phase tile
+    int32_t ncombo;      // N of the MMA (multiple of 16)
+    int64_t b_off;       // bytes into d_btiles
+};
+
 struct pwmscan_plan {
     pwmscan_ctx* ctx = nullptr;
     const pwmscan_motifs* motifs = nullptr;
@@ -93,6 +100,15 @@ struct pwmscan_plan {
     double* d_th = nullptr;            // th[k] = thres - sigma[k] per (motif,strand)
     double cand_rate = 0;              // expected candidates per sequence position
     int max_n = 0;
+    // tensor-core first stage (mma_prefilter.cu): its own blocks of 128 motifs
+    int mma_nblocks = 0;
+    std::vector<pwmscan::MmaBlockPlan> mma_blocks;
+    std::vector<DevCombo> mma_generic;
+    DevMmaBlock* d_mma_blocks = nullptr;
+    DevCombo* d_mma_combos = nullptr;  // mma_nblocks * 256
+    DevCombo* d_mma_generic = nullptr;
+    int8_t* d_btiles = nullptr;
+    double mma_cand_rate = 0;
 };
 
 struct pwmscan_hits {
@@ -119,6 +135,8 @@ void* dev_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
 void dev_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
 void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
+int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
+                         const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap);
 
 #define PWM_CUDA(call)                                                          \
     do {                                                                        \

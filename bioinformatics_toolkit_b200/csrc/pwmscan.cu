@@ -22,6 +22,7 @@ using namespace pwmscan;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+constexpr bool kDefaultMma = false;                  // default first stage: shared-memory look-up kernel (PWMSCAN_PREFILTER=mma|lds overrides)
 constexpr int kMaxChunks = 120;                      // host->device chunks of one pipelined scan
 constexpr int kCounterWords = 8 + kMaxChunks + 8;    // [0..7] scalars, [8..] one work counter per launch
 
@@ -473,6 +474,10 @@ extern "C" void pwmscan_plan_free(pwmscan_plan* pl) {
     if (pl->d_generic) cudaFree(pl->d_generic);
     if (pl->d_tables) cudaFree(pl->d_tables);
     if (pl->d_th) cudaFree(pl->d_th);
+    if (pl->d_mma_blocks) cudaFree(pl->d_mma_blocks);
+    if (pl->d_mma_combos) cudaFree(pl->d_mma_combos);
+    if (pl->d_mma_generic) cudaFree(pl->d_mma_generic);
+    if (pl->d_btiles) cudaFree(pl->d_btiles);
     delete pl;
 }
 
@@ -547,6 +552,38 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
     if ((rc = up((void**)&pl->d_combos, h_combos.data(), h_combos.size() * sizeof(DevCombo), "upload combos"))) return bail(rc);
     if ((rc = up((void**)&pl->d_tables, h_tables.data(), h_tables.size() * 4, "upload tables"))) return bail(rc);
     if ((rc = up((void**)&pl->d_generic, pl->generic.data(), pl->generic.size() * sizeof(DevCombo), "upload generic"))) return bail(rc);
+    {   // tensor-core first stage: blocks of 128 motifs, any motif length
+        MmaHostPlan mp;
+        const char* fst = std::getenv("PWMSCAN_FORCE_STEPS");
+        build_mma_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, mp, fst ? std::atoi(fst) : 0);
+        pl->mma_blocks = std::move(mp.blocks);
+        pl->mma_nblocks = (int)pl->mma_blocks.size();
+        pl->mma_cand_rate = mp.cand_rate;
+        for (auto& g : mp.generic) pl->mma_generic.push_back(dev_combo(g.first, g.second));
+        std::vector<DevMmaBlock> hb(pl->mma_nblocks);
+        std::vector<DevCombo> hc((size_t)pl->mma_nblocks * kMmaCombos);
+        std::vector<int8_t> ht;
+        for (int b = 0; b < pl->mma_nblocks; ++b) {
+            const MmaBlockPlan& bp = pl->mma_blocks[b];
+            while (ht.size() % 128) ht.push_back(0);
+            hb[b].steps = bp.steps; hb[b].ncombo = bp.ncombo; hb[b].b_off = (int64_t)ht.size();
+            ht.insert(ht.end(), bp.btiles.begin(), bp.btiles.end());
+            for (int ci = 0; ci < kMmaCombos; ++ci) {
+                DevCombo dc;
+                const MmaCombo& mc = bp.combo[ci];
+                if (mc.motif >= 0) { dc = dev_combo(mc.motif, mc.strand); dc.c = mc.c; }
+                else { dc.motif = -1; dc.strand = 0; dc.n = 0; dc.c = 0; dc.tab_off = 0; dc.th_off = 0; }
+                hc[(size_t)b * kMmaCombos + ci] = dc;
+            }
+            if (std::getenv("PWMSCAN_VERBOSE"))
+                std::fprintf(stderr, "[pwmscan] mma block %d: steps=%d (K1=%d cols) N=%d cand_rate=%.3e cost=%.1f\n", b, bp.steps, 8 * bp.steps, bp.ncombo, bp.cand_rate, bp.cost);
+        }
+        while (ht.size() % 128) ht.push_back(0);
+        if ((rc = up((void**)&pl->d_mma_blocks, hb.data(), hb.size() * sizeof(DevMmaBlock), "upload mma blocks"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_mma_combos, hc.data(), hc.size() * sizeof(DevCombo), "upload mma combos"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_mma_generic, pl->mma_generic.data(), pl->mma_generic.size() * sizeof(DevCombo), "upload mma generic"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_btiles, ht.data(), ht.size(), "upload btiles"))) return bail(rc);
+    }
     *out = pl;
     return PWMSCAN_OK;
 }
@@ -678,6 +715,7 @@ __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsi
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < ncand;
          k += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long cd = cand[k];
+        if (cd == ~0ull) continue;                       // unused slot of a warp's chunk (tensor-core prefilter)
         const DevCombo cb = combos[cd >> 40];
         const int64_t u = (int64_t)(cd & ((1ull << 40) - 1));
         const int64_t i = u - kPadFront - cb.c;
@@ -774,16 +812,29 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
             ctx->smem_attr_set = true;
         }
     }
+    // which first stage: the shared-memory look-up kernel or the tensor-core (tcgen05) one
+    static const char* mode_env = std::getenv("PWMSCAN_PREFILTER");
+    const bool use_mma = mode_env ? (std::strcmp(mode_env, "mma") == 0) : kDefaultMma;
+    const int n_pre_blocks = use_mma ? pl->mma_nblocks : pl->nblocks;
+    const std::vector<DevCombo>& generic = use_mma ? pl->mma_generic : pl->generic;
+    const DevCombo* d_generic = use_mma ? pl->d_mma_generic : pl->d_generic;
+    const DevCombo* d_combos = use_mma ? pl->d_mma_combos : pl->d_combos;
+    const double cand_rate = use_mma ? pl->mma_cand_rate : pl->cand_rate;
     // capacities: expected + slack, grown and re-run on overflow
-    unsigned long long cand_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
-    unsigned long long hit_cap = cand_cap;
-    if (!pl->generic.empty() && hit_cap < (1ull << 22)) hit_cap = 1ull << 22;
+    unsigned long long cand_cap = (unsigned long long)(cand_rate * (double)len * 1.5) + (1ull << 20);
+    unsigned long long hit_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
+    if (!generic.empty() && hit_cap < (1ull << 22)) hit_cap = 1ull << 22;
     unsigned long long nhits = 0, ncand = 0;
     unsigned long long *d_cand = nullptr, *d_keys = nullptr;
     double* d_sc = nullptr;
     float ms_pre = 0, ms_res = 0, ms_sort = 0, ms_tot = 0;
     int launches = 0;
     auto launch_prefilter = [&](long long a0, long long a1, int slot) -> int {
+        if (use_mma) {
+            if (pl->mma_nblocks == 0) return PWMSCAN_OK;
+            ++launches;
+            return launch_mma_prefilter(ctx, seq->d_seq2, a0, a1, pl->mma_nblocks, pl->d_mma_blocks, pl->d_btiles, d_cand, cand_cap);
+        }
         if (pl->nblocks == 0) return PWMSCAN_OK;
         int iters = kIters;                                   // short inputs: smaller items so that every SM gets work
         while (iters > 1 && items_of(a1 - a0, iters) < 4LL * ctx->sm_count) iters >>= 1;
@@ -813,6 +864,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         if (!d_cand || !d_keys || !d_sc) return PWMSCAN_ECUDA;
         PWM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
         PWM_CUDA(cudaMemsetAsync(ctx->d_counters + 8, 0, (kCounterWords - 8) * sizeof(unsigned long long), ctx->stream));
+        if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, cand_cap * 8, ctx->stream));     // sentinel: warps reserve whole chunks
         PWM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
         if (job && attempt == 0) {
             // chunk boundaries are multiples of the anchor rounding unit, so every launch covers whole work items
@@ -847,17 +899,17 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
             if ((rc = launch_prefilter(0, n_anchor, 0))) return rc;
         }
         PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        if (pl->nblocks > 0) {
-            rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, pl->d_combos, seq->d_seq2, seq->d_mask,
+        if (n_pre_blocks > 0) {
+            rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, d_combos, seq->d_seq2, seq->d_mask,
                                                                       seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
                                                                       d_sc, hit_cap, ctx->d_counters);
             PWM_CUDA(cudaGetLastError());
         }
-        if (!pl->generic.empty() && len > 0) {
+        if (!generic.empty() && len > 0) {
             const int bs = 256;
             const long long gx = std::min<long long>((len + bs - 1) / bs, 65535LL * 16);
-            dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(pl->generic.size(), 65535));
-            exact_kernel<<<grid, bs, 0, ctx->stream>>>(pl->d_generic, (int)pl->generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
+            dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(generic.size(), 65535));
+            exact_kernel<<<grid, bs, 0, ctx->stream>>>(d_generic, (int)generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
                                                       seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, hit_cap, ctx->d_counters);
             PWM_CUDA(cudaGetLastError());
         }
@@ -866,6 +918,8 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         PWM_CUDA(cudaStreamSynchronize(ctx->stream));
         if (job && attempt == 0) seq_finish(ctx, job->seq);
         ncand = ctx->h_counters[0]; nhits = ctx->h_counters[1];
+        if (use_mma && ctx->h_counters[3] != 0) ncand = std::max(ncand, cand_cap) + 2 * ctx->h_counters[3];   // candidates that did not fit
+        if (ctx->h_counters[2] & 2ull) return set_err(ctx, PWMSCAN_ECUDA, "pwmscan_scan: tensor-core prefilter pipeline aborted (bounded wait expired)");
         if (ctx->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.Search.lookAheadSearch: invalid nucleotide");
         if (ncand <= cand_cap && nhits <= hit_cap) break;
         if (attempt == 3) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit buffers kept overflowing");

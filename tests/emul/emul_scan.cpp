@@ -118,3 +118,81 @@ void emul_align(int n1, const double* m1, int n2, const double* m2, int penal_ki
     *ambiguous = 0;
     align_pair(cfg, m1, l1.data(), n1, m2, l2.data(), m2r.data(), l2r.data(), n2, o1.data(), o2.data(), d_out, same_dir, pos, ambiguous);
 }
+
+// ---- tensor-core first stage: the host plan (csrc/plan_mma.h) evaluated with plain integer loops -------
+#include "../../bioinformatics_toolkit_b200/csrc/plan_mma.h"
+
+extern "C" __attribute__((visibility("default")))
+int64_t emul_mma_scan(int M, const int* ncol, const double* mats, const double* bg, const double* thres, int strands,
+                      const unsigned char* ascii, int64_t len, int force_steps,
+                      int32_t* out_motif, unsigned char* out_strand, int64_t* out_pos, double* out_sc, int64_t cap, int64_t* stats) {
+    std::vector<MotifHost> mh(M);
+    std::vector<int64_t> col_off(2 * (size_t)M);
+    int64_t cols = 0;
+    const double* p = mats;
+    for (int m = 0; m < M; ++m) {
+        motif_prepare(mh[m], ncol[m], p, bg);
+        p += 4 * ncol[m];
+        for (int s = 0; s < 2; ++s) { col_off[2 * m + s] = cols; cols += ncol[m]; }
+    }
+    MmaHostPlan hp;
+    build_mma_host_plan(mh, col_off, cols, thres, strands, 1, hp, force_steps);
+    const int64_t kRound = 16384 * 32;
+    const int64_t n_anchor = (len + kPadFront + 64 + kRound - 1) / kRound * kRound;
+    std::vector<uint32_t> seq2_alloc((size_t)(n_anchor / 16 + 9), 0u), mask((size_t)(n_anchor / 32 + 4), 0u);
+    uint32_t* seq2 = seq2_alloc.data() + 1;
+    for (int64_t u = 0; u < (int64_t)mask.size() * 32; ++u) {
+        const int64_t pos = u - kPadFront;
+        const int code = (pos >= 0 && pos < len) ? iupac_code(ascii[pos]) : 15;
+        uint32_t c2;
+        if (code < 4) c2 = (uint32_t)code; else { c2 = pad_hash(u); mask[u >> 5] |= 1u << (u & 31); }
+        seq2[u >> 4] |= c2 << (2 * (u & 15));
+    }
+    struct Hit { int32_t motif; unsigned char strand; int64_t pos; double sc; };
+    std::vector<Hit> hits;
+    int64_t ncand = 0;
+    const int64_t scan_to = std::min<int64_t>(n_anchor, len + kPadFront + 64);
+    for (size_t b = 0; b < hp.blocks.size(); ++b) {
+        const MmaBlockPlan& bp = hp.blocks[b];
+        for (int64_t u = 0; u < scan_to; ++u)
+            for (int ci = 0; ci < bp.ncombo; ++ci) {
+                const MmaCombo& mc = bp.combo[ci];
+                if (mc.motif < 0) continue;
+                int32_t acc = 0;                              // what the int8 GEMM accumulates for (anchor u, combo ci)
+                for (int k = 0; k < 8 * bp.steps; ++k) {
+                    const uint32_t base = packed_base(seq2, u + k);
+                    acc += bp.btiles[(size_t)(k / 8) * bp.ncombo * 32 + detail::btile_offset(ci, 4 * (k % 8) + (int)base)];
+                }
+                if (acc >= 0) continue;
+                ++ncand;
+                const int64_t i = u - kPadFront - mc.c;
+                if (i < 0 || i + mc.n > len) continue;
+                double sc;
+                if (replay_skip(seq2, mask.data(), i + kPadFront, mc.n, mh[mc.motif].tab16[mc.strand].data(),
+                                hp.th.data() + col_off[2 * mc.motif + mc.strand], &sc))
+                    hits.push_back({mc.motif, (unsigned char)mc.strand, i, sc});
+            }
+    }
+    for (auto& g : hp.generic) {
+        const int m = g.first, s = g.second, n = mh[m].n;
+        for (int64_t i = 0; i + n <= len; ++i) {
+            double sc;
+            if (replay_skip(seq2, mask.data(), i + kPadFront, n, mh[m].tab16[s].data(), hp.th.data() + col_off[2 * m + s], &sc))
+                hits.push_back({m, (unsigned char)s, i, sc});
+        }
+    }
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) {
+        if (a.motif != b.motif) return a.motif < b.motif;
+        if (a.strand != b.strand) return a.strand < b.strand;
+        return a.pos < b.pos;
+    });
+    for (size_t k = 0; k < hits.size() && (int64_t)k < cap; ++k) {
+        out_motif[k] = hits[k].motif; out_strand[k] = hits[k].strand; out_pos[k] = hits[k].pos; out_sc[k] = hits[k].sc;
+    }
+    if (stats) {
+        stats[0] = ncand; stats[2] = (int64_t)hp.blocks.size(); stats[3] = (int64_t)hp.generic.size();
+        stats[1] = (int64_t)(1e6 * hp.cand_rate);
+        stats[4] = hp.blocks.empty() ? 0 : hp.blocks[0].steps;
+    }
+    return (int64_t)hits.size();
+}

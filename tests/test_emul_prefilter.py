@@ -104,3 +104,55 @@ def test_tiny_and_empty_sequences(emul, oracle, ref_motifs):
             assert h[0].size == 0
         else:
             assert _same(h, o)
+
+
+@pytest.fixture(scope="module")
+def emul_mma(emul):
+    L = C.CDLL(os.path.join(HERE, "emul", "libemul.so"))
+    L.emul_mma_scan.restype = C.c_int64
+
+    def run(mats, thres, dna, strands=2, force_steps=0, bg=BG):
+        ncol = np.array([m.shape[0] for m in mats], dtype=np.int32)
+        flat = np.concatenate([np.ascontiguousarray(m, dtype=np.float64).reshape(-1) for m in mats])
+        cap = 1 << 21
+        om, os_, op, osc = np.empty(cap, np.int32), np.empty(cap, np.uint8), np.empty(cap, np.int64), np.empty(cap)
+        st = np.zeros(8, np.int64)
+        bga, th = np.array(bg, float), np.array(thres, float)
+        d = np.ascontiguousarray(np.frombuffer(bytes(dna), dtype=np.uint8))
+        vp = C.c_void_p
+        n = L.emul_mma_scan(C.c_int(len(mats)), ncol.ctypes.data_as(vp), flat.ctypes.data_as(vp), bga.ctypes.data_as(vp),
+                            th.ctypes.data_as(vp), C.c_int(strands), d.ctypes.data_as(vp), C.c_int64(d.size), C.c_int(force_steps),
+                            om.ctypes.data_as(vp), os_.ctypes.data_as(vp), op.ctypes.data_as(vp), osc.ctypes.data_as(vp),
+                            C.c_int64(cap), st.ctypes.data_as(vp))
+        assert 0 <= n <= cap
+        return (om[:n].copy(), os_[:n].copy(), op[:n].copy(), osc[:n].copy()), st
+    return run
+
+
+@pytest.mark.parametrize("force_steps", [0, 1, 2, 4])
+def test_mma_plan_never_loses_a_hit(emul_mma, oracle, force_steps):
+    """csrc/plan_mma.h: the int8 weights of the tensor-core first stage, summed with plain integer
+    loops over the same layout the MMA reads, must flag every window the oracle reports."""
+    mats = synth.synth_pwms(40, 23, nmin=5, nmax=40)
+    dna = synth.synth_dna(30000, 10, gc=0.45, n_runs=[(0, 30), (12000, 500), (29990, 10)])
+    thres = [0.55 * oracle.optimal_score(BG, m) for m in mats]
+    thres[3] = -1e9
+    thres[4] = 2.0 * abs(thres[4]) + 50
+    h, st = emul_mma(mats, thres, dna[:6000], force_steps=force_steps)
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna[:6000], mode=1, nthreads=4, cap=1 << 21)
+    assert cnt > 100 and _same(h, o)
+    assert st[3] == 0          # no motif-length limit on this path
+
+
+def test_mma_plan_pvalue_cutoffs_are_tight(emul_mma, oracle, ref_motifs, ref_motifs_meme):
+    mats = [m for _, m in ref_motifs] + [m for _, m in ref_motifs_meme]
+    dna = synth.synth_dna(60000, 3)
+    thres = [oracle.pvalue_to_score(1e-4, BG, m) for m in mats]
+    h, st = emul_mma(mats, thres, dna, strands=1)
+    ref = []
+    for m, (mat, th) in enumerate(zip(mats, thres)):
+        pos, sc = oracle.find_tfbs(BG, mat, dna, th, True)
+        ref.append((np.full(pos.size, m, np.int32), np.zeros(pos.size, np.uint8), pos, sc))
+    o = tuple(np.concatenate([r[k] for r in ref]) for k in range(4))
+    assert _same(h, o) and len(o[0]) > 10
+    assert st[0] < 30 * len(o[0]) + 200

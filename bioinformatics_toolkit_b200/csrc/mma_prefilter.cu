@@ -32,6 +32,7 @@ namespace {
 
 constexpr int kMmaThreads = 672;             // 21 warps: 4 producers, 1 MMA issuer, 16 epilogue
 constexpr int kEpiWarps = 16;
+constexpr int kAccStages = 2;                // TMEM accumulator buffers of 256 columns (N <= 256)
 constexpr int kWarpChunk = 256;              // candidate-list entries a warp reserves per global atomic
 constexpr int kTile = 512;                   // anchors per one-hot tile (4 phases x 128 rows)
 constexpr int kOhWords = 576;                // one-hot words (= bases) per phase copy: 512 + 32 + slack, multiple of 32
@@ -55,14 +56,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// bounded wait; false = timed out (pipeline broken)
+// bounded wait; false = timed out (pipeline broken).  g_wait_mode (debug): 0 = test_wait spin, 1 = try_wait
+// (hardware-suspended), 2 = test_wait with a short nanosleep between polls.
+__device__ int g_wait_mode = 1;
 __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, volatile int* abort_flag) {
     const uint32_t a = smem_u32(b);
+    const int mode = g_wait_mode;
     for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
         uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (mode == 1)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
         if (done) return true;
+        if (mode == 2) __nanosleep(32);
         if ((spin & 1023u) == 1023u && *abort_flag) return false;
     }
     *abort_flag = 1;
@@ -74,12 +83,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* b) {
 
 struct __align__(16) MmaSmem {
     uint8_t onehot[2][4][kOhWords * 4];      // [stage][phase copy][bytes]   2 x 4 x 2304 B
-    uint64_t full_oh[2], empty_oh[2], full_acc[2], empty_acc[2];
+    uint64_t full_oh[2], empty_oh[2], full_acc[kAccStages], empty_acc[kAccStages];
     uint32_t tmem_base;
     int abort_flag;
+    unsigned int rec_used[kEpiWarps];        // records written into each epilogue warp's current chunk of the list
+    unsigned long long rec_base[kEpiWarps];  // first slot of that chunk
 };
 
-// counters: [0] candidate slots reserved, [1] hits, [2] error flag (bit 1 = pipeline abort), [3] candidates that did not fit
+// counters: [0] record slots reserved, [1] hits, [2] error flag (bit 1 = pipeline abort), [3] records that did not fit
+// candidate record: anchor [0,40) | block [40,56) | 32-combo chunk [56,59); all ones = unused slot
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor /* of this launch, multiple of 16384 */,
                      int nblocks, const DevMmaBlock* __restrict__ blocks, const int8_t* __restrict__ btiles,
@@ -90,8 +102,10 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->full_oh[i], 4); mbar_init(&sm->empty_oh[i], 1); mbar_init(&sm->full_acc[i], 1); mbar_init(&sm->empty_acc[i], kEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->full_oh[i], 4); mbar_init(&sm->empty_oh[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&sm->full_acc[i], 1); mbar_init(&sm->empty_acc[i], kEpiWarps); }
         sm->abort_flag = 0;
+        for (int i = 0; i < kEpiWarps; ++i) sm->rec_used[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 4) {
@@ -157,11 +171,11 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     bool ok = true;
                     for (int p = 0; p < 4 && ok; ++p, ++g_cnt) {
-                        const int a = g_cnt & 1;
-                        if (g_cnt >= 2 && !mbar_wait(&sm->empty_acc[a], ((g_cnt >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
+                        const int a = g_cnt & (kAccStages - 1);
+                        if (g_cnt >= kAccStages && !mbar_wait(&sm->empty_acc[a], ((g_cnt / kAccStages) - 1) & 1, abort_flag)) { ok = false; break; }
                         asm volatile("tcgen05.fence::after_thread_sync;");
                         if (lane == 0) {
-                            const uint32_t d_tmem = tmem + (uint32_t)(a * 256);
+                            const uint32_t d_tmem = tmem + (uint32_t)(a * (512 / kAccStages));
                             for (int j = 0; j < steps && !(dbg & 4); ++j) {
                                 const uint64_t adesc = umma_desc(smem_u32(&sm->onehot[s][p][0]) + 32u * j, 16, 128);   // Toeplitz rows
                                 const uint64_t bdesc = umma_desc(smem_u32(bsm) + (uint32_t)(j * N * 32), 128, 256);
@@ -183,18 +197,28 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
             // ================= epilogue: 16 warps, four per TMEM lane quarter =================
             const int quarter = warp & 3;                 // hardware rule: warp w may touch TMEM lanes 32*(w%4) .. +31
             const int sub = (warp - 5) >> 2;              // which of the quarter's four warps
-            const unsigned long long combo_base = (unsigned long long)blk * kMmaCombos;
-            unsigned long long w_base = 0;                // this warp's current chunk of the candidate list
-            int w_used = kWarpChunk;                      // (full => the first survivor allocates)
+            // Survivors are rare and must not hold the TMEM buffer: a lane whose 32-column chunk still has a
+            // possible combo only records (anchor, block, chunk) — one shared-memory atomic + one store — into
+            // its warp's private 256-record chunk of the candidate list; the re-score kernel replays the 32
+            // combos of such a record exactly.  New chunks are reserved after the buffer has been released.
+            const int e = warp - 5;
+            unsigned long long w_base = 0;
+            if (e >= 0) {                                  // (always true here) first chunk of this warp
+                unsigned long long nb = 0;
+                if (lane == 0 && blk == 0) nb = atomicAdd(&counters[0], (unsigned long long)kWarpChunk);
+                if (blk == 0) { w_base = __shfl_sync(0xFFFFFFFFu, nb, 0); if (lane == 0) sm->rec_base[e] = w_base; }
+                __syncwarp();
+                w_base = sm->rec_base[e];
+            }
             for (long long item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
                 for (int tt = 0; tt < kItemTiles; ++tt) {
                     const long long U = anchor0 + (item * kItemTiles + tt) * (long long)kTile;
                     bool ok = true;
                     for (int p = 0; p < 4; ++p, ++g_cnt) {
-                        const int a = g_cnt & 1;
-                        if (!mbar_wait(&sm->full_acc[a], (g_cnt >> 1) & 1, abort_flag)) { ok = false; break; }
+                        const int a = g_cnt & (kAccStages - 1);
+                        if (!mbar_wait(&sm->full_acc[a], (g_cnt / kAccStages) & 1, abort_flag)) { ok = false; break; }
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * 256);
+                        const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * (512 / kAccStages));
                         const long long u = U + p + 4 * (32 * quarter + lane);          // this thread's anchor
                         for (int c0 = 32 * sub; c0 < N && !(dbg & 1); c0 += 128) {
                             uint32_t v[32];
@@ -213,37 +237,24 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
                             const uint32_t o4 = v[12] | v[13] | v[14], o5 = v[15] | v[16] | v[17], o6 = v[18] | v[19] | v[20], o7 = v[21] | v[22] | v[23];
                             const uint32_t o8 = v[24] | v[25] | v[26], o9 = v[27] | v[28] | v[29], o10 = v[30] | v[31];
                             const uint32_t q0 = o0 | o1 | o2, q1 = o3 | o4 | o5, q2 = o6 | o7 | o8, q3 = o9 | o10;
-                            // Survivors are rare.  The warp appends them to a private 256-entry chunk of the candidate
-                            // list (one global atomic per chunk, not per candidate: an atomic round trip in this loop
-                            // would hold the TMEM buffer and stall the tensor pipe).  Unused chunk slots keep the
-                            // sentinel the host memsets (all ones) and are skipped by the re-score kernel.
                             if (dbg & 2) { if ((q0 | q1 | q2 | q3) == 0x12345678u) counters[5] = 1; continue; }
-                            if (__any_sync(0xFFFFFFFFu, (int32_t)(q0 | q1 | q2 | q3) < 0)) {
-#pragma unroll
-                                for (int k = 0; k < 32; ++k) {
-                                    const bool alive = (int32_t)v[k] < 0;
-                                    const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
-                                    if (m) {
-                                        const int cnt = __popc(m);
-                                        if (w_used + cnt > kWarpChunk) {
-                                            unsigned long long nb = 0;
-                                            if (lane == 0) nb = atomicAdd(&counters[0], (unsigned long long)kWarpChunk);
-                                            w_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
-                                            w_used = 0;
-                                        }
-                                        if (alive) {
-                                            const unsigned long long slot = w_base + (unsigned)w_used + (unsigned)__popc(m & ((1u << lane) - 1u));
-                                            if (slot < cand_cap) cand[slot] = ((combo_base + (unsigned)(c0 + k)) << 40) | (unsigned long long)u;
-                                            else atomicAdd(&counters[3], 1ull);           // overflow: the host grows the list and re-runs
-                                        }
-                                        w_used += cnt;
-                                    }
-                                }
+                            if ((int32_t)(q0 | q1 | q2 | q3) < 0) {                     // some combo of this (anchor, chunk) is still possible
+                                const unsigned idx = atomicAdd(&sm->rec_used[e], 1u);
+                                const unsigned long long slot = w_base + idx;
+                                if (slot < cand_cap) cand[slot] = (unsigned long long)u | ((unsigned long long)blk << 40) | ((unsigned long long)(c0 >> 5) << 56);
+                                else atomicAdd(&counters[3], 1ull);                     // list full: the host grows it and re-runs
                             }
                         }
                         asm volatile("tcgen05.fence::before_thread_sync;");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&sm->empty_acc[a]);
+                        // off the critical path: a warp adds at most 64 records per phase tile, so refilling at 128 keeps idx < 256
+                        if (sm->rec_used[e] > (unsigned)(kWarpChunk / 2)) {
+                            unsigned long long nb = 0;
+                            if (lane == 0) { nb = atomicAdd(&counters[0], (unsigned long long)kWarpChunk); sm->rec_used[e] = 0; sm->rec_base[e] = nb; }
+                            w_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
+                        }
+                        __syncwarp();
                     }
                     if (!ok) break;
                 }
@@ -265,6 +276,7 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
 namespace pwmscan {
 
 size_t mma_prefilter_smem_bytes() { return ((sizeof(MmaSmem) + 127) & ~size_t(127)) + (size_t)kMmaMaxSteps * kMmaCombos * 32 + 128; }
+static_assert(kMmaCombos * kAccStages <= 512, "accumulator stages must fit the 512 TMEM columns");
 
 int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap) {
@@ -276,6 +288,12 @@ int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0,
     const long long n_items = (a1 - a0) / ((long long)kItemTiles * kTile);
     const int grid = (int)std::min<long long>(ctx->sm_count, n_items);
     static const int dbg = std::getenv("PWMSCAN_MMA_DBG") ? std::atoi(std::getenv("PWMSCAN_MMA_DBG")) : 0;
+    static bool mode_set = false;
+    if (!mode_set) {
+        const int wm = std::getenv("PWMSCAN_MMA_WAIT") ? std::atoi(std::getenv("PWMSCAN_MMA_WAIT")) : 1;
+        PWM_CUDA(cudaMemcpyToSymbol(g_wait_mode, &wm, sizeof(int)));
+        mode_set = true;
+    }
     mma_prefilter_kernel<<<grid, kMmaThreads, mma_prefilter_smem_bytes(), ctx->stream>>>(d_seq2, a0, a1 - a0, nblocks, d_blocks, d_btiles,
                                                                                         d_cand, cand_cap, ctx->d_counters, dbg);
     PWM_CUDA(cudaGetLastError());

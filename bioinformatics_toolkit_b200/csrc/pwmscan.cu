@@ -730,6 +730,48 @@ __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsi
     }
 }
 
+// Tensor-core prefilter records (anchor, block, 32-combo chunk): one warp per record, lane = combo of the chunk,
+// exact fp64 replay as in rescore_kernel (the first stage only said "some combo of this chunk may still hit").
+__global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec, unsigned long long cap,
+                                      const DevMmaBlock* __restrict__ blocks, const int8_t* __restrict__ btiles,
+                                      const DevCombo* __restrict__ combos, const uint32_t* __restrict__ seq2,
+                                      const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
+                                      const double* __restrict__ tab16, const double* __restrict__ th,
+                                      unsigned long long* __restrict__ hit_keys, double* __restrict__ hit_sc,
+                                      unsigned long long hit_cap, unsigned long long* counters) {
+    unsigned long long nrec = counters[0];
+    if (nrec > cap) nrec = cap;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < nrec; k += nwarps) {
+        const unsigned long long r = rec[k];
+        if (r == ~0ull) continue;
+        const int64_t u = (int64_t)(r & ((1ull << 40) - 1));
+        const unsigned blk = (unsigned)((r >> 40) & 0xFFFF), chunk = (unsigned)((r >> 56) & 7);
+        {   // which of the chunk's 32 combos did the tensor core flag?  Redo this lane's int8 dot product.
+            const DevMmaBlock db = blocks[blk];
+            const int n = (int)chunk * 32 + lane;
+            const int8_t* bt = btiles + db.b_off + (size_t)(n / 8) * 256 + (size_t)(n % 8) * 16;
+            int acc = 0;
+            for (int k = 0; k < 8 * db.steps; ++k) {
+                const int x = 4 * (k & 7) + (int)packed_base(seq2, u + k);
+                acc += bt[(size_t)(k >> 3) * db.ncombo * 32 + (size_t)(x >> 4) * 128 + (x & 15)];
+            }
+            if (acc >= 0) continue;
+        }
+        const DevCombo cb = combos[(size_t)blk * kMmaCombos + chunk * 32 + lane];
+        const int64_t i = u - kPadFront - cb.c;
+        if (cb.motif < 0 || i < 0 || i + cb.n > len) continue;
+        const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
+        if (i + cb.n > seg_off[seg + 1]) continue;
+        double sc;
+        if (replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
+            const unsigned long long slot = atomicAdd(&counters[1], 1ull);
+            if (slot < hit_cap) { hit_keys[slot] = hit_key(seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+        }
+    }
+}
+
 // Sorted (key, score) pairs -> the column layout handed to the caller (one D2H copy).
 __global__ void decode_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, long long n,
                               long long* __restrict__ pos, double* __restrict__ score, int32_t* __restrict__ motif,
@@ -822,6 +864,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     const double cand_rate = use_mma ? pl->mma_cand_rate : pl->cand_rate;
     // capacities: expected + slack, grown and re-run on overflow
     unsigned long long cand_cap = (unsigned long long)(cand_rate * (double)len * 1.5) + (1ull << 20);
+    if (use_mma) cand_cap += (unsigned long long)ctx->sm_count * 16 * 256 * 2;             // every epilogue warp reserves whole 256-record chunks
     unsigned long long hit_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
     if (!generic.empty() && hit_cap < (1ull << 22)) hit_cap = 1ull << 22;
     unsigned long long nhits = 0, ncand = 0;
@@ -900,9 +943,14 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         }
         PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
         if (n_pre_blocks > 0) {
-            rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, d_combos, seq->d_seq2, seq->d_mask,
-                                                                      seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                                      d_sc, hit_cap, ctx->d_counters);
+            if (use_mma)
+                rescore_chunks_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(d_cand, cand_cap, pl->d_mma_blocks, pl->d_btiles, d_combos, seq->d_seq2, seq->d_mask,
+                                                                                  seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
+                                                                                  d_sc, hit_cap, ctx->d_counters);
+            else
+                rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, d_combos, seq->d_seq2, seq->d_mask,
+                                                                          seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
+                                                                          d_sc, hit_cap, ctx->d_counters);
             PWM_CUDA(cudaGetLastError());
         }
         if (!generic.empty() && len > 0) {

@@ -285,3 +285,32 @@ def test_many_segments_and_many_motifs(ctx, oracle):
     assert np.array_equal(h.segment, seg[inside][order]) and np.array_equal(h.motif, o[0][inside][order])
     assert np.array_equal(h.pos, (o[2] - off[seg])[inside][order])
     assert np.array_equal(h.score.view(np.uint64), o[3][inside][order].view(np.uint64))
+
+
+def test_tensor_core_prefilter_variant_parity():
+    """The experimental tcgen05 (int8 one-hot x deficit GEMM) first stage, selected with
+    PWMSCAN_PREFILTER=mma, must give the same bit-identical hit lists (own process: the mode is read once)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from bioinformatics_toolkit_b200 import _lib, synth
+from oracle import oracle as O
+BG = (0.25,) * 4
+ctx = _lib.default_context(0)
+for count, L, lo, hi in ((150, 300000, 6, 40), (3, 100000, 8, 12)):
+    mats = synth.synth_pwms(count, 21 + count, nmin=lo, nmax=hi)
+    dna = synth.synth_dna(L, 9, gc=0.45, n_runs=[(0, 40), (L // 3, 700)])
+    thres = [0.55 * O.optimal_score(BG, m) for m in mats]
+    h = _lib.Plan(_lib.DeviceMotifs(ctx, mats, BG), thres).scan_host(dna)
+    cnt, o = O.scan_mt(BG, mats, thres, dna, mode=1, nthreads=8, cap=1 << 23)
+    assert cnt == len(h) and cnt > 100
+    assert np.array_equal(h.motif, o[0]) and np.array_equal(h.strand, o[1]) and np.array_equal(h.pos, o[2])
+    assert np.array_equal(h.score.view(np.uint64), o[3].view(np.uint64))
+assert ctx.timing()["prefilter_launches"] >= 1
+print("MMA-PARITY-OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PWMSCAN_PREFILTER="mma")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MMA-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

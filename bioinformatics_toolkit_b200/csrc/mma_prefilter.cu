@@ -2,18 +2,18 @@
 //
 //   D[anchor, combo] = sum_{k<K1} sum_b onehot[anchor + k][b] * W[combo][4k+b]      (int8 x int8 -> int32)
 //
-// One persistent CTA per SM (21 warps), warp-specialised:
-//   warps 0..3   producers: read the 2-bit genome and write the one-hot byte stream of a 512-anchor tile into
-//                shared memory, four times (warp p writes the copy for phase p = anchor mod 4, so that every
-//                copy is 16-byte aligned at its first anchor); double-buffered;
-//   warp 4       one elected thread issues tcgen05.mma.kind::i8 (M = 128 anchors of one phase, N = combos,
+// One persistent CTA per SM (31 warps), warp-specialised:
+//   warps 0..1   producers: read the 2-bit genome and write the one-hot byte stream of a 512-anchor tile into
+//                shared memory, four times (one copy per phase p = anchor mod 4, two copies per warp, so that
+//                every copy is 16-byte aligned at its first anchor); double-buffered;
+//   warp 2       one elected thread issues tcgen05.mma.kind::i8 (M = 128 anchors of one phase, N = combos,
 //                K = 32 bytes = 8 motif columns per instruction).  The A descriptor is a Toeplitz view of
 //                the one-hot stream (row r starts 16 bytes = 4 bases after row r-1: LBO = 16 B, SBO = 128 B),
 //                so no im2col matrix is ever built.  Accumulators live in TMEM, double-buffered (2 x 256 columns);
-//   warps 5..20  epilogue: four warps per 32-lane quarter of TMEM (= 32 anchors), each pulling every fourth
-//                32-column chunk of its rows with tcgen05.ld.32x32b.x32, OR-reducing it (the sign bit of D
-//                says "still possible") and appending the survivors (combo, anchor) to the candidate list for
-//                the exact fp64 replay.  (TMEM read: ~900 B/clk/SM with 16+ warps, scratch/tmem/tmem_x32.cu.)
+//   warps 3..30  epilogue: seven warps per 32-lane quarter of TMEM (= 32 anchors), each pulling one 32-column
+//                chunk of its rows with tcgen05.ld.32x32b.x32, OR-reducing it (the sign bit of D says "still
+//                possible") and recording (anchor, block, chunk) for the exact fp64 replay of the survivors.
+//                (TMEM read: ~900 B/clk/SM with 16+ warps, scratch/tmem/tmem_x32.cu.)
 // Stages hand over through mbarriers (tcgen05.commit arrives for the tensor pipe).  Every wait is bounded:
 // a broken pipeline sets an abort flag and the kernel ends instead of hanging the GPU.
 //
@@ -30,8 +30,9 @@ using namespace pwmscan;
 
 namespace {
 
-constexpr int kMmaThreads = 672;             // 21 warps: 4 producers, 1 MMA issuer, 16 epilogue
-constexpr int kEpiWarps = 16;
+constexpr int kMmaThreads = 992;             // 31 warps: 2 producers, 1 MMA issuer, 28 epilogue
+constexpr int kEpiWarps = 28;                // 7 chunks of 32 combos x 4 TMEM lane quarters: one tcgen05.ld.x32 per warp and phase tile
+constexpr int kFirstEpiWarp = 3;
 constexpr int kAccStages = 2;                // TMEM accumulator buffers of 256 columns (N <= 256)
 constexpr int kWarpChunk = 256;              // candidate-list entries a warp reserves per global atomic
 constexpr int kTile = 512;                   // anchors per one-hot tile (4 phases x 128 rows)
@@ -56,22 +57,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// bounded wait; false = timed out (pipeline broken).  g_wait_mode (debug): 0 = test_wait spin, 1 = try_wait
-// (hardware-suspended), 2 = test_wait with a short nanosleep between polls.
-__device__ int g_wait_mode = 1;
+// bounded wait (mbarrier.try_wait lets the hardware park the warp); false = timed out (pipeline broken)
 __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, volatile int* abort_flag) {
     const uint32_t a = smem_u32(b);
-    const int mode = g_wait_mode;
     for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
         uint32_t done;
-        if (mode == 1)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        else
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
         if (done) return true;
-        if (mode == 2) __nanosleep(32);
         if ((spin & 1023u) == 1023u && *abort_flag) return false;
     }
     *abort_flag = 1;
@@ -102,13 +95,13 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm->full_oh[i], 4); mbar_init(&sm->empty_oh[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->full_oh[i], 2); mbar_init(&sm->empty_oh[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&sm->full_acc[i], 1); mbar_init(&sm->empty_acc[i], kEpiWarps); }
         sm->abort_flag = 0;
         for (int i = 0; i < kEpiWarps; ++i) sm->rec_used[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    if (warp == 4) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -137,9 +130,9 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
         const uint32_t idesc = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (1u << 10) /* B = s8 */ |
                                ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // both operands K-major
 
-        if (warp < 4) {
-            // ================= producers: warp p writes the one-hot copy of phase p =================
-            const int p = warp;
+        if (warp < 2) {
+            // ================= producers: warp w writes the one-hot copies of phases 2w and 2w+1 =================
+            const int p0 = 2 * warp;
             for (long long item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
                 for (int tt = 0; tt < kItemTiles; ++tt, ++t_cnt) {
                     const int s = t_cnt & 1;
@@ -148,21 +141,23 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
                     const uint32_t w0 = __ldg(w + lane);                       // 36 packed words cover the 576 bases of a tile
                     const uint32_t w1 = lane < 4 ? __ldg(w + 32 + lane) : 0u;
                     if (t_cnt >= 2 && !mbar_wait(&sm->empty_oh[s], ((t_cnt >> 1) - 1) & 1, abort_flag)) break;
-                    uint8_t* dst = &sm->onehot[s][p][0];
+                    uint8_t* dst0 = &sm->onehot[s][p0][0];
+                    uint8_t* dst1 = &sm->onehot[s][p0 + 1][0];
 #pragma unroll
                     for (int m = 0; m < kOhWords / 32 && !(dbg & 8); ++m) {
                         const int a = lane + 32 * m;                           // base index relative to U
                         const int widx = a >> 4;                               // = 2m + (lane >> 4)
                         const uint32_t word = widx < 32 ? __shfl_sync(0xFFFFFFFFu, w0, widx & 31) : __shfl_sync(0xFFFFFFFFu, w1, widx & 31);
                         const uint32_t oh = 1u << (8 * ((word >> (2 * (a & 15))) & 3u));
-                        if (a >= p) *reinterpret_cast<uint32_t*>(dst + 4 * (a - p)) = oh;
+                        if (a >= p0) *reinterpret_cast<uint32_t*>(dst0 + 4 * (a - p0)) = oh;
+                        if (a >= p0 + 1) *reinterpret_cast<uint32_t*>(dst1 + 4 * (a - p0 - 1)) = oh;
                     }
                     asm volatile("fence.proxy.async.shared::cta;");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm->full_oh[s]);
                 }
             }
-        } else if (warp == 4) {
+        } else if (warp == 2) {
             // ================= MMA issuer =================
             for (long long item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
                 for (int tt = 0; tt < kItemTiles; ++tt, ++t_cnt) {
@@ -194,14 +189,14 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
                 }
             }
         } else {
-            // ================= epilogue: 16 warps, four per TMEM lane quarter =================
+            // ================= epilogue: 28 warps, seven per TMEM lane quarter =================
             const int quarter = warp & 3;                 // hardware rule: warp w may touch TMEM lanes 32*(w%4) .. +31
-            const int sub = (warp - 5) >> 2;              // which of the quarter's four warps
+            const int sub = (warp - kFirstEpiWarp) >> 2;  // which 32-combo chunk of the quarter's rows this warp scans
             // Survivors are rare and must not hold the TMEM buffer: a lane whose 32-column chunk still has a
             // possible combo only records (anchor, block, chunk) — one shared-memory atomic + one store — into
             // its warp's private 256-record chunk of the candidate list; the re-score kernel replays the 32
             // combos of such a record exactly.  New chunks are reserved after the buffer has been released.
-            const int e = warp - 5;
+            const int e = warp - kFirstEpiWarp;
             unsigned long long w_base = 0;
             if (e >= 0) {                                  // (always true here) first chunk of this warp
                 unsigned long long nb = 0;
@@ -220,7 +215,7 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
                         asm volatile("tcgen05.fence::after_thread_sync;");
                         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * (512 / kAccStages));
                         const long long u = U + p + 4 * (32 * quarter + lane);          // this thread's anchor
-                        for (int c0 = 32 * sub; c0 < N && !(dbg & 1); c0 += 128) {
+                        for (int c0 = 32 * sub; c0 < N && !(dbg & 1); c0 += 32 * (kEpiWarps / 4)) {
                             uint32_t v[32];
                             asm volatile(
                                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -268,7 +263,7 @@ mma_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long 
     }
     if (*abort_flag && tid == 0) atomicOr(&counters[2], 2ull);
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 }  // namespace
@@ -288,12 +283,6 @@ int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0,
     const long long n_items = (a1 - a0) / ((long long)kItemTiles * kTile);
     const int grid = (int)std::min<long long>(ctx->sm_count, n_items);
     static const int dbg = std::getenv("PWMSCAN_MMA_DBG") ? std::atoi(std::getenv("PWMSCAN_MMA_DBG")) : 0;
-    static bool mode_set = false;
-    if (!mode_set) {
-        const int wm = std::getenv("PWMSCAN_MMA_WAIT") ? std::atoi(std::getenv("PWMSCAN_MMA_WAIT")) : 1;
-        PWM_CUDA(cudaMemcpyToSymbol(g_wait_mode, &wm, sizeof(int)));
-        mode_set = true;
-    }
     mma_prefilter_kernel<<<grid, kMmaThreads, mma_prefilter_smem_bytes(), ctx->stream>>>(d_seq2, a0, a1 - a0, nblocks, d_blocks, d_btiles,
                                                                                         d_cand, cand_cap, ctx->d_counters, dbg);
     PWM_CUDA(cudaGetLastError());

@@ -106,7 +106,7 @@ inline double mma_fill_block(const std::vector<ComboInput>& in, const std::vecto
     // (measured on B200: a tcgen05.commit completes about every 500 clk at best, so a phase tile costs
     //  max(tensor time, ~500 clk) plus the epilogue that does not overlap; records cost ~600 clk each downstream)
     const double nfrac = bp.ncombo / 256.0;
-    bp.cost = std::max(128.0 * steps * nfrac, 500.0) + 300.0 * nfrac + 600.0 * rate;
+    bp.cost = std::max(128.0 * steps * nfrac, 500.0) + 600.0 * rate;
     return rate;
 }
 

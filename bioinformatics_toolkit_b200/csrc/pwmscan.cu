@@ -864,7 +864,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     const double cand_rate = use_mma ? pl->mma_cand_rate : pl->cand_rate;
     // capacities: expected + slack, grown and re-run on overflow
     unsigned long long cand_cap = (unsigned long long)(cand_rate * (double)len * 1.5) + (1ull << 20);
-    if (use_mma) cand_cap += (unsigned long long)ctx->sm_count * 16 * 256 * 2;             // every epilogue warp reserves whole 256-record chunks
+    if (use_mma) cand_cap += (unsigned long long)ctx->sm_count * 28 * 256 * 2;             // every epilogue warp reserves whole 256-record chunks
     unsigned long long hit_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
     if (!generic.empty() && hit_cap < (1ull << 22)) hit_cap = 1ull << 22;
     unsigned long long nhits = 0, ncand = 0;

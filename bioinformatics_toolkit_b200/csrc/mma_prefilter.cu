@@ -13,12 +13,12 @@
 //   warps 3..30  epilogue: seven warps per 32-lane quarter of TMEM (= 32 anchors), each pulling one 32-column
 //                chunk of its rows with tcgen05.ld.32x32b.x32, OR-reducing it (the sign bit of D says "still
 //                possible") and recording (anchor, block, chunk) for the exact fp64 replay of the survivors.
-//                (TMEM read: ~900 B/clk/SM with 16+ warps, scratch/tmem/tmem_x32.cu.)
+//                (TMEM read: ~900 B/clk/SM with 16+ warps, experiments/tmem/tmem_x32.cu.)
 // Stages hand over through mbarriers (tcgen05.commit arrives for the tensor pipe).  Every wait is bounded:
 // a broken pipeline sets an abort flag and the kernel ends instead of hanging the GPU.
 //
 // Roofline: tensor pipe, 128 * N / 256 clocks per MMA (measured 129.4 clk for M128 N256 K32,
-// scratch/mma/i8_toeplitz.cu) => (K1/8) * N/256 clocks per anchor per SM; 2 * 4 * K1 int8 MACs... per
+// experiments/mma/i8_toeplitz.cu) => (K1/8) * N/256 clocks per anchor per SM; 2 * 4 * K1 int8 MACs... per
 // anchor and combo (algorithmic ops = 8 * K1 per bp*combo).
 #include <cstdio>
 #include <cstdlib>

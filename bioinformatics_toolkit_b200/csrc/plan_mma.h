@@ -11,7 +11,7 @@
 // folded into the four entries of column k = 0 (exactly one of them is selected by the one-hot), so
 // that "still possible" <=> D < 0 (the sign bit).  The A operand is never materialised: the UMMA
 // shared-memory descriptor walks a linear one-hot byte stream with overlapping rows (row r = the
-// 32 bytes from 16 r: LBO = 16 B, SBO = 128 B), i.e. a Toeplitz view (scratch/mma/i8_toeplitz.cu).
+// 32 bytes from 16 r: LBO = 16 B, SBO = 128 B), i.e. a Toeplitz view (experiments/mma/i8_toeplitz.cu).
 // Survivors go straight to the exact fp64 replay (rescore_kernel).
 #pragma once
 #include "plan.h"

@@ -130,7 +130,7 @@ PWM_HD void process32(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32
 // tcgen05.ld.32x32b.x1 hands thread l of a warp the 32-bit cell (lane 32*(warp%4)+l, column c) of
 // TMEM for a warp-uniform column c — exactly the access pattern of the first stage (all lanes of a
 // warp look at the same anchor, lane l wants row `kmer`, bank/column l of the table).  Measured on
-// B200 (scratch/tmem/tmem_bench.cu): LDTM 0.77 clk per warp-load per SM, LDS 1.00, interleaved 0.6,
+// B200 (experiments/tmem/tmem_bench.cu): LDTM 0.77 clk per warp-load per SM, LDS 1.00, interleaved 0.6,
 // i.e. the two ports run side by side.  The first two first-stage slots live in TMEM (512 columns =
 // 2 x 256 k-mers, every 32-lane quarter holds a copy), the others stay in shared memory.
 __device__ __forceinline__ uint32_t tmem_ld32(uint32_t taddr) {

@@ -9,7 +9,7 @@ if which=='c2':
     mats = synth.synth_pwms(100, 12)
 else:
     mats = synth.config_c4_motifs(200)
-cache=f'scratch/thres_{which}.pkl'
+cache=f'experiments/thres_{which}.pkl'
 if os.path.exists(cache):
     thres=pickle.load(open(cache,'rb'))
 else:

@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.device), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -292,12 +292,15 @@ def main():
     ncol_mean = float(np.mean([m.shape[0] for m in mats]))
     lane_ops = 2.0 * ncol_mean * bp_launch * M                     # brute-force look-ups + adds, both strands
     issue_peak = 148 * 128 * clk / 1e12
+    # DRAM traffic of one prefilter launch on this exact workload, from the committed ncu --set full capture
+    # (profiles/r1b_prefilter_ncu_full_metrics.json: dram__bytes_read.sum 62.9 MB + dram__bytes_write.sum 3.1 MB)
+    traffic = 66.0e6 if (args.workload == "c2" and M == 100) else None
     roofline = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
-                "traffic": None, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
+                "traffic": traffic, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
                 "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md) x sm_max_mhz (%s)" % peaks["source"],
                 "algorithmic_bytes_per_launch": smem_bytes,
                 "note": "shared-memory-bandwidth bound look-up kernel; ncu (profiles/) reports the LSU/shared pipe at the same fraction"}
-    roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+    roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peaks["source"],
                     "note": "HBM is not the governing roof at >= 64 motifs (0.25 B/base per 64-motif block pass)"}
     issue = {"bound": "int/fp32 issue of the brute-force algorithm", "achieved": lane_ops / (pre_ms_launch / 1e3) / 1e12,

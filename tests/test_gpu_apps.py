@@ -102,3 +102,45 @@ def test_reference_api_invariants(ref_motifs):
         a = np.round(1e5 * Mo.scores(bg, p, dna))
         b = np.round(1e5 * Mo.scores(bg, Mo.rcPWM(p), rc(dna))[::-1])
         assert np.array_equal(a, b)
+
+
+def test_command_line_apps(small_genome, tmp_path, oracle):
+    """apps/scan_motif.py and apps/merge_motifs.py end to end (argument parsing, file formats)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path, chroms = small_genome
+    mats = synth.synth_pwms(6, 101, nmin=8, nmax=14)
+    motifs = [Mo.Motif(b"motif_%d" % i, Mo.PWM(20, m)) for i, m in enumerate(mats)]
+    meme = os.path.join(tmp_path, "m.meme")
+    Mo.writeMEME(meme, motifs)
+    back = Mo.readMEME(meme)
+    assert [m._name for m in back] == [m._name for m in motifs]
+    assert all(np.array_equal(a._pwm._mat, b._pwm._mat) for a, b in zip(back, motifs))     # shortest round-trip printing
+    bed = os.path.join(tmp_path, "r.bed")
+    beds = [(b"chr1", 100, 5100), (b"chr2", 0, 3000), (b"chr9", 1, 2)]
+    with open(bed, "wb") as f:
+        for c, s, e in beds:
+            f.write(b"%s\t%d\t%d\n" % (c, s, e))
+    r = subprocess.run([sys.executable, os.path.join(root, "apps", "scan_motif.py"), path, meme, bed, "-p", "1e-3"],
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    from oracle import app_oracle
+    exp = app_oracle.scan_motif_lines(chroms, [m._name for m in motifs], mats, beds, p=1e-3)
+    assert r.stdout.split(b"\n")[:-1] == exp and len(exp) > 10
+    assert b"Warning: no sequence for region" in r.stderr
+    # merge_motifs dist
+    r = subprocess.run([sys.executable, os.path.join(root, "apps", "merge_motifs.py"), "dist", "-a", meme], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    lines = r.stdout.split(b"\n")[:-1]
+    assert len(lines) == 15
+    a, b, d = lines[0].split(b"\t")
+    od, _ = oracle.alignment(mats[0], mats[1])
+    assert (a, b) == (b"motif_0", b"motif_1") and abs(float(d) - od) <= 1e-12 * max(od, 1e-300)
+    # merge_motifs merge (iter) and cluster
+    outp = os.path.join(tmp_path, "merged.meme")
+    r = subprocess.run([sys.executable, os.path.join(root, "apps", "merge_motifs.py"), "merge", meme, "-t", "0.3", "-o", outp], capture_output=True, timeout=300)
+    assert r.returncode == 0 and b"Read 6 motifs" in r.stderr, r.stderr.decode()[-2000:]
+    assert 1 <= len(Mo.readMEME(outp)) <= 6
+    r = subprocess.run([sys.executable, os.path.join(root, "apps", "merge_motifs.py"), "cluster", meme, "-h", "0.3"], capture_output=True, timeout=300)
+    assert r.returncode == 0 and sorted(b"\t".join(r.stdout.split(b"\n")[:-1]).split(b"\t")) == sorted(m._name for m in motifs)

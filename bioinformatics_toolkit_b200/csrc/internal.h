@@ -9,6 +9,7 @@
 #include "../../include/pwmscan.h"
 #include "plan.h"
 #include "plan_mma.h"
+#include "plan_km.h"
 
 struct pwmscan_ctx {
     int device = 0;
@@ -21,6 +22,7 @@ struct pwmscan_ctx {
     double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int sm_count = 148;
     bool lut_ready = false, dense_lut_ready = false, smem_attr_set = false, mma_attr_set = false;   // per-context one-time device setup
+    bool km_attr_set = false, km_build_attr_set = false;
     // grow-only device scratch
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -85,7 +87,17 @@ struct DevMmaBlock {
     int64_t b_off;       // bytes into d_btiles
 };
 
+struct DevKmBlock {
+    int32_t nt, max_n;   // mask tables of this block; longest motif (row stride of q16)
+    int32_t order[4];    // gather order of the tables (most selective first)
+    int64_t table_off;   // bytes into d_km_tables (table t at + t * 2 MiB)
+    int64_t q16_off;     // uint16 elements into d_km_q16 ([256][max_n][4])
+};
+
+enum { PWM_MODE_LDS = 0, PWM_MODE_MMA = 1, PWM_MODE_KMER = 2 };
+
 struct pwmscan_plan {
+    int mode = PWM_MODE_LDS;           // which first stage this plan was built for
     pwmscan_ctx* ctx = nullptr;
     const pwmscan_motifs* motifs = nullptr;
     int strands = 2, skip = 1;
@@ -109,6 +121,16 @@ struct pwmscan_plan {
     DevCombo* d_mma_generic = nullptr;
     int8_t* d_btiles = nullptr;
     double mma_cand_rate = 0;
+    // k-mer mask first stage (km_prefilter.cu): blocks of 128 motifs
+    int km_nblocks = 0, km_max_n = 1;
+    std::vector<pwmscan::KmBlockPlan> km_blocks;
+    std::vector<DevCombo> km_generic;
+    DevKmBlock* d_km_blocks = nullptr;
+    DevCombo* d_km_combos = nullptr;   // km_nblocks * 256
+    DevCombo* d_km_generic = nullptr;
+    uint8_t* d_km_tables = nullptr;
+    uint16_t* d_km_q16 = nullptr;
+    double km_cand_rate = 0, km_surv_rate = 0, km_req_rate = 0;
 };
 
 struct pwmscan_hits {
@@ -137,6 +159,11 @@ void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
 void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap);
+
+int km_build_tables(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int nt, uint8_t* d_tables);
+int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, int max_n,
+                        const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
+                        unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter);
 
 #define PWM_CUDA(call)                                                          \
     do {                                                                        \

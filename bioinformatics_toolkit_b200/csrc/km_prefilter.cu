@@ -1,0 +1,295 @@
+// km_prefilter.cu — k-mer mask first stage of the thresholded scan (plan_km.h has the maths).
+//
+//   alive(u) = T_0[8-mer at u] & T_1[8-mer at u+8] & ... & T_{nt-1}[8-mer at u+8(nt-1)]        (256-bit masks)
+//
+// The tables (nt x 2 MiB per block of 128 motifs) stay in L2; every stored position gathers one
+// 32-byte sector per table with a single 256-bit load (ld.global.nc.v8.u32 — sm_100), the next
+// table only while the AND is still non-zero.  The measured bound is the gather rate of the SM's
+// L1 (about one sector per clock and SM: experiments/masktab/l2gather.cu, 2.7 ms for 3 x 249 M
+// sectors), not bytes — hence 256 combos per sector and as few tables as the motif lengths allow.
+//
+// One persistent CTA per SM (32 warps) pulls work items (block, 8192 positions).  A surviving bit
+// (position, combo) goes into the warp's shared-memory queue; whenever 32 are queued the warp runs
+// the middle stage on them, one per lane: the whole-window deficit in 16-bit fixed point from the
+// block's q16 table in shared memory (bases from the item's staged 2-bit words), early exit once
+// the budget kKmQ is exceeded.  What passes (about the hit rate) is appended to the candidate
+// list and replayed exactly in fp64 by rescore_kernel.
+#include <cstdio>
+#include <cstdlib>
+
+#include "internal.h"
+#include "plan_km.h"
+
+using namespace pwmscan;
+
+namespace {
+
+constexpr int kKmThreads = 1024;
+constexpr int kKmItemPos = 8192;                 // positions per work item
+constexpr int kKmIterPos = 2048;                 // positions per CTA iteration (2 per thread)
+constexpr int kKmHaloWords = 4;                  // 64 stored bases in front of the item (window starts reach back n-1 <= 63)
+constexpr int kKmSeqWords = kKmHaloWords + kKmItemPos / 16 + 5;     // windows end <= 8191 + 7 + 64 bases after the item start
+constexpr int kKmQueue = 64;
+constexpr size_t kKmTableBytes = (size_t)kKmEntries * kKmWords * 4;      // 2 MiB
+
+struct Mask { uint32_t v[8]; };
+
+__device__ __forceinline__ Mask ldg_mask(const uint8_t* p) {
+    Mask r;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t mask_any(const Mask& m) {
+    return (m.v[0] | m.v[1] | m.v[2]) | (m.v[3] | m.v[4] | m.v[5]) | (m.v[6] | m.v[7]);
+}
+
+// Table build: bit j of T_t[x] = (sum_p wdef[t][j][p][base p of x] <= dsafe[j]).  grid = (256, nt), one 8-mer per thread.
+__global__ void __launch_bounds__(256) km_build_kernel(const double* __restrict__ wdef, const double* __restrict__ dsafe,
+                                                       uint32_t* __restrict__ tables) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_w = reinterpret_cast<double*>(smem_raw);               // [256][8][4]
+    double* s_d = s_w + kKmCombos * 32;                              // [256]
+    const int t = blockIdx.y;
+    const double* src = wdef + (size_t)t * kKmCombos * 32;
+    for (int i = threadIdx.x; i < kKmCombos * 32; i += blockDim.x) s_w[i] = src[i];
+    for (int i = threadIdx.x; i < kKmCombos; i += blockDim.x) s_d[i] = dsafe[i];
+    __syncthreads();
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    int off[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) off[p] = 4 * p + (int)((x >> (2 * p)) & 3u);
+    uint32_t out[kKmWords];
+#pragma unroll 1
+    for (int w = 0; w < kKmWords; ++w) {
+        uint32_t bits = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const double* wd = s_w + (w * 32 + j) * 32;
+            double s = wd[off[0]];
+#pragma unroll
+            for (int p = 1; p < 8; ++p) s = __dadd_rn(s, wd[off[p]]);
+            bits |= (s <= s_d[w * 32 + j]) ? (1u << j) : 0u;
+        }
+        out[w] = bits;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(tables + ((size_t)t * kKmEntries + x) * kKmWords);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+struct KmShared {
+    uint32_t seq[kKmSeqWords];
+    uint32_t queue[kKmThreads / 32][kKmQueue];
+    uint32_t cn[kKmCombos];                      // c (low 16 bits, signed) | n << 16
+    long long item;
+};
+
+// Middle stage on up to 32 queued (position, combo) entries of one warp, one per lane.
+__device__ __forceinline__ void km_drain(const KmShared& sh, const uint16_t* __restrict__ s_q16, int max_n, uint32_t entry, bool active,
+                                         long long U0, long long len, unsigned long long combo_base,
+                                         unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t combo = entry & 255u;
+    const int p = (int)(entry >> 8);
+    const uint32_t cn = sh.cn[combo];
+    const int c = (int)(short)(cn & 0xFFFFu), n = (int)(cn >> 16);
+    const long long i = U0 + p - c - kPadFront;                     // window start in sequence coordinates
+    bool ok = active && i >= 0 && i + n <= len;
+    if (ok) {
+        const int rel = p - c + 16 * kKmHaloWords;                  // window start relative to sh.seq[0]
+        const int wi = rel >> 4, s2 = 2 * (rel & 15);
+        const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
+        unsigned long long X = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
+        const unsigned long long* row = reinterpret_cast<const unsigned long long*>(s_q16) + (size_t)combo * max_n;
+        uint32_t sum = 0;
+        const int n1 = n < 32 ? n : 32;
+        int k = 0;
+        for (; k < n1; ++k) {
+            const unsigned long long r = row[k];
+            sum += (uint32_t)(r >> (16 * (int)(X & 3ull))) & 0xFFFFu;
+            X >>= 2;
+            if (sum > (uint32_t)kKmQ) break;
+        }
+        if (n > 32 && sum <= (uint32_t)kKmQ) {
+            const uint32_t w3 = sh.seq[wi + 3], w4 = sh.seq[wi + 4];
+            X = (unsigned long long)__funnelshift_r(w2, w3, s2) | ((unsigned long long)__funnelshift_r(w3, w4, s2) << 32);
+            for (; k < n; ++k) {
+                const unsigned long long r = row[k];
+                sum += (uint32_t)(r >> (16 * (int)(X & 3ull))) & 0xFFFFu;
+                X >>= 2;
+                if (sum > (uint32_t)kKmQ) break;
+            }
+        }
+        ok = sum <= (uint32_t)kKmQ;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+    if (bal) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[0], (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (ok) {
+            const unsigned long long slot = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
+            if (slot < cand_cap) cand[slot] = ((combo_base + combo) << 40) | (unsigned long long)(U0 + p);
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const DevKmBlock& db, const uint8_t* __restrict__ tab,
+                                        long long U0, long long len, unsigned long long combo_base,
+                                        unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* q = sh.queue[warp];
+    int qcnt = 0;
+    const uint8_t* tp[NT];
+    int tsh[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) { tp[s] = tab + (size_t)db.order[s] * kKmTableBytes; tsh[s] = 16 * db.order[s]; }
+#pragma unroll 1
+    for (int it = 0; it < kKmItemPos / kKmIterPos; ++it) {
+        Mask m[2];
+        unsigned long long x[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int p = it * kKmIterPos + warp * 64 + 32 * j + lane;
+            const int wi = (p >> 4) + kKmHaloWords, s2 = 2 * (p & 15);
+            const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
+            x[j] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
+            m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & 0xFFFFu) * 32);
+        }
+#pragma unroll
+        for (int s = 1; s < NT; ++s) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (mask_any(m[j])) {
+                    const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x[j] >> tsh[s]) & 0xFFFFu) * 32);
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) m[j].v[w] &= t.v[w];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t p = (uint32_t)(it * kKmIterPos + warp * 64 + 32 * j + lane);
+            uint32_t any = mask_any(m[j]);
+            unsigned bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
+            while (bal) {
+                if (any) {
+                    uint32_t bit;
+                    if (m[j].v[0]) { bit = __ffs((int)m[j].v[0]) - 1; m[j].v[0] &= m[j].v[0] - 1; }
+                    else if (m[j].v[1]) { bit = 32 + __ffs((int)m[j].v[1]) - 1; m[j].v[1] &= m[j].v[1] - 1; }
+                    else if (m[j].v[2]) { bit = 64 + __ffs((int)m[j].v[2]) - 1; m[j].v[2] &= m[j].v[2] - 1; }
+                    else if (m[j].v[3]) { bit = 96 + __ffs((int)m[j].v[3]) - 1; m[j].v[3] &= m[j].v[3] - 1; }
+                    else if (m[j].v[4]) { bit = 128 + __ffs((int)m[j].v[4]) - 1; m[j].v[4] &= m[j].v[4] - 1; }
+                    else if (m[j].v[5]) { bit = 160 + __ffs((int)m[j].v[5]) - 1; m[j].v[5] &= m[j].v[5] - 1; }
+                    else if (m[j].v[6]) { bit = 192 + __ffs((int)m[j].v[6]) - 1; m[j].v[6] &= m[j].v[6] - 1; }
+                    else { bit = 224 + __ffs((int)m[j].v[7]) - 1; m[j].v[7] &= m[j].v[7] - 1; }
+                    q[qcnt + __popc(bal & ((1u << lane) - 1u))] = (p << 8) | bit;
+                    any = mask_any(m[j]);
+                }
+                qcnt += __popc(bal);
+                __syncwarp();
+                if (qcnt >= 32) {
+                    const uint32_t e = q[lane];
+                    const uint32_t rest = (lane + 32 < qcnt) ? q[lane + 32] : 0u;
+                    __syncwarp();
+                    if (lane + 32 < qcnt) q[lane] = rest;
+                    qcnt -= 32;
+                    km_drain(sh, s_q16, db.max_n, e, true, U0, len, combo_base, cand, cand_cap, counters);
+                    __syncwarp();
+                }
+                bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
+            }
+        }
+    }
+    if (qcnt > 0) {
+        const uint32_t e = lane < qcnt ? q[lane] : 0u;
+        km_drain(sh, s_q16, db.max_n, e, lane < qcnt, U0, len, combo_base, cand, cand_cap, counters);
+    }
+}
+
+__global__ void __launch_bounds__(kKmThreads, 1)
+km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long total_items,
+                    const DevKmBlock* __restrict__ blocks, const uint8_t* __restrict__ tables, const uint16_t* __restrict__ q16,
+                    const DevCombo* __restrict__ combos, long long len, unsigned long long* __restrict__ cand, unsigned long long cand_cap,
+                    unsigned long long* counters, unsigned long long* work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ KmShared sh;
+    uint16_t* s_q16 = reinterpret_cast<uint16_t*>(smem_raw);
+    const int tid = threadIdx.x;
+    const long long items_per_block = n_anchor / kKmItemPos;
+    int cur_blk = -1;
+    DevKmBlock db = blocks[0];
+    for (;;) {
+        if (tid == 0) sh.item = (long long)atomicAdd(work_counter, 1ull);
+        __syncthreads();
+        const long long item = sh.item;
+        if (item >= total_items) break;
+        const int blk = (int)(item / items_per_block);                 // block-major: tables change rarely
+        const long long U0 = anchor0 + (item - (long long)blk * items_per_block) * kKmItemPos;
+        if (blk != cur_blk) {
+            db = blocks[blk];
+            const uint4* src = reinterpret_cast<const uint4*>(q16 + db.q16_off);
+            uint4* dst = reinterpret_cast<uint4*>(s_q16);
+            const int n16 = kKmCombos * db.max_n * 8 / 16;
+            for (int i = tid; i < n16; i += kKmThreads) dst[i] = __ldg(src + i);
+            if (tid < kKmCombos) {
+                const DevCombo dc = combos[(size_t)blk * kKmCombos + tid];
+                sh.cn[tid] = ((uint32_t)dc.c & 0xFFFFu) | ((uint32_t)dc.n << 16);
+            }
+            cur_blk = blk;
+        }
+        {   // stage the item's 2-bit words (64 bases of history in front; the allocation has one front word)
+            const long long w0 = (U0 >> 4) - kKmHaloWords;
+            for (int i = tid; i < kKmSeqWords; i += kKmThreads) sh.seq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
+        }
+        __syncthreads();
+        const uint8_t* tab = tables + db.table_off;
+        const unsigned long long combo_base = (unsigned long long)blk * kKmCombos;
+        switch (db.nt) {
+            case 1: km_item<1>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
+            case 2: km_item<2>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
+            case 3: km_item<3>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
+            default: km_item<4>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
+        }
+        __syncthreads();   // everyone is done with sh.seq / s_q16 / sh.item
+    }
+}
+
+}  // namespace
+
+namespace pwmscan {
+
+size_t km_q16_smem_bytes(int max_n) { return (size_t)kKmCombos * max_n * 8; }
+
+// Builds the nt mask tables of one block on the device (stream-ordered).
+int km_build_tables(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int nt, uint8_t* d_tables) {
+    const int smem = (kKmCombos * 32 + kKmCombos) * 8;
+    if (!ctx->km_build_attr_set) {
+        PWM_CUDA(cudaFuncSetAttribute(km_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ctx->km_build_attr_set = true;
+    }
+    km_build_kernel<<<dim3(kKmEntries / 256, nt), 256, smem, ctx->stream>>>(d_wdef, d_dsafe, reinterpret_cast<uint32_t*>(d_tables));
+    PWM_CUDA(cudaGetLastError());
+    return PWMSCAN_OK;
+}
+
+int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, int max_n,
+                        const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
+                        unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter) {
+    if (nblocks == 0 || a1 <= a0) return PWMSCAN_OK;
+    if (!ctx->km_attr_set) {
+        PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km_q16_smem_bytes(kMaxCols)));
+        ctx->km_attr_set = true;
+    }
+    const long long items = (a1 - a0) / kKmItemPos * nblocks;
+    const int grid = (int)std::min<long long>(ctx->sm_count, items);
+    km_prefilter_kernel<<<grid, kKmThreads, km_q16_smem_bytes(max_n), ctx->stream>>>(d_seq2, a0, a1 - a0, items, d_blocks, d_tables, d_q16, d_combos, len,
+                                                                                    d_cand, cand_cap, ctx->d_counters, work_counter);
+    PWM_CUDA(cudaGetLastError());
+    return PWMSCAN_OK;
+}
+
+}  // namespace pwmscan

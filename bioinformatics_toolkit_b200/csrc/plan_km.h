@@ -1,0 +1,245 @@
+// plan_km.h — host-side planning of the k-mer mask first stage (km_prefilter.cu).
+//
+// Necessary condition used (same deficits as plan.h): a window can be a hit only if its total
+// deficit sum_k d_k(b_k) stays <= Dsafe, hence only if the deficit of EVERY sub-window stays
+// <= Dsafe.  A block holds up to 256 combos (128 motifs x 2 strands) = the 256 bits of a 32-byte
+// mask.  Table t (t < nt <= 4) has one mask per 8-mer (65 536 x 32 B = 2 MiB, L2-resident): bit j of
+// T_t[x] says "the 8 bases x, read as motif columns c_j + 8t .. c_j + 8t + 7 of combo j, cost at most
+// Dsafe_j" (columns outside [0, n) cost nothing).  For the stored sequence position u the kernel
+// gathers T_t[8-mer at u + 8t], ANDs the masks, and a surviving bit j is the window that starts at
+// u - c_j.  Every combo picks its own offset c_j in [-7, n-1] (which 8-column windows the tables
+// see); the product of the windows' pass rates under iid uniform bases is what c_j minimises.
+//
+// Survivors (~0.1 per position for 200 combos at p = 1e-5) go through a middle stage in the same
+// kernel: the whole-window deficit in 16-bit fixed point from shared memory (q16), and what is left
+// (about the hit rate) to the exact fp64 replay (rescore_kernel).  The selectivity experiment behind
+// this design is experiments/exp_masktable.py, the L2 gather rate experiments/masktab/l2gather.cu.
+#pragma once
+#include "plan.h"
+
+namespace pwmscan {
+
+constexpr int kKmCombos = 256;                  // bits of one mask entry
+constexpr int kKmMotifsPerBlock = 128;
+constexpr int kKmWords = kKmCombos / 32;        // 8 x uint32 = one 32-byte sector
+constexpr int kKmMaxTables = 4;
+constexpr int kKmEntries = 65536;               // 8-mers
+constexpr int kKmQ = 60000;                     // fixed-point budget of the middle stage (entries saturate at 65535)
+
+struct KmCombo {
+    int motif = -1, strand = 0, n = 0, c = 0;
+    bool enabled = false;
+    double sigma1 = 0;                          // P(all windows pass): first-stage survivors per position
+    double sigma_mid = 0;                       // P(middle stage passes): candidates per position
+    double pass[kKmMaxTables] = {1, 1, 1, 1};   // per-table pass rates
+};
+
+struct KmBlockPlan {
+    int nt = 1;
+    int max_n = 1;
+    int order[kKmMaxTables] = {0, 1, 2, 3};     // gather order: most selective table first
+    KmCombo combo[kKmCombos];
+    std::vector<double> wdef;                   // [nt][256][8][4] deficit of base b at window position p (0 outside the motif)
+    std::vector<double> dsafe;                  // [256]; < 0: bit never set
+    std::vector<uint16_t> q16;                  // [256][max_n][4] middle-stage entries, natural column order
+    double surv_rate = 0;                       // expected first-stage survivors per position
+    double cand_rate = 0;                       // expected candidates (middle-stage survivors) per position
+    double req_rate = 0;                        // expected table sectors gathered per position
+    double cost = 0;
+};
+
+namespace detail {
+
+// P(sum of the deficits of columns [a, a+8) ∩ [0, n) <= dsafe), exact: meet in the middle over two
+// halves of <= 4 columns (256 sums each).
+inline double km_window_pass(const ComboDef& cd, int a) {
+    const int lo = std::max(0, a), hi = std::min(cd.n, a + 8);
+    if (hi <= lo) return 1.0;
+    const int mid = lo + (hi - lo) / 2;
+    auto sums = [&](int x0, int x1, std::vector<double>& out) {
+        out.assign(1, 0.0);
+        for (int k = x0; k < x1; ++k) {
+            std::vector<double> nx(out.size() * 4);
+            for (size_t i = 0; i < out.size(); ++i)
+                for (int b = 0; b < 4; ++b) nx[i * 4 + b] = out[i] + cd.dk[k][b];
+            out.swap(nx);
+        }
+    };
+    std::vector<double> A, B;
+    sums(lo, mid, A);
+    sums(mid, hi, B);
+    std::sort(B.begin(), B.end());
+    double cnt = 0;
+    for (double x : A) cnt += (double)(std::upper_bound(B.begin(), B.end(), cd.dsafe - x) - B.begin());
+    return cnt / ((double)A.size() * (double)B.size());
+}
+
+// P(sum over all columns of the clamped deficits <= limit), 1024-bin convolution (rounded down, so a slight over-estimate)
+inline double km_total_pass(const ComboDef& cd, double limit) {
+    const int NB = 1024;
+    if (!(limit > 0)) return 0.0;
+    std::vector<double> h(NB + 1, 0.0), nx(NB + 1);
+    h[0] = 1.0;
+    const double sc = NB / limit;
+    for (int k = 0; k < cd.n; ++k) {
+        std::fill(nx.begin(), nx.end(), 0.0);
+        int q[4];
+        for (int b = 0; b < 4; ++b) { const double v = std::floor(cd.dk[k][b] * sc); q[b] = v >= NB ? NB + 1 : (int)v; }
+        for (int s = 0; s <= NB; ++s) if (h[s] != 0)
+            for (int b = 0; b < 4; ++b) if (s + q[b] <= NB) nx[s + q[b]] += 0.25 * h[s];
+        h.swap(nx);
+    }
+    double t = 0;
+    for (int s = 0; s <= NB; ++s) t += h[s];
+    return t;
+}
+
+}  // namespace detail
+
+// Builds the plan of one block.  `in`: 256 combos (motif < 0 = unused bit).
+inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, int force_nt = 0) {
+    std::vector<ComboDef> defs(kKmCombos);
+    int max_n = 1;
+    for (int ci = 0; ci < kKmCombos; ++ci)
+        if (in[ci].motif >= 0) { combo_deficits(in[ci], defs[ci]); max_n = std::max(max_n, in[ci].n); }
+    // pass rate of every window start a in [-7, n-1], per combo
+    std::vector<std::vector<double>> pass(kKmCombos);
+    for (int ci = 0; ci < kKmCombos; ++ci) {
+        const ComboDef& cd = defs[ci];
+        if (!cd.present || !cd.possible) continue;
+        pass[ci].resize(cd.n + 7);
+        for (int a = -7; a < cd.n; ++a) pass[ci][a + 7] = detail::km_window_pass(cd, a);
+    }
+    auto pass_at = [&](int ci, int a) { return (a < -7 || a >= defs[ci].n) ? 1.0 : pass[ci][a + 7]; };
+    bool have = false;
+    KmBlockPlan best;
+    for (int nt = 1; nt <= kKmMaxTables; ++nt) {
+        if (force_nt && nt != force_nt) continue;
+        if (!force_nt && nt > 1 && 8 * (nt - 1) >= max_n + 7) break;       // the extra table could never see a column
+        KmBlockPlan cur;
+        cur.nt = nt; cur.max_n = max_n;
+        double tab_sum[kKmMaxTables] = {0, 0, 0, 0};
+        for (int ci = 0; ci < kKmCombos; ++ci) {
+            KmCombo& kc = cur.combo[ci];
+            kc = KmCombo();
+            const ComboDef& cd = defs[ci];
+            if (!cd.present) continue;
+            kc.motif = in[ci].motif; kc.strand = in[ci].strand; kc.n = in[ci].n;
+            if (!cd.possible) continue;
+            kc.enabled = true;
+            double bestp = 2; int bestc = 0;
+            for (int c = -7; c < cd.n; ++c) {
+                double p = 1;
+                for (int t = 0; t < nt; ++t) p *= pass_at(ci, c + 8 * t);
+                if (p < bestp) { bestp = p; bestc = c; }
+            }
+            kc.c = bestc; kc.sigma1 = bestp;
+            for (int t = 0; t < nt; ++t) { kc.pass[t] = pass_at(ci, bestc + 8 * t); tab_sum[t] += kc.pass[t]; }
+            cur.surv_rate += bestp;
+        }
+        for (int t = 0; t < kKmMaxTables; ++t) cur.order[t] = t;
+        std::stable_sort(cur.order, cur.order + nt, [&](int a, int b) { return tab_sum[a] < tab_sum[b]; });
+        // sectors gathered per position: table order[0] always, the next one only while the AND is still non-zero
+        double req = 1;
+        for (int s = 1; s < nt; ++s) {
+            double lam = 0;                                               // expected surviving bits after the first s tables
+            for (int ci = 0; ci < kKmCombos; ++ci) if (cur.combo[ci].enabled) {
+                double p = 1;
+                for (int k = 0; k < s; ++k) p *= cur.combo[ci].pass[cur.order[k]];
+                lam += p;
+            }
+            req += 1.0 - std::exp(-lam);
+        }
+        cur.req_rate = req;
+        // clocks per position and SM: one gathered sector per clock (measured), ~2.5 clocks per middle-stage candidate
+        cur.cost = req + 2.5 * cur.surv_rate;
+        if (!have || cur.cost < best.cost) { best = std::move(cur); have = true; }
+    }
+    bp = std::move(best);
+    const int nt = bp.nt;
+    bp.wdef.assign((size_t)nt * kKmCombos * 32, 0.0);
+    bp.dsafe.assign(kKmCombos, -1.0);
+    bp.q16.assign((size_t)kKmCombos * max_n * 4, 0);
+    bp.cand_rate = 0;
+    for (int ci = 0; ci < kKmCombos; ++ci) {
+        KmCombo& kc = bp.combo[ci];
+        if (!kc.enabled) continue;
+        const ComboDef& cd = defs[ci];
+        bp.dsafe[ci] = cd.dsafe;
+        for (int t = 0; t < nt; ++t)
+            for (int p = 0; p < 8; ++p) {
+                const int col = kc.c + 8 * t + p;
+                if (col < 0 || col >= cd.n) continue;
+                for (int b = 0; b < 4; ++b) bp.wdef[(((size_t)t * kKmCombos + ci) * 8 + p) * 4 + b] = cd.dk[col][b];
+            }
+        const double scale = cd.dsafe > 0 ? (double)kKmQ / cd.dsafe : 1e300;
+        for (int k = 0; k < cd.n; ++k)
+            for (int b = 0; b < 4; ++b) {
+                const double v = std::floor(scale * cd.dk[k][b] * (1.0 - 1e-9));
+                bp.q16[((size_t)ci * max_n + k) * 4 + b] = (uint16_t)(v < 65535.0 ? (v < 0 ? 0.0 : v) : 65535.0);
+            }
+        kc.sigma_mid = detail::km_total_pass(cd, cd.dsafe * (1.0 + (double)(cd.n + 1) / kKmQ));
+        bp.cand_rate += kc.sigma_mid;
+    }
+}
+
+struct KmHostPlan {
+    std::vector<double> th;
+    std::vector<KmBlockPlan> blocks;
+    std::vector<std::pair<int, int>> generic;
+    double cand_rate = 0, surv_rate = 0, req_rate = 0;
+    int max_n = 0;
+};
+
+inline void build_km_host_plan(const std::vector<MotifHost>& mh, const std::vector<int64_t>& col_off, int64_t total_cols2,
+                               const double* thres, int strands, int skip, KmHostPlan& hp, int force_nt = 0) {
+    const int M = (int)mh.size();
+    hp.th.assign((size_t)total_cols2, 0.0);
+    for (int m = 0; m < M; ++m)
+        for (int s = 0; s < 2; ++s) {
+            for (int k = 0; k < mh[m].n; ++k) hp.th[(size_t)col_off[2 * m + s] + k] = thres[m] - mh[m].sigma[s][k];   // Search.hs:139,182
+            hp.max_n = std::max(hp.max_n, mh[m].n);
+        }
+    std::vector<int> pre;
+    for (int m = 0; m < M; ++m) {
+        bool ok = skip != 0;
+        for (int s = 0; s < strands && ok; ++s) {
+            if (!std::isfinite(hp.th[(size_t)col_off[2 * m + s] + mh[m].n - 1])) ok = false;
+            for (int k = 0; k < mh[m].n && ok; ++k)
+                for (int b = 0; b < 4; ++b) if (!std::isfinite(mh[m].tab16[s][16 * k + b])) ok = false;
+        }
+        if (ok) pre.push_back(m);
+        else for (int s = 0; s < strands; ++s) hp.generic.emplace_back(m, s);
+    }
+    std::stable_sort(pre.begin(), pre.end(), [&](int a, int b) { return mh[a].n < mh[b].n; });
+    const int per_block = strands == 2 ? kKmMotifsPerBlock : kKmCombos;        // forward-only: 256 motifs per block
+    const int nblocks = (int)((pre.size() + per_block - 1) / per_block);
+    hp.blocks.resize(nblocks);
+    auto build_one = [&](int b) {
+        std::vector<ComboInput> in(kKmCombos);
+        for (int ci = 0; ci < kKmCombos; ++ci) {
+            in[ci].motif = -1; in[ci].strand = 0; in[ci].n = 0; in[ci].tab16 = nullptr; in[ci].th_last = 0;
+            const size_t mi = (size_t)b * per_block + (strands == 2 ? ci >> 1 : ci);
+            const int s = strands == 2 ? (ci & 1) : 0;
+            if (mi >= pre.size()) continue;
+            const int m = pre[mi];
+            in[ci].motif = m; in[ci].strand = s; in[ci].n = mh[m].n; in[ci].tab16 = mh[m].tab16[s].data();
+            in[ci].th_last = hp.th[(size_t)col_off[2 * m + s] + mh[m].n - 1];
+        }
+        km_build_block(in, hp.blocks[b], force_nt);
+    };
+    {
+        const int nth = std::max(1, std::min<int>(nblocks, (int)std::min<unsigned>(8u, std::thread::hardware_concurrency())));
+        std::atomic<int> next(0);
+        auto worker = [&]() { for (;;) { const int b = next.fetch_add(1); if (b >= nblocks) return; build_one(b); } };
+        if (nth <= 1) worker();
+        else { std::vector<std::thread> th; for (int t = 0; t < nth; ++t) th.emplace_back(worker); for (auto& t : th) t.join(); }
+    }
+    for (int b = 0; b < nblocks; ++b) {
+        hp.cand_rate += hp.blocks[b].cand_rate;
+        hp.surv_rate += hp.blocks[b].surv_rate;
+        hp.req_rate += hp.blocks[b].req_rate;
+    }
+}
+
+}  // namespace pwmscan

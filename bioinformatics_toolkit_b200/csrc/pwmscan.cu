@@ -22,7 +22,7 @@ using namespace pwmscan;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-constexpr bool kDefaultMma = false;                  // default first stage: shared-memory look-up kernel (PWMSCAN_PREFILTER=mma|lds overrides)
+constexpr int kDefaultMode = PWM_MODE_LDS;              // default first stage (PWMSCAN_PREFILTER=kmer|lds|mma overrides)
 constexpr int kMaxChunks = 120;                      // host->device chunks of one pipelined scan
 constexpr int kCounterWords = 8 + kMaxChunks + 8;    // [0..7] scalars, [8..] one work counter per launch
 
@@ -462,6 +462,19 @@ extern "C" int pwmscan_plan_info(const pwmscan_plan* pl, double* out, int n) {
     }
     v[2] = (double)pl->generic.size();
     v[3] = pl->cand_rate;
+    v[7] = pl->mode;
+    if (pl->mode == PWM_MODE_KMER) {
+        v[0] = pl->km_nblocks;
+        v[1] = pl->km_req_rate;                // expected 32-byte table sectors gathered per sequence position
+        v[2] = (double)pl->km_generic.size();
+        v[3] = pl->km_cand_rate;
+        v[4] = 0;
+        for (const auto& b : pl->km_blocks) v[4] += (double)b.nt * kKmEntries * kKmWords * 4;    // L2-resident table bytes
+        v[5] = pl->km_nblocks;
+        v[6] = pl->km_surv_rate;               // expected first-stage survivors per position
+    } else if (pl->mode == PWM_MODE_MMA) {
+        v[0] = pl->mma_nblocks; v[2] = (double)pl->mma_generic.size(); v[3] = pl->mma_cand_rate; v[5] = pl->mma_nblocks;
+    }
     for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
     return PWMSCAN_OK;
 }
@@ -478,7 +491,25 @@ extern "C" void pwmscan_plan_free(pwmscan_plan* pl) {
     if (pl->d_mma_combos) cudaFree(pl->d_mma_combos);
     if (pl->d_mma_generic) cudaFree(pl->d_mma_generic);
     if (pl->d_btiles) cudaFree(pl->d_btiles);
+    if (pl->d_km_blocks) cudaFree(pl->d_km_blocks);
+    if (pl->d_km_combos) cudaFree(pl->d_km_combos);
+    if (pl->d_km_generic) cudaFree(pl->d_km_generic);
+    if (pl->d_km_tables) cudaFree(pl->d_km_tables);
+    if (pl->d_km_q16) cudaFree(pl->d_km_q16);
     delete pl;
+}
+
+// Which first stage plans are built for and scans run with (PWMSCAN_PREFILTER=kmer|lds|mma, read once).
+static int prefilter_mode() {
+    static const int mode = [] {
+        const char* e = std::getenv("PWMSCAN_PREFILTER");
+        if (!e) return kDefaultMode;
+        if (std::strcmp(e, "mma") == 0) return (int)PWM_MODE_MMA;
+        if (std::strcmp(e, "lds") == 0) return (int)PWM_MODE_LDS;
+        if (std::strcmp(e, "kmer") == 0) return (int)PWM_MODE_KMER;
+        return kDefaultMode;
+    }();
+    return mode;
 }
 
 extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, const double* thres, int strands,
@@ -491,53 +522,15 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
     pwmscan_plan* pl = new (std::nothrow) pwmscan_plan();
     if (!pl) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
     pl->ctx = ctx; pl->motifs = mo; pl->strands = strands; pl->skip = skip_ambiguous ? 1 : 0;
-    HostPlan hp;
-    const char* fs1 = std::getenv("PWMSCAN_FORCE_S1");
-    if (!build_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, hp, fs1 ? std::atoi(fs1) : 0)) {
-        pwmscan_plan_free(pl);
-        return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_plan_create: internal: block cannot be placed");
-    }
+    pl->mode = prefilter_mode();
+    const bool verbose = std::getenv("PWMSCAN_VERBOSE") != nullptr;
     auto dev_combo = [&](int m, int s) {
         DevCombo dc;
         dc.motif = m; dc.strand = s; dc.n = mo->mh[m].n; dc.c = 0;
         dc.tab_off = mo->tab_off[2 * m + s]; dc.th_off = mo->col_off[2 * m + s];
         return dc;
     };
-    std::vector<double>& h_th = hp.th;
-    pl->max_n = hp.max_n; pl->max_nslot = hp.max_nslot;
-    for (auto& g : hp.generic) pl->generic.push_back(dev_combo(g.first, g.second));
-    pl->blocks = std::move(hp.blocks);
-    pl->nblocks = (int)pl->blocks.size();
-    std::vector<DevBlock> h_blocks(pl->nblocks);
-    std::vector<DevCombo> h_combos((size_t)pl->nblocks * kCombosPerBlock);
-    std::vector<uint32_t> h_tables;
-    const double cand_rate = hp.cand_rate;
-    if (std::getenv("PWMSCAN_VERBOSE")) {
-        for (int b = 0; b < pl->nblocks; ++b) {
-            const BlockPlan& bp = pl->blocks[b];
-            int nmin = 999, nmax = 0, nen = 0;
-            for (int ci = 0; ci < kCombosPerBlock; ++ci) if (bp.combo[ci].motif >= 0) { nmin = std::min(nmin, bp.combo[ci].n); nmax = std::max(nmax, bp.combo[ci].n); nen += bp.combo[ci].enabled; }
-            std::fprintf(stderr, "[pwmscan] block %d: s1=%d nl=%d nr=%d nslot=%d Q=%d cols %d..%d enabled=%d rep=%d p_warp=%.4f cost=%.3f\n",
-                         b, bp.s1, bp.nl, bp.nr, bp.nslot, bp.Q, nmin, nmax, nen, bp.rep, bp.p_warp, bp.cost);
-        }
-        std::fprintf(stderr, "[pwmscan] generic combos=%zu cand_rate=%.3e\n", pl->generic.size(), cand_rate);
-    }
-    for (int b = 0; b < pl->nblocks; ++b) {
-        const BlockPlan& bp = pl->blocks[b];
-        h_blocks[b].s1 = bp.s1; h_blocks[b].nl = bp.nl; h_blocks[b].nslot = bp.nslot;
-        h_blocks[b].rep_log2 = 0;
-        while ((1 << h_blocks[b].rep_log2) < bp.rep) ++h_blocks[b].rep_log2;
-        h_blocks[b].table_off = (int64_t)h_tables.size();
-        h_tables.insert(h_tables.end(), bp.table.begin(), bp.table.end());
-        for (int ci = 0; ci < kCombosPerBlock; ++ci) {
-            DevCombo dc;
-            const ComboPlan& cp = bp.combo[ci];
-            if (cp.motif >= 0) { dc = dev_combo(cp.motif, cp.strand); dc.c = cp.c; }
-            else { dc.motif = -1; dc.strand = 0; dc.n = 0; dc.c = 0; dc.tab_off = 0; dc.th_off = 0; }
-            h_combos[(size_t)b * kCombosPerBlock + ci] = dc;
-        }
-    }
-    pl->cand_rate = cand_rate;
+    auto empty_combo = [] { DevCombo dc; dc.motif = -1; dc.strand = 0; dc.n = 0; dc.c = 0; dc.tab_off = 0; dc.th_off = 0; return dc; };
     cudaError_t e;
     auto bail = [&](int code) { pwmscan_plan_free(pl); return code; };
     auto up = [&](void** dst, const void* src, size_t bytes, const char* what) -> int {
@@ -547,18 +540,56 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
         return 0;
     };
     int rc;
-    if ((rc = up((void**)&pl->d_th, h_th.data(), h_th.size() * 8, "upload th"))) return bail(rc);
-    if ((rc = up((void**)&pl->d_blocks, h_blocks.data(), h_blocks.size() * sizeof(DevBlock), "upload blocks"))) return bail(rc);
-    if ((rc = up((void**)&pl->d_combos, h_combos.data(), h_combos.size() * sizeof(DevCombo), "upload combos"))) return bail(rc);
-    if ((rc = up((void**)&pl->d_tables, h_tables.data(), h_tables.size() * 4, "upload tables"))) return bail(rc);
-    if ((rc = up((void**)&pl->d_generic, pl->generic.data(), pl->generic.size() * sizeof(DevCombo), "upload generic"))) return bail(rc);
-    {   // tensor-core first stage: blocks of 128 motifs, any motif length
+    if (pl->mode == PWM_MODE_LDS) {          // shared-memory 4-mer deficit tables: blocks of 64 motifs
+        HostPlan hp;
+        const char* fs1 = std::getenv("PWMSCAN_FORCE_S1");
+        if (!build_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, hp, fs1 ? std::atoi(fs1) : 0)) {
+            pwmscan_plan_free(pl);
+            return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_plan_create: internal: block cannot be placed");
+        }
+        pl->max_n = hp.max_n; pl->max_nslot = hp.max_nslot;
+        for (auto& g : hp.generic) pl->generic.push_back(dev_combo(g.first, g.second));
+        pl->blocks = std::move(hp.blocks);
+        pl->nblocks = (int)pl->blocks.size();
+        pl->cand_rate = hp.cand_rate;
+        std::vector<DevBlock> h_blocks(pl->nblocks);
+        std::vector<DevCombo> h_combos((size_t)pl->nblocks * kCombosPerBlock);
+        std::vector<uint32_t> h_tables;
+        for (int b = 0; b < pl->nblocks; ++b) {
+            const BlockPlan& bp = pl->blocks[b];
+            if (verbose) {
+                int nmin = 999, nmax = 0, nen = 0;
+                for (int ci = 0; ci < kCombosPerBlock; ++ci) if (bp.combo[ci].motif >= 0) { nmin = std::min(nmin, bp.combo[ci].n); nmax = std::max(nmax, bp.combo[ci].n); nen += bp.combo[ci].enabled; }
+                std::fprintf(stderr, "[pwmscan] block %d: s1=%d nl=%d nr=%d nslot=%d Q=%d cols %d..%d enabled=%d rep=%d p_warp=%.4f cost=%.3f\n",
+                             b, bp.s1, bp.nl, bp.nr, bp.nslot, bp.Q, nmin, nmax, nen, bp.rep, bp.p_warp, bp.cost);
+            }
+            h_blocks[b].s1 = bp.s1; h_blocks[b].nl = bp.nl; h_blocks[b].nslot = bp.nslot;
+            h_blocks[b].rep_log2 = 0;
+            while ((1 << h_blocks[b].rep_log2) < bp.rep) ++h_blocks[b].rep_log2;
+            h_blocks[b].table_off = (int64_t)h_tables.size();
+            h_tables.insert(h_tables.end(), bp.table.begin(), bp.table.end());
+            for (int ci = 0; ci < kCombosPerBlock; ++ci) {
+                const ComboPlan& cp = bp.combo[ci];
+                DevCombo dc = empty_combo();
+                if (cp.motif >= 0) { dc = dev_combo(cp.motif, cp.strand); dc.c = cp.c; }
+                h_combos[(size_t)b * kCombosPerBlock + ci] = dc;
+            }
+        }
+        if (verbose) std::fprintf(stderr, "[pwmscan] generic combos=%zu cand_rate=%.3e\n", pl->generic.size(), pl->cand_rate);
+        if ((rc = up((void**)&pl->d_th, hp.th.data(), hp.th.size() * 8, "upload th"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_blocks, h_blocks.data(), h_blocks.size() * sizeof(DevBlock), "upload blocks"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_combos, h_combos.data(), h_combos.size() * sizeof(DevCombo), "upload combos"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_tables, h_tables.data(), h_tables.size() * 4, "upload tables"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_generic, pl->generic.data(), pl->generic.size() * sizeof(DevCombo), "upload generic"))) return bail(rc);
+    } else if (pl->mode == PWM_MODE_MMA) {   // tensor-core first stage: blocks of 128 motifs, any motif length
         MmaHostPlan mp;
         const char* fst = std::getenv("PWMSCAN_FORCE_STEPS");
         build_mma_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, mp, fst ? std::atoi(fst) : 0);
+        pl->max_n = mp.max_n;
         pl->mma_blocks = std::move(mp.blocks);
         pl->mma_nblocks = (int)pl->mma_blocks.size();
         pl->mma_cand_rate = mp.cand_rate;
+        pl->cand_rate = mp.cand_rate;
         for (auto& g : mp.generic) pl->mma_generic.push_back(dev_combo(g.first, g.second));
         std::vector<DevMmaBlock> hb(pl->mma_nblocks);
         std::vector<DevCombo> hc((size_t)pl->mma_nblocks * kMmaCombos);
@@ -569,20 +600,80 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
             hb[b].steps = bp.steps; hb[b].ncombo = bp.ncombo; hb[b].b_off = (int64_t)ht.size();
             ht.insert(ht.end(), bp.btiles.begin(), bp.btiles.end());
             for (int ci = 0; ci < kMmaCombos; ++ci) {
-                DevCombo dc;
                 const MmaCombo& mc = bp.combo[ci];
+                DevCombo dc = empty_combo();
                 if (mc.motif >= 0) { dc = dev_combo(mc.motif, mc.strand); dc.c = mc.c; }
-                else { dc.motif = -1; dc.strand = 0; dc.n = 0; dc.c = 0; dc.tab_off = 0; dc.th_off = 0; }
                 hc[(size_t)b * kMmaCombos + ci] = dc;
             }
-            if (std::getenv("PWMSCAN_VERBOSE"))
+            if (verbose)
                 std::fprintf(stderr, "[pwmscan] mma block %d: steps=%d (K1=%d cols) N=%d cand_rate=%.3e cost=%.1f\n", b, bp.steps, 8 * bp.steps, bp.ncombo, bp.cand_rate, bp.cost);
         }
         while (ht.size() % 128) ht.push_back(0);
+        if ((rc = up((void**)&pl->d_th, mp.th.data(), mp.th.size() * 8, "upload th"))) return bail(rc);
         if ((rc = up((void**)&pl->d_mma_blocks, hb.data(), hb.size() * sizeof(DevMmaBlock), "upload mma blocks"))) return bail(rc);
         if ((rc = up((void**)&pl->d_mma_combos, hc.data(), hc.size() * sizeof(DevCombo), "upload mma combos"))) return bail(rc);
         if ((rc = up((void**)&pl->d_mma_generic, pl->mma_generic.data(), pl->mma_generic.size() * sizeof(DevCombo), "upload mma generic"))) return bail(rc);
         if ((rc = up((void**)&pl->d_btiles, ht.data(), ht.size(), "upload btiles"))) return bail(rc);
+    } else {                                 // k-mer mask tables in L2: blocks of 128 motifs, any motif length
+        KmHostPlan kp;
+        const char* fnt = std::getenv("PWMSCAN_FORCE_NT");
+        build_km_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, kp, fnt ? std::atoi(fnt) : 0);
+        pl->max_n = kp.max_n;
+        pl->km_blocks = std::move(kp.blocks);
+        pl->km_nblocks = (int)pl->km_blocks.size();
+        pl->km_cand_rate = kp.cand_rate; pl->km_surv_rate = kp.surv_rate; pl->km_req_rate = kp.req_rate;
+        pl->cand_rate = kp.cand_rate;
+        for (auto& g : kp.generic) pl->km_generic.push_back(dev_combo(g.first, g.second));
+        std::vector<DevKmBlock> hb(pl->km_nblocks);
+        std::vector<DevCombo> hc((size_t)pl->km_nblocks * kKmCombos);
+        std::vector<uint16_t> hq;
+        std::vector<double> hw, hd;
+        std::vector<size_t> w_off(pl->km_nblocks);
+        size_t table_bytes = 0;
+        for (int b = 0; b < pl->km_nblocks; ++b) {
+            KmBlockPlan& bp = pl->km_blocks[b];
+            hb[b].nt = bp.nt; hb[b].max_n = bp.max_n;
+            for (int t = 0; t < 4; ++t) hb[b].order[t] = bp.order[t];
+            hb[b].table_off = (int64_t)table_bytes;
+            table_bytes += (size_t)bp.nt * kKmEntries * kKmWords * 4;
+            hb[b].q16_off = (int64_t)hq.size();
+            hq.insert(hq.end(), bp.q16.begin(), bp.q16.end());
+            w_off[b] = hw.size();
+            hw.insert(hw.end(), bp.wdef.begin(), bp.wdef.end());
+            hd.insert(hd.end(), bp.dsafe.begin(), bp.dsafe.end());
+            pl->km_max_n = std::max(pl->km_max_n, bp.max_n);
+            int nmin = 999, nmax = 0, nen = 0;
+            for (int ci = 0; ci < kKmCombos; ++ci) {
+                const KmCombo& kc = bp.combo[ci];
+                DevCombo dc = empty_combo();
+                if (kc.motif >= 0) { dc = dev_combo(kc.motif, kc.strand); dc.c = kc.c; nmin = std::min(nmin, kc.n); nmax = std::max(nmax, kc.n); nen += kc.enabled; }
+                hc[(size_t)b * kKmCombos + ci] = dc;
+            }
+            if (verbose)
+                std::fprintf(stderr, "[pwmscan] kmer block %d: nt=%d order=%d%d%d%d cols %d..%d enabled=%d sectors/pos=%.3f survivors/pos=%.4f cand/pos=%.3e cost=%.3f\n",
+                             b, bp.nt, bp.order[0], bp.order[1], bp.order[2], bp.order[3], nmin, nmax, nen, bp.req_rate, bp.surv_rate, bp.cand_rate, bp.cost);
+            std::vector<double>().swap(bp.wdef);         // only needed for the device build
+            std::vector<uint16_t>().swap(bp.q16);
+        }
+        if (verbose) std::fprintf(stderr, "[pwmscan] generic combos=%zu cand_rate=%.3e\n", pl->km_generic.size(), pl->cand_rate);
+        if ((rc = up((void**)&pl->d_th, kp.th.data(), kp.th.size() * 8, "upload th"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_km_blocks, hb.data(), hb.size() * sizeof(DevKmBlock), "upload kmer blocks"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_km_combos, hc.data(), hc.size() * sizeof(DevCombo), "upload kmer combos"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_km_generic, pl->km_generic.data(), pl->km_generic.size() * sizeof(DevCombo), "upload kmer generic"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_km_q16, hq.data(), hq.size() * 2, "upload q16"))) return bail(rc);
+        if (pl->km_nblocks > 0) {
+            // the mask tables are computed on the device from the per-window deficits
+            double *d_w = nullptr, *d_d = nullptr;
+            if ((e = cudaMalloc((void**)&pl->d_km_tables, table_bytes)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(kmer tables)"));
+            if ((rc = up((void**)&d_w, hw.data(), hw.size() * 8, "upload window deficits"))) return bail(rc);
+            if ((rc = up((void**)&d_d, hd.data(), hd.size() * 8, "upload dsafe"))) { cudaFree(d_w); return bail(rc); }
+            for (int b = 0; b < pl->km_nblocks && rc == 0; ++b)
+                rc = km_build_tables(ctx, d_w + w_off[b], d_d + (size_t)b * kKmCombos, hb[b].nt, pl->d_km_tables + hb[b].table_off);
+            e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_w); cudaFree(d_d);
+            if (rc) return bail(rc);
+            if (e != cudaSuccess) return bail(cuda_fail(ctx, e, "kmer table build"));
+        }
     }
     *out = pl;
     return PWMSCAN_OK;
@@ -855,13 +946,12 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         }
     }
     // which first stage: the shared-memory look-up kernel or the tensor-core (tcgen05) one
-    static const char* mode_env = std::getenv("PWMSCAN_PREFILTER");
-    const bool use_mma = mode_env ? (std::strcmp(mode_env, "mma") == 0) : kDefaultMma;
-    const int n_pre_blocks = use_mma ? pl->mma_nblocks : pl->nblocks;
-    const std::vector<DevCombo>& generic = use_mma ? pl->mma_generic : pl->generic;
-    const DevCombo* d_generic = use_mma ? pl->d_mma_generic : pl->d_generic;
-    const DevCombo* d_combos = use_mma ? pl->d_mma_combos : pl->d_combos;
-    const double cand_rate = use_mma ? pl->mma_cand_rate : pl->cand_rate;
+    const bool use_mma = pl->mode == PWM_MODE_MMA, use_km = pl->mode == PWM_MODE_KMER;
+    const int n_pre_blocks = use_mma ? pl->mma_nblocks : use_km ? pl->km_nblocks : pl->nblocks;
+    const std::vector<DevCombo>& generic = use_mma ? pl->mma_generic : use_km ? pl->km_generic : pl->generic;
+    const DevCombo* d_generic = use_mma ? pl->d_mma_generic : use_km ? pl->d_km_generic : pl->d_generic;
+    const DevCombo* d_combos = use_mma ? pl->d_mma_combos : use_km ? pl->d_km_combos : pl->d_combos;
+    const double cand_rate = pl->cand_rate;
     // capacities: expected + slack, grown and re-run on overflow
     unsigned long long cand_cap = (unsigned long long)(cand_rate * (double)len * 1.5) + (1ull << 20);
     if (use_mma) cand_cap += (unsigned long long)ctx->sm_count * 28 * 256 * 2;             // every epilogue warp reserves whole 256-record chunks
@@ -873,6 +963,12 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     float ms_pre = 0, ms_res = 0, ms_sort = 0, ms_tot = 0;
     int launches = 0;
     auto launch_prefilter = [&](long long a0, long long a1, int slot) -> int {
+        if (use_km) {
+            if (pl->km_nblocks == 0) return PWMSCAN_OK;
+            ++launches;
+            return launch_km_prefilter(ctx, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_max_n, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
+                                       pl->d_km_combos, d_cand, cand_cap, ctx->d_counters + 8 + slot);
+        }
         if (use_mma) {
             if (pl->mma_nblocks == 0) return PWMSCAN_OK;
             ++launches;

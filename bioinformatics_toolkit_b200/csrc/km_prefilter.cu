@@ -25,10 +25,11 @@ using namespace pwmscan;
 namespace {
 
 constexpr int kKmThreads = 1024;
-constexpr int kKmItemPos = 8192;                 // positions per work item
 constexpr int kKmIterPos = 2048;                 // positions per CTA iteration (2 per thread)
+constexpr int kKmMaxIters = 16;                  // iterations per work item: 16 (32 768 positions), fewer for short inputs
+constexpr int kKmMinItemPos = kKmIterPos;        // launches cover multiples of kAnchorRound, a multiple of every item size
 constexpr int kKmHaloWords = 4;                  // 64 stored bases in front of the item (window starts reach back n-1 <= 63)
-constexpr int kKmSeqWords = kKmHaloWords + kKmItemPos / 16 + 5;     // windows end <= 8191 + 7 + 64 bases after the item start
+constexpr int kKmSeqWords = kKmHaloWords + kKmMaxIters * kKmIterPos / 16 + 5;   // windows end <= 7 + 64 bases after the item's last position
 constexpr int kKmQueue = 64;
 constexpr size_t kKmTableBytes = (size_t)kKmEntries * kKmWords * 4;      // 2 MiB
 
@@ -101,26 +102,22 @@ __device__ __forceinline__ void km_drain(const KmShared& sh, const uint16_t* __r
         const int rel = p - c + 16 * kKmHaloWords;                  // window start relative to sh.seq[0]
         const int wi = rel >> 4, s2 = 2 * (rel & 15);
         const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
-        unsigned long long X = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
-        const unsigned long long* row = reinterpret_cast<const unsigned long long*>(s_q16) + (size_t)combo * max_n;
-        uint32_t sum = 0;
-        const int n1 = n < 32 ? n : 32;
-        int k = 0;
-        for (; k < n1; ++k) {
-            const unsigned long long r = row[k];
-            sum += (uint32_t)(r >> (16 * (int)(X & 3ull))) & 0xFFFFu;
-            X >>= 2;
-            if (sum > (uint32_t)kKmQ) break;
-        }
-        if (n > 32 && sum <= (uint32_t)kKmQ) {
+        const uint32_t x0 = __funnelshift_r(w0, w1, s2), x1 = __funnelshift_r(w1, w2, s2);
+        uint32_t x2 = 0, x3 = 0;
+        if (n > 32) {
             const uint32_t w3 = sh.seq[wi + 3], w4 = sh.seq[wi + 4];
-            X = (unsigned long long)__funnelshift_r(w2, w3, s2) | ((unsigned long long)__funnelshift_r(w3, w4, s2) << 32);
-            for (; k < n; ++k) {
-                const unsigned long long r = row[k];
-                sum += (uint32_t)(r >> (16 * (int)(X & 3ull))) & 0xFFFFu;
-                X >>= 2;
-                if (sum > (uint32_t)kKmQ) break;
-            }
+            x2 = __funnelshift_r(w2, w3, s2); x3 = __funnelshift_r(w3, w4, s2);
+        }
+        const uint2* row = reinterpret_cast<const uint2*>(s_q16) + (size_t)combo * max_n;
+        uint32_t sum = 0;
+        for (int k = 0; k < n; ++k) {                               // rows in order of decreasing expected deficit
+            const uint2 r = row[k];
+            const uint32_t col = ((r.x >> 12) & 15u) | ((r.x >> 24) & 0x30u);
+            const uint32_t xs = col < 32u ? (col < 16u ? x0 : x1) : (col < 48u ? x2 : x3);
+            const uint32_t b = (xs >> (2u * (col & 15u))) & 3u;
+            const uint32_t f = (b & 2u) ? r.y : r.x;
+            sum += (f >> (16u * (b & 1u))) & 0xFFFu;
+            if (sum > (uint32_t)kKmQ) break;
         }
         ok = sum <= (uint32_t)kKmQ;
     }
@@ -138,7 +135,7 @@ __device__ __forceinline__ void km_drain(const KmShared& sh, const uint16_t* __r
 
 template <int NT>
 __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const DevKmBlock& db, const uint8_t* __restrict__ tab,
-                                        long long U0, long long len, unsigned long long combo_base,
+                                        long long U0, int iters, long long len, unsigned long long combo_base,
                                         unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* q = sh.queue[warp];
@@ -148,7 +145,7 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
 #pragma unroll
     for (int s = 0; s < NT; ++s) { tp[s] = tab + (size_t)db.order[s] * kKmTableBytes; tsh[s] = 16 * db.order[s]; }
 #pragma unroll 1
-    for (int it = 0; it < kKmItemPos / kKmIterPos; ++it) {
+    for (int it = 0; it < iters; ++it) {
         Mask m[2];
         unsigned long long x[2];
 #pragma unroll
@@ -211,7 +208,7 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
 }
 
 __global__ void __launch_bounds__(kKmThreads, 1)
-km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long total_items,
+km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long total_items, int iters,
                     const DevKmBlock* __restrict__ blocks, const uint8_t* __restrict__ tables, const uint16_t* __restrict__ q16,
                     const DevCombo* __restrict__ combos, long long len, unsigned long long* __restrict__ cand, unsigned long long cand_cap,
                     unsigned long long* counters, unsigned long long* work_counter) {
@@ -219,7 +216,8 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
     __shared__ KmShared sh;
     uint16_t* s_q16 = reinterpret_cast<uint16_t*>(smem_raw);
     const int tid = threadIdx.x;
-    const long long items_per_block = n_anchor / kKmItemPos;
+    const int item_pos = iters * kKmIterPos;
+    const long long items_per_block = n_anchor / item_pos;
     int cur_blk = -1;
     DevKmBlock db = blocks[0];
     for (;;) {
@@ -228,7 +226,7 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
         const long long item = sh.item;
         if (item >= total_items) break;
         const int blk = (int)(item / items_per_block);                 // block-major: tables change rarely
-        const long long U0 = anchor0 + (item - (long long)blk * items_per_block) * kKmItemPos;
+        const long long U0 = anchor0 + (item - (long long)blk * items_per_block) * item_pos;
         if (blk != cur_blk) {
             db = blocks[blk];
             const uint4* src = reinterpret_cast<const uint4*>(q16 + db.q16_off);
@@ -243,16 +241,17 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
         }
         {   // stage the item's 2-bit words (64 bases of history in front; the allocation has one front word)
             const long long w0 = (U0 >> 4) - kKmHaloWords;
-            for (int i = tid; i < kKmSeqWords; i += kKmThreads) sh.seq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
+            const int nw = kKmHaloWords + item_pos / 16 + 5;
+            for (int i = tid; i < nw; i += kKmThreads) sh.seq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
         }
         __syncthreads();
         const uint8_t* tab = tables + db.table_off;
         const unsigned long long combo_base = (unsigned long long)blk * kKmCombos;
         switch (db.nt) {
-            case 1: km_item<1>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
-            case 2: km_item<2>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
-            case 3: km_item<3>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
-            default: km_item<4>(sh, s_q16, db, tab, U0, len, combo_base, cand, cand_cap, counters); break;
+            case 1: km_item<1>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
+            case 2: km_item<2>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
+            case 3: km_item<3>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
+            default: km_item<4>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
         }
         __syncthreads();   // everyone is done with sh.seq / s_q16 / sh.item
     }
@@ -284,9 +283,11 @@ int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, 
         PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km_q16_smem_bytes(kMaxCols)));
         ctx->km_attr_set = true;
     }
-    const long long items = (a1 - a0) / kKmItemPos * nblocks;
+    int iters = kKmMaxIters;                                  // short inputs: smaller items so that every SM gets several
+    while (iters > 1 && (a1 - a0) / (iters * kKmIterPos) * nblocks < 8LL * ctx->sm_count) iters >>= 1;
+    const long long items = (a1 - a0) / (iters * kKmIterPos) * nblocks;
     const int grid = (int)std::min<long long>(ctx->sm_count, items);
-    km_prefilter_kernel<<<grid, kKmThreads, km_q16_smem_bytes(max_n), ctx->stream>>>(d_seq2, a0, a1 - a0, items, d_blocks, d_tables, d_q16, d_combos, len,
+    km_prefilter_kernel<<<grid, kKmThreads, km_q16_smem_bytes(max_n), ctx->stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
                                                                                     d_cand, cand_cap, ctx->d_counters, work_counter);
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;

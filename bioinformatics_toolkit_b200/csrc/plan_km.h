@@ -24,7 +24,7 @@ constexpr int kKmMotifsPerBlock = 128;
 constexpr int kKmWords = kKmCombos / 32;        // 8 x uint32 = one 32-byte sector
 constexpr int kKmMaxTables = 4;
 constexpr int kKmEntries = 65536;               // 8-mers
-constexpr int kKmQ = 60000;                     // fixed-point budget of the middle stage (entries saturate at 65535)
+constexpr int kKmQ = 4000;                      // fixed-point budget of the middle stage; entries saturate at 4095 (12 bits)
 
 struct KmCombo {
     int motif = -1, strand = 0, n = 0, c = 0;
@@ -41,7 +41,10 @@ struct KmBlockPlan {
     KmCombo combo[kKmCombos];
     std::vector<double> wdef;                   // [nt][256][8][4] deficit of base b at window position p (0 outside the motif)
     std::vector<double> dsafe;                  // [256]; < 0: bit never set
-    std::vector<uint16_t> q16;                  // [256][max_n][4] middle-stage entries, natural column order
+    // Middle-stage rows, [256][max_n] x 8 bytes, visited in order of decreasing expected deficit (early exit):
+    // four 16-bit fields (bases A, C, G, T), bits 0..11 the quantised deficit of the row's motif column;
+    // bits 12..15 of field 0 / field 1 carry the low 4 / high 2 bits of that column's index.
+    std::vector<uint16_t> q16;
     double surv_rate = 0;                       // expected first-stage survivors per position
     double cand_rate = 0;                       // expected candidates (middle-stage survivors) per position
     double req_rate = 0;                        // expected table sectors gathered per position
@@ -173,11 +176,19 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
                 for (int b = 0; b < 4; ++b) bp.wdef[(((size_t)t * kKmCombos + ci) * 8 + p) * 4 + b] = cd.dk[col][b];
             }
         const double scale = cd.dsafe > 0 ? (double)kKmQ / cd.dsafe : 1e300;
-        for (int k = 0; k < cd.n; ++k)
+        int perm[kMaxCols];
+        for (int k = 0; k < cd.n; ++k) perm[k] = k;
+        std::stable_sort(perm, perm + cd.n, [&](int a, int b) { return cd.w[a] > cd.w[b]; });
+        for (int r = 0; r < cd.n; ++r) {
+            const int col = perm[r];
+            uint16_t* row = &bp.q16[((size_t)ci * max_n + r) * 4];
             for (int b = 0; b < 4; ++b) {
-                const double v = std::floor(scale * cd.dk[k][b] * (1.0 - 1e-9));
-                bp.q16[((size_t)ci * max_n + k) * 4 + b] = (uint16_t)(v < 65535.0 ? (v < 0 ? 0.0 : v) : 65535.0);
+                const double v = std::floor(scale * cd.dk[col][b] * (1.0 - 1e-9));
+                row[b] = (uint16_t)(v < 4095.0 ? (v < 0 ? 0.0 : v) : 4095.0);
             }
+            row[0] |= (uint16_t)((col & 15) << 12);
+            row[1] |= (uint16_t)((col >> 4) << 12);
+        }
         kc.sigma_mid = detail::km_total_pass(cd, cd.dsafe * (1.0 + (double)(cd.n + 1) / kKmQ));
         bp.cand_rate += kc.sigma_mid;
     }

@@ -282,31 +282,45 @@ def main():
     pre_ms_launch = pre_ms_tot / args.steps / max(1, len(dev_seqs))
     bp_launch = sum(int(a.size) for _, a in seqs_host) / max(1, len(dev_seqs))
     clk = peaks["sm_max_mhz"] * 1e6
-    # governing roof: shared-memory crossbar, one 128-B wavefront per clock per SM (B300_MICROARCH.md; not a
-    # MEASURED_PEAKS.json entry).  Algorithmic bytes: first-stage look-up rows, S1_b x 128 B per position per block.
-    smem_bytes = info["smem_wavefronts_per_position"] * 128.0 * bp_launch
-    smem_peak = 148 * 128 * clk / 1e9
-    smem_ach = smem_bytes / (pre_ms_launch / 1e3) / 1e9
     hbm_bytes = 0.25 * bp_launch * info["genome_passes"]          # 2-bit genome read once per block pass
     hbm_ach = hbm_bytes / (pre_ms_launch / 1e3) / 1e9
     ncol_mean = float(np.mean([m.shape[0] for m in mats]))
     lane_ops = 2.0 * ncol_mean * bp_launch * M                     # brute-force look-ups + adds, both strands
     issue_peak = 148 * 128 * clk / 1e12
-    # DRAM traffic of one prefilter launch on this exact workload, from the committed ncu --set full capture
-    # (profiles/r1b_prefilter_ncu_full_metrics.json: dram__bytes_read.sum 62.9 MB + dram__bytes_write.sum 3.1 MB)
-    traffic = 66.0e6 if (args.workload == "c2" and M == 100) else None
-    roofline = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
-                "traffic": traffic, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
-                "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md) x sm_max_mhz (%s)" % peaks["source"],
-                "algorithmic_bytes_per_launch": smem_bytes,
-                "note": "shared-memory-bandwidth bound look-up kernel; ncu (profiles/) reports the LSU/shared pipe at the same fraction"}
+    traffic = None
+    if info["mode"] == "kmer":
+        # governing roof: the L1 gather rate, one 32-byte sector per clock per SM (experiments/masktab/l2gather.cu
+        # reaches 96 % of it: 8.9 TB/s).  Algorithmic bytes: the plan's expected mask sectors per position x 32 B.
+        alg_bytes = info["table_sectors_per_position"] * 32.0 * bp_launch
+        peak = 148 * 32 * clk / 1e9
+        ach = alg_bytes / (pre_ms_launch / 1e3) / 1e9
+        # DRAM traffic of one launch on this exact workload, from the committed ncu --set full capture
+        traffic = 68.1e6 if (args.workload == "c2" and M == 100) else None
+        roofline = {"bound": "l1-gather", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "kernel": "km_prefilter_kernel", "ms_per_launch": pre_ms_launch,
+                    "peak_source": "148 SMs x one 32-B sector per clk x sm_max_mhz (%s); measured 8.9 TB/s by experiments/masktab/l2gather.cu" % peaks["source"],
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "L2-resident k-mer mask tables gathered with 256-bit loads; the L1 sector rate, not HBM or L2 bytes, is the roof"}
+    else:
+        # governing roof: shared-memory crossbar, one 128-B wavefront per clock per SM (B300_MICROARCH.md; not a
+        # MEASURED_PEAKS.json entry).  Algorithmic bytes: first-stage look-up rows, S1_b x 128 B per position per block.
+        smem_bytes = info.get("smem_wavefronts_per_position", 0.0) * 128.0 * bp_launch
+        smem_peak = 148 * 128 * clk / 1e9
+        smem_ach = smem_bytes / (pre_ms_launch / 1e3) / 1e9
+        # (profiles/r1b_prefilter_ncu_full_metrics.json: dram__bytes_read.sum 62.9 MB + dram__bytes_write.sum 3.1 MB)
+        traffic = 66.0e6 if (args.workload == "c2" and M == 100 and info["mode"] == "lds") else None
+        roofline = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
+                    "traffic": traffic, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
+                    "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md) x sm_max_mhz (%s)" % peaks["source"],
+                    "algorithmic_bytes_per_launch": smem_bytes,
+                    "note": "shared-memory-bandwidth bound look-up kernel; ncu (profiles/) reports the LSU/shared pipe at the same fraction"}
     roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peaks["source"],
-                    "note": "HBM is not the governing roof at >= 64 motifs (0.25 B/base per 64-motif block pass)"}
+                    "note": "HBM is not the governing roof (0.25 B/base per block pass)"}
     issue = {"bound": "int/fp32 issue of the brute-force algorithm", "achieved": lane_ops / (pre_ms_launch / 1e3) / 1e12,
              "peak": issue_peak, "unit": "T lane-ops/s (2*n per bp*motif)",
              "frac": lane_ops / (pre_ms_launch / 1e3) / 1e12 / issue_peak,
-             "note": "> 1 means the 4-mer/SIMD-byte restructuring does fewer operations than the brute-force count"}
+             "note": "> 1 means the table-driven prefilter does fewer operations than the brute-force count"}
 
     # ---- CPU baseline (oracle port, bounded sample), rank 0 at N=1 only ---------------------------------
     cpu = None
@@ -329,7 +343,7 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
-            "vs_baseline": None, "dtype": "u8 prefilter + f64 re-score", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bit-mask / u16 prefilter + f64 re-score", "data": "synthetic",
             "config": {"workload": desc, "l2": "256 MiB flush write between steps", "thresholds": th_src,
                        "hits_per_step_rank0": int(nh),
                        "device_ms_breakdown_last_step": {k: round(float(v), 4) for k, v in last_timing.items()}},

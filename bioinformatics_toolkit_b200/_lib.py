@@ -320,8 +320,16 @@ class Plan:
     def info(self):
         out = np.zeros(8)
         self.ctx.L.pwmscan_plan_info(self.h, _ptr(out), C.c_int(8))
-        return {"blocks": int(out[0]), "smem_wavefronts_per_position": out[1], "exact_combos": int(out[2]),
-                "candidates_per_position": out[3], "table_bytes": out[4], "genome_passes": out[5], "p_second_stage_sum": out[6]}
+        mode = ("lds", "mma", "kmer")[int(out[7])]
+        d = {"mode": mode, "blocks": int(out[0]), "exact_combos": int(out[2]), "candidates_per_position": out[3],
+             "table_bytes": out[4], "genome_passes": out[5]}
+        if mode == "kmer":       # k-mer mask tables gathered from L2
+            d["table_sectors_per_position"] = out[1]
+            d["first_stage_survivors_per_position"] = out[6]
+        elif mode == "lds":      # 4-mer deficit tables in shared memory
+            d["smem_wavefronts_per_position"] = out[1]
+            d["p_second_stage_sum"] = out[6]
+        return d
 
     def scan_host(self, data, seg_off=None, uppercase=False):
         """One-shot scan of host bytes (pwmscan_scan_host): upload, packing and scan are pipelined."""

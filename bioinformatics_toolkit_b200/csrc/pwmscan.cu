@@ -22,7 +22,7 @@ using namespace pwmscan;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-constexpr int kDefaultMode = PWM_MODE_LDS;              // default first stage (PWMSCAN_PREFILTER=kmer|lds|mma overrides)
+constexpr int kDefaultMode = PWM_MODE_KMER;             // default first stage (PWMSCAN_PREFILTER=kmer|lds|mma overrides)
 constexpr int kMaxChunks = 120;                      // host->device chunks of one pipelined scan
 constexpr int kCounterWords = 8 + kMaxChunks + 8;    // [0..7] scalars, [8..] one work counter per launch
 

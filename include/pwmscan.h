@@ -100,10 +100,14 @@ void pwmscan_motifs_free(pwmscan_motifs* motifs);
 int  pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, const double* thres,
                          int strands, int skip_ambiguous, pwmscan_plan** out);
 void pwmscan_plan_free(pwmscan_plan* plan);
-/* Plan facts for the roofline arithmetic: out[0] prefilter blocks, out[1] first-stage shared-memory
- * wavefronts (128 B each) per sequence position summed over blocks, out[2] (motif,strand) combos on
- * the exact kernel, out[3] expected candidates per position, out[4] table bytes, out[5] passes over
- * the packed genome, out[6] sum over blocks of P(a warp enters the second stage). */
+/* Plan facts for the roofline arithmetic: out[7] the first stage the plan was built for (2 = k-mer
+ * mask tables in L2, the default; 0 = shared-memory 4-mer tables; 1 = tensor-core variant),
+ * out[0] prefilter blocks, out[2] (motif,strand) combos on the exact kernel, out[3] expected
+ * candidates per position, out[4] table bytes, out[5] passes over the packed genome;
+ * mode 2: out[1] expected 32-byte table sectors gathered per sequence position (summed over blocks),
+ *         out[6] expected first-stage survivors per position;
+ * mode 0: out[1] first-stage shared-memory wavefronts (128 B) per position, out[6] sum over blocks
+ *         of P(a warp enters the second stage). */
 int  pwmscan_plan_info(const pwmscan_plan* plan, double* out, int n);
 /* Hit list sorted by (segment, motif, strand, position); position is the 0-based window start
  * within its segment on the forward sequence (also for strand 1: Utils.hs:109-111); score is the

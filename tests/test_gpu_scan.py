@@ -287,9 +287,11 @@ def test_many_segments_and_many_motifs(ctx, oracle):
     assert np.array_equal(h.score.view(np.uint64), o[3][inside][order].view(np.uint64))
 
 
-def test_tensor_core_prefilter_variant_parity():
-    """The experimental tcgen05 (int8 one-hot x deficit GEMM) first stage, selected with
-    PWMSCAN_PREFILTER=mma, must give the same bit-identical hit lists (own process: the mode is read once)."""
+@pytest.mark.parametrize("variant", ["kmer", "lds", "mma"])
+def test_prefilter_variant_parity(variant):
+    """Every first stage — the k-mer mask tables in L2 (kmer), the shared-memory 4-mer deficit tables (lds)
+    and the experimental tcgen05 int8 one-hot x deficit GEMM (mma), selected with PWMSCAN_PREFILTER —
+    must give the same bit-identical hit lists (own process: the mode is read once)."""
     import subprocess
     import sys
     code = r'''
@@ -309,8 +311,8 @@ for count, L, lo, hi in ((150, 300000, 6, 40), (3, 100000, 8, 12)):
     assert np.array_equal(h.motif, o[0]) and np.array_equal(h.strand, o[1]) and np.array_equal(h.pos, o[2])
     assert np.array_equal(h.score.view(np.uint64), o[3].view(np.uint64))
 assert ctx.timing()["prefilter_launches"] >= 1
-print("MMA-PARITY-OK")
+print("VARIANT-PARITY-OK")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PWMSCAN_PREFILTER="mma")
+    env = dict(os.environ, PWMSCAN_PREFILTER=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MMA-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "VARIANT-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

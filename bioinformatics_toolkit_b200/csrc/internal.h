@@ -89,8 +89,11 @@ struct DevMmaBlock {
 
 struct DevKmBlock {
     int32_t nt, max_n;   // mask tables of this block; longest motif (row stride of q16)
-    int32_t order[4];    // gather order of the tables (most selective first)
-    int64_t table_off;   // bytes into d_km_tables (table t at + t * 2 MiB)
+    // per gather step s (most selective table first): the table's k-mer is bits [shift, shift + 2L) of the
+    // 64-bit window (32 bases from the stored position); its masks start table_off[s] bytes into d_km_tables
+    int32_t shift[4];
+    uint32_t kmask[4];   // 4^L - 1
+    int64_t table_off[4];
     int64_t q16_off;     // uint16 elements into d_km_q16 ([256][max_n][4])
 };
 
@@ -160,7 +163,7 @@ void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap);
 
-int km_build_tables(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int nt, uint8_t* d_tables);
+int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int L, uint8_t* d_table);
 int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, int max_n,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter);

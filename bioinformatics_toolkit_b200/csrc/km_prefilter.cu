@@ -1,12 +1,13 @@
 // km_prefilter.cu — k-mer mask first stage of the thresholded scan (plan_km.h has the maths).
 //
-//   alive(u) = T_0[8-mer at u] & T_1[8-mer at u+8] & ... & T_{nt-1}[8-mer at u+8(nt-1)]        (256-bit masks)
+//   alive(u) = T_0[k-mer at u] & T_1[k-mer at u + L_0] & ... & T_{nt-1}[k-mer at u + L_0 + .. + L_{nt-2}]    (256-bit masks)
 //
-// The tables (nt x 2 MiB per block of 128 motifs) stay in L2; every stored position gathers one
-// 32-byte sector per table with a single 256-bit load (ld.global.nc.v8.u32 — sm_100), the next
-// table only while the AND is still non-zero.  The measured bound is the gather rate of the SM's
-// L1 (about one sector per clock and SM: experiments/masktab/l2gather.cu, 2.7 ms for 3 x 249 M
-// sectors), not bytes — hence 256 combos per sector and as few tables as the motif lengths allow.
+// (table t indexed by an 8-, 9- or 10-mer: 2, 8 or 32 MiB.)  The tables of the running block stay
+// in L2; every stored position gathers one 32-byte sector per table with a single 256-bit load
+// (ld.global.nc.v8.u32 — sm_100), the next table only while the AND is still non-zero.  The
+// measured bound is the gather rate of the SM's L1 (about one sector per clock and SM, the same
+// for 4 MiB and 64 MiB of tables: experiments/masktab/l2gather.cu, l2gather_L.cu), not bytes —
+// hence 256 combos per sector and a selective first table.
 //
 // One persistent CTA per SM (32 warps) pulls work items (block, 8192 positions).  A surviving bit
 // (position, combo) goes into the warp's shared-memory queue; whenever 32 are queued the warp runs
@@ -31,7 +32,6 @@ constexpr int kKmMinItemPos = kKmIterPos;        // launches cover multiples of 
 constexpr int kKmHaloWords = 4;                  // 64 stored bases in front of the item (window starts reach back n-1 <= 63)
 constexpr int kKmSeqWords = kKmHaloWords + kKmMaxIters * kKmIterPos / 16 + 5;   // windows end <= 7 + 64 bases after the item's last position
 constexpr int kKmQueue = 64;
-constexpr size_t kKmTableBytes = (size_t)kKmEntries * kKmWords * 4;      // 2 MiB
 
 struct Mask { uint32_t v[8]; };
 
@@ -46,36 +46,34 @@ __device__ __forceinline__ uint32_t mask_any(const Mask& m) {
     return (m.v[0] | m.v[1] | m.v[2]) | (m.v[3] | m.v[4] | m.v[5]) | (m.v[6] | m.v[7]);
 }
 
-// Table build: bit j of T_t[x] = (sum_p wdef[t][j][p][base p of x] <= dsafe[j]).  grid = (256, nt), one 8-mer per thread.
-__global__ void __launch_bounds__(256) km_build_kernel(const double* __restrict__ wdef, const double* __restrict__ dsafe,
-                                                       uint32_t* __restrict__ tables) {
+// Table build: bit j of T[x] = (sum_{p<L} wdef[j][p][base p of x] <= dsafe[j]).  One L-mer x per thread.
+__global__ void __launch_bounds__(256) km_build_kernel(const double* __restrict__ wdef, const double* __restrict__ dsafe, int L,
+                                                       uint32_t* __restrict__ table) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_w = reinterpret_cast<double*>(smem_raw);               // [256][8][4]
-    double* s_d = s_w + kKmCombos * 32;                              // [256]
-    const int t = blockIdx.y;
-    const double* src = wdef + (size_t)t * kKmCombos * 32;
-    for (int i = threadIdx.x; i < kKmCombos * 32; i += blockDim.x) s_w[i] = src[i];
+    double* s_w = reinterpret_cast<double*>(smem_raw);               // [256][kKmMaxL][4]
+    double* s_d = s_w + kKmCombos * kKmMaxL * 4;                     // [256]
+    for (int i = threadIdx.x; i < kKmCombos * kKmMaxL * 4; i += blockDim.x) s_w[i] = wdef[i];
     for (int i = threadIdx.x; i < kKmCombos; i += blockDim.x) s_d[i] = dsafe[i];
     __syncthreads();
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    int off[8];
+    int off[kKmMaxL];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) off[p] = 4 * p + (int)((x >> (2 * p)) & 3u);
+    for (int p = 0; p < kKmMaxL; ++p) off[p] = 4 * p + (int)((x >> (2 * p)) & 3u);     // p >= L: base 0 of an all-zero row
     uint32_t out[kKmWords];
 #pragma unroll 1
     for (int w = 0; w < kKmWords; ++w) {
         uint32_t bits = 0;
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < 32; ++j) {
-            const double* wd = s_w + (w * 32 + j) * 32;
+            const double* wd = s_w + (w * 32 + j) * (kKmMaxL * 4);
             double s = wd[off[0]];
 #pragma unroll
-            for (int p = 1; p < 8; ++p) s = __dadd_rn(s, wd[off[p]]);
+            for (int p = 1; p < kKmMaxL; ++p) if (p < L) s = __dadd_rn(s, wd[off[p]]);
             bits |= (s <= s_d[w * 32 + j]) ? (1u << j) : 0u;
         }
         out[w] = bits;
     }
-    uint4* dst = reinterpret_cast<uint4*>(tables + ((size_t)t * kKmEntries + x) * kKmWords);
+    uint4* dst = reinterpret_cast<uint4*>(table + (size_t)x * kKmWords);
     dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
     dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
@@ -142,8 +140,9 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
     int qcnt = 0;
     const uint8_t* tp[NT];
     int tsh[NT];
+    uint32_t tmk[NT];
 #pragma unroll
-    for (int s = 0; s < NT; ++s) { tp[s] = tab + (size_t)db.order[s] * kKmTableBytes; tsh[s] = 16 * db.order[s]; }
+    for (int s = 0; s < NT; ++s) { tp[s] = tab + db.table_off[s]; tsh[s] = db.shift[s]; tmk[s] = db.kmask[s]; }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         Mask m[2];
@@ -154,14 +153,14 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
             const int wi = (p >> 4) + kKmHaloWords, s2 = 2 * (p & 15);
             const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
             x[j] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
-            m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & 0xFFFFu) * 32);
+            m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32);
         }
 #pragma unroll
         for (int s = 1; s < NT; ++s) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (mask_any(m[j])) {
-                    const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x[j] >> tsh[s]) & 0xFFFFu) * 32);
+                    const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x[j] >> tsh[s]) & tmk[s]) * 32);
 #pragma unroll
                     for (int w = 0; w < 8; ++w) m[j].v[w] &= t.v[w];
                 }
@@ -245,7 +244,7 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
             for (int i = tid; i < nw; i += kKmThreads) sh.seq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
         }
         __syncthreads();
-        const uint8_t* tab = tables + db.table_off;
+        const uint8_t* tab = tables;
         const unsigned long long combo_base = (unsigned long long)blk * kKmCombos;
         switch (db.nt) {
             case 1: km_item<1>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
@@ -263,14 +262,14 @@ namespace pwmscan {
 
 size_t km_q16_smem_bytes(int max_n) { return (size_t)kKmCombos * max_n * 8; }
 
-// Builds the nt mask tables of one block on the device (stream-ordered).
-int km_build_tables(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int nt, uint8_t* d_tables) {
-    const int smem = (kKmCombos * 32 + kKmCombos) * 8;
+// Builds one mask table (4^L entries) on the device (stream-ordered).  d_wdef: [256][kKmMaxL][4], d_dsafe: [256].
+int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int L, uint8_t* d_table) {
+    const int smem = (kKmCombos * kKmMaxL * 4 + kKmCombos) * 8;
     if (!ctx->km_build_attr_set) {
         PWM_CUDA(cudaFuncSetAttribute(km_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ctx->km_build_attr_set = true;
     }
-    km_build_kernel<<<dim3(kKmEntries / 256, nt), 256, smem, ctx->stream>>>(d_wdef, d_dsafe, reinterpret_cast<uint32_t*>(d_tables));
+    km_build_kernel<<<(unsigned)(((size_t)1 << (2 * L)) / 256), 256, smem, ctx->stream>>>(d_wdef, d_dsafe, L, reinterpret_cast<uint32_t*>(d_table));
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;
 }

@@ -3,12 +3,14 @@
 // Necessary condition used (same deficits as plan.h): a window can be a hit only if its total
 // deficit sum_k d_k(b_k) stays <= Dsafe, hence only if the deficit of EVERY sub-window stays
 // <= Dsafe.  A block holds up to 256 combos (128 motifs x 2 strands) = the 256 bits of a 32-byte
-// mask.  Table t (t < nt <= 4) has one mask per 8-mer (65 536 x 32 B = 2 MiB, L2-resident): bit j of
-// T_t[x] says "the 8 bases x, read as motif columns c_j + 8t .. c_j + 8t + 7 of combo j, cost at most
-// Dsafe_j" (columns outside [0, n) cost nothing).  For the stored sequence position u the kernel
-// gathers T_t[8-mer at u + 8t], ANDs the masks, and a surviving bit j is the window that starts at
-// u - c_j.  Every combo picks its own offset c_j in [-7, n-1] (which 8-column windows the tables
-// see); the product of the windows' pass rates under iid uniform bases is what c_j minimises.
+// mask.  Table t (t < nt <= 4) has one mask per L_t-mer, L_t = 8, 9 or 10 (4^L x 32 B = 2, 8 or 32 MiB,
+// L2-resident): bit j of T_t[x] says "the L_t bases x, read as motif columns c_j + off_t ..
+// c_j + off_t + L_t - 1 of combo j, cost at most Dsafe_j" (columns outside [0, n) cost nothing;
+// off_t = L_0 + .. + L_{t-1}).  For the stored sequence position u the kernel gathers
+// T_t[L_t-mer at u + off_t], ANDs the masks, and a surviving bit j is the window that starts at
+// u - c_j.  Every combo picks its own offset c_j in [-(L_0 - 1), n-1] (which windows the tables see);
+// the product of the windows' pass rates under iid uniform bases is what c_j minimises.  The block
+// picks the layout (L_t) that minimises gathered sectors + 6 x first-stage survivors per position.
 //
 // Survivors (~0.1 per position for 200 combos at p = 1e-5) go through a middle stage in the same
 // kernel: the whole-window deficit in 16-bit fixed point from shared memory (q16), and what is left
@@ -23,8 +25,11 @@ constexpr int kKmCombos = 256;                  // bits of one mask entry
 constexpr int kKmMotifsPerBlock = 128;
 constexpr int kKmWords = kKmCombos / 32;        // 8 x uint32 = one 32-byte sector
 constexpr int kKmMaxTables = 4;
-constexpr int kKmEntries = 65536;               // 8-mers
+constexpr int kKmMinL = 8, kKmMaxL = 10;        // window lengths: 8-, 9- or 10-mers (2, 8, 32 MiB per table)
+constexpr size_t kKmMaxTableBytes = (size_t)72 << 20;   // per block, so that the tables of the running block stay in the 126 MB L2
 constexpr int kKmQ = 4000;                      // fixed-point budget of the middle stage; entries saturate at 4095 (12 bits)
+
+inline size_t km_table_bytes(int L) { return ((size_t)1 << (2 * L)) * kKmWords * 4; }
 
 struct KmCombo {
     int motif = -1, strand = 0, n = 0, c = 0;
@@ -37,9 +42,11 @@ struct KmCombo {
 struct KmBlockPlan {
     int nt = 1;
     int max_n = 1;
+    int L[kKmMaxTables] = {8, 8, 8, 8};         // window length of table t
+    int off[kKmMaxTables] = {0, 8, 16, 24};     // table t sees motif columns c + off[t] .. c + off[t] + L[t] - 1
     int order[kKmMaxTables] = {0, 1, 2, 3};     // gather order: most selective table first
     KmCombo combo[kKmCombos];
-    std::vector<double> wdef;                   // [nt][256][8][4] deficit of base b at window position p (0 outside the motif)
+    std::vector<double> wdef;                   // [nt][256][kKmMaxL][4] deficit of base b at window position p (0 outside the motif)
     std::vector<double> dsafe;                  // [256]; < 0: bit never set
     // Middle-stage rows, [256][max_n] x 8 bytes, visited in order of decreasing expected deficit (early exit):
     // four 16-bit fields (bases A, C, G, T), bits 0..11 the quantised deficit of the row's motif column;
@@ -49,32 +56,53 @@ struct KmBlockPlan {
     double cand_rate = 0;                       // expected candidates (middle-stage survivors) per position
     double req_rate = 0;                        // expected table sectors gathered per position
     double cost = 0;
+    size_t table_bytes() const { size_t t = 0; for (int i = 0; i < nt; ++i) t += km_table_bytes(L[i]); return t; }
 };
 
 namespace detail {
 
-// P(sum of the deficits of columns [a, a+8) ∩ [0, n) <= dsafe), exact: meet in the middle over two
-// halves of <= 4 columns (256 sums each).
-inline double km_window_pass(const ComboDef& cd, int a) {
-    const int lo = std::max(0, a), hi = std::min(cd.n, a + 8);
-    if (hi <= lo) return 1.0;
-    const int mid = lo + (hi - lo) / 2;
-    auto sums = [&](int x0, int x1, std::vector<double>& out) {
-        out.assign(1, 0.0);
-        for (int k = x0; k < x1; ++k) {
-            std::vector<double> nx(out.size() * 4);
-            for (size_t i = 0; i < out.size(); ++i)
-                for (int b = 0; b < 4; ++b) nx[i * 4 + b] = out[i] + cd.dk[k][b];
-            out.swap(nx);
+// Pass rates P(window deficit <= dsafe) of the windows [a, a+L) ∩ [0, n), L = 8, 9, 10, for every start
+// a in [-9, n-1], under iid uniform bases: 128-bin convolution of the per-column deficits (rounded to
+// the nearest bin: a planning estimate, not a bound).  out[L-8][a+9].
+inline void km_window_rates(const ComboDef& cd, std::vector<float> out[3]) {
+    constexpr int NB = 128;
+    const int n = cd.n;
+    for (int l = 0; l < 3; ++l) out[l].assign(n + 9, 1.0f);
+    if (!(cd.dsafe > 0)) {                       // only zero-deficit windows pass
+        for (int l = 0; l < 3; ++l)
+            for (int a = -9; a < n; ++a) {
+                double p = 1;
+                for (int k = std::max(0, a); k < std::min(n, a + 8 + l); ++k) { int z = 0; for (int b = 0; b < 4; ++b) z += cd.dk[k][b] <= 0; p *= z / 4.0; }
+                out[l][a + 9] = (float)p;
+            }
+        return;
+    }
+    std::vector<int> q((size_t)n * 4);
+    const double sc = NB / cd.dsafe;
+    for (int k = 0; k < n; ++k)
+        for (int b = 0; b < 4; ++b) { const double v = std::floor(cd.dk[k][b] * sc + 0.5); q[4 * k + b] = v > NB ? NB + 1 : (int)v; }
+    double h[NB + 1], nx[NB + 1];
+    for (int a = -9; a < n; ++a) {
+        std::fill(h, h + NB + 1, 0.0);
+        h[0] = 1.0;
+        int top = 0;                              // highest occupied bin
+        for (int j = 0; j < kKmMaxL; ++j) {
+            const int k = a + j;
+            if (k >= 0 && k < n) {
+                std::fill(nx, nx + NB + 1, 0.0);
+                int ntop = 0;
+                for (int s = 0; s <= top; ++s) if (h[s] != 0)
+                    for (int b = 0; b < 4; ++b) { const int t = s + q[4 * k + b]; if (t <= NB) { nx[t] += 0.25 * h[s]; ntop = std::max(ntop, t); } }
+                std::copy(nx, nx + NB + 1, h);
+                top = ntop;
+            }
+            if (j + 1 >= kKmMinL) {
+                double t = 0;
+                for (int s = 0; s <= top; ++s) t += h[s];
+                out[j + 1 - kKmMinL][a + 9] = (float)t;
+            }
         }
-    };
-    std::vector<double> A, B;
-    sums(lo, mid, A);
-    sums(mid, hi, B);
-    std::sort(B.begin(), B.end());
-    double cnt = 0;
-    for (double x : A) cnt += (double)(std::upper_bound(B.begin(), B.end(), cd.dsafe - x) - B.begin());
-    return cnt / ((double)A.size() * (double)B.size());
+    }
 }
 
 // P(sum over all columns of the clamped deficits <= limit), 1024-bin convolution (rounded down, so a slight over-estimate)
@@ -97,70 +125,101 @@ inline double km_total_pass(const ComboDef& cd, double limit) {
     return t;
 }
 
+struct KmConfig { int nt; int L[kKmMaxTables]; };
+// table layouts the planner chooses from (sum of L <= 32: the kernel indexes them from one 64-bit window of 32 bases)
+inline const std::vector<KmConfig>& km_configs() {
+    static const std::vector<KmConfig> c = {
+        {1, {8, 0, 0, 0}},  {2, {8, 8, 0, 0}},  {3, {8, 8, 8, 0}},  {4, {8, 8, 8, 8}},
+        {1, {9, 0, 0, 0}},  {2, {9, 9, 0, 0}},  {3, {9, 9, 9, 0}},
+        {1, {10, 0, 0, 0}}, {2, {10, 10, 0, 0}}, {3, {10, 10, 8, 0}}, {3, {10, 10, 9, 0}},
+    };
+    return c;
+}
+
 }  // namespace detail
 
-// Builds the plan of one block.  `in`: 256 combos (motif < 0 = unused bit).
-inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, int force_nt = 0) {
+// Builds the plan of one block.  `in`: 256 combos (motif < 0 = unused bit).  force_nt / force_L restrict the layouts tried.
+inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, int force_nt = 0, int force_L = 0) {
     std::vector<ComboDef> defs(kKmCombos);
     int max_n = 1;
     for (int ci = 0; ci < kKmCombos; ++ci)
         if (in[ci].motif >= 0) { combo_deficits(in[ci], defs[ci]); max_n = std::max(max_n, in[ci].n); }
-    // pass rate of every window start a in [-7, n-1], per combo
-    std::vector<std::vector<double>> pass(kKmCombos);
-    for (int ci = 0; ci < kKmCombos; ++ci) {
-        const ComboDef& cd = defs[ci];
-        if (!cd.present || !cd.possible) continue;
-        pass[ci].resize(cd.n + 7);
-        for (int a = -7; a < cd.n; ++a) pass[ci][a + 7] = detail::km_window_pass(cd, a);
-    }
-    auto pass_at = [&](int ci, int a) { return (a < -7 || a >= defs[ci].n) ? 1.0 : pass[ci][a + 7]; };
+    std::vector<std::vector<float>> rates((size_t)kKmCombos * 3);
+    for (int ci = 0; ci < kKmCombos; ++ci)
+        if (defs[ci].present && defs[ci].possible) detail::km_window_rates(defs[ci], &rates[(size_t)ci * 3]);
+    auto pass_at = [&](int ci, int L, int a) -> double {
+        return (a <= -L || a >= defs[ci].n) ? 1.0 : (double)rates[(size_t)ci * 3 + (L - kKmMinL)][a + 9];
+    };
     bool have = false;
     KmBlockPlan best;
-    for (int nt = 1; nt <= kKmMaxTables; ++nt) {
-        if (force_nt && nt != force_nt) continue;
-        if (!force_nt && nt > 1 && 8 * (nt - 1) >= max_n + 7) break;       // the extra table could never see a column
+    for (const detail::KmConfig& cf : detail::km_configs()) {
+        if (force_nt && cf.nt != force_nt) continue;
+        if (force_L && cf.L[0] != force_L) continue;
         KmBlockPlan cur;
-        cur.nt = nt; cur.max_n = max_n;
-        double tab_sum[kKmMaxTables] = {0, 0, 0, 0};
-        for (int ci = 0; ci < kKmCombos; ++ci) {
-            KmCombo& kc = cur.combo[ci];
-            kc = KmCombo();
-            const ComboDef& cd = defs[ci];
-            if (!cd.present) continue;
-            kc.motif = in[ci].motif; kc.strand = in[ci].strand; kc.n = in[ci].n;
-            if (!cd.possible) continue;
-            kc.enabled = true;
-            double bestp = 2; int bestc = 0;
-            for (int c = -7; c < cd.n; ++c) {
-                double p = 1;
-                for (int t = 0; t < nt; ++t) p *= pass_at(ci, c + 8 * t);
-                if (p < bestp) { bestp = p; bestc = c; }
+        cur.nt = cf.nt; cur.max_n = max_n;
+        int o = 0;
+        for (int t = 0; t < cf.nt; ++t) { cur.L[t] = cf.L[t]; cur.off[t] = o; o += cf.L[t]; }
+        if (cur.table_bytes() > kKmMaxTableBytes) continue;
+        if (!force_nt && cf.nt > 1 && cur.off[cf.nt - 1] >= max_n + cf.L[0] - 1) continue;     // the last table could never see a column
+        // Every combo picks its offset c.  What it costs the block: its chance of keeping the AND non-zero after
+        // the first gathered table (a second sector, weight alpha = d sectors / d lambda = exp(-lambda)) and its
+        // first-stage survivors (weight kSurvClk).  Solved by a few rounds per choice of the first table.
+        constexpr double kSurvClk = 6.0;
+        double req = 0;
+        bool have_cur = false;
+        KmBlockPlan trial = cur;
+        for (int first = 0; first < cur.nt; ++first) {
+            double alpha = 1.0;
+            for (int round = 0; round < 3; ++round) {
+                double tab_sum[kKmMaxTables] = {0, 0, 0, 0};
+                trial.surv_rate = 0;
+                for (int ci = 0; ci < kKmCombos; ++ci) {
+                    KmCombo& kc = trial.combo[ci];
+                    kc = KmCombo();
+                    const ComboDef& cd = defs[ci];
+                    if (!cd.present) continue;
+                    kc.motif = in[ci].motif; kc.strand = in[ci].strand; kc.n = in[ci].n;
+                    if (!cd.possible) continue;
+                    kc.enabled = true;
+                    double bestv = 1e300, bestp = 1; int bestc = 0;
+                    for (int c = -(cur.L[0] - 1); c < cd.n; ++c) {
+                        double p = 1;
+                        for (int t = 0; t < cur.nt; ++t) p *= pass_at(ci, cur.L[t], c + cur.off[t]);
+                        const double v = (cur.nt > 1 ? alpha * pass_at(ci, cur.L[first], c + cur.off[first]) : 0.0) + kSurvClk * p;
+                        if (v < bestv) { bestv = v; bestp = p; bestc = c; }
+                    }
+                    kc.c = bestc; kc.sigma1 = bestp;
+                    for (int t = 0; t < cur.nt; ++t) { kc.pass[t] = pass_at(ci, cur.L[t], bestc + cur.off[t]); tab_sum[t] += kc.pass[t]; }
+                    trial.surv_rate += bestp;
+                }
+                for (int t = 0; t < kKmMaxTables; ++t) trial.order[t] = t;
+                std::stable_sort(trial.order, trial.order + cur.nt, [&](int a, int b) { return tab_sum[a] < tab_sum[b]; });
+                // sectors gathered per position: table order[0] always, the next one only while the AND is still non-zero
+                double r = 1;
+                for (int s = 1; s < cur.nt; ++s) {
+                    double lam = 0;                                           // expected surviving bits after the first s tables
+                    for (int ci = 0; ci < kKmCombos; ++ci) if (trial.combo[ci].enabled) {
+                        double p = 1;
+                        for (int k = 0; k < s; ++k) p *= trial.combo[ci].pass[trial.order[k]];
+                        lam += p;
+                    }
+                    r += 1.0 - std::exp(-lam);
+                }
+                const double cost = r + kSurvClk * trial.surv_rate;
+                if (!have_cur || cost < cur.cost) { cur = trial; cur.cost = cost; req = r; have_cur = true; }
+                alpha = std::exp(-tab_sum[first]);
+                if (cur.nt == 1) break;
             }
-            kc.c = bestc; kc.sigma1 = bestp;
-            for (int t = 0; t < nt; ++t) { kc.pass[t] = pass_at(ci, bestc + 8 * t); tab_sum[t] += kc.pass[t]; }
-            cur.surv_rate += bestp;
-        }
-        for (int t = 0; t < kKmMaxTables; ++t) cur.order[t] = t;
-        std::stable_sort(cur.order, cur.order + nt, [&](int a, int b) { return tab_sum[a] < tab_sum[b]; });
-        // sectors gathered per position: table order[0] always, the next one only while the AND is still non-zero
-        double req = 1;
-        for (int s = 1; s < nt; ++s) {
-            double lam = 0;                                               // expected surviving bits after the first s tables
-            for (int ci = 0; ci < kKmCombos; ++ci) if (cur.combo[ci].enabled) {
-                double p = 1;
-                for (int k = 0; k < s; ++k) p *= cur.combo[ci].pass[cur.order[k]];
-                lam += p;
-            }
-            req += 1.0 - std::exp(-lam);
+            if (cur.nt == 1) break;
         }
         cur.req_rate = req;
-        // clocks per position and SM: one gathered sector per clock (measured), ~2.5 clocks per middle-stage candidate
-        cur.cost = req + 2.5 * cur.surv_rate;
+        // (clocks per position and SM, measured on B200 / C2: about one gathered sector per clock, ~6 clocks per
+        //  first-stage survivor for queueing + middle stage)
         if (!have || cur.cost < best.cost) { best = std::move(cur); have = true; }
     }
     bp = std::move(best);
     const int nt = bp.nt;
-    bp.wdef.assign((size_t)nt * kKmCombos * 32, 0.0);
+    bp.wdef.assign((size_t)nt * kKmCombos * kKmMaxL * 4, 0.0);
     bp.dsafe.assign(kKmCombos, -1.0);
     bp.q16.assign((size_t)kKmCombos * max_n * 4, 0);
     bp.cand_rate = 0;
@@ -170,10 +229,10 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
         const ComboDef& cd = defs[ci];
         bp.dsafe[ci] = cd.dsafe;
         for (int t = 0; t < nt; ++t)
-            for (int p = 0; p < 8; ++p) {
-                const int col = kc.c + 8 * t + p;
+            for (int p = 0; p < bp.L[t]; ++p) {
+                const int col = kc.c + bp.off[t] + p;
                 if (col < 0 || col >= cd.n) continue;
-                for (int b = 0; b < 4; ++b) bp.wdef[(((size_t)t * kKmCombos + ci) * 8 + p) * 4 + b] = cd.dk[col][b];
+                for (int b = 0; b < 4; ++b) bp.wdef[(((size_t)t * kKmCombos + ci) * kKmMaxL + p) * 4 + b] = cd.dk[col][b];
             }
         const double scale = cd.dsafe > 0 ? (double)kKmQ / cd.dsafe : 1e300;
         int perm[kMaxCols];
@@ -203,7 +262,7 @@ struct KmHostPlan {
 };
 
 inline void build_km_host_plan(const std::vector<MotifHost>& mh, const std::vector<int64_t>& col_off, int64_t total_cols2,
-                               const double* thres, int strands, int skip, KmHostPlan& hp, int force_nt = 0) {
+                               const double* thres, int strands, int skip, KmHostPlan& hp, int force_nt = 0, int force_L = 0) {
     const int M = (int)mh.size();
     hp.th.assign((size_t)total_cols2, 0.0);
     for (int m = 0; m < M; ++m)
@@ -237,7 +296,7 @@ inline void build_km_host_plan(const std::vector<MotifHost>& mh, const std::vect
             in[ci].motif = m; in[ci].strand = s; in[ci].n = mh[m].n; in[ci].tab16 = mh[m].tab16[s].data();
             in[ci].th_last = hp.th[(size_t)col_off[2 * m + s] + mh[m].n - 1];
         }
-        km_build_block(in, hp.blocks[b], force_nt);
+        km_build_block(in, hp.blocks[b], force_nt, force_L);
     };
     {
         const int nth = std::max(1, std::min<int>(nblocks, (int)std::min<unsigned>(8u, std::thread::hardware_concurrency())));

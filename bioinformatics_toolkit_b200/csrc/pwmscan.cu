@@ -469,7 +469,7 @@ extern "C" int pwmscan_plan_info(const pwmscan_plan* pl, double* out, int n) {
         v[2] = (double)pl->km_generic.size();
         v[3] = pl->km_cand_rate;
         v[4] = 0;
-        for (const auto& b : pl->km_blocks) v[4] += (double)b.nt * kKmEntries * kKmWords * 4;    // L2-resident table bytes
+        for (const auto& b : pl->km_blocks) v[4] += (double)b.table_bytes();    // mask table bytes (one block's share is L2-resident at a time)
         v[5] = pl->km_nblocks;
         v[6] = pl->km_surv_rate;               // expected first-stage survivors per position
     } else if (pl->mode == PWM_MODE_MMA) {
@@ -616,8 +616,8 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
         if ((rc = up((void**)&pl->d_btiles, ht.data(), ht.size(), "upload btiles"))) return bail(rc);
     } else {                                 // k-mer mask tables in L2: blocks of 128 motifs, any motif length
         KmHostPlan kp;
-        const char* fnt = std::getenv("PWMSCAN_FORCE_NT");
-        build_km_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, kp, fnt ? std::atoi(fnt) : 0);
+        const char *fnt = std::getenv("PWMSCAN_FORCE_NT"), *fl = std::getenv("PWMSCAN_FORCE_L");
+        build_km_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, kp, fnt ? std::atoi(fnt) : 0, fl ? std::atoi(fl) : 0);
         pl->max_n = kp.max_n;
         pl->km_blocks = std::move(kp.blocks);
         pl->km_nblocks = (int)pl->km_blocks.size();
@@ -633,9 +633,12 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
         for (int b = 0; b < pl->km_nblocks; ++b) {
             KmBlockPlan& bp = pl->km_blocks[b];
             hb[b].nt = bp.nt; hb[b].max_n = bp.max_n;
-            for (int t = 0; t < 4; ++t) hb[b].order[t] = bp.order[t];
-            hb[b].table_off = (int64_t)table_bytes;
-            table_bytes += (size_t)bp.nt * kKmEntries * kKmWords * 4;
+            int64_t toff[kKmMaxTables] = {0, 0, 0, 0};
+            for (int t = 0; t < bp.nt; ++t) { toff[t] = (int64_t)table_bytes; table_bytes += km_table_bytes(bp.L[t]); }
+            for (int s = 0; s < 4; ++s) {
+                const int t = s < bp.nt ? bp.order[s] : 0;
+                hb[b].shift[s] = 2 * bp.off[t]; hb[b].kmask[s] = (1u << (2 * bp.L[t])) - 1u; hb[b].table_off[s] = toff[t];
+            }
             hb[b].q16_off = (int64_t)hq.size();
             hq.insert(hq.end(), bp.q16.begin(), bp.q16.end());
             w_off[b] = hw.size();
@@ -650,8 +653,9 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
                 hc[(size_t)b * kKmCombos + ci] = dc;
             }
             if (verbose)
-                std::fprintf(stderr, "[pwmscan] kmer block %d: nt=%d order=%d%d%d%d cols %d..%d enabled=%d sectors/pos=%.3f survivors/pos=%.4f cand/pos=%.3e cost=%.3f\n",
-                             b, bp.nt, bp.order[0], bp.order[1], bp.order[2], bp.order[3], nmin, nmax, nen, bp.req_rate, bp.surv_rate, bp.cand_rate, bp.cost);
+                std::fprintf(stderr, "[pwmscan] kmer block %d: nt=%d L=%d,%d,%d,%d order=%d%d%d%d cols %d..%d enabled=%d sectors/pos=%.3f survivors/pos=%.4f cand/pos=%.3e cost=%.3f\n",
+                             b, bp.nt, bp.L[0], bp.nt > 1 ? bp.L[1] : 0, bp.nt > 2 ? bp.L[2] : 0, bp.nt > 3 ? bp.L[3] : 0, bp.order[0], bp.order[1], bp.order[2], bp.order[3],
+                             nmin, nmax, nen, bp.req_rate, bp.surv_rate, bp.cand_rate, bp.cost);
             std::vector<double>().swap(bp.wdef);         // only needed for the device build
             std::vector<uint16_t>().swap(bp.q16);
         }
@@ -667,8 +671,14 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
             if ((e = cudaMalloc((void**)&pl->d_km_tables, table_bytes)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(kmer tables)"));
             if ((rc = up((void**)&d_w, hw.data(), hw.size() * 8, "upload window deficits"))) return bail(rc);
             if ((rc = up((void**)&d_d, hd.data(), hd.size() * 8, "upload dsafe"))) { cudaFree(d_w); return bail(rc); }
-            for (int b = 0; b < pl->km_nblocks && rc == 0; ++b)
-                rc = km_build_tables(ctx, d_w + w_off[b], d_d + (size_t)b * kKmCombos, hb[b].nt, pl->d_km_tables + hb[b].table_off);
+            for (int b = 0; b < pl->km_nblocks && rc == 0; ++b) {
+                const KmBlockPlan& bp = pl->km_blocks[b];
+                for (int s = 0; s < bp.nt && rc == 0; ++s) {
+                    const int t = bp.order[s];
+                    rc = km_build_table(ctx, d_w + w_off[b] + (size_t)t * kKmCombos * kKmMaxL * 4, d_d + (size_t)b * kKmCombos, bp.L[t],
+                                        pl->d_km_tables + hb[b].table_off[s]);
+                }
+            }
             e = cudaStreamSynchronize(ctx->stream);
             cudaFree(d_w); cudaFree(d_d);
             if (rc) return bail(rc);

@@ -7,7 +7,9 @@ hits come back in the reference's order (region, motif, forward hits ascending, 
 ascending).  The per-hit BED score (toAffinity of 1 - cdf) is host-side formatting, as in Haskell.
 """
 import math
+import os
 import sys
+import time
 
 import numpy as np
 
@@ -85,11 +87,15 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
     if not motifs:
         return 0 if out is not None else []
     bg = motifs[0]._background
+    trace = os.environ.get("PWMSCAN_APP_TIMING") is not None
+    t_start = time.perf_counter()
     mo = _lib.DeviceMotifs(ctx, [m._motif_pwm._mat for m in motifs], bg.freqs)
     for i, m in enumerate(motifs):                                 # findTFBSWith takes the stored sigmas
         mo.set_sigma(i, 0, m._motif_sigma)
         mo.set_sigma(i, 1, m._motif_sigma_rc)
     plan = _lib.Plan(mo, [m._cutoff for m in motifs], strands=2, skip_ambiguous=True)
+    if trace:
+        print("[scanMotif] motifs + plan %.1f ms" % (1e3 * (time.perf_counter() - t_start)), file=sys.stderr)
     nlen = np.array([size(m._motif_pwm) for m in motifs], dtype=np.int64)
     names = [m._motif_name for m in motifs]
     valid = np.zeros(256, dtype=bool)
@@ -110,8 +116,11 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
         lens = np.array([c.size for c in chunks], dtype=np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         data = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+        t_scan = time.perf_counter()
         h = plan.scan_host(data, seg_off=off, uppercase=True)
         n = len(h)
+        if trace:
+            print("[scanMotif] scan_host %d regions, %d bases, %d hits: %.1f ms" % (len(regs), data.size, n, 1e3 * (time.perf_counter() - t_scan)), file=sys.stderr)
         if n == 0:
             return
         # per-hit p-value and affinity, motif by motif (hits grouped with one stable argsort)
@@ -187,6 +196,12 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
             submit(regs, chunks)
             regs, chunks, nb = [], [], 0
     submit(regs, chunks)
+    # release the device tables now (hundreds of MiB for 800 motifs) rather than whenever the collector gets to them
+    t_free = time.perf_counter()
+    plan.free()
+    mo.free()
+    if trace:
+        print("[scanMotif] free %.1f ms, total %.1f ms" % (1e3 * (time.perf_counter() - t_free), 1e3 * (time.perf_counter() - t_start)), file=sys.stderr)
     return total if out is not None else results
 
 

@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 
@@ -617,6 +618,7 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
     } else {                                 // k-mer mask tables in L2: blocks of 128 motifs, any motif length
         KmHostPlan kp;
         const char *fnt = std::getenv("PWMSCAN_FORCE_NT"), *fl = std::getenv("PWMSCAN_FORCE_L");
+        const auto t_plan0 = std::chrono::steady_clock::now();
         build_km_host_plan(mo->mh, mo->col_off, mo->total_cols2, thres, strands, pl->skip, kp, fnt ? std::atoi(fnt) : 0, fl ? std::atoi(fl) : 0);
         pl->max_n = kp.max_n;
         pl->km_blocks = std::move(kp.blocks);
@@ -659,6 +661,7 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
             std::vector<double>().swap(bp.wdef);         // only needed for the device build
             std::vector<uint16_t>().swap(bp.q16);
         }
+        const auto t_plan1 = std::chrono::steady_clock::now();
         if (verbose) std::fprintf(stderr, "[pwmscan] generic combos=%zu cand_rate=%.3e\n", pl->km_generic.size(), pl->cand_rate);
         if ((rc = up((void**)&pl->d_th, kp.th.data(), kp.th.size() * 8, "upload th"))) return bail(rc);
         if ((rc = up((void**)&pl->d_km_blocks, hb.data(), hb.size() * sizeof(DevKmBlock), "upload kmer blocks"))) return bail(rc);
@@ -683,6 +686,12 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
             cudaFree(d_w); cudaFree(d_d);
             if (rc) return bail(rc);
             if (e != cudaSuccess) return bail(cuda_fail(ctx, e, "kmer table build"));
+        }
+        if (verbose) {
+            const auto t_plan2 = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[pwmscan] kmer plan: host %.1f ms, upload + device table build (%.0f MiB) %.1f ms\n",
+                         std::chrono::duration<double, std::milli>(t_plan1 - t_plan0).count(), table_bytes / 1048576.0,
+                         std::chrono::duration<double, std::milli>(t_plan2 - t_plan1).count());
         }
     }
     *out = pl;

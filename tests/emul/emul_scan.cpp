@@ -196,3 +196,95 @@ int64_t emul_mma_scan(int M, const int* ncol, const double* mats, const double* 
     }
     return (int64_t)hits.size();
 }
+
+// ---- k-mer mask first stage: the host plan (csrc/plan_km.h) evaluated with plain loops ---------------------
+// The device gathers precomputed masks; here every mask bit is recomputed on the fly with the same fp64 sum
+// (km_build_kernel's order) and the middle stage decodes the same packed q16 rows as km_drain.
+#include "../../bioinformatics_toolkit_b200/csrc/plan_km.h"
+
+extern "C" __attribute__((visibility("default")))
+int64_t emul_km_scan(int M, const int* ncol, const double* mats, const double* bg, const double* thres, int strands,
+                     const unsigned char* ascii, int64_t len, int force_nt, int force_L,
+                     int32_t* out_motif, unsigned char* out_strand, int64_t* out_pos, double* out_sc, int64_t cap, int64_t* stats) {
+    std::vector<MotifHost> mh(M);
+    std::vector<int64_t> col_off(2 * (size_t)M);
+    int64_t cols = 0;
+    const double* p = mats;
+    for (int m = 0; m < M; ++m) {
+        motif_prepare(mh[m], ncol[m], p, bg);
+        p += 4 * ncol[m];
+        for (int s = 0; s < 2; ++s) { col_off[2 * m + s] = cols; cols += ncol[m]; }
+    }
+    KmHostPlan hp;
+    build_km_host_plan(mh, col_off, cols, thres, strands, 1, hp, force_nt, force_L);
+    const int64_t kRound = 16384 * 32;
+    const int64_t n_anchor = (len + kPadFront + 64 + kRound - 1) / kRound * kRound;
+    std::vector<uint32_t> seq2_alloc((size_t)(n_anchor / 16 + 9), 0u), mask((size_t)(n_anchor / 32 + 4), 0u);
+    uint32_t* seq2 = seq2_alloc.data() + 1;
+    for (int64_t u = 0; u < (int64_t)mask.size() * 32; ++u) {
+        const int64_t pos = u - kPadFront;
+        const int code = (pos >= 0 && pos < len) ? iupac_code(ascii[pos]) : 15;
+        uint32_t c2;
+        if (code < 4) c2 = (uint32_t)code; else { c2 = pad_hash(u); mask[u >> 5] |= 1u << (u & 31); }
+        seq2[u >> 4] |= c2 << (2 * (u & 15));
+    }
+    struct Hit { int32_t motif; unsigned char strand; int64_t pos; double sc; };
+    std::vector<Hit> hits;
+    int64_t nsurv = 0, ncand = 0;
+    const int64_t scan_to = std::min<int64_t>(n_anchor, len + kPadFront + 64);
+    for (size_t b = 0; b < hp.blocks.size(); ++b) {
+        const KmBlockPlan& bp = hp.blocks[b];
+        for (int ci = 0; ci < kKmCombos; ++ci) {
+            const KmCombo& kc = bp.combo[ci];
+            if (kc.motif < 0 || bp.dsafe[ci] < 0) continue;
+            for (int64_t u = 0; u < scan_to; ++u) {
+                bool alive = true;
+                for (int t = 0; t < bp.nt && alive; ++t) {
+                    const double* wd = &bp.wdef[(((size_t)t * kKmCombos + ci) * kKmMaxL) * 4];
+                    double s = wd[packed_base(seq2, u + bp.off[t])];
+                    for (int q = 1; q < bp.L[t]; ++q) s = s + wd[4 * q + packed_base(seq2, u + bp.off[t] + q)];
+                    alive = s <= bp.dsafe[ci];
+                }
+                if (!alive) continue;
+                ++nsurv;
+                const int64_t i = u - kPadFront - kc.c;
+                if (i < 0 || i + kc.n > len) continue;
+                uint32_t sum = 0;                              // middle stage (km_drain)
+                for (int r = 0; r < kc.n; ++r) {
+                    const uint16_t* row = &bp.q16[((size_t)ci * bp.max_n + r) * 4];
+                    const int col = (row[0] >> 12) | ((row[1] >> 12) << 4);
+                    sum += row[packed_base(seq2, i + kPadFront + col)] & 0xFFFu;
+                    if (sum > (uint32_t)kKmQ) break;
+                }
+                if (sum > (uint32_t)kKmQ) continue;
+                ++ncand;
+                double sc;
+                if (replay_skip(seq2, mask.data(), i + kPadFront, kc.n, mh[kc.motif].tab16[kc.strand].data(),
+                                hp.th.data() + col_off[2 * kc.motif + kc.strand], &sc))
+                    hits.push_back({kc.motif, (unsigned char)kc.strand, i, sc});
+            }
+        }
+    }
+    for (auto& g : hp.generic) {
+        const int m = g.first, s = g.second, n = mh[m].n;
+        for (int64_t i = 0; i + n <= len; ++i) {
+            double sc;
+            if (replay_skip(seq2, mask.data(), i + kPadFront, n, mh[m].tab16[s].data(), hp.th.data() + col_off[2 * m + s], &sc))
+                hits.push_back({m, (unsigned char)s, i, sc});
+        }
+    }
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) {
+        if (a.motif != b.motif) return a.motif < b.motif;
+        if (a.strand != b.strand) return a.strand < b.strand;
+        return a.pos < b.pos;
+    });
+    for (size_t k = 0; k < hits.size() && (int64_t)k < cap; ++k) {
+        out_motif[k] = hits[k].motif; out_strand[k] = hits[k].strand; out_pos[k] = hits[k].pos; out_sc[k] = hits[k].sc;
+    }
+    if (stats) {
+        stats[0] = ncand; stats[1] = (int64_t)(1e6 * hp.cand_rate); stats[2] = (int64_t)hp.blocks.size(); stats[3] = (int64_t)hp.generic.size();
+        stats[4] = hp.blocks.empty() ? 0 : hp.blocks[0].nt; stats[5] = hp.blocks.empty() ? 0 : hp.blocks[0].L[0];
+        stats[6] = nsurv; stats[7] = (int64_t)(1e6 * hp.surv_rate);
+    }
+    return (int64_t)hits.size();
+}

@@ -156,3 +156,61 @@ def test_mma_plan_pvalue_cutoffs_are_tight(emul_mma, oracle, ref_motifs, ref_mot
     o = tuple(np.concatenate([r[k] for r in ref]) for k in range(4))
     assert _same(h, o) and len(o[0]) > 10
     assert st[0] < 30 * len(o[0]) + 200
+
+
+@pytest.fixture(scope="module")
+def emul_km(emul):
+    L = C.CDLL(os.path.join(HERE, "emul", "libemul.so"))
+    L.emul_km_scan.restype = C.c_int64
+
+    def run(mats, thres, dna, strands=2, force_nt=0, force_L=0, bg=BG):
+        ncol = np.array([m.shape[0] for m in mats], dtype=np.int32)
+        flat = np.concatenate([np.ascontiguousarray(m, dtype=np.float64).reshape(-1) for m in mats])
+        cap = 1 << 21
+        om, os_, op, osc = np.empty(cap, np.int32), np.empty(cap, np.uint8), np.empty(cap, np.int64), np.empty(cap)
+        st = np.zeros(8, np.int64)
+        bga, th = np.array(bg, float), np.array(thres, float)
+        d = np.ascontiguousarray(np.frombuffer(bytes(dna), dtype=np.uint8))
+        vp = C.c_void_p
+        n = L.emul_km_scan(C.c_int(len(mats)), ncol.ctypes.data_as(vp), flat.ctypes.data_as(vp), bga.ctypes.data_as(vp),
+                           th.ctypes.data_as(vp), C.c_int(strands), d.ctypes.data_as(vp), C.c_int64(d.size), C.c_int(force_nt), C.c_int(force_L),
+                           om.ctypes.data_as(vp), os_.ctypes.data_as(vp), op.ctypes.data_as(vp), osc.ctypes.data_as(vp),
+                           C.c_int64(cap), st.ctypes.data_as(vp))
+        assert 0 <= n <= cap
+        return (om[:n].copy(), os_[:n].copy(), op[:n].copy(), osc[:n].copy()), st
+    return run
+
+
+@pytest.mark.parametrize("force_nt,force_L", [(0, 0), (1, 8), (2, 9), (3, 10), (4, 8)])
+def test_km_plan_never_loses_a_hit(emul_km, oracle, force_nt, force_L):
+    """csrc/plan_km.h: the k-mer mask bits (window deficit <= Dsafe, the sum km_build_kernel forms) and the
+    12-bit middle stage, evaluated with plain loops, must keep every window the oracle reports — for every
+    table layout, motifs of 5..40 columns, N runs, an unreachable and an always-true cutoff."""
+    mats = synth.synth_pwms(40, 23, nmin=5, nmax=40)
+    dna = synth.synth_dna(30000, 10, gc=0.45, n_runs=[(0, 30), (12000, 500), (29990, 10)])
+    thres = [0.55 * oracle.optimal_score(BG, m) for m in mats]
+    thres[3] = -1e9
+    thres[4] = 2.0 * abs(thres[4]) + 50
+    h, st = emul_km(mats, thres, dna[:5000], force_nt=force_nt, force_L=force_L)
+    cnt, o = oracle.scan_mt(BG, mats, thres, dna[:5000], mode=1, nthreads=4, cap=1 << 21)
+    assert cnt > 100 and _same(h, o)
+    assert st[3] == 0                                    # no motif-length limit on this path
+    if force_nt:
+        assert st[4] == force_nt and st[5] == force_L
+
+
+def test_km_plan_pvalue_cutoffs_are_selective(emul_km, oracle, ref_motifs, ref_motifs_meme):
+    """At p-value cutoffs the two stages must be tight: candidates close to the hit count, first-stage
+    survivors within a small factor of the planner's own estimate."""
+    mats = [m for _, m in ref_motifs] + [m for _, m in ref_motifs_meme]
+    dna = synth.synth_dna(60000, 3)
+    thres = [oracle.pvalue_to_score(1e-4, BG, m) for m in mats]
+    h, st = emul_km(mats, thres, dna, strands=1)
+    ref = []
+    for m, (mat, th) in enumerate(zip(mats, thres)):
+        pos, sc = oracle.find_tfbs(BG, mat, dna, th, True)
+        ref.append((np.full(pos.size, m, np.int32), np.zeros(pos.size, np.uint8), pos, sc))
+    o = tuple(np.concatenate([r[k] for r in ref]) for k in range(4))
+    assert _same(h, o) and len(o[0]) > 10
+    assert st[0] < 1.2 * len(o[0]) + 20                  # middle stage: candidates ~ hits
+    assert st[6] < 3.0 * st[7] * 1e-6 * dna.size + 200   # first stage: survivors ~ the plan's estimate

@@ -809,9 +809,29 @@ __device__ __forceinline__ int find_segment(const int64_t* __restrict__ seg_off,
     return lo;
 }
 
-__device__ __forceinline__ unsigned long long hit_key(int seg, int motif, int strand, int64_t pos_in_seg) {
-    return ((unsigned long long)seg << 48) | ((unsigned long long)motif << 33) | ((unsigned long long)strand << 32) |
+// Sort key of a hit, packed as tightly as this scan allows so that the radix sort runs over as few bits as
+// possible: [segment | motif : mb bits | strand : 1 bit | position in segment : pb bits].
+struct KeyLayout { int pb, mb; };
+__device__ __forceinline__ unsigned long long hit_key(KeyLayout kl, int seg, int motif, int strand, int64_t pos_in_seg) {
+    return ((((((unsigned long long)seg << kl.mb) | (unsigned long long)motif) << 1) | (unsigned long long)strand) << kl.pb) |
            (unsigned long long)pos_in_seg;
+}
+
+// Appends the hits of the calling lanes with one atomicAdd per warp (all lanes of the warp that are in the
+// surrounding loop iteration must call it; `hit` selects the ones that have something to append).
+__device__ __forceinline__ void append_hits(bool hit, unsigned long long key, double sc, unsigned long long* __restrict__ hit_keys,
+                                            double* __restrict__ hit_sc, unsigned long long hit_cap, unsigned long long* counters) {
+    const unsigned act = __activemask();
+    const unsigned bal = __ballot_sync(act, hit);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)bal) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&counters[1], (unsigned long long)__popc(bal));
+    base = __shfl_sync(act, base, leader);
+    if (hit) {
+        const unsigned long long slot = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
+        if (slot < hit_cap) { hit_keys[slot] = key; hit_sc[slot] = sc; }
+    }
 }
 
 __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsigned long long cand_cap,
@@ -819,24 +839,29 @@ __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsi
                                const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
                                const double* __restrict__ tab16, const double* __restrict__ th,
                                unsigned long long* __restrict__ hit_keys, double* __restrict__ hit_sc,
-                               unsigned long long hit_cap, unsigned long long* counters) {
+                               unsigned long long hit_cap, unsigned long long* counters, KeyLayout kl) {
     unsigned long long ncand = counters[0];
     if (ncand > cand_cap) ncand = cand_cap;
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < ncand;
          k += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long cd = cand[k];
-        if (cd == ~0ull) continue;                       // unused slot of a warp's chunk (tensor-core prefilter)
-        const DevCombo cb = combos[cd >> 40];
-        const int64_t u = (int64_t)(cd & ((1ull << 40) - 1));
-        const int64_t i = u - kPadFront - cb.c;
-        if (cb.motif < 0 || i < 0 || i + cb.n > len) continue;
-        const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
-        if (i + cb.n > seg_off[seg + 1]) continue;
-        double sc;
-        if (replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
-            const unsigned long long slot = atomicAdd(&counters[1], 1ull);
-            if (slot < hit_cap) { hit_keys[slot] = hit_key(seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+        bool hit = false;
+        unsigned long long key = 0;
+        double sc = 0.0;
+        if (cd != ~0ull) {                               // ~0: unused slot of a warp's chunk (tensor-core prefilter)
+            const DevCombo cb = combos[cd >> 40];
+            const int64_t u = (int64_t)(cd & ((1ull << 40) - 1));
+            const int64_t i = u - kPadFront - cb.c;
+            if (cb.motif >= 0 && i >= 0 && i + cb.n <= len) {
+                const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
+                if (i + cb.n <= seg_off[seg + 1] &&
+                    replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
+                    hit = true;
+                    key = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]);
+                }
+            }
         }
+        append_hits(hit, key, sc, hit_keys, hit_sc, hit_cap, counters);
     }
 }
 
@@ -848,7 +873,7 @@ __global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec
                                       const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
                                       const double* __restrict__ tab16, const double* __restrict__ th,
                                       unsigned long long* __restrict__ hit_keys, double* __restrict__ hit_sc,
-                                      unsigned long long hit_cap, unsigned long long* counters) {
+                                      unsigned long long hit_cap, unsigned long long* counters, KeyLayout kl) {
     unsigned long long nrec = counters[0];
     if (nrec > cap) nrec = cap;
     const int lane = threadIdx.x & 31;
@@ -877,22 +902,22 @@ __global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec
         double sc;
         if (replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
             const unsigned long long slot = atomicAdd(&counters[1], 1ull);
-            if (slot < hit_cap) { hit_keys[slot] = hit_key(seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+            if (slot < hit_cap) { hit_keys[slot] = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
         }
     }
 }
 
 // Sorted (key, score) pairs -> the column layout handed to the caller (one D2H copy).
-__global__ void decode_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, long long n,
+__global__ void decode_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, long long n, KeyLayout kl,
                               long long* __restrict__ pos, double* __restrict__ score, int32_t* __restrict__ motif,
                               int32_t* __restrict__ segment, uint8_t* __restrict__ strand) {
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const unsigned long long key = keys[k];
-        pos[k] = (long long)(key & 0xFFFFFFFFull);
+        pos[k] = (long long)(key & ((1ull << kl.pb) - 1ull));
         score[k] = sc[k];
-        motif[k] = (int32_t)((key >> 33) & 0x7FFF);
-        segment[k] = (int32_t)(key >> 48);
-        strand[k] = (uint8_t)((key >> 32) & 1);
+        strand[k] = (uint8_t)((key >> kl.pb) & 1ull);
+        motif[k] = (int32_t)((key >> (kl.pb + 1)) & ((1ull << kl.mb) - 1ull));
+        segment[k] = (int32_t)(key >> (kl.pb + 1 + kl.mb));
     }
 }
 
@@ -902,7 +927,7 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
                              const uint32_t* __restrict__ mask, const uint8_t* __restrict__ ascii,
                              const int64_t* __restrict__ seg_off, int nseg, int64_t len, const double* __restrict__ tab16,
                              const double* __restrict__ th, unsigned long long* __restrict__ hit_keys,
-                             double* __restrict__ hit_sc, unsigned long long hit_cap, unsigned long long* counters) {
+                             double* __restrict__ hit_sc, unsigned long long hit_cap, unsigned long long* counters, KeyLayout kl) {
   for (int ci = blockIdx.y; ci < ncombo; ci += gridDim.y) {
     const DevCombo cb = combos[ci];
     const double* tb = tab16 + cb.tab_off;
@@ -925,7 +950,7 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
         }
         if (hit) {
             const unsigned long long slot = atomicAdd(&counters[1], 1ull);
-            if (slot < hit_cap) { hit_keys[slot] = hit_key(seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+            if (slot < hit_cap) { hit_keys[slot] = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
         }
     }
   }
@@ -951,6 +976,13 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     const pwmscan_motifs* mo = pl->motifs;
     const int64_t len = seq->len;
     const int64_t n_anchor = round_up(len + kPadFront + 64, kAnchorRound);
+    auto bits_for = [](uint64_t max_value) { int b = 1; while (b < 63 && (max_value >> b) != 0) ++b; return b; };
+    int64_t max_seg = 0;
+    for (int32_t g = 0; g < seq->nseg; ++g) max_seg = std::max(max_seg, seq->seg_off[g + 1] - seq->seg_off[g]);
+    KeyLayout kl;
+    kl.pb = bits_for((uint64_t)max_seg); kl.mb = bits_for((uint64_t)std::max(1, mo->M - 1));
+    const int key_bits = kl.pb + 1 + kl.mb + bits_for((uint64_t)std::max(1, seq->nseg - 1));
+    if (key_bits > 64) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: segments x motifs x segment length exceed the 64-bit hit key");
     auto items_of = [&](long long anchors, int iters) {
         long long t = 0;
         for (int b = 0; b < pl->nblocks; ++b) t += (anchors / ((long long)kWarps * 32 * iters)) / pl->blocks[b].rep;
@@ -1061,11 +1093,11 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
             if (use_mma)
                 rescore_chunks_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(d_cand, cand_cap, pl->d_mma_blocks, pl->d_btiles, d_combos, seq->d_seq2, seq->d_mask,
                                                                                   seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                                                  d_sc, hit_cap, ctx->d_counters);
+                                                                                  d_sc, hit_cap, ctx->d_counters, kl);
             else
                 rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, d_combos, seq->d_seq2, seq->d_mask,
                                                                           seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                                          d_sc, hit_cap, ctx->d_counters);
+                                                                          d_sc, hit_cap, ctx->d_counters, kl);
             PWM_CUDA(cudaGetLastError());
         }
         if (!generic.empty() && len > 0) {
@@ -1073,7 +1105,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
             const long long gx = std::min<long long>((len + bs - 1) / bs, 65535LL * 16);
             dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(generic.size(), 65535));
             exact_kernel<<<grid, bs, 0, ctx->stream>>>(d_generic, (int)generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
-                                                      seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, hit_cap, ctx->d_counters);
+                                                      seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, hit_cap, ctx->d_counters, kl);
             PWM_CUDA(cudaGetLastError());
         }
         PWM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1098,12 +1130,12 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         double* d_sc2 = (double*)scratch_get(ctx, 5, nhits * 8);
         if (!d_keys2 || !d_sc2) { delete h; return PWMSCAN_ECUDA; }
         size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, 64, ctx->stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, key_bits, ctx->stream);
         const size_t n8 = (nhits + 7) & ~7ull;                       // keeps every column 8-byte aligned
         const size_t col_bytes = n8 * 25;
         unsigned char* d_tmp = (unsigned char*)scratch_get(ctx, 6, tmp_bytes + 256 + col_bytes);
         if (!d_tmp) { delete h; return PWMSCAN_ECUDA; }
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, 64, ctx->stream);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, key_bits, ctx->stream);
         if (e != cudaSuccess) { delete h; return cuda_fail(ctx, e, "cub::DeviceRadixSort"); }
         unsigned char* d_cols = d_tmp + ((tmp_bytes + 255) & ~(size_t)255);
         long long* c_pos = (long long*)d_cols;
@@ -1111,7 +1143,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         int32_t* c_mo = (int32_t*)(d_cols + n8 * 16);
         int32_t* c_sg = (int32_t*)(d_cols + n8 * 20);
         uint8_t* c_st = (uint8_t*)(d_cols + n8 * 24);
-        decode_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_keys2, d_sc2, (long long)nhits, c_pos, c_sc, c_mo, c_sg, c_st);
+        decode_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_keys2, d_sc2, (long long)nhits, kl, c_pos, c_sc, c_mo, c_sg, c_st);
         if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "decode_kernel"); }
         cudaEventRecord(ctx->ev[3], ctx->stream);
         h->buf = pin_pool_get(ctx, col_bytes, &h->buf_bytes);

@@ -64,3 +64,69 @@ def merge_hits(per_item):
     cols = [np.concatenate([np.asarray(h[k]) for h in per_item]) for k in range(5)]
     order = np.lexsort((cols[3], cols[2], cols[1], cols[0]))
     return tuple(c[order] for c in cols)
+
+
+class ScanWorkers:
+    """Several independent scans in flight on ONE device.
+
+    A rank that owns many (motif block x chromosome chunk) items does not have to run them one
+    after the other: every worker is a library context of its own (its own stream, scratch
+    buffers and copy of the plan) driven by a host thread (the C calls release the GIL), so the
+    tail of one item — exact replay, sort, decode, hit-list D2H — overlaps the prefilter kernel of
+    the next item.  Same results as scanning the items sequentially, in the order given.
+    (Haskell side: `mapConcurrently` over the items with one `withDevice` context per worker.)
+    """
+
+    def __init__(self, device, mats, bg, thres, strands=2, skip_ambiguous=True, workers=2):
+        from concurrent.futures import ThreadPoolExecutor
+        from . import _lib
+        self._lib = _lib
+        self.ctxs = [_lib.Context(device) for _ in range(workers)]
+        self.motifs = [_lib.DeviceMotifs(c, mats, bg) for c in self.ctxs]
+        self.plans = [_lib.Plan(m, thres, strands=strands, skip_ambiguous=skip_ambiguous) for m in self.motifs]
+        self.pool = ThreadPoolExecutor(workers)
+
+    def __len__(self):
+        return len(self.ctxs)
+
+    def upload(self, arrays):
+        """Packs every array into HBM; item i lives with worker i mod k."""
+        return [self._lib.DeviceSeq(self.ctxs[i % len(self.ctxs)], a) for i, a in enumerate(arrays)]
+
+    def _run(self, items, fn):
+        k = len(self.ctxs)
+        out = [None] * len(items)
+        timing = [dict() for _ in range(k)]
+
+        def work(w):
+            for i in range(w, len(items), k):
+                out[i] = fn(w, items[i])
+                for key, v in self.ctxs[w].timing().items():
+                    timing[w][key] = timing[w].get(key, 0.0) + float(v)
+        for f in [self.pool.submit(work, w) for w in range(k)]:
+            f.result()
+        total = {}
+        for t in timing:
+            for key, v in t.items():
+                total[key] = total.get(key, 0.0) + v
+        return out, total
+
+    def scan(self, dev_seqs, consume=None):
+        """dev_seqs from `upload`.  Returns ([Hits per item], summed device timing).  With `consume`, every
+        hit list is handed to consume(hits) in its worker thread and only the return value is kept — the
+        pinned hit buffer goes back to the pool at once instead of piling up until the end (a streaming
+        consumer, like the BED writer of scan_motif)."""
+        c = consume or (lambda h: h)
+        return self._run(dev_seqs, lambda w, s: c(self.plans[w].scan(s)))
+
+    def scan_host(self, arrays, consume=None):
+        """Host byte arrays (pinned for full PCIe speed) -> ([Hits per item], summed device timing)."""
+        c = consume or (lambda h: h)
+        return self._run(arrays, lambda w, a: c(self.plans[w].scan_host(a)))
+
+    def close(self):
+        self.pool.shutdown()
+        for p in self.plans:
+            p.free()
+        for m in self.motifs:
+            m.free()

@@ -316,3 +316,25 @@ print("VARIANT-PARITY-OK")
     env = dict(os.environ, PWMSCAN_PREFILTER=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "VARIANT-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_scan_workers_overlap_same_results(ctx):
+    """shard.ScanWorkers: two contexts / host threads with scans in flight on one device give exactly the
+    hit lists of a sequential scan, item by item, for resident and for host inputs."""
+    from bioinformatics_toolkit_b200.shard import ScanWorkers
+    mats = synth.synth_pwms(30, 77, nmin=6, nmax=24)
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    th = mo.pvalue_to_score(1e-4)
+    plan = _lib.Plan(mo, th)
+    chunks = [synth.synth_dna(300_000 + 7919 * i, 100 + i, gc=0.4 + 0.02 * i, n_runs=[(1000 * i, 50)]) for i in range(5)]
+    ref = [plan.scan_host(c) for c in chunks]
+    w = ScanWorkers(0, mats, BG, th, workers=2)
+    try:
+        for hits, t in (w.scan(w.upload(chunks)), w.scan_host(chunks)):
+            assert t["prefilter_launches"] >= len(chunks)
+            for a, b in zip(hits, ref):
+                assert len(a) == len(b) and len(b) > 50
+                assert np.array_equal(a.motif, b.motif) and np.array_equal(a.strand, b.strand) and np.array_equal(a.pos, b.pos)
+                assert np.array_equal(a.score.view(np.uint64), b.score.view(np.uint64))
+    finally:
+        w.close()

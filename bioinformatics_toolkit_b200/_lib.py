@@ -256,8 +256,8 @@ class DeviceMotifs:
 class _HitsHandle:
     """Owns a pwmscan_hits (pinned host columns); released when the last array view dies."""
 
-    def __init__(self, L, h):
-        self.L, self.h = L, h
+    def __init__(self, ctx, h):
+        self.ctx, self.L, self.h = ctx, ctx.L, h        # the hit buffer goes back to the context's pool: keep the context alive
 
     def __del__(self):
         try:
@@ -349,7 +349,7 @@ class Plan:
 
     def _hits(self, hh):
         L = self.ctx.L
-        owner = _HitsHandle(L, hh)
+        owner = _HitsHandle(self.ctx, hh)
         n = L.pwmscan_hits_count(hh)
         if n == 0:
             return Hits(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0))

@@ -147,14 +147,15 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
     for (int it = 0; it < iters; ++it) {
         Mask m[2];
         unsigned long long x[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int p = it * kKmIterPos + warp * 64 + 32 * j + lane;
+        {   // a thread takes two adjacent positions (even, odd): the same three 2-bit words serve both
+            const int p = it * kKmIterPos + warp * 64 + 2 * lane;
             const int wi = (p >> 4) + kKmHaloWords, s2 = 2 * (p & 15);
             const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
-            x[j] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
-            m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32);
+            x[0] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
+            x[1] = (unsigned long long)__funnelshift_r(w0, w1, s2 + 2) | ((unsigned long long)__funnelshift_r(w1, w2, s2 + 2) << 32);
         }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32);
 #pragma unroll
         for (int s = 1; s < NT; ++s) {
 #pragma unroll
@@ -168,7 +169,7 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const uint32_t p = (uint32_t)(it * kKmIterPos + warp * 64 + 32 * j + lane);
+            const uint32_t p = (uint32_t)(it * kKmIterPos + warp * 64 + 2 * lane + j);
             uint32_t any = mask_any(m[j]);
             unsigned bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
             while (bal) {

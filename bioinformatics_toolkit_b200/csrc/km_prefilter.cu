@@ -35,11 +35,18 @@ constexpr int kKmQueue = 64;
 
 struct Mask { uint32_t v[8]; };
 
-__device__ __forceinline__ Mask ldg_mask(const uint8_t* p) {
+// One 256-bit load = one mask.  The tables are the only data worth keeping in L2 (the genome and the hit
+// lists stream through once), so the loads carry an evict_last cache policy.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ Mask ldg_mask(const uint8_t* p, uint64_t pol) {
     Mask r;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ uint32_t mask_any(const Mask& m) {
@@ -138,6 +145,7 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* q = sh.queue[warp];
     int qcnt = 0;
+    const uint64_t pol = l2_keep_policy();
     const uint8_t* tp[NT];
     int tsh[NT];
     uint32_t tmk[NT];
@@ -155,13 +163,13 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
             x[1] = (unsigned long long)__funnelshift_r(w0, w1, s2 + 2) | ((unsigned long long)__funnelshift_r(w1, w2, s2 + 2) << 32);
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32);
+        for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32, pol);
 #pragma unroll
         for (int s = 1; s < NT; ++s) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (mask_any(m[j])) {
-                    const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x[j] >> tsh[s]) & tmk[s]) * 32);
+                    const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x[j] >> tsh[s]) & tmk[s]) * 32, pol);
 #pragma unroll
                     for (int w = 0; w < 8; ++w) m[j].v[w] &= t.v[w];
                 }

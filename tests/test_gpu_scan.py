@@ -338,3 +338,29 @@ def test_scan_workers_overlap_same_results(ctx):
                 assert np.array_equal(a.score.view(np.uint64), b.score.view(np.uint64))
     finally:
         w.close()
+
+
+def test_kmer_tables_extreme_shapes(ctx, oracle):
+    """The k-mer mask first stage at its edges: motifs of 1, 2, 7, 10, 11, 33, 63 and 64 columns in one plan
+    (the tables see at most 32 columns, the middle stage all of them), forward-only with more than 256 motifs
+    (two blocks of 256 single-strand combos), thresholds from loose to consensus-only, a short sequence that
+    is mostly one work item, and a non-uniform background."""
+    bg = (0.2, 0.3, 0.3, 0.2)
+    lengths = [1, 2, 7, 10, 11, 33, 63, 64]
+    mats = synth.synth_pwms(len(lengths), 31, lengths=lengths)
+    dna = synth.synth_dna(70000, 12, gc=0.55, n_runs=[(0, 5), (33000, 200), (69900, 100)])
+    opt = [oracle.optimal_score(bg, m) for m in mats]
+    thres = [0.5 * o for o in opt]
+    thres[3] = opt[3] - 1e-9          # consensus only
+    thres[5], thres[6], thres[7] = -0.6 * opt[5], -1.0 * opt[6], -1.0 * opt[7]      # long motifs: cutoffs that random sequence reaches (71 / 258 / 403 hits)
+    h = gpu_scan(ctx, mats, thres, dna[:20000], bg=bg)
+    o = oracle_scan(oracle, mats, thres, dna[:20000], bg=bg)
+    assert_same(h, o)
+    assert len(h.select(motif=0)) > 1000 and len(h.select(motif=3)) < 10
+    assert all(len(h.select(motif=m)) > 0 for m in (5, 6, 7)), [len(h.select(motif=m)) for m in range(8)]
+    # forward-only, 300 motifs: blocks of 256 + 44 single-strand combos
+    mats = synth.synth_pwms(300, 32, nmin=6, nmax=20)
+    thres = [0.6 * oracle.optimal_score(BG, m) for m in mats]
+    h = gpu_scan(ctx, mats, thres, dna, strands=1)
+    assert_same(h, oracle_scan(oracle, mats, thres, dna, strands=1))
+    assert len(h) > 1000

@@ -102,6 +102,13 @@ class Context:
         return {"prefilter_ms": out[0], "rescore_ms": out[1], "sort_ms": out[2], "device_ms": out[3],
                 "h2d_bytes": out[4], "d2h_bytes": out[5], "candidates": out[6], "prefilter_launches": out[7]}
 
+    def scan_host_first_invalid(self, alphabet="IUPAC"):
+        """fromBS verdict of the bytes of the last Plan.scan_host on this context: offset of the first byte
+        outside the alphabet ("DNA" = ACGT, "IUPAC"), or -1."""
+        pos = C.c_int64(-1)
+        self.check(self.L.pwmscan_scan_host_first_invalid(self.h, C.c_int(0 if alphabet == "DNA" else 1), C.byref(pos)))
+        return int(pos.value)
+
     def close(self):
         if self.h:
             self.L.pwmscan_ctx_destroy(self.h)
@@ -292,6 +299,22 @@ class Hits:
 
     def __len__(self):
         return int(self.pos.size)
+
+    def affinity(self, cdf_off, cdf_x, cdf_y, want_pvalue=False):
+        """scanMotif's per-hit BED score (and p-value) on the device: pwmscan_hits_affinity.  cdf_off[M+1]
+        indexes the concatenated (score, cumulative probability) points of every motif's truncated CDF."""
+        n = len(self)
+        aff = np.empty(n, dtype=np.int64)
+        pv = np.empty(n) if want_pvalue else None
+        owner = getattr(self.pos, "_owner", None)
+        if n:
+            if owner is None or not owner.h:
+                raise ValueError("Hits.affinity needs the library-owned hit list (not a select()/copy)")
+            off, cx, cy = _arr(cdf_off, np.int64), _arr(cdf_x, np.float64), _arr(cdf_y, np.float64)
+            ctx = owner.ctx
+            ctx.check(ctx.L.pwmscan_hits_affinity(ctx.h, owner.h, C.c_int32(off.size - 1), _ptr(off), _ptr(cx), _ptr(cy),
+                                                  _ptr(pv) if want_pvalue else None, _ptr(aff)))
+        return (aff, pv) if want_pvalue else aff
 
     def select(self, motif=None, strand=None, segment=None):
         k = np.ones(self.pos.size, dtype=bool)

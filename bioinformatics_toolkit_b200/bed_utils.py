@@ -4,7 +4,8 @@ CutoffMotif (78-86), mkCutoffMotif (88-98), scanMotif (101-124).  scanMotif batc
 regions: the region bytes are gathered from the genome file, laid end to end (one segment per
 region), packed and scanned on the device in one launch per batch for all motifs and both strands;
 hits come back in the reference's order (region, motif, forward hits ascending, reverse hits
-ascending).  The per-hit BED score (toAffinity of 1 - cdf) is host-side formatting, as in Haskell.
+ascending).  The per-hit BED score (toAffinity of 1 - cdf score) is computed on the device too
+(pwmscan_hits_affinity); `_cdf_vec` / `_affinity_vec` are the host restatement the tests compare it with.
 """
 import math
 import os
@@ -109,35 +110,62 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
     mname_buf = b"".join(names)
     mlen32 = nlen.astype(np.int32)
 
-    def flush(regs, chunks):
+    # every motif's truncated CDF, concatenated, for the device-side per-hit p-value (pwmscan_hits_affinity)
+    cdf_off = np.concatenate([[0], np.cumsum([m._cdf.xs.size for m in motifs])]).astype(np.int64)
+    cdf_x = np.concatenate([m._cdf.xs for m in motifs]) if motifs else np.zeros(0)
+    cdf_y = np.concatenate([m._cdf.ps for m in motifs]) if motifs else np.zeros(0)
+
+    def submit(regs, chunks):
+        """One batch of regions: a single pipelined scan of the concatenated bytes (one segment per region),
+        per-hit scores on the device, BED text in the library."""
         nonlocal total
         if not regs:
             return
+        t_sub = time.perf_counter()
         lens = np.array([c.size for c in chunks], dtype=np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        data = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+        data = np.concatenate(chunks)
         t_scan = time.perf_counter()
         h = plan.scan_host(data, seg_off=off, uppercase=True)
         n = len(h)
         if trace:
-            print("[scanMotif] scan_host %d regions, %d bases, %d hits: %.1f ms" % (len(regs), data.size, n, 1e3 * (time.perf_counter() - t_scan)), file=sys.stderr)
+            print("[scanMotif] concatenate %.1f ms; scan_host %d regions, %d bases, %d hits: %.1f ms"
+                  % (1e3 * (t_scan - t_sub), len(regs), data.size, n, 1e3 * (time.perf_counter() - t_scan)), file=sys.stderr)
+        # fromBS per region (Seq.hs:86-95): a region with a byte outside the IUPAC alphabet is a Left (warning,
+        # skipped).  The pack kernel has already looked at every byte; only if it saw one is the batch examined
+        # region by region on the host.
+        keep = None
+        if data.size and ctx.scan_host_first_invalid("IUPAC") >= 0:
+            bad = ~valid[_UPPER[data]]
+            nz = lens > 0
+            nbad = np.zeros(len(regs), dtype=np.int64)
+            nbad[nz] = np.add.reduceat(bad.astype(np.int64), off[:-1][nz])
+            bad_regions = nbad > 0
+            if warn is not None:
+                for r in (regs[i] for i in np.flatnonzero(bad_regions)):
+                    print("Warning: no sequence for region: " + repr((r[0].decode("latin1"), r[1], r[2])), file=warn)
+            keep = ~bad_regions[h.segment]
         if n == 0:
             return
-        # per-hit p-value and affinity, motif by motif (hits grouped with one stable argsort)
-        score = np.empty(n, dtype=np.int64)
-        order = np.argsort(h.motif, kind="stable")
-        ms = h.motif[order]
-        cuts = np.flatnonzero(np.diff(ms)) + 1
-        for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [n]])):
-            idx = order[a:b]
-            score[idx] = _affinity_vec(1 - _cdf_vec(motifs[int(ms[a])]._cdf, h.score[idx]))
+        # per-hit p-value (1 - cdf score on the motif's truncated CDF) and affinity, on the device
+        t_pv = time.perf_counter()
+        score = h.affinity(cdf_off, cdf_x, cdf_y)
+        seg, mot, strand, pos = h.segment, h.motif, h.strand, h.pos
+        if keep is not None:
+            seg, mot, strand, pos, score = seg[keep], mot[keep], strand[keep], pos[keep], score[keep]
+            n = int(seg.size)
+            if n == 0:
+                return
         total += n
+        if trace:
+            print("[scanMotif] p-values + affinities: %.1f ms" % (1e3 * (time.perf_counter() - t_pv)), file=sys.stderr)
+        t_fmt = time.perf_counter()
         starts = np.array([r[1] for r in regs], dtype=np.int64)
         if out is None:
-            st = starts[h.segment] + h.pos
-            en = st + nlen[h.motif]
+            st = starts[seg] + pos
+            en = st + nlen[mot]
             for k in range(n):
-                results.append((regs[h.segment[k]][0], int(st[k]), int(en[k]), names[h.motif[k]], int(score[k]), h.strand[k] == 0))
+                results.append((regs[seg[k]][0], int(st[k]), int(en[k]), names[mot[k]], int(score[k]), strand[k] == 0))
             return
         chroms = sorted(set(r[0] for r in regs))
         cidx = {c: i for i, c in enumerate(chroms)}
@@ -147,39 +175,20 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
         text = C.c_char_p()
         tlen = C.c_int64(0)
         p = _lib._ptr
-        rc = L.pwmscan_format_bed6(C.c_int64(n), p(np.ascontiguousarray(h.segment)), p(np.ascontiguousarray(h.motif)),
-                                   p(np.ascontiguousarray(h.strand)), p(np.ascontiguousarray(h.pos)), p(score), p(rchrom), p(starts),
+        rc = L.pwmscan_format_bed6(C.c_int64(n), p(np.ascontiguousarray(seg)), p(np.ascontiguousarray(mot)),
+                                   p(np.ascontiguousarray(strand)), p(np.ascontiguousarray(pos)), p(score), p(rchrom), p(starts),
                                    C.c_char_p(cbuf), p(coff), C.c_char_p(mname_buf), p(mname_off), p(mlen32),
                                    C.byref(text), C.byref(tlen))
         if rc != 0:
             raise _lib.PwmScanError(rc, "pwmscan_format_bed6 failed")
-        out.write(C.string_at(text, tlen.value))
+        out.write(memoryview((C.c_char * tlen.value).from_address(C.cast(text, C.c_void_p).value)))   # no intermediate bytes object
         L.pwmscan_free(text)
-
-    def submit(regs, chunks):
-        """fromBS per region (Seq.hs:86-95), vectorised over the batch: a region with a byte outside the
-        IUPAC alphabet is a Left (warning, skipped)."""
-        if not regs:
-            return
-        lens = np.array([c.size for c in chunks], dtype=np.int64)
-        data = np.concatenate(chunks)
-        if data.size:
-            bad = ~valid[_UPPER[data]]
-            if bad.any():
-                starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
-                nz = lens > 0
-                nbad = np.zeros(len(regs), dtype=np.int64)
-                nbad[nz] = np.add.reduceat(bad.astype(np.int64), starts[nz])
-                keep = nbad == 0
-                for r, k in zip(regs, keep):
-                    if not k and warn is not None:
-                        print("Warning: no sequence for region: " + repr((r[0].decode("latin1"), r[1], r[2])), file=warn)
-                regs = [r for r, k in zip(regs, keep) if k]
-                chunks = [c for c, k in zip(chunks, keep) if k]
-        flush(regs, chunks)
+        if trace:
+            print("[scanMotif] BED text: %.1f ms" % (1e3 * (time.perf_counter() - t_fmt)), file=sys.stderr)
 
     index, hsize, gdata = genome.index, genome.header_size, genome.data
     regs, chunks, nb = [], [], 0
+    t_loop = time.perf_counter()
     for (chr_, start, end) in beds:
         if isinstance(chr_, str):
             chr_ = chr_.encode()
@@ -195,6 +204,8 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
         if nb >= batch_bases or len(regs) >= 65000:
             submit(regs, chunks)
             regs, chunks, nb = [], [], 0
+    if trace:
+        print("[scanMotif] BED loop + region views: %.1f ms (includes earlier batches)" % (1e3 * (time.perf_counter() - t_loop)), file=sys.stderr)
     submit(regs, chunks)
     # release the device tables now (hundreds of MiB for 800 motifs) rather than whenever the collector gets to them
     t_free = time.perf_counter()

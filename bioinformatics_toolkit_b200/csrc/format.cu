@@ -35,26 +35,31 @@ extern "C" int pwmscan_format_bed6(int64_t nhits, const int32_t* segment, const 
     *text = nullptr; *text_len = 0;
     if (nhits == 0) return PWMSCAN_OK;
     const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), nhits / 65536 + 1));
-    std::vector<int64_t> lens((size_t)nthreads + 1, 0);
-    auto line_len = [&](int64_t k) -> int64_t {
+    auto ndigits = [](int64_t v) { int n = v < 0 ? 2 : 1; uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1 : (uint64_t)v; while (u >= 10) { u /= 10; ++n; } return n; };
+    auto line_len = [&](int64_t k) -> int64_t {           // exact
         const int32_t r = segment[k], m = motif[k];
         const int32_t c = region_chrom[r];
-        return (chrom_off[c + 1] - chrom_off[c]) + (motif_off[m + 1] - motif_off[m]) + 3 * 20 + 8;   // upper bound
+        const int64_t st = region_start[r] + pos[k];
+        return (chrom_off[c + 1] - chrom_off[c]) + (motif_off[m + 1] - motif_off[m]) + ndigits(st) + ndigits(st + motif_len[m]) + ndigits(score[k]) + 7;
     };
     auto range = [&](int t, int64_t* a, int64_t* b) { *a = nhits * t / nthreads; *b = nhits * (t + 1) / nthreads; };
-    {   // upper bounds per thread
+    std::vector<int64_t> start((size_t)nthreads + 1, 0);
+    {   // pass 1: exact bytes per thread range, so that every thread can write straight into the one output buffer
         std::vector<std::thread> th;
-        for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t] { int64_t a, b, s = 0; range(t, &a, &b); for (int64_t k = a; k < b; ++k) s += line_len(k); lens[t + 1] = s; });
+        for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t] { int64_t a, b, s = 0; range(t, &a, &b); for (int64_t k = a; k < b; ++k) s += line_len(k); start[t + 1] = s; });
         for (auto& x : th) x.join();
     }
-    std::vector<char*> bufs(nthreads, nullptr);
-    std::vector<int64_t> used(nthreads, 0);
-    for (int t = 0; t < nthreads; ++t) { bufs[t] = (char*)std::malloc((size_t)lens[t + 1] + 1); if (!bufs[t]) { for (auto b : bufs) std::free(b); return PWMSCAN_EINVAL; } }
+    for (int t = 0; t < nthreads; ++t) start[t + 1] += start[t];
+    const int64_t tot = start[nthreads];
+    char* out = (char*)std::malloc((size_t)tot + 1);
+    if (!out) return PWMSCAN_EINVAL;
+    bool ok = true;
     {
         std::vector<std::thread> th;
+        std::vector<char> good((size_t)nthreads, 1);
         for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t] {
             int64_t a, b; range(t, &a, &b);
-            char* p = bufs[t];
+            char* p = out + start[t];
             for (int64_t k = a; k < b; ++k) {
                 const int32_t r = segment[k], m = motif[k], c = region_chrom[r];
                 const int64_t st = region_start[r] + pos[k];
@@ -67,16 +72,13 @@ extern "C" int pwmscan_format_bed6(int64_t nhits, const int32_t* segment, const 
                 *p++ = strand[k] == 0 ? '+' : '-';
                 *p++ = '\n';
             }
-            used[t] = p - bufs[t];
+            good[t] = (p == out + start[t + 1]);
         });
         for (auto& x : th) x.join();
+        for (char g : good) ok = ok && g;
     }
-    int64_t tot = 0;
-    for (int t = 0; t < nthreads; ++t) tot += used[t];
-    char* out = (char*)std::malloc((size_t)tot + 1);
-    if (!out) { for (auto b : bufs) std::free(b); return PWMSCAN_EINVAL; }
-    int64_t o = 0;
-    for (int t = 0; t < nthreads; ++t) { std::memcpy(out + o, bufs[t], (size_t)used[t]); o += used[t]; std::free(bufs[t]); }
+    if (!ok) { std::free(out); return PWMSCAN_EINVAL; }
+    out[tot] = 0;
     *text = out; *text_len = tot;
     return PWMSCAN_OK;
 }

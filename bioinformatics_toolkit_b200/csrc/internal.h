@@ -20,6 +20,7 @@ struct pwmscan_ctx {
     std::string err;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t last_host_non_acgt = -1, last_host_non_iupac = -1;   // fromBS verdict of the last pwmscan_scan_host
     int sm_count = 148;
     bool lut_ready = false, dense_lut_ready = false, smem_attr_set = false, mma_attr_set = false;   // per-context one-time device setup
     bool km_attr_set = false, km_build_attr_set = false;
@@ -132,6 +133,7 @@ struct pwmscan_plan {
     DevCombo* d_km_combos = nullptr;   // km_nblocks * 256
     DevCombo* d_km_generic = nullptr;
     uint8_t* d_km_tables = nullptr;
+    size_t km_tables_cap = 0;          // pooled allocation size
     uint16_t* d_km_q16 = nullptr;
     double km_cand_rate = 0, km_surv_rate = 0, km_req_rate = 0;
 };

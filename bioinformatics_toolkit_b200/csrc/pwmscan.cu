@@ -495,7 +495,7 @@ extern "C" void pwmscan_plan_free(pwmscan_plan* pl) {
     if (pl->d_km_blocks) cudaFree(pl->d_km_blocks);
     if (pl->d_km_combos) cudaFree(pl->d_km_combos);
     if (pl->d_km_generic) cudaFree(pl->d_km_generic);
-    if (pl->d_km_tables) cudaFree(pl->d_km_tables);
+    if (pl->d_km_tables) { if (pl->ctx) dev_pool_put(pl->ctx, pl->d_km_tables, pl->km_tables_cap); else cudaFree(pl->d_km_tables); }
     if (pl->d_km_q16) cudaFree(pl->d_km_q16);
     delete pl;
 }
@@ -671,7 +671,8 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
         if (pl->km_nblocks > 0) {
             // the mask tables are computed on the device from the per-window deficits
             double *d_w = nullptr, *d_d = nullptr;
-            if ((e = cudaMalloc((void**)&pl->d_km_tables, table_bytes)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(kmer tables)"));
+            // from the context's device pool: cudaMalloc / cudaFree of hundreds of MiB per plan cost tens of ms
+            if (!(pl->d_km_tables = (uint8_t*)dev_pool_get(ctx, table_bytes, &pl->km_tables_cap))) return bail(PWMSCAN_ECUDA);
             if ((rc = up((void**)&d_w, hw.data(), hw.size() * 8, "upload window deficits"))) return bail(rc);
             if ((rc = up((void**)&d_d, hd.data(), hd.size() * 8, "upload dsafe"))) { cudaFree(d_w); return bail(rc); }
             for (int b = 0; b < pl->km_nblocks && rc == 0; ++b) {
@@ -1120,7 +1121,10 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         PWM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
         PWM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         PWM_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (job && attempt == 0) seq_finish(ctx, job->seq);
+        if (job && attempt == 0) {
+            seq_finish(ctx, job->seq);
+            ctx->last_host_non_acgt = job->seq->first_non_acgt; ctx->last_host_non_iupac = job->seq->first_non_iupac;
+        }
         ncand = ctx->h_counters[0]; nhits = ctx->h_counters[1];
         if (use_mma && ctx->h_counters[3] != 0) ncand = std::max(ncand, cand_cap) + 2 * ctx->h_counters[3];   // candidates that did not fit
         if (ctx->h_counters[2] & 2ull) return set_err(ctx, PWMSCAN_ECUDA, "pwmscan_scan: tensor-core prefilter pipeline aborted (bounded wait expired)");
@@ -1207,6 +1211,13 @@ extern "C" int pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* pl, const
     ctx->timing[4] = (double)s->len + (double)(nseg + 1) * 8;
     pwmscan_seq_free(s);
     return rc;
+}
+
+extern "C" int pwmscan_scan_host_first_invalid(pwmscan_ctx* ctx, int alphabet, int64_t* pos_out) {
+    if (!ctx || !pos_out || alphabet < 0 || alphabet > 1) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_host_first_invalid: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *pos_out = alphabet == 0 ? ctx->last_host_non_acgt : ctx->last_host_non_iupac;
+    return PWMSCAN_OK;
 }
 
 extern "C" int pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs, const double* thres,

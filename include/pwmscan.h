@@ -119,6 +119,10 @@ int  pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* 
  * (pass {0,len}, 1 for a single sequence).  Same result as seq_upload + scan. */
 int  pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* plan, const uint8_t* ascii, const int64_t* seg_off,
                        int32_t nseg, int flags, pwmscan_hits** out);
+/* fromBS verdict (Seq.hs:86-95) of the bytes the last pwmscan_scan_host on this context consumed: offset in
+ * the concatenated input of the first byte outside the alphabet (0 = ACGT, 1 = IUPAC; after upper-casing
+ * if PWMSCAN_SEQ_UPPERCASE was given), -1 if there is none. */
+int  pwmscan_scan_host_first_invalid(pwmscan_ctx* ctx, int alphabet, int64_t* pos_out);
 /* Convenience: plan_create + scan + plan_free. */
 int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
                        const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);
@@ -169,6 +173,15 @@ int  pwmscan_align_all_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int
 int  pwmscan_align_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int64_t npairs, const int32_t* a,
                          const int32_t* b, int penalty_kind, double gap, int combine_kind,
                          double* dist, uint8_t* same_dir, int32_t* pos);
+
+/* ---- scanMotif's per-hit columns (Data/Bed/Utils.hs:109-123), computed on the device for the hits of a scan:
+ *      p = 1 - cdf score on the motif's (truncated) CDF (Motif.hs:236-249; bit-identical fp64) and
+ *      the BED score toAffinity p = round (1000 / (1 + exp (-(-log10 (max 1e-20 p) - 5)))) (round half even;
+ *      values within 1e-6 of a rounding tie are settled on the host with the C library's log/exp).
+ *      cdf_off[M+1] indexes cdf_x / cdf_y, the (score, cumulative probability) points of every motif
+ *      (pwmscan_cutoff_cdfs' output).  out_pvalue and/or out_affinity may be NULL; hits_count entries. -------- */
+int  pwmscan_hits_affinity(pwmscan_ctx* ctx, const pwmscan_hits* hits, int32_t M, const int64_t* cdf_off,
+                           const double* cdf_x, const double* cdf_y, double* out_pvalue, int64_t* out_affinity);
 
 /* ---- host-side helper: BED6 text of scanMotif hits (toLine, Data/Bed/Types.hs:139-149, of mkBed,
  *      Data/Bed/Utils.hs:109-111).  Names are concatenated bytes with count+1 offsets; region r has

@@ -38,3 +38,40 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_bed6_formatter_host_only():
+    """pwmscan_format_bed6 is pure host code (toLine of mkBed): exact text for random hits, negative numbers,
+    multi-digit boundaries; threads write into one exactly-sized buffer."""
+    import ctypes as C
+    import numpy as np
+    L = C.CDLL(_lib.LIB_PATH)
+    n = 150000
+    rng = np.random.default_rng(1)
+    seg = rng.integers(0, 50, n).astype(np.int32)
+    mot = rng.integers(0, 7, n).astype(np.int32)
+    strand = rng.integers(0, 2, n).astype(np.uint8)
+    pos = rng.integers(0, 10 ** 9, n).astype(np.int64)
+    pos[:20] = [0, 9, 10, 99, 100, 999, 1000, 9999, 10 ** 4, 10 ** 5 - 1, 10 ** 5, 10 ** 6 - 1, 10 ** 6, 10 ** 7, 10 ** 8 - 1, 10 ** 8, 10 ** 9 - 1, 1, 2, 3]
+    score = rng.integers(-5, 1001, n).astype(np.int64)
+    chroms = [b"chr1", b"chrX_long_name", b"c"]
+    rchrom = rng.integers(0, 3, 50).astype(np.int32)
+    rstart = rng.integers(0, 10 ** 8, 50).astype(np.int64)
+    rstart[0] = 0
+    coff = np.concatenate([[0], np.cumsum([len(c) for c in chroms])]).astype(np.int64)
+    names = [b"m%d name" % i for i in range(7)]
+    moff = np.concatenate([[0], np.cumsum([len(c) for c in names])]).astype(np.int64)
+    mlen = rng.integers(5, 30, 7).astype(np.int32)
+    text, tlen = C.c_char_p(), C.c_int64(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    rc = L.pwmscan_format_bed6(C.c_int64(n), p(seg), p(mot), p(strand), p(pos), p(score), p(rchrom), p(rstart),
+                               C.c_char_p(b"".join(chroms)), p(coff), C.c_char_p(b"".join(names)), p(moff), p(mlen),
+                               C.byref(text), C.byref(tlen))
+    assert rc == 0
+    got = C.string_at(text, tlen.value).split(b"\n")
+    L.pwmscan_free.argtypes = [C.c_void_p]
+    L.pwmscan_free(text)
+    assert got[-1] == b"" and len(got) == n + 1
+    for k in list(range(40)) + list(rng.integers(0, n, 2000)):
+        st = int(rstart[seg[k]] + pos[k])
+        assert got[k] == b"%s\t%d\t%d\t%s\t%d\t%s" % (chroms[rchrom[seg[k]]], st, st + mlen[mot[k]], names[mot[k]], score[k], b"+" if strand[k] == 0 else b"-")

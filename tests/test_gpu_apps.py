@@ -144,3 +144,34 @@ def test_command_line_apps(small_genome, tmp_path, oracle):
     assert 1 <= len(Mo.readMEME(outp)) <= 6
     r = subprocess.run([sys.executable, os.path.join(root, "apps", "merge_motifs.py"), "cluster", meme, "-h", "0.3"], capture_output=True, timeout=300)
     assert r.returncode == 0 and sorted(b"\t".join(r.stdout.split(b"\n")[:-1]).split(b"\t")) == sorted(m._name for m in motifs)
+
+
+def test_device_affinity_equals_host_formula():
+    """pwmscan_hits_affinity: per-hit p = 1 - cdf score (bit-identical fp64) and toAffinity p (identical
+    integers, including values near a rounding tie) against the host restatement of Utils.hs:109-123."""
+    from bioinformatics_toolkit_b200 import _lib, bed_utils
+    ctx = _lib.default_context(0)
+    mats = synth.synth_pwms(40, 91, nmin=6, nmax=22)
+    motifs = [Mo.Motif(b"m%d" % i, Mo.PWM(None, m)) for i, m in enumerate(mats)]
+    cms = mkCutoffMotifs(Mo.default_bkgd, 1e-3, motifs, ctx)
+    mo = _lib.DeviceMotifs(ctx, mats, Mo.default_bkgd.freqs)
+    plan = _lib.Plan(mo, [c._cutoff for c in cms])
+    h = plan.scan_host(synth.synth_dna(400_000, 17, gc=0.47))
+    assert len(h) > 5000
+    off = np.concatenate([[0], np.cumsum([c._cdf.xs.size for c in cms])]).astype(np.int64)
+    cx = np.concatenate([c._cdf.xs for c in cms])
+    cy = np.concatenate([c._cdf.ps for c in cms])
+    aff, pv = h.affinity(off, cx, cy, want_pvalue=True)
+    exp_p = np.empty(len(h))
+    for m in range(len(cms)):
+        k = h.motif == m
+        exp_p[k] = 1 - bed_utils._cdf_vec(cms[m]._cdf, h.score[k])
+    assert np.array_equal(pv.view(np.uint64), exp_p.view(np.uint64))
+    assert np.array_equal(aff, np.array([bed_utils.toAffinity(float(p)) for p in exp_p], dtype=np.int64))
+    assert aff.min() >= 0 and aff.max() <= 1000 and np.unique(aff).size > 20
+    # scores outside the CDF's support and exactly on its points
+    aff2 = h.affinity(off, cx + 1000.0, cy)            # every score left of the first point: cdf 0 -> p = 1 -> affinity of 1.0
+    assert np.all(aff2 == bed_utils.toAffinity(1.0))
+    aff3 = h.affinity(off, cx - 1000.0, cy)            # every score right of the last point: cdf = last p
+    last_p = np.array([1 - c._cdf.ps[-1] for c in cms])
+    assert np.array_equal(aff3, np.array([bed_utils.toAffinity(float(last_p[m])) for m in h.motif], dtype=np.int64))

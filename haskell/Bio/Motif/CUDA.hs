@@ -14,6 +14,7 @@ module Bio.Motif.CUDA
     , pValueToScoreGPU
     , scoreCDFGPU
     , scanRegionsGPU
+    , hitsAffinityGPU
     , alignAllPairsGPU
     ) where
 
@@ -49,6 +50,8 @@ foreign import ccall safe "pwmscan_scan_host"        c_scan_host    :: Ptr Ctx -
 foreign import ccall safe "pwmscan_hits_count"       c_hits_count   :: Ptr Hits -> IO Int64
 foreign import ccall safe "pwmscan_hits_columns"     c_hits_columns :: Ptr Hits -> Ptr (Ptr Int32) -> Ptr (Ptr Word8) -> Ptr (Ptr Int32) -> Ptr (Ptr Int64) -> Ptr (Ptr Double) -> IO CInt
 foreign import ccall safe "pwmscan_hits_free"        c_hits_free    :: Ptr Hits -> IO ()
+foreign import ccall safe "pwmscan_hits_affinity"    c_hits_affinity :: Ptr Ctx -> Ptr Hits -> Int32 -> Ptr Int64 -> Ptr Double -> Ptr Double -> Ptr Double -> Ptr Int64 -> IO CInt
+foreign import ccall safe "pwmscan_scan_host_first_invalid" c_first_invalid :: Ptr Ctx -> CInt -> Ptr Int64 -> IO CInt
 foreign import ccall safe "pwmscan_seq_upload"       c_seq_upload   :: Ptr Ctx -> Ptr Word8 -> Int64 -> CInt -> Ptr (Ptr Seq) -> IO CInt
 foreign import ccall safe "pwmscan_seq_free"         c_seq_free     :: Ptr Seq -> IO ()
 foreign import ccall safe "pwmscan_scores"           c_scores       :: Ptr Ctx -> Ptr Seq -> Ptr Motifs -> Int32 -> CInt -> Ptr Double -> Int64 -> IO CInt
@@ -156,6 +159,20 @@ scanRegionsGPU plan bytes lens =
             return [ (fromIntegral g, fromIntegral m, s == 0, fromIntegral q, v) | (g, m, s, q, v) <- zip5' sg ms st ps sc ]
   where zip5' (a:as) (b:bs) (c:cs) (d:ds) (e:es) = (a, b, c, d, e) : zip5' as bs cs ds es
         zip5' _ _ _ _ _ = []
+
+-- | scanMotif's per-hit BED score on the device (Bio/Data/Bed/Utils.hs:109-123): `toAffinity (1 - cdf c sc)` for
+-- every hit of `h`, given every motif's truncated CDF (the `_cdf` fields of the CutoffMotifs) as one
+-- concatenated (offsets, scores, probabilities) triple.  Same integers as the Haskell expression.
+hitsAffinityGPU :: Ptr Hits -> [CDF] -> IO [Int]
+hitsAffinityGPU h cdfs = do
+    cnt <- fromIntegral <$> c_hits_count h
+    let pts  = [ U.toList v | CDF v <- cdfs ]
+        offs = scanl (+) 0 (map length pts)
+    withArray (map fromIntegral offs) $ \poff ->
+      withArray (concatMap (map fst) pts) $ \px -> withArray (concatMap (map snd) pts) $ \py ->
+      allocaArray (max 1 cnt) $ \pa -> do
+        c_hits_affinity theCtx h (fromIntegral $ length cdfs) poff px py nullPtr pa >>= check theCtx
+        map fromIntegral <$> peekArray cnt (pa :: Ptr Int64)
 
 -- | All i<j alignments for `alignmentBy jsd (pFn gap) combFn` (Bio/Motif/Alignment.hs:83-132),
 -- packed upper triangle in the order iterativeMerge initialises its matrix (Bio/Motif/Merge.hs:161-165).

@@ -5,7 +5,8 @@
 //   seq2   2 bits/base, 16 bases per 32-bit word, stored base index u = position + 32
 //   mask   1 bit/base, 1 = not one of ACGT (or padding)
 //   ascii  optional upper-cased copy (IUPAC-aware entry points only)
-//   tables per 64-motif block: nslot x 256 x 32 words, staged into shared memory by the kernel
+//   tables k-mer mask tables per 128-motif block (km_prefilter.cu; default first stage), built on the device;
+//          the other first stages keep their own (shared-memory 4-mer tables / int8 GEMM tiles)
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
@@ -1034,7 +1035,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         const int grid = (int)std::min<long long>(ctx->sm_count, items);
         // Experimental variant (off by default): first-stage slots 0/1 read through TMEM (tcgen05.ld) next to the
         // shared-memory port.  Correct (same parity tests) but measured slower on C2 (9.7 vs 7.6 ms): the extra
-        // R2UR / address instructions cost more issue slots than the second port saves (DESIGN.md §4.1).
+        // R2UR / address instructions cost more issue slots than the second port saves (DESIGN.md §4.9).
         static const bool use_tmem = std::getenv("PWMSCAN_TMEM") != nullptr;
         bool any_full = false;                                        // TMEM serves blocks whose 32 lanes carry distinct motifs
         for (const auto& b : pl->blocks) any_full |= (b.rep == 1);

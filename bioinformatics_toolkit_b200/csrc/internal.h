@@ -96,6 +96,9 @@ struct DevKmBlock {
     uint32_t kmask[4];   // 4^L - 1
     int64_t table_off[4];
     int64_t q16_off;     // uint16 elements into d_km_q16 ([256][max_n][4])
+    int64_t bitmap_off;  // bytes into d_km_tables of the "first mask non-zero" bitmap (one bit per k-mer of step 0)
+    int32_t bitmap_words;  // 32-bit words of it; 0 = this block runs without the bitmap
+    int32_t pad_;
 };
 
 enum { PWM_MODE_LDS = 0, PWM_MODE_MMA = 1, PWM_MODE_KMER = 2 };
@@ -127,6 +130,7 @@ struct pwmscan_plan {
     double mma_cand_rate = 0;
     // k-mer mask first stage (km_prefilter.cu): blocks of 128 motifs
     int km_nblocks = 0, km_max_n = 1;
+    size_t km_smem_bytes = 0;          // dynamic shared memory the prefilter kernel needs (largest block)
     std::vector<pwmscan::KmBlockPlan> km_blocks;
     std::vector<DevCombo> km_generic;
     DevKmBlock* d_km_blocks = nullptr;
@@ -166,7 +170,8 @@ int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap);
 
 int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int L, uint8_t* d_table);
-int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, int max_n,
+int km_build_bitmap(pwmscan_ctx* ctx, const uint8_t* d_table, int L, uint8_t* d_bitmap);
+int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter);
 

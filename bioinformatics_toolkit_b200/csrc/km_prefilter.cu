@@ -26,7 +26,7 @@ using namespace pwmscan;
 namespace {
 
 constexpr int kKmThreads = 1024;
-constexpr int kKmIterPos = 2048;                 // positions per CTA iteration (2 per thread)
+constexpr int kKmIterPos = 2048;                 // item sizes are multiples of this (2 positions per thread)
 constexpr int kKmMaxIters = 16;                  // iterations per work item: 16 (32 768 positions), fewer for short inputs
 constexpr int kKmMinItemPos = kKmIterPos;        // launches cover multiples of kAnchorRound, a multiple of every item size
 constexpr int kKmHaloWords = 4;                  // 64 stored bases in front of the item (window starts reach back n-1 <= 63)
@@ -85,6 +85,16 @@ __global__ void __launch_bounds__(256) km_build_kernel(const double* __restrict_
     dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
+// bit x of the bitmap = (mask of k-mer x is non-zero); one warp per 32 consecutive k-mers
+__global__ void __launch_bounds__(256) km_bitmap_kernel(const uint32_t* __restrict__ table, uint32_t* __restrict__ bitmap) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4* e = reinterpret_cast<const uint4*>(table + x * kKmWords);
+    const uint4 a = e[0], b = e[1];
+    const bool nz = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0u;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, nz);
+    if ((threadIdx.x & 31) == 0) bitmap[x >> 5] = bal;
+}
+
 struct KmShared {
     uint32_t seq[kKmSeqWords];
     uint32_t queue[kKmThreads / 32][kKmQueue];
@@ -138,8 +148,13 @@ __device__ __forceinline__ void km_drain(const KmShared& sh, const uint16_t* __r
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const DevKmBlock& db, const uint8_t* __restrict__ tab,
+// One work item: per iteration a thread takes two adjacent positions (the same three staged 2-bit words serve
+// both), gathers their masks, expands surviving bits into the warp's queue and drains it 32 entries at a time.
+// (A software-pipelined variant — gathers of the next stage issued before the current masks are expanded — was
+// measured 1.6-2x SLOWER: a third live mask no longer fits 64 registers and the spills go through the very L1
+// path that bounds the kernel.)
+template <int NT, bool BM>
+__device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const uint32_t* __restrict__ s_bm, const DevKmBlock& db, const uint8_t* __restrict__ tab,
                                         long long U0, int iters, long long len, unsigned long long combo_base,
                                         unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -155,17 +170,37 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
     for (int it = 0; it < iters; ++it) {
         Mask m[2];
         unsigned long long x[2];
-        {   // a thread takes two adjacent positions (even, odd): the same three 2-bit words serve both
+        {
             const int p = it * kKmIterPos + warp * 64 + 2 * lane;
             const int wi = (p >> 4) + kKmHaloWords, s2 = 2 * (p & 15);
             const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
             x[0] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
             x[1] = (unsigned long long)__funnelshift_r(w0, w1, s2 + 2) | ((unsigned long long)__funnelshift_r(w1, w2, s2 + 2) << 32);
         }
+        if (BM) {
+            // the shared-memory bitmap says whether the first mask is non-zero at all; only then gather — and then
+            // the second table right away (its load does not have to wait for the first one)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32, pol);
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t i0 = (uint32_t)(x[j] >> tsh[0]) & tmk[0];
+                if ((s_bm[i0 >> 5] >> (i0 & 31u)) & 1u) {
+                    m[j] = ldg_mask(tp[0] + (size_t)i0 * 32, pol);
+                    if (NT > 1) {
+                        const Mask t = ldg_mask(tp[1] + (size_t)((uint32_t)(x[j] >> tsh[1]) & tmk[1]) * 32, pol);
 #pragma unroll
-        for (int s = 1; s < NT; ++s) {
+                        for (int w = 0; w < 8; ++w) m[j].v[w] &= t.v[w];
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) m[j].v[w] = 0u;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32, pol);
+        }
+#pragma unroll
+        for (int s = (BM ? 2 : 1); s < NT; ++s) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (mask_any(m[j])) {
@@ -228,6 +263,7 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
     const long long items_per_block = n_anchor / item_pos;
     int cur_blk = -1;
     DevKmBlock db = blocks[0];
+    const uint32_t* s_bm = nullptr;
     for (;;) {
         if (tid == 0) sh.item = (long long)atomicAdd(work_counter, 1ull);
         __syncthreads();
@@ -241,6 +277,12 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
             uint4* dst = reinterpret_cast<uint4*>(s_q16);
             const int n16 = kKmCombos * db.max_n * 8 / 16;
             for (int i = tid; i < n16; i += kKmThreads) dst[i] = __ldg(src + i);
+            s_bm = reinterpret_cast<const uint32_t*>(smem_raw + (size_t)n16 * 16);       // bitmap right behind the rows
+            if (db.bitmap_words > 0) {
+                const uint4* bsrc = reinterpret_cast<const uint4*>(tables + db.bitmap_off);
+                uint4* bdst = reinterpret_cast<uint4*>(smem_raw + (size_t)n16 * 16);
+                for (int i = tid; i < db.bitmap_words / 4; i += kKmThreads) bdst[i] = __ldg(bsrc + i);
+            }
             if (tid < kKmCombos) {
                 const DevCombo dc = combos[(size_t)blk * kKmCombos + tid];
                 sh.cn[tid] = ((uint32_t)dc.c & 0xFFFFu) | ((uint32_t)dc.n << 16);
@@ -255,12 +297,16 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
         __syncthreads();
         const uint8_t* tab = tables;
         const unsigned long long combo_base = (unsigned long long)blk * kKmCombos;
+#define KM_RUN(NT_) \
+        if (db.bitmap_words > 0) km_item<NT_, true>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); \
+        else km_item<NT_, false>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters);
         switch (db.nt) {
-            case 1: km_item<1>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
-            case 2: km_item<2>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
-            case 3: km_item<3>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
-            default: km_item<4>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); break;
+            case 1: KM_RUN(1) break;
+            case 2: KM_RUN(2) break;
+            case 3: KM_RUN(3) break;
+            default: KM_RUN(4) break;
         }
+#undef KM_RUN
         __syncthreads();   // everyone is done with sh.seq / s_q16 / sh.item
     }
 }
@@ -269,7 +315,12 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
 
 namespace pwmscan {
 
-size_t km_q16_smem_bytes(int max_n) { return (size_t)kKmCombos * max_n * 8; }
+// Bitmap of one mask table: bit x = mask of k-mer x is non-zero (stream-ordered).
+int km_build_bitmap(pwmscan_ctx* ctx, const uint8_t* d_table, int L, uint8_t* d_bitmap) {
+    km_bitmap_kernel<<<(unsigned)(((size_t)1 << (2 * L)) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_table), reinterpret_cast<uint32_t*>(d_bitmap));
+    PWM_CUDA(cudaGetLastError());
+    return PWMSCAN_OK;
+}
 
 // Builds one mask table (4^L entries) on the device (stream-ordered).  d_wdef: [256][kKmMaxL][4], d_dsafe: [256].
 int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int L, uint8_t* d_table) {
@@ -283,19 +334,19 @@ int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe
     return PWMSCAN_OK;
 }
 
-int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, int max_n,
+int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter) {
     if (nblocks == 0 || a1 <= a0) return PWMSCAN_OK;
     if (!ctx->km_attr_set) {
-        PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km_q16_smem_bytes(kMaxCols)));
+        PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmSmemBudget));
         ctx->km_attr_set = true;
     }
     int iters = kKmMaxIters;                                  // short inputs: smaller items so that every SM gets several
     while (iters > 1 && (a1 - a0) / (iters * kKmIterPos) * nblocks < 8LL * ctx->sm_count) iters >>= 1;
     const long long items = (a1 - a0) / (iters * kKmIterPos) * nblocks;
     const int grid = (int)std::min<long long>(ctx->sm_count, items);
-    km_prefilter_kernel<<<grid, kKmThreads, km_q16_smem_bytes(max_n), ctx->stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
+    km_prefilter_kernel<<<grid, kKmThreads, smem_bytes, ctx->stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
                                                                                     d_cand, cand_cap, ctx->d_counters, work_counter);
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;

@@ -10,7 +10,7 @@
 // T_t[L_t-mer at u + off_t], ANDs the masks, and a surviving bit j is the window that starts at
 // u - c_j.  Every combo picks its own offset c_j in [-(L_0 - 1), n-1] (which windows the tables see);
 // the product of the windows' pass rates under iid uniform bases is what c_j minimises.  The block
-// picks the layout (L_t) that minimises gathered sectors + 6 x first-stage survivors per position.
+// picks the layout (L_t) that minimises gathered sectors + 15 x first-stage survivors per position.
 //
 // Survivors (~0.1 per position for 200 combos at p = 1e-5) go through a middle stage in the same
 // kernel: the whole-window deficit in 16-bit fixed point from shared memory (q16), and what is left
@@ -27,6 +27,9 @@ constexpr int kKmWords = kKmCombos / 32;        // 8 x uint32 = one 32-byte sect
 constexpr int kKmMaxTables = 4;
 constexpr int kKmMinL = 8, kKmMaxL = 10;        // window lengths: 8-, 9- or 10-mers (2, 8, 32 MiB per table)
 constexpr size_t kKmMaxTableBytes = (size_t)72 << 20;   // per block, so that the tables of the running block stay in the 126 MB L2
+constexpr size_t kKmSmemBudget = (size_t)204 << 10;     // dynamic shared memory of the kernel: middle-stage rows + first-table bitmap
+constexpr double kKmBitmapClk = 0.4;            // clocks per position and SM of the shared-memory bitmap look-up: its wavefronts (~0.11, bank
+                                                // conflicts included) share L1TEX with the gathers, plus index/test instructions — fitted on C2
 constexpr int kKmQ = 4000;                      // fixed-point budget of the middle stage; entries saturate at 4095 (12 bits)
 
 inline size_t km_table_bytes(int L) { return ((size_t)1 << (2 * L)) * kKmWords * 4; }
@@ -45,6 +48,9 @@ struct KmBlockPlan {
     int L[kKmMaxTables] = {8, 8, 8, 8};         // window length of table t
     int off[kKmMaxTables] = {0, 8, 16, 24};     // table t sees motif columns c + off[t] .. c + off[t] + L[t] - 1
     int order[kKmMaxTables] = {0, 1, 2, 3};     // gather order: most selective table first
+    // One bit per k-mer of table order[0], "the mask is non-zero", kept in shared memory (4^L / 8 bytes): a position
+    // whose bit is clear gathers nothing at all.  Used whenever it fits next to the middle-stage rows.
+    bool bitmap = false;
     KmCombo combo[kKmCombos];
     std::vector<double> wdef;                   // [nt][256][kKmMaxL][4] deficit of base b at window position p (0 outside the motif)
     std::vector<double> dsafe;                  // [256]; < 0: bit never set
@@ -57,6 +63,8 @@ struct KmBlockPlan {
     double req_rate = 0;                        // expected table sectors gathered per position
     double cost = 0;
     size_t table_bytes() const { size_t t = 0; for (int i = 0; i < nt; ++i) t += km_table_bytes(L[i]); return t; }
+    size_t q16_bytes() const { return (size_t)kKmCombos * max_n * 8; }
+    size_t bitmap_bytes() const { return bitmap ? ((size_t)1 << (2 * L[order[0]])) / 8 : 0; }
 };
 
 namespace detail {
@@ -164,12 +172,15 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
         // Every combo picks its offset c.  What it costs the block: its chance of keeping the AND non-zero after
         // the first gathered table (a second sector, weight alpha = d sectors / d lambda = exp(-lambda)) and its
         // first-stage survivors (weight kSurvClk).  Solved by a few rounds per choice of the first table.
-        constexpr double kSurvClk = 6.0;
+        constexpr double kSurvClk = 15.0;
         double req = 0;
         bool have_cur = false;
         KmBlockPlan trial = cur;
+        auto bitmap_fits = [&](int t) { return (size_t)kKmCombos * max_n * 8 + (((size_t)1 << (2 * cur.L[t])) / 8) <= kKmSmemBudget; };
         for (int first = 0; first < cur.nt; ++first) {
             double alpha = 1.0;
+            // with the bitmap a non-zero first mask costs the first AND the second sector (both are then gathered at once)
+            const double w_first = bitmap_fits(first) ? 2.0 : 1.0;      // (an estimate: the bitmap may still be declined below)
             for (int round = 0; round < 3; ++round) {
                 double tab_sum[kKmMaxTables] = {0, 0, 0, 0};
                 trial.surv_rate = 0;
@@ -185,7 +196,7 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
                     for (int c = -(cur.L[0] - 1); c < cd.n; ++c) {
                         double p = 1;
                         for (int t = 0; t < cur.nt; ++t) p *= pass_at(ci, cur.L[t], c + cur.off[t]);
-                        const double v = (cur.nt > 1 ? alpha * pass_at(ci, cur.L[first], c + cur.off[first]) : 0.0) + kSurvClk * p;
+                        const double v = (cur.nt > 1 ? w_first * alpha * pass_at(ci, cur.L[first], c + cur.off[first]) : 0.0) + kSurvClk * p;
                         if (v < bestv) { bestv = v; bestp = p; bestc = c; }
                     }
                     kc.c = bestc; kc.sigma1 = bestp;
@@ -194,18 +205,25 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
                 }
                 for (int t = 0; t < kKmMaxTables; ++t) trial.order[t] = t;
                 std::stable_sort(trial.order, trial.order + cur.nt, [&](int a, int b) { return tab_sum[a] < tab_sum[b]; });
-                // sectors gathered per position: table order[0] always, the next one only while the AND is still non-zero
-                double r = 1;
-                for (int s = 1; s < cur.nt; ++s) {
+                // sectors gathered per position.  Without the bitmap: table order[0] always, the next one only while
+                // the AND is still non-zero.  With it: nothing unless the first mask is non-zero, then the first two
+                // tables at once, the third only while the AND is still non-zero.
+                double pnz[kKmMaxTables] = {1, 1, 1, 1};                      // P(AND of the first s masks non-zero), s = 1..nt-1
+                for (int s = 1; s < cur.nt || s == 1; ++s) {
                     double lam = 0;                                           // expected surviving bits after the first s tables
                     for (int ci = 0; ci < kKmCombos; ++ci) if (trial.combo[ci].enabled) {
                         double p = 1;
                         for (int k = 0; k < s; ++k) p *= trial.combo[ci].pass[trial.order[k]];
                         lam += p;
                     }
-                    r += 1.0 - std::exp(-lam);
+                    pnz[s] = 1.0 - std::exp(-lam);
                 }
-                const double cost = r + kSurvClk * trial.surv_rate;
+                double r_bm = pnz[1] * (cur.nt > 1 ? 2.0 : 1.0), r_plain = 1;
+                for (int s = 2; s < cur.nt; ++s) r_bm += pnz[s];
+                for (int s = 1; s < cur.nt; ++s) r_plain += pnz[s];
+                trial.bitmap = bitmap_fits(trial.order[0]) && r_bm + kKmBitmapClk < r_plain;
+                const double r = trial.bitmap ? r_bm : r_plain;
+                const double cost = r + (trial.bitmap ? kKmBitmapClk : 0.0) + kSurvClk * trial.surv_rate;
                 if (!have_cur || cost < cur.cost) { cur = trial; cur.cost = cost; req = r; have_cur = true; }
                 alpha = std::exp(-tab_sum[first]);
                 if (cur.nt == 1) break;
@@ -213,8 +231,8 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
             if (cur.nt == 1) break;
         }
         cur.req_rate = req;
-        // (clocks per position and SM, measured on B200 / C2: about one gathered sector per clock, ~6 clocks per
-        //  first-stage survivor for queueing + middle stage)
+        // (clocks per position and SM, measured on B200 / C2: about one gathered sector per clock, ~15 clocks per
+        //  first-stage survivor for bit extraction, queueing and the middle stage — fitted to forced layouts)
         if (!have || cur.cost < best.cost) { best = std::move(cur); have = true; }
     }
     bp = std::move(best);

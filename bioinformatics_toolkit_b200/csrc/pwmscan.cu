@@ -642,6 +642,9 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
                 const int t = s < bp.nt ? bp.order[s] : 0;
                 hb[b].shift[s] = 2 * bp.off[t]; hb[b].kmask[s] = (1u << (2 * bp.L[t])) - 1u; hb[b].table_off[s] = toff[t];
             }
+            hb[b].bitmap_off = (int64_t)table_bytes; hb[b].bitmap_words = (int32_t)(bp.bitmap_bytes() / 4); hb[b].pad_ = 0;
+            table_bytes += (bp.bitmap_bytes() + 255) / 256 * 256;
+            pl->km_smem_bytes = std::max(pl->km_smem_bytes, bp.q16_bytes() + bp.bitmap_bytes());
             hb[b].q16_off = (int64_t)hq.size();
             hq.insert(hq.end(), bp.q16.begin(), bp.q16.end());
             w_off[b] = hw.size();
@@ -656,8 +659,8 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
                 hc[(size_t)b * kKmCombos + ci] = dc;
             }
             if (verbose)
-                std::fprintf(stderr, "[pwmscan] kmer block %d: nt=%d L=%d,%d,%d,%d order=%d%d%d%d cols %d..%d enabled=%d sectors/pos=%.3f survivors/pos=%.4f cand/pos=%.3e cost=%.3f\n",
-                             b, bp.nt, bp.L[0], bp.nt > 1 ? bp.L[1] : 0, bp.nt > 2 ? bp.L[2] : 0, bp.nt > 3 ? bp.L[3] : 0, bp.order[0], bp.order[1], bp.order[2], bp.order[3],
+                std::fprintf(stderr, "[pwmscan] kmer block %d: nt=%d L=%d,%d,%d,%d order=%d%d%d%d bitmap=%d cols %d..%d enabled=%d sectors/pos=%.3f survivors/pos=%.4f cand/pos=%.3e cost=%.3f\n",
+                             b, bp.nt, bp.L[0], bp.nt > 1 ? bp.L[1] : 0, bp.nt > 2 ? bp.L[2] : 0, bp.nt > 3 ? bp.L[3] : 0, bp.order[0], bp.order[1], bp.order[2], bp.order[3], (int)bp.bitmap,
                              nmin, nmax, nen, bp.req_rate, bp.surv_rate, bp.cand_rate, bp.cost);
             std::vector<double>().swap(bp.wdef);         // only needed for the device build
             std::vector<uint16_t>().swap(bp.q16);
@@ -683,6 +686,7 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
                     rc = km_build_table(ctx, d_w + w_off[b] + (size_t)t * kKmCombos * kKmMaxL * 4, d_d + (size_t)b * kKmCombos, bp.L[t],
                                         pl->d_km_tables + hb[b].table_off[s]);
                 }
+                if (rc == 0 && bp.bitmap) rc = km_build_bitmap(ctx, pl->d_km_tables + hb[b].table_off[0], bp.L[bp.order[0]], pl->d_km_tables + hb[b].bitmap_off);
             }
             e = cudaStreamSynchronize(ctx->stream);
             cudaFree(d_w); cudaFree(d_d);
@@ -1019,7 +1023,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         if (use_km) {
             if (pl->km_nblocks == 0) return PWMSCAN_OK;
             ++launches;
-            return launch_km_prefilter(ctx, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_max_n, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
+            return launch_km_prefilter(ctx, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_smem_bytes, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
                                        pl->d_km_combos, d_cand, cand_cap, ctx->d_counters + 8 + slot);
         }
         if (use_mma) {

@@ -32,6 +32,7 @@ constexpr int kKmMinItemPos = kKmIterPos;        // launches cover multiples of 
 constexpr int kKmHaloWords = 4;                  // 64 stored bases in front of the item (window starts reach back n-1 <= 63)
 constexpr int kKmSeqWords = kKmHaloWords + kKmMaxIters * kKmIterPos / 16 + 5;   // windows end <= 7 + 64 bases after the item's last position
 constexpr int kKmQueue = 64;
+constexpr int kKmHitQueue = 96;                  // < 32 waiting + up to 32 new per ballot, rounded up
 
 struct Mask { uint32_t v[8]; };
 
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) km_bitmap_kernel(const uint32_t* __restri
 struct KmShared {
     uint32_t seq[kKmSeqWords];
     uint32_t queue[kKmThreads / 32][kKmQueue];
+    uint16_t hitq[kKmThreads / 32][kKmHitQueue]; // bitmap path: positions whose first mask is non-zero, waiting for their gathers
     uint32_t cn[kKmCombos];                      // c (low 16 bits, signed) | n << 16
     long long item;
 };
@@ -145,6 +147,43 @@ __device__ __forceinline__ void km_drain(const KmShared& sh, const uint16_t* __r
             const unsigned long long slot = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
             if (slot < cand_cap) cand[slot] = ((combo_base + combo) << 40) | (unsigned long long)(U0 + p);
         }
+    }
+}
+
+// Expands the set bits of the 32 lanes' masks (position p per lane) into the warp's queue, draining it through the
+// middle stage whenever 32 entries are queued.  All 32 lanes must call it.
+__device__ __forceinline__ void km_expand(Mask& m, uint32_t p, uint32_t* q, int& qcnt, const KmShared& sh, const uint16_t* __restrict__ s_q16, int max_n,
+                                          long long U0, long long len, unsigned long long combo_base,
+                                          unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+    const int lane = threadIdx.x & 31;
+    uint32_t any = mask_any(m);
+    unsigned bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
+    while (bal) {
+        if (any) {
+            uint32_t bit;
+            if (m.v[0]) { bit = __ffs((int)m.v[0]) - 1; m.v[0] &= m.v[0] - 1; }
+            else if (m.v[1]) { bit = 32 + __ffs((int)m.v[1]) - 1; m.v[1] &= m.v[1] - 1; }
+            else if (m.v[2]) { bit = 64 + __ffs((int)m.v[2]) - 1; m.v[2] &= m.v[2] - 1; }
+            else if (m.v[3]) { bit = 96 + __ffs((int)m.v[3]) - 1; m.v[3] &= m.v[3] - 1; }
+            else if (m.v[4]) { bit = 128 + __ffs((int)m.v[4]) - 1; m.v[4] &= m.v[4] - 1; }
+            else if (m.v[5]) { bit = 160 + __ffs((int)m.v[5]) - 1; m.v[5] &= m.v[5] - 1; }
+            else if (m.v[6]) { bit = 192 + __ffs((int)m.v[6]) - 1; m.v[6] &= m.v[6] - 1; }
+            else { bit = 224 + __ffs((int)m.v[7]) - 1; m.v[7] &= m.v[7] - 1; }
+            q[qcnt + __popc(bal & ((1u << lane) - 1u))] = (p << 8) | bit;
+            any = mask_any(m);
+        }
+        qcnt += __popc(bal);
+        __syncwarp();
+        if (qcnt >= 32) {
+            const uint32_t e = q[lane];
+            const uint32_t rest = (lane + 32 < qcnt) ? q[lane + 32] : 0u;
+            __syncwarp();
+            if (lane + 32 < qcnt) q[lane] = rest;
+            qcnt -= 32;
+            km_drain(sh, s_q16, max_n, e, true, U0, len, combo_base, cand, cand_cap, counters);
+            __syncwarp();
+        }
+        bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
     }
 }
 
@@ -211,38 +250,110 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
             }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const uint32_t p = (uint32_t)(it * kKmIterPos + warp * 64 + 2 * lane + j);
-            uint32_t any = mask_any(m[j]);
-            unsigned bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
-            while (bal) {
-                if (any) {
-                    uint32_t bit;
-                    if (m[j].v[0]) { bit = __ffs((int)m[j].v[0]) - 1; m[j].v[0] &= m[j].v[0] - 1; }
-                    else if (m[j].v[1]) { bit = 32 + __ffs((int)m[j].v[1]) - 1; m[j].v[1] &= m[j].v[1] - 1; }
-                    else if (m[j].v[2]) { bit = 64 + __ffs((int)m[j].v[2]) - 1; m[j].v[2] &= m[j].v[2] - 1; }
-                    else if (m[j].v[3]) { bit = 96 + __ffs((int)m[j].v[3]) - 1; m[j].v[3] &= m[j].v[3] - 1; }
-                    else if (m[j].v[4]) { bit = 128 + __ffs((int)m[j].v[4]) - 1; m[j].v[4] &= m[j].v[4] - 1; }
-                    else if (m[j].v[5]) { bit = 160 + __ffs((int)m[j].v[5]) - 1; m[j].v[5] &= m[j].v[5] - 1; }
-                    else if (m[j].v[6]) { bit = 192 + __ffs((int)m[j].v[6]) - 1; m[j].v[6] &= m[j].v[6] - 1; }
-                    else { bit = 224 + __ffs((int)m[j].v[7]) - 1; m[j].v[7] &= m[j].v[7] - 1; }
-                    q[qcnt + __popc(bal & ((1u << lane) - 1u))] = (p << 8) | bit;
-                    any = mask_any(m[j]);
-                }
-                qcnt += __popc(bal);
-                __syncwarp();
-                if (qcnt >= 32) {
-                    const uint32_t e = q[lane];
-                    const uint32_t rest = (lane + 32 < qcnt) ? q[lane + 32] : 0u;
-                    __syncwarp();
-                    if (lane + 32 < qcnt) q[lane] = rest;
-                    qcnt -= 32;
-                    km_drain(sh, s_q16, db.max_n, e, true, U0, len, combo_base, cand, cand_cap, counters);
-                    __syncwarp();
-                }
-                bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
+        for (int j = 0; j < 2; ++j)
+            km_expand(m[j], (uint32_t)(it * kKmIterPos + warp * 64 + 2 * lane + j), q, qcnt, sh, s_q16, db.max_n, U0, len, combo_base, cand, cand_cap, counters);
+    }
+    if (qcnt > 0) {
+        const uint32_t e = lane < qcnt ? q[lane] : 0u;
+        km_drain(sh, s_q16, db.max_n, e, lane < qcnt, U0, len, combo_base, cand, cand_cap, counters);
+    }
+}
+
+// Gathers, ANDs and expands the masks of up to 32 queued positions (one per lane; lanes >= count idle).
+template <int NT>
+__device__ __forceinline__ void km_hits(KmShared& sh, const uint16_t* __restrict__ s_q16, const DevKmBlock& db, const uint8_t* const (&tp)[NT],
+                                        const int (&tsh)[NT], const uint32_t (&tmk)[NT], uint64_t pol, uint32_t p, bool active,
+                                        uint32_t* q, int& qcnt, long long U0, long long len, unsigned long long combo_base,
+                                        unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+    Mask m;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m.v[w] = 0u;
+    if (active) {
+        const int wi = (int)(p >> 4) + kKmHaloWords, s2 = 2 * (int)(p & 15u);
+        const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2];
+        const unsigned long long x = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
+        m = ldg_mask(tp[0] + (size_t)((uint32_t)(x >> tsh[0]) & tmk[0]) * 32, pol);
+        if (NT > 1) {                                       // the first mask is known to be non-zero: no need to wait for it
+            const Mask t = ldg_mask(tp[1] + (size_t)((uint32_t)(x >> tsh[1]) & tmk[1]) * 32, pol);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) m.v[w] &= t.v[w];
+        }
+#pragma unroll
+        for (int s = 2; s < NT; ++s) {
+            if (mask_any(m)) {
+                const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x >> tsh[s]) & tmk[s]) * 32, pol);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) m.v[w] &= t.v[w];
             }
         }
+    }
+    km_expand(m, p, q, qcnt, sh, s_q16, db.max_n, U0, len, combo_base, cand, cand_cap, counters);
+}
+
+// Work item of a block with a first-table bitmap, in two phases.  Scan: a thread tests the bitmap for 8 consecutive
+// positions (four staged words, two funnel shifts and one shared-memory bit per position) and the positions whose
+// bit is set are compacted into the warp's hit queue.  Hits: whenever 32 are queued, one per lane gathers its masks
+// (km_hits).  Sparse blocks — most positions of a many-motif scan — so cost ~0.2 instructions per position.
+template <int NT>
+__device__ __forceinline__ void km_item_bitmap(KmShared& sh, const uint16_t* __restrict__ s_q16, const uint32_t* __restrict__ s_bm, const DevKmBlock& db,
+                                               const uint8_t* __restrict__ tab, long long U0, int iters, long long len, unsigned long long combo_base,
+                                               unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* q = sh.queue[warp];
+    uint16_t* hq = sh.hitq[warp];
+    int qcnt = 0, hcnt = 0;
+    const uint64_t pol = l2_keep_policy();
+    const uint8_t* tp[NT];
+    int tsh[NT];
+    uint32_t tmk[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) { tp[s] = tab + db.table_off[s]; tsh[s] = db.shift[s]; tmk[s] = db.kmask[s]; }
+    const int per_warp = iters * (kKmIterPos / (kKmThreads / 32));      // 64 * iters positions, contiguous
+    const int kpt = per_warp >= 256 ? 8 : per_warp / 32;                // positions per thread and scan step (2, 4 or 8)
+    const int nscan = per_warp / (32 * kpt);
+    const int sh0 = tsh[0];
+    const uint32_t mk0 = tmk[0];
+#pragma unroll 1
+    for (int si = 0; si < nscan; ++si) {
+        const int pb = warp * per_warp + si * 32 * kpt + lane * kpt;    // (pb & 15) + kpt <= 16
+        const int wi = (pb >> 4) + kKmHaloWords;
+        const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2], w3 = sh.seq[wi + 3];
+        const int s0 = 2 * (pb & 15);
+        uint32_t hm = 0;                                                // bit k: position pb + k has a non-zero first mask
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < kpt) {
+                // bases pb+k .. pb+k+47: enough for the first table's k-mer at any offset (shift + 2L <= 64 bits, plan_km.h)
+                const int s2 = s0 + 2 * k;
+                const uint32_t lo = __funnelshift_r(w0, w1, s2), mid = __funnelshift_r(w1, w2, s2), hi = __funnelshift_r(w2, w3, s2);
+                const uint32_t i0 = (sh0 < 32 ? __funnelshift_r(lo, mid, sh0) : __funnelshift_r(mid, hi, sh0 - 32)) & mk0;
+                hm |= ((s_bm[i0 >> 5] >> (i0 & 31u)) & 1u) << k;
+            }
+        }
+        // compaction: per round every thread that still has a hit queues its lowest one
+        unsigned bal = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+        while (bal) {
+            if (hm) {
+                hq[hcnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(pb + __ffs((int)hm) - 1);
+                hm &= hm - 1u;
+            }
+            hcnt += __popc(bal);
+            __syncwarp();
+            if (hcnt >= 32) {
+                const uint32_t p = hq[lane];
+                const uint32_t rest = (lane + 32 < hcnt) ? hq[lane + 32] : 0u;
+                __syncwarp();
+                if (lane + 32 < hcnt) hq[lane] = (uint16_t)rest;
+                hcnt -= 32;
+                km_hits<NT>(sh, s_q16, db, tp, tsh, tmk, pol, p, true, q, qcnt, U0, len, combo_base, cand, cand_cap, counters);
+                __syncwarp();
+            }
+            bal = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+        }
+    }
+    if (hcnt > 0) {
+        const uint32_t p = lane < hcnt ? hq[lane] : 0u;
+        km_hits<NT>(sh, s_q16, db, tp, tsh, tmk, pol, p, lane < hcnt, q, qcnt, U0, len, combo_base, cand, cand_cap, counters);
     }
     if (qcnt > 0) {
         const uint32_t e = lane < qcnt ? q[lane] : 0u;
@@ -298,7 +409,7 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
         const uint8_t* tab = tables;
         const unsigned long long combo_base = (unsigned long long)blk * kKmCombos;
 #define KM_RUN(NT_) \
-        if (db.bitmap_words > 0) km_item<NT_, true>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); \
+        if (db.bitmap_words > 0) km_item_bitmap<NT_>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); \
         else km_item<NT_, false>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters);
         switch (db.nt) {
             case 1: KM_RUN(1) break;

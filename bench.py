@@ -309,7 +309,7 @@ def main():
         peak = 148 * 32 * clk / 1e9
         ach = alg_bytes / (pre_ms_launch / 1e3) / 1e9
         # DRAM traffic of one launch on this exact workload, from the committed ncu --set full capture
-        traffic = 755.4e6 if (args.workload == "c2" and M == 100) else None   # profiles/r1g: 746.9 MB read (64 MiB of tables + L2 misses) + 8.5 MB written
+        traffic = 761.9e6 if (args.workload == "c2" and M == 100) else None   # profiles/r1j: 752.8 MB read (64 MiB of tables + L2 misses) + 9.1 MB written
         roofline = {"bound": "l1-gather", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "kernel": "km_prefilter_kernel", "ms_per_launch": pre_ms_launch,
                     "peak_source": "148 SMs x one 32-B sector per clk x sm_max_mhz (%s); measured 8.9 TB/s by experiments/masktab/l2gather.cu" % peaks["source"],

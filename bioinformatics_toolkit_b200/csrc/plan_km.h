@@ -17,6 +17,8 @@
 // (about the hit rate) to the exact fp64 replay (rescore_kernel).  The selectivity experiment behind
 // this design is experiments/exp_masktable.py, the L2 gather rate experiments/masktab/l2gather.cu.
 #pragma once
+#include <cstdlib>
+
 #include "plan.h"
 
 namespace pwmscan {
@@ -221,7 +223,8 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
                 double r_bm = pnz[1] * (cur.nt > 1 ? 2.0 : 1.0), r_plain = 1;
                 for (int s = 2; s < cur.nt; ++s) r_bm += pnz[s];
                 for (int s = 1; s < cur.nt; ++s) r_plain += pnz[s];
-                trial.bitmap = bitmap_fits(trial.order[0]) && r_bm + kKmBitmapClk < r_plain;
+                static const int force_bm = std::getenv("PWMSCAN_FORCE_BITMAP") ? std::atoi(std::getenv("PWMSCAN_FORCE_BITMAP")) : -1;   // experiments
+                trial.bitmap = bitmap_fits(trial.order[0]) && (force_bm < 0 ? r_bm + kKmBitmapClk < r_plain : force_bm != 0);
                 const double r = trial.bitmap ? r_bm : r_plain;
                 const double cost = r + (trial.bitmap ? kKmBitmapClk : 0.0) + kSurvClk * trial.surv_rate;
                 if (!have_cur || cost < cur.cost) { cur = trial; cur.cost = cost; req = r; have_cur = true; }

@@ -187,13 +187,14 @@ __device__ __forceinline__ void km_expand(Mask& m, uint32_t p, uint32_t* q, int&
     }
 }
 
-// One work item: per iteration a thread takes two adjacent positions (the same three staged 2-bit words serve
-// both), gathers their masks, expands surviving bits into the warp's queue and drains it 32 entries at a time.
+// One work item of a block WITHOUT a first-table bitmap: per iteration a thread takes two adjacent positions (the
+// same three staged 2-bit words serve both), gathers the first mask, the next ones only while the AND is non-zero,
+// expands surviving bits into the warp's queue and drains it 32 entries at a time.
 // (A software-pipelined variant — gathers of the next stage issued before the current masks are expanded — was
 // measured 1.6-2x SLOWER: a third live mask no longer fits 64 registers and the spills go through the very L1
 // path that bounds the kernel.)
-template <int NT, bool BM>
-__device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const uint32_t* __restrict__ s_bm, const DevKmBlock& db, const uint8_t* __restrict__ tab,
+template <int NT>
+__device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const DevKmBlock& db, const uint8_t* __restrict__ tab,
                                         long long U0, int iters, long long len, unsigned long long combo_base,
                                         unsigned long long* __restrict__ cand, unsigned long long cand_cap, unsigned long long* counters) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,30 +217,10 @@ __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict
             x[0] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
             x[1] = (unsigned long long)__funnelshift_r(w0, w1, s2 + 2) | ((unsigned long long)__funnelshift_r(w1, w2, s2 + 2) << 32);
         }
-        if (BM) {
-            // the shared-memory bitmap says whether the first mask is non-zero at all; only then gather — and then
-            // the second table right away (its load does not have to wait for the first one)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t i0 = (uint32_t)(x[j] >> tsh[0]) & tmk[0];
-                if ((s_bm[i0 >> 5] >> (i0 & 31u)) & 1u) {
-                    m[j] = ldg_mask(tp[0] + (size_t)i0 * 32, pol);
-                    if (NT > 1) {
-                        const Mask t = ldg_mask(tp[1] + (size_t)((uint32_t)(x[j] >> tsh[1]) & tmk[1]) * 32, pol);
+        for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32, pol);
 #pragma unroll
-                        for (int w = 0; w < 8; ++w) m[j].v[w] &= t.v[w];
-                    }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) m[j].v[w] = 0u;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32, pol);
-        }
-#pragma unroll
-        for (int s = (BM ? 2 : 1); s < NT; ++s) {
+        for (int s = 1; s < NT; ++s) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (mask_any(m[j])) {
@@ -410,7 +391,7 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
         const unsigned long long combo_base = (unsigned long long)blk * kKmCombos;
 #define KM_RUN(NT_) \
         if (db.bitmap_words > 0) km_item_bitmap<NT_>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters); \
-        else km_item<NT_, false>(sh, s_q16, s_bm, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters);
+        else km_item<NT_>(sh, s_q16, db, tab, U0, iters, len, combo_base, cand, cand_cap, counters);
         switch (db.nt) {
             case 1: KM_RUN(1) break;
             case 2: KM_RUN(2) break;

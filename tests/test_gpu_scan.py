@@ -287,11 +287,12 @@ def test_many_segments_and_many_motifs(ctx, oracle):
     assert np.array_equal(h.score.view(np.uint64), o[3][inside][order].view(np.uint64))
 
 
-@pytest.mark.parametrize("variant", ["kmer", "lds", "mma"])
+@pytest.mark.parametrize("variant", ["kmer", "kmer+bitmap", "kmer-bitmap", "lds", "mma"])
 def test_prefilter_variant_parity(variant):
-    """Every first stage — the k-mer mask tables in L2 (kmer), the shared-memory 4-mer deficit tables (lds)
-    and the experimental tcgen05 int8 one-hot x deficit GEMM (mma), selected with PWMSCAN_PREFILTER —
-    must give the same bit-identical hit lists (own process: the mode is read once)."""
+    """Every first stage — the k-mer mask tables in L2 (kmer; with the first-table bitmap forced on and off),
+    the shared-memory 4-mer deficit tables (lds) and the experimental tcgen05 int8 one-hot x deficit GEMM
+    (mma), selected with PWMSCAN_PREFILTER — must give the same bit-identical hit lists (own process: the
+    mode is read once)."""
     import subprocess
     import sys
     code = r'''
@@ -313,7 +314,11 @@ for count, L, lo, hi in ((150, 300000, 6, 40), (3, 100000, 8, 12)):
 assert ctx.timing()["prefilter_launches"] >= 1
 print("VARIANT-PARITY-OK")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PWMSCAN_PREFILTER=variant)
+    env = dict(os.environ, PWMSCAN_PREFILTER=variant.split("+")[0].split("-")[0])
+    if variant == "kmer+bitmap":
+        env["PWMSCAN_FORCE_BITMAP"] = "1"        # every block through the two-phase bitmap path
+    elif variant == "kmer-bitmap":
+        env["PWMSCAN_FORCE_BITMAP"] = "0"        # every block through the plain gather path
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "VARIANT-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 

@@ -190,9 +190,9 @@ __device__ __forceinline__ void km_expand(Mask& m, uint32_t p, uint32_t* q, int&
 // One work item of a block WITHOUT a first-table bitmap: per iteration a thread takes two adjacent positions (the
 // same three staged 2-bit words serve both), gathers the first mask, the next ones only while the AND is non-zero,
 // expands surviving bits into the warp's queue and drains it 32 entries at a time.
-// (A software-pipelined variant — gathers of the next stage issued before the current masks are expanded — was
-// measured 1.6-2x SLOWER: a third live mask no longer fits 64 registers and the spills go through the very L1
-// path that bounds the kernel.)
+// (Software-pipelined variants — gathers of the next stage / the next batch of bitmap hits issued before the
+// current masks are expanded — were measured 1.5-2x SLOWER: a third live mask, or two masks live across the middle
+// stage, no longer fit 64 registers and the spills go through the very L1 path that bounds the kernel.)
 template <int NT>
 __device__ __forceinline__ void km_item(KmShared& sh, const uint16_t* __restrict__ s_q16, const DevKmBlock& db, const uint8_t* __restrict__ tab,
                                         long long U0, int iters, long long len, unsigned long long combo_base,

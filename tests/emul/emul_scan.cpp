@@ -288,3 +288,34 @@ int64_t emul_km_scan(int M, const int* ncol, const double* mats, const double* b
     }
     return (int64_t)hits.size();
 }
+
+// Planner facts per block of the k-mer mask plan: out[8*b + ..] = nt, L of the first gathered table, bitmap used,
+// 1e6 * expected sectors per position, 1e6 * expected first-stage survivors, 1e6 * expected candidates, max_n, table MiB.
+extern "C" __attribute__((visibility("default")))
+int emul_km_plan_info(int M, const int* ncol, const double* mats, const double* bg, const double* thres, int strands,
+                      int64_t* out, int max_blocks) {
+    std::vector<MotifHost> mh(M);
+    std::vector<int64_t> col_off(2 * (size_t)M);
+    int64_t cols = 0;
+    const double* p = mats;
+    for (int m = 0; m < M; ++m) {
+        motif_prepare(mh[m], ncol[m], p, bg);
+        p += 4 * ncol[m];
+        for (int s = 0; s < 2; ++s) { col_off[2 * m + s] = cols; cols += ncol[m]; }
+    }
+    KmHostPlan hp;
+    build_km_host_plan(mh, col_off, cols, thres, strands, 1, hp);
+    const int nb = (int)hp.blocks.size();
+    for (int b = 0; b < nb && b < max_blocks; ++b) {
+        const KmBlockPlan& bp = hp.blocks[b];
+        int64_t* o = out + 8 * b;
+        o[0] = bp.nt; o[1] = bp.L[bp.order[0]]; o[2] = bp.bitmap ? 1 : 0;
+        o[3] = (int64_t)(1e6 * bp.req_rate); o[4] = (int64_t)(1e6 * bp.surv_rate); o[5] = (int64_t)(1e6 * bp.cand_rate);
+        o[6] = bp.max_n; o[7] = (int64_t)(bp.table_bytes() >> 20);
+        // invariants of the layout the kernel relies on
+        int sumL = 0;
+        for (int t = 0; t < bp.nt; ++t) sumL += bp.L[t];
+        if (sumL > 32 || bp.table_bytes() > kKmMaxTableBytes || bp.q16_bytes() + bp.bitmap_bytes() > kKmSmemBudget) return -1;
+    }
+    return nb;
+}

@@ -214,3 +214,35 @@ def test_km_plan_pvalue_cutoffs_are_selective(emul_km, oracle, ref_motifs, ref_m
     assert _same(h, o) and len(o[0]) > 10
     assert st[0] < 1.2 * len(o[0]) + 20                  # middle stage: candidates ~ hits
     assert st[6] < 3.0 * st[7] * 1e-6 * dna.size + 200   # first stage: survivors ~ the plan's estimate
+
+
+def test_km_planner_decisions(emul):
+    """The k-mer mask planner on the benchmark motif sets (thresholds = the committed p < 1e-5 fixtures): C2's single
+    dense block gathers two 10-mer tables without the bitmap; the many-motif set (sorted by length) gets sparse blocks
+    with the first-table bitmap and far fewer sectors than one per block and position; every layout respects the
+    kernel's limits (k-mers of all tables within 32 bases, tables <= 72 MiB per block, shared-memory budget)."""
+    import json
+    L = C.CDLL(os.path.join(HERE, "emul", "libemul.so"))
+    th_all = json.load(open(os.path.join(HERE, "golden", "config_thresholds.json")))
+
+    def plan(mats, thres, strands=2):
+        ncol = np.array([m.shape[0] for m in mats], dtype=np.int32)
+        flat = np.concatenate([np.ascontiguousarray(m, dtype=np.float64).reshape(-1) for m in mats])
+        out = np.zeros(8 * 64, np.int64)
+        vp = C.c_void_p
+        nb = L.emul_km_plan_info(C.c_int(len(mats)), ncol.ctypes.data_as(vp), flat.ctypes.data_as(vp), np.array(BG, float).ctypes.data_as(vp),
+                                 np.array(thres, float).ctypes.data_as(vp), C.c_int(strands), out.ctypes.data_as(vp), C.c_int(64))
+        assert nb >= 0, "a block violates the kernel's layout limits"
+        return out[:8 * nb].reshape(nb, 8)
+
+    c2 = plan(synth.synth_pwms(100, 12), [float.fromhex(v) for v in th_all["c2"]])
+    assert c2.shape[0] == 1
+    nt, l0, bitmap, sectors, surv, cand, max_n, mib = c2[0]
+    assert (nt, l0, bitmap) == (2, 10, 0) and 1.5e6 < sectors < 1.8e6 and surv < 0.06e6 and 1.5e3 < cand < 3e3 and mib == 64
+    c4 = plan(synth.config_c4_motifs(800), [float.fromhex(v) for v in th_all["c4"]])
+    assert c4.shape[0] == 7                                    # 800 motifs / 128 per block
+    assert c4[:, 2].sum() >= 6                                 # sparse first tables -> bitmap
+    assert c4[:, 3].sum() < 2.0e6                              # < 2 sectors per position over all seven blocks
+    assert np.all(np.diff(c4[:, 6]) >= 0)                      # blocks are sorted by motif length
+    one = plan([synth.ctcf_like_pwm()], [float.fromhex(th_all["c1"][0])])
+    assert one.shape[0] == 1 and one[0, 3] < 0.05e6            # one motif: almost every position stops at the bitmap

@@ -35,6 +35,10 @@ struct pwmscan_ctx {
     struct PoolBuf { void* p; size_t bytes; };
     std::vector<PoolBuf> dev_pool, pin_pool;
     std::mutex pool_mu;
+    // all-zero int32 column shared by the hit lists of single-segment scans (their segment column is not transferred);
+    // grown by allocating a new zeroed block — older blocks stay alive for the hit lists that point into them
+    std::vector<void*> zero_blocks;
+    size_t zero_count = 0;
     unsigned long long* d_counters = nullptr;   // [0] candidates [1] hits [2] error flag [3] work counter (32-bit view)
     unsigned long long* h_counters = nullptr;   // pinned mirror
 };

@@ -102,6 +102,19 @@ void dev_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes) {
     ctx->dev_pool.push_back({p, bytes});
 }
 
+// >= n zero int32 values that nobody ever writes (calloc: untouched pages cost nothing)
+static const int32_t* zero_column(pwmscan_ctx* ctx, size_t n) {
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    if (n > ctx->zero_count || ctx->zero_blocks.empty()) {
+        const size_t want = std::max<size_t>(n + n / 2, 1 << 20);
+        void* p = std::calloc(want, sizeof(int32_t));
+        if (!p) return nullptr;
+        ctx->zero_blocks.push_back(p);
+        ctx->zero_count = want;
+    }
+    return (const int32_t*)ctx->zero_blocks.back();
+}
+
 void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
     {
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
@@ -170,6 +183,7 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
     for (auto& p : ctx->pinned) if (p) cudaFreeHost(p);
     for (auto& b : ctx->dev_pool) cudaFree(b.p);
     for (auto& b : ctx->pin_pool) cudaFreeHost(b.p);
+    for (void* z : ctx->zero_blocks) std::free(z);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -923,7 +937,7 @@ __global__ void decode_kernel(const unsigned long long* __restrict__ keys, const
         score[k] = sc[k];
         strand[k] = (uint8_t)((key >> kl.pb) & 1ull);
         motif[k] = (int32_t)((key >> (kl.pb + 1)) & ((1ull << kl.mb) - 1ull));
-        segment[k] = (int32_t)(key >> (kl.pb + 1 + kl.mb));
+        if (segment) segment[k] = (int32_t)(key >> (kl.pb + 1 + kl.mb));
     }
 }
 
@@ -1150,7 +1164,8 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, key_bits, ctx->stream);
         const size_t n8 = (nhits + 7) & ~7ull;                       // keeps every column 8-byte aligned
-        const size_t col_bytes = n8 * 25;
+        const bool one_seg = seq->nseg == 1;                        // the segment column (all zero) is then not materialised
+        const size_t col_bytes = n8 * (one_seg ? 21 : 25);
         unsigned char* d_tmp = (unsigned char*)scratch_get(ctx, 6, tmp_bytes + 256 + col_bytes);
         if (!d_tmp) { delete h; return PWMSCAN_ECUDA; }
         cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, key_bits, ctx->stream);
@@ -1159,8 +1174,8 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         long long* c_pos = (long long*)d_cols;
         double* c_sc = (double*)(d_cols + n8 * 8);
         int32_t* c_mo = (int32_t*)(d_cols + n8 * 16);
-        int32_t* c_sg = (int32_t*)(d_cols + n8 * 20);
-        uint8_t* c_st = (uint8_t*)(d_cols + n8 * 24);
+        int32_t* c_sg = one_seg ? nullptr : (int32_t*)(d_cols + n8 * 20);
+        uint8_t* c_st = (uint8_t*)(d_cols + n8 * (one_seg ? 20 : 24));
         decode_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_keys2, d_sc2, (long long)nhits, kl, c_pos, c_sc, c_mo, c_sg, c_st);
         if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "decode_kernel"); }
         cudaEventRecord(ctx->ev[3], ctx->stream);
@@ -1170,7 +1185,12 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { pwmscan_hits_free(h); return cuda_fail(ctx, e, "scan sync"); }
         unsigned char* hb = (unsigned char*)h->buf;
         h->pos = (const int64_t*)hb; h->score = (const double*)(hb + n8 * 8); h->motif = (const int32_t*)(hb + n8 * 16);
-        h->segment = (const int32_t*)(hb + n8 * 20); h->strand = (const uint8_t*)(hb + n8 * 24);
+        h->strand = (const uint8_t*)(hb + n8 * (one_seg ? 20 : 24));
+        if (one_seg) {
+            if (!(h->segment = zero_column(ctx, n8))) { pwmscan_hits_free(h); return set_err(ctx, PWMSCAN_EINVAL, "out of host memory"); }
+        } else {
+            h->segment = (const int32_t*)(hb + n8 * 20);
+        }
         cudaEventElapsedTime(&ms_sort, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&ms_tot, ctx->ev[0], ctx->ev[3]);
     } else {
@@ -1179,7 +1199,7 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
     cudaEventElapsedTime(&ms_pre, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ms_res, ctx->ev[1], ctx->ev[2]);
     ctx->timing[0] = ms_pre; ctx->timing[1] = ms_res; ctx->timing[2] = ms_sort; ctx->timing[3] = ms_tot;
-    ctx->timing[5] = (double)nhits * 25 + 32;
+    ctx->timing[5] = (double)nhits * (seq->nseg == 1 ? 21 : 25) + 32;
     ctx->timing[6] = (double)ncand;
     ctx->timing[7] = (double)launches;
     *out = h;

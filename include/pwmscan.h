@@ -127,7 +127,9 @@ int  pwmscan_scan_host_first_invalid(pwmscan_ctx* ctx, int alphabet, int64_t* po
 int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
                        const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);
 int64_t pwmscan_hits_count(const pwmscan_hits* hits);
-/* Column views (host memory owned by `hits`); any pointer argument may be NULL. */
+/* Column views (read-only host memory, valid until pwmscan_hits_free / pwmscan_ctx_destroy); any pointer
+ * argument may be NULL.  (For a single-segment scan the segment column is a shared all-zero array of the
+ * context: it is not transferred from the device.) */
 int  pwmscan_hits_columns(const pwmscan_hits* hits, const int32_t** motif, const uint8_t** strand,
                           const int32_t** segment, const int64_t** pos, const double** score);
 void pwmscan_hits_free(pwmscan_hits* hits);

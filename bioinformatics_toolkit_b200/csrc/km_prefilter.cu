@@ -1,4 +1,6 @@
-// km_prefilter.cu — k-mer mask first stage of the thresholded scan (plan_km.h has the maths).
+// km_prefilter.cu — k-mer mask first stage of the thresholded scan (plan_km.h has the maths): decides, for every
+// sequence position and every (motif, strand), whether the reference's lookAheadSearch' (Motif/Search.hs:169-198)
+// could still report the window — never a false negative; survivors are replayed exactly (rescore_kernel).
 //
 //   alive(u) = T_0[k-mer at u] & T_1[k-mer at u + L_0] & ... & T_{nt-1}[k-mer at u + L_0 + .. + L_{nt-2}]    (256-bit masks)
 //

@@ -298,7 +298,7 @@ __device__ __forceinline__ void km_item_bitmap(KmShared& sh, const uint16_t* __r
     const uint32_t mk0 = tmk[0];
 #pragma unroll 1
     for (int si = 0; si < nscan; ++si) {
-        const int pb = warp * per_warp + si * 32 * kpt + lane * kpt;    // (pb & 15) + kpt <= 16
+        const int pb = (si * (kKmThreads / 32) + warp) * 32 * kpt + lane * kpt;    // scan steps interleaved over the warps; (pb & 15) + kpt <= 16
         const int wi = (pb >> 4) + kKmHaloWords;
         const uint32_t w0 = sh.seq[wi], w1 = sh.seq[wi + 1], w2 = sh.seq[wi + 2], w3 = sh.seq[wi + 3];
         const int s0 = 2 * (pb & 15);

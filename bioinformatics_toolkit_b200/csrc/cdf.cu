@@ -376,7 +376,9 @@ extern "C" int pwmscan_cutoff_cdfs(pwmscan_ctx* ctx, const pwmscan_motifs* mo, d
                                    int64_t* offsets /* M+1 */) {
     if (!ctx || !mo || !thres_out || !x || !P || !offsets) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_cutoff_cdfs: NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const int M = mo->M, batch = 128;
+    // one launch per batch; a batch is a multiple of the SM count (one persistent CTA per SM walks its motifs),
+    // bounded by the output staging (2 x batch x 1.6 MB of device memory)
+    const int M = mo->M, batch = 6 * std::max(1, ctx->sm_count);
     std::vector<double> ax, ap;
     std::vector<int64_t> cnt(M);
     offsets[0] = 0;

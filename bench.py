@@ -363,7 +363,11 @@ def main():
                        "hits_per_step_rank0": int(nh),
                        "device_ms_breakdown_last_step": {k: round(float(v), 4) for k, v in last_timing.items()}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * el2.item() / args.steps, "pinned_h2d_gbs_this_box": h2d_gbs},
+                    "ms_per_step": 1e3 * el2.item() / args.steps, "pinned_h2d_gbs_this_box": h2d_gbs,
+                    # the end-to-end path is bound by the host->device copy of the ASCII bytes (1 B per base): this rank's share
+                    "pcie_roofline": {"bound": "pcie-h2d", "achieved": h2d / (el2.item() / args.steps) / 1e9, "peak": h2d_gbs, "unit": "GB/s",
+                                      "frac": h2d / (el2.item() / args.steps) / 1e9 / h2d_gbs,
+                                      "peak_source": "plain cudaMemcpy of the same pinned buffer, measured in this run"}},
             "gpu_launches": int(args.steps * len(dev_seqs) * 3), "clocks": clocks,   # km_prefilter + rescore + decode per scan (the radix sort is CUB)
             "roofline": roofline, "roofline_hbm": roofline_hbm, "issue_roofline": issue, "plan": info, "cpu_baseline": cpu}), flush=True)
     if world > 1:

@@ -1080,7 +1080,8 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
             // chunk boundaries are multiples of the anchor rounding unit, so every launch covers whole work items.
             // 16 Mi bases per chunk (smaller chunks cost more in per-launch overhead than they hide), except that
             // the end is split off as a short last chunk so that little work is left once the last byte has landed.
-            int64_t cb = 32 * kAnchorRound;
+            static const int chunk_units = std::getenv("PWMSCAN_CHUNK_UNITS") ? std::max(8, std::atoi(std::getenv("PWMSCAN_CHUNK_UNITS"))) : 32;   // experiments
+            int64_t cb = chunk_units * kAnchorRound;
             while ((len + cb - 1) / cb > kMaxChunks - 1) cb *= 2;
             const int64_t tail = 4 * kAnchorRound;
             std::vector<int64_t> bounds(1, 0);

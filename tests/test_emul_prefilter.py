@@ -246,3 +246,34 @@ def test_km_planner_decisions(emul):
     assert np.all(np.diff(c4[:, 6]) >= 0)                      # blocks are sorted by motif length
     one = plan([synth.ctcf_like_pwm()], [float.fromhex(th_all["c1"][0])])
     assert one.shape[0] == 1 and one[0, 3] < 0.05e6            # one motif: almost every position stops at the bitmap
+
+
+def test_km_plan_property_random_cases(emul_km, oracle):
+    """Randomised sweep (fixed seeds): motif counts, lengths 1..64, skewed backgrounds, one or both strands, cutoffs
+    from very loose to consensus-only, forced and free table layouts — the k-mer mask plan + middle stage never lose
+    or invent a hit relative to the oracle."""
+    rng = np.random.default_rng(2024)
+    layouts = [(0, 0), (1, 8), (1, 10), (2, 8), (2, 10), (3, 9), (3, 10), (4, 8)]
+    for case in range(24):
+        nm = int(rng.integers(1, 9))
+        lengths = [int(rng.choice([1, 2, 3, 5, 8, 9, 10, 11, 16, 17, 21, 31, 33, 48, 64])) for _ in range(nm)]
+        mats = synth.synth_pwms(nm, 500 + case, lengths=lengths, alpha=float(rng.choice([0.15, 0.3, 1.0])), zero_frac=float(rng.choice([0.0, 0.125, 0.4])))
+        bgw = rng.dirichlet([8, 8, 8, 8])
+        bg = tuple(float(x) for x in bgw / bgw.sum())
+        dna = synth.synth_dna(int(rng.integers(50, 2500)), 900 + case, gc=float(rng.uniform(0.3, 0.7)),
+                              n_runs=[(int(rng.integers(0, 40)), int(rng.integers(1, 30)))] if rng.random() < 0.5 else [])
+        thres = []
+        for m in mats:
+            opt = oracle.optimal_score(bg, m)
+            thres.append(float(rng.choice([-1e9, -2.0 * abs(opt), -0.5 * abs(opt), 0.0, 0.3 * opt, 0.7 * opt, opt - 1e-9, opt, opt + 1.0])))
+        strands = int(rng.integers(1, 3))
+        nt, L = layouts[case % len(layouts)]
+        h, st = emul_km(mats, thres, dna, strands=strands, force_nt=nt, force_L=L, bg=bg)
+        ref = []
+        for mi, (mat, th) in enumerate(zip(mats, thres)):
+            for s in range(strands):
+                mm = mat if s == 0 else oracle.rc_pwm(mat)
+                pos, sc = oracle.find_tfbs(bg, mm, dna, th, True, mode=1)
+                ref.append((np.full(pos.size, mi, np.int32), np.full(pos.size, s, np.uint8), pos, sc))
+        o = tuple(np.concatenate([r[k] for r in ref]) for k in range(4))
+        assert _same(h, o), (case, lengths, thres, strands, nt, L)

@@ -369,3 +369,25 @@ def test_kmer_tables_extreme_shapes(ctx, oracle):
     h = gpu_scan(ctx, mats, thres, dna, strands=1)
     assert_same(h, oracle_scan(oracle, mats, thres, dna, strands=1))
     assert len(h) > 1000
+
+
+def test_random_sweep_small_cases(ctx, oracle):
+    """Randomised sweep through the C ABI (fixed seeds): 1-8 motifs of 1..64 columns, skewed backgrounds, one or both
+    strands, cutoffs from always-true to unreachable, short sequences with N runs — bit-identical to the oracle."""
+    rng = np.random.default_rng(4242)
+    for case in range(30):
+        nm = int(rng.integers(1, 9))
+        lengths = [int(rng.choice([1, 2, 3, 5, 8, 9, 10, 11, 16, 17, 21, 31, 33, 48, 64])) for _ in range(nm)]
+        mats = synth.synth_pwms(nm, 700 + case, lengths=lengths, alpha=float(rng.choice([0.15, 0.3, 1.0])), zero_frac=float(rng.choice([0.0, 0.125, 0.4])))
+        bgw = rng.dirichlet([8, 8, 8, 8])
+        bg = tuple(float(x) for x in bgw / bgw.sum())
+        dna = synth.synth_dna(int(rng.integers(1, 6000)), 1100 + case, gc=float(rng.uniform(0.3, 0.7)),
+                              n_runs=[(int(rng.integers(0, 40)), int(rng.integers(1, 30)))] if rng.random() < 0.5 else [])
+        thres = []
+        for m in mats:
+            opt = oracle.optimal_score(bg, m)
+            thres.append(float(rng.choice([-1e9, -2.0 * abs(opt), -0.5 * abs(opt), 0.0, 0.3 * opt, 0.7 * opt, opt - 1e-9, opt, opt + 1.0])))
+        strands = int(rng.integers(1, 3))
+        h = gpu_scan(ctx, mats, thres, dna, strands=strands, bg=bg)
+        o = oracle_scan(oracle, mats, thres, dna, strands=strands, bg=bg)
+        assert_same(h, o)

@@ -65,6 +65,7 @@ def load():
         L.pwmscan_plan_free.argtypes = [_vp]
         L.pwmscan_hits_free.argtypes = [_vp]
         L.pwmscan_free.argtypes = [_vp]
+        L.pwmscan_alnset_free.argtypes = [_vp]
         _lib = L
         return L
 
@@ -251,6 +252,52 @@ class DeviceMotifs:
     def free(self):
         if self.h:
             self.ctx.L.pwmscan_motifs_free(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class AlignSet:
+    """PWMs resident on the device for iterativeMerge (pwmscan_alnset_*): all-pairs initialisation, per-merge slot
+    update and row refresh without re-uploading the set."""
+
+    def __init__(self, ctx, mats, penal="exp", gap=0.05, comb="l1"):
+        self.ctx = ctx
+        mats = [_arr(m, np.float64).reshape(-1, 4) for m in mats]
+        self.M = len(mats)
+        ncol = np.array([m.shape[0] for m in mats], dtype=np.int32)
+        flat = np.concatenate([m.reshape(-1) for m in mats]) if mats else np.zeros(0)
+        self.h = _vp()
+        ctx.check(ctx.L.pwmscan_alnset_create(ctx.h, C.c_int32(self.M), _ptr(ncol), _ptr(flat), C.c_int(PENAL[penal]),
+                                              C.c_double(gap), C.c_int(COMB[comb]), C.byref(self.h)))
+
+    def update(self, slot, mat):
+        m = _arr(mat, np.float64).reshape(-1, 4)
+        self.ctx.check(self.ctx.L.pwmscan_alnset_update(self.h, C.c_int32(slot), C.c_int32(m.shape[0]), _ptr(m)))
+
+    def pairs(self, a=None, b=None):
+        """align pwm_a[k] pwm_b[k]; a = b = None: all i < j (packed upper triangle, row-major)."""
+        if a is None:
+            n = self.M * (self.M - 1) // 2
+            pa = pb = None
+        else:
+            a, b = _arr(a, np.int32), _arr(b, np.int32)
+            n = a.size
+            pa, pb = _ptr(a), _ptr(b)
+        d = np.empty(n)
+        sd = np.empty(n, dtype=np.uint8)
+        pos = np.empty(n, dtype=np.int32)
+        if n:
+            self.ctx.check(self.ctx.L.pwmscan_alnset_pairs(self.h, C.c_int64(n), pa, pb, _ptr(d), _ptr(sd), _ptr(pos)))
+        return d, sd, pos
+
+    def free(self):
+        if self.h:
+            self.ctx.L.pwmscan_alnset_free(self.h)
             self.h = _vp()
 
     def __del__(self):

@@ -32,6 +32,11 @@ class AlignFn:
     def pairs(self, pwms, a, b):
         return self._motifs(pwms).align_pairs(a, b, self.penal, self.gap, self.comb)
 
+    def resident(self, pwms, ctx=None):
+        """The PWMs kept on the device for a merge loop (`_lib.AlignSet`): `.pairs()` = all i < j, `.update(slot, mat)`,
+        `.pairs(a, b)` = row refresh."""
+        return _lib.AlignSet(ctx or _lib.default_context(), [p._mat for p in pwms], self.penal, self.gap, self.comb)
+
 
 def alignmentBy(distance="jsd", penal=("exp", 0.05), comb="l1"):
     """alignmentBy jsd (pFn gap) combFn (Alignment.hs:83-86).  Only the Jensen-Shannon distance the

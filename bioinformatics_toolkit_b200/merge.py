@@ -117,42 +117,83 @@ def mergeTreeWeighted(align, t):
 
 
 def iterativeMerge(align, th, motifs):
-    """Merge.hs:113-170.  Returns [([names], PWM, weights)]."""
+    """Merge.hs:113-170.  Returns [([names], PWM, weights)].
+
+    The distance matrix is initialised with one all-pairs call; with a device AlignFn the PWMs then stay resident on
+    the device (`align.resident`): a merge replaces one slot and refreshes one row, and the minimum is tracked per row
+    instead of re-scanning the N x N matrix.  An arbitrary Python `align` callable falls back to per-call alignment."""
     n = len(motifs)
     items = [([m._name], m._pwm, [1] * size(m._pwm)) for m in motifs]
     if n < 2:
         return items
-    d, sd, pos = align.all_pairs([m._pwm for m in motifs])         # initialisation, Merge.hs:161-165
+    resident = align.resident([m._pwm for m in motifs]) if hasattr(align, "resident") else None
+    if resident is not None:
+        d, sd, pos = resident.pairs()                              # initialisation, Merge.hs:161-165
+    else:
+        d, sd, pos = align.all_pairs([m._pwm for m in motifs])
     D = np.full((n, n), np.inf)
     S = np.zeros((n, n), dtype=bool)
     P = np.zeros((n, n), dtype=np.int64)
     iu = np.triu_indices(n, 1)                                     # row-major order == packed order
     D[iu], S[iu], P[iu] = d, sd.astype(bool), pos
-    alive = [True] * n
-    while True:
-        # first minimum in the scan order i ascending, j ascending (strict <, Merge.hs:149-158)
-        k = int(np.argmin(D))
-        i, j = divmod(k, n)
-        if not (D[i, j] < th):
-            break
-        same, p = bool(S[i, j]), int(P[i, j])
-        nm1, pwm1, w1 = items[i]
-        nm2, pwm2, w2 = items[j]
-        pwm_, w_ = mergePWMWeighted((pwm1, w1), (pwm2, w2), p) if same else mergePWMWeighted((pwm1, w1), (rcPWM(pwm2), w2[::-1]), p)
-        D[:, j] = np.inf                                           # Merge.hs:135 (column j; row j becomes unreachable too)
-        D[j, :] = np.inf
-        items[i] = (nm1 + nm2, pwm_, w_)
-        items[j] = None
-        alive[j] = False
-        others = [q for q in range(n) if q != i and alive[q]]
-        if others:                                                 # row refresh, Merge.hs:138-145, argument order kept
-            pw = [pwm_] + [items[q][1] for q in others]
-            a = [0 if i < q else k2 + 1 for k2, q in enumerate(others)]
-            b = [k2 + 1 if i < q else 0 for k2, q in enumerate(others)]
-            dd, ss, pp = align.pairs(pw, a, b)
-            for k2, q in enumerate(others):
-                r, c = (i, q) if i < q else (q, i)
-                D[r, c], S[r, c], P[r, c] = dd[k2], bool(ss[k2]), int(pp[k2])
+    alive = np.ones(n, dtype=bool)
+    # per-row minimum (first one in the row) of the upper triangle: the global "first minimum in the scan order i
+    # ascending, j ascending" (strict <, Merge.hs:149-158) is the first row whose minimum is smallest
+    rmin_col = np.argmin(D, axis=1)
+    rmin_val = D[np.arange(n), rmin_col]
+
+    def recompute(rows):
+        for r in rows:
+            c = int(np.argmin(D[r]))
+            rmin_col[r], rmin_val[r] = c, D[r, c]
+
+    try:
+        while True:
+            i = int(np.argmin(rmin_val))
+            j = int(rmin_col[i])
+            if not (rmin_val[i] < th):
+                break
+            same, p = bool(S[i, j]), int(P[i, j])
+            nm1, pwm1, w1 = items[i]
+            nm2, pwm2, w2 = items[j]
+            pwm_, w_ = mergePWMWeighted((pwm1, w1), (pwm2, w2), p) if same else mergePWMWeighted((pwm1, w1), (rcPWM(pwm2), w2[::-1]), p)
+            D[:, j] = np.inf                                       # Merge.hs:135 (column j; row j becomes unreachable too)
+            D[j, :] = np.inf
+            items[i] = (nm1 + nm2, pwm_, w_)
+            items[j] = None
+            alive[j] = False
+            rmin_val[j], rmin_col[j] = np.inf, 0
+            dirty = set(int(r) for r in np.flatnonzero((rmin_col == j) & np.isfinite(rmin_val)))   # their minimum sat in column j
+            dirty.add(i)
+            others = np.flatnonzero(alive)
+            others = others[others != i]
+            if others.size:                                        # row refresh, Merge.hs:138-145, argument order kept
+                if resident is not None:
+                    resident.update(i, pwm_._mat)
+                    a = np.where(i < others, i, others).astype(np.int32)
+                    b = np.where(i < others, others, i).astype(np.int32)
+                    dd, ss, pp = resident.pairs(a, b)
+                else:
+                    pw = [pwm_] + [items[q][1] for q in others]
+                    k2 = np.arange(others.size)
+                    a = np.where(i < others, 0, k2 + 1)
+                    b = np.where(i < others, k2 + 1, 0)
+                    dd, ss, pp = align.pairs(pw, a, b)
+                r = np.minimum(i, others)
+                c = np.maximum(i, others)
+                D[r, c], S[r, c], P[r, c] = dd, ss.astype(bool), pp
+                low = others[others < i]                           # rows q < i: their entry in column i changed
+                if low.size:
+                    v = D[low, i]
+                    was = rmin_col[low] == i
+                    better = ~was & ((v < rmin_val[low]) | ((v == rmin_val[low]) & (i < rmin_col[low])))
+                    rmin_val[low[better]] = v[better]
+                    rmin_col[low[better]] = i
+                    dirty.update(int(q) for q in low[was])
+            recompute(dirty)
+    finally:
+        if resident is not None:
+            resident.free()
     return [it for it in items if it is not None]
 
 

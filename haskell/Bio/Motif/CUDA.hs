@@ -35,7 +35,7 @@ import           System.IO.Unsafe         (unsafePerformIO)
 import           Bio.Motif                (Bkgd (..), CDF (..), PWM (..), size)
 import           Bio.Seq                  (DNA, toBS)
 
-data Ctx; data Seq; data Motifs; data Plan; data Hits
+data Ctx; data Seq; data Motifs; data Plan; data Hits; data AlnSet
 
 -- `safe` so that a long scan does not block the GHC runtime.
 foreign import ccall safe "pwmscan_ctx_create"       c_ctx_create   :: CInt -> Ptr (Ptr Ctx) -> IO CInt
@@ -59,6 +59,10 @@ foreign import ccall safe "pwmscan_max_match_sc"     c_max_match    :: Ptr Ctx -
 foreign import ccall safe "pwmscan_pvalue_to_score"  c_pvalue       :: Ptr Ctx -> Ptr Motifs -> Double -> Ptr Double -> IO CInt
 foreign import ccall safe "pwmscan_score_cdf"        c_score_cdf    :: Ptr Ctx -> Ptr Motifs -> Int32 -> Ptr (Ptr Double) -> Ptr (Ptr Double) -> Ptr Int64 -> IO CInt
 foreign import ccall safe "pwmscan_free"             c_free         :: Ptr a -> IO ()
+foreign import ccall safe "pwmscan_alnset_create"    c_alnset_create :: Ptr Ctx -> Int32 -> Ptr Int32 -> Ptr Double -> CInt -> Double -> CInt -> Ptr (Ptr AlnSet) -> IO CInt
+foreign import ccall safe "pwmscan_alnset_update"    c_alnset_update :: Ptr AlnSet -> Int32 -> Int32 -> Ptr Double -> IO CInt
+foreign import ccall safe "pwmscan_alnset_pairs"     c_alnset_pairs  :: Ptr AlnSet -> Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
+foreign import ccall safe "pwmscan_alnset_free"      c_alnset_free   :: Ptr AlnSet -> IO ()
 foreign import ccall safe "pwmscan_align_all_pairs"  c_align_all    :: Ptr Ctx -> Ptr Motifs -> CInt -> Double -> CInt -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
 
 -- | The reference signals failure with `error` (pure code) — so do we.

@@ -176,6 +176,19 @@ int  pwmscan_align_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* motifs, int64_t
                          const int32_t* b, int penalty_kind, double gap, int combine_kind,
                          double* dist, uint8_t* same_dir, int32_t* pos);
 
+/* ---- iterativeMerge with the PWMs resident on the device (Motif/Merge.hs:113-170): create the set once (all-pairs
+ *      initialisation = pwmscan_alnset_pairs with a = b = NULL, packed upper triangle as pwmscan_align_all_pairs), then
+ *      per merge replace the merged PWM in its slot (pwmscan_alnset_update) and refresh its row with a pair list
+ *      (result k = `align pwm_{a[k]} pwm_{b[k]}`, argument order preserved, Merge.hs:138-145).  Same results as
+ *      pwmscan_align_pairs on a freshly built motif set; nothing else is re-uploaded or recomputed. ---------------- */
+typedef struct pwmscan_alnset pwmscan_alnset;
+int  pwmscan_alnset_create(pwmscan_ctx* ctx, int32_t M, const int32_t* ncol, const double* mats_rowmajor, int penalty_kind,
+                           double gap, int combine_kind, pwmscan_alnset** out);
+int  pwmscan_alnset_update(pwmscan_alnset* set, int32_t slot, int32_t ncol, const double* mat_rowmajor);
+int  pwmscan_alnset_pairs(pwmscan_alnset* set, int64_t npairs, const int32_t* a, const int32_t* b, double* dist,
+                          uint8_t* same_dir, int32_t* pos);
+void pwmscan_alnset_free(pwmscan_alnset* set);
+
 /* ---- scanMotif's per-hit columns (Data/Bed/Utils.hs:109-123), computed on the device for the hits of a scan:
  *      p = 1 - cdf score on the motif's (truncated) CDF (Motif.hs:236-249; bit-identical fp64) and
  *      the BED score toAffinity p = round (1000 / (1 + exp (-(-log10 (max 1e-20 p) - 5)))) (round half even;

@@ -175,3 +175,22 @@ def test_device_affinity_equals_host_formula():
     aff3 = h.affinity(off, cx - 1000.0, cy)            # every score right of the last point: cdf = last p
     last_p = np.array([1 - c._cdf.ps[-1] for c in cms])
     assert np.array_equal(aff3, np.array([bed_utils.toAffinity(float(last_p[m])) for m in h.motif], dtype=np.int64))
+
+
+def test_iterative_merge_resident_equals_per_call_path():
+    """iterativeMerge with the PWMs resident on the device (pwmscan_alnset_*: slot updates, row refreshes, per-row
+    minimum tracking) gives exactly the result of the per-call path (motif set rebuilt and the full matrix re-scanned
+    at every merge) — 160 motifs with duplicates, reverse-complement duplicates and palindromes, two thresholds."""
+    mats = synth.config_c5_motifs(160, seed=41)
+    motifs = [Mo.Motif(b"m%d" % i, Mo.PWM(20, m)) for i, m in enumerate(mats)]
+
+    class PerCall:                       # same device alignments, but without `.resident`
+        def __init__(self, f):
+            self.all_pairs, self.pairs = f.all_pairs, f.pairs
+
+    for th in (0.1, 0.3):
+        a = M.iterativeMerge(alignment, th, motifs)
+        b = M.iterativeMerge(PerCall(alignment), th, motifs)
+        assert len(a) == len(b) and len(a) < len(motifs)
+        for x, y in zip(a, b):
+            assert x[0] == y[0] and x[2] == y[2] and np.array_equal(x[1]._mat, y[1]._mat)

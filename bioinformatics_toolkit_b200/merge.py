@@ -197,6 +197,47 @@ def iterativeMerge(align, th, motifs):
     return [it for it in items if it is not None]
 
 
+def _upgma(D, leaves):
+    """Average linkage on a symmetric distance matrix (inf on the diagonal), closest pair first, ties to the lowest
+    indices.  The minimum is tracked per row, so a merge costs O(n) plus the few rows whose nearest neighbour was
+    one of the merged clusters."""
+    n = D.shape[0]
+    nodes = dict(enumerate(leaves))
+    sizes = np.ones(n)
+    alive = np.ones(n, dtype=bool)
+    rmin_col = np.argmin(D, axis=1)
+    rmin_val = D[np.arange(n), rmin_col]
+    for _ in range(n - 1):
+        a = int(np.argmin(rmin_val))
+        b = int(rmin_col[a])
+        if a > b:
+            a, b = b, a
+        dist = float(D[a, b])
+        na, nb = sizes[a], sizes[b]
+        alive[b] = False
+        cs = np.flatnonzero(alive)
+        cs = cs[cs != a]
+        v = (na * D[a, cs] + nb * D[b, cs]) / (na + nb)
+        D[a, cs] = v
+        D[cs, a] = v
+        D[b, :] = np.inf
+        D[:, b] = np.inf
+        rmin_val[b] = np.inf
+        nodes[a] = Branch(int(na + nb), dist, nodes[a], nodes[b])
+        sizes[a] = na + nb
+        if cs.size:
+            gone = (rmin_col[cs] == a) | (rmin_col[cs] == b)                     # their nearest neighbour was merged
+            better = ~gone & ((v < rmin_val[cs]) | ((v == rmin_val[cs]) & (a < rmin_col[cs])))
+            rmin_val[cs[better]] = v[better]
+            rmin_col[cs[better]] = a
+            for r in list(cs[gone]) + [a]:
+                c = int(np.argmin(D[r]))
+                rmin_col[r], rmin_val[r] = c, D[r, c]
+        else:
+            rmin_val[a] = np.inf
+    return nodes[int(np.flatnonzero(alive)[0])]
+
+
 def buildTree(align, motifs):
     """hclust Average motifs (fst . align) (Merge.hs:173-176).  `clustering`'s hclust is a
     third-party package the reference does not pin; this is plain average linkage (UPGMA) merging
@@ -209,28 +250,7 @@ def buildTree(align, motifs):
     iu = np.triu_indices(n, 1)
     D[iu] = d
     D = np.minimum(D, D.T)
-    nodes = {i: Leaf(motifs[i]) for i in range(n)}
-    sizes = {i: 1 for i in range(n)}
-    active = list(range(n))
-    while len(active) > 1:
-        sub = D[np.ix_(active, active)]
-        k = int(np.argmin(sub))
-        ai, bi = divmod(k, len(active))
-        a, b = active[ai], active[bi]
-        if a > b:
-            a, b = b, a
-        dist = float(D[a, b])
-        na, nb = sizes[a], sizes[b]
-        for c in active:
-            if c != a and c != b:
-                v = (na * D[a, c] + nb * D[b, c]) / (na + nb)
-                D[a, c] = D[c, a] = v
-        D[b, :] = np.inf
-        D[:, b] = np.inf
-        nodes[a] = Branch(na + nb, dist, nodes[a], nodes[b])
-        sizes[a] = na + nb
-        active.remove(b)
-    return nodes[active[0]]
+    return _upgma(D, [Leaf(m) for m in motifs])
 
 
 def cutAt(tree, h):

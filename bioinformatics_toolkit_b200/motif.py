@@ -245,8 +245,37 @@ def readMEME(path):
 
 
 def _shortest(x):
-    r = repr(float(x))
-    return r[:-2] if r.endswith(".0") else r   # double-conversion toShortest prints 1 not 1.0
+    """Data.Double.Conversion.ByteString.toShortest (the `double-conversion` library's ToShortest, i.e. the ECMAScript
+    Number-to-string rules): shortest round-trip digits; plain decimals for 1e-6 <= |x| < 1e21 ("0.00001", "1", "123.5"),
+    otherwise d[.ddd]e[+-]n without zero padding ("1e-7", "1.5e+21").  Used by toMEME / writeFasta (Motif.hs:334,355)
+    and `merge_motifs dist` (MergeMotifs.hs:167)."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "0"                                   # ToShortest prints -0.0 as "-0"; probabilities / distances are never -0
+    sign = "-" if x < 0 else ""
+    r = repr(abs(x))                                 # shortest round-trip digits (David Gay / Ryu-equivalent)
+    mant, _, ex = r.partition("e")
+    ip, _, fp = mant.partition(".")
+    if fp == "0":
+        fp = ""
+    digits = (ip + fp).lstrip("0")
+    n = len(ip) + (int(ex) if ex else 0)             # value = 0.DIGITS x 10^n, with leading zeros of ip+fp accounted for
+    n -= len(ip + fp) - len((ip + fp).lstrip("0"))
+    digits = digits.rstrip("0") or "0"
+    k = len(digits)
+    if k <= n <= 21:
+        return sign + digits + "0" * (n - k)
+    if 0 < n <= 21:
+        return sign + digits[:n] + "." + digits[n:]
+    if -6 < n <= 0:
+        return sign + "0." + "0" * (-n) + digits
+    e = n - 1
+    body = digits if k == 1 else digits[0] + "." + digits[1:]
+    return sign + body + "e" + ("+" if e >= 0 else "-") + str(abs(e))
 
 
 def toMEME(motifs, bg=default_bkgd):

@@ -50,3 +50,19 @@ def test_upgma_equals_plain_formulation():
         D = sym(n, rng, levels)
         leaves = [Leaf(i) for i in range(n)]
         assert ser(_upgma(D.copy(), leaves)) == ser(upgma_plain(D.copy(), leaves)), (n, levels)
+
+
+def test_to_shortest_formatting():
+    """toShortest (double-conversion / ECMAScript rules) as used by toMEME, writeFasta and `merge_motifs dist`."""
+    from bioinformatics_toolkit_b200.motif import _shortest as f
+    cases = {1.0: "1", 0.5: "0.5", 123.5: "123.5", 0.1: "0.1", 1e-5: "0.00001", 1e-6: "0.000001", 1e-7: "1e-7", 1.5e-7: "1.5e-7",
+             1.2345e-10: "1.2345e-10", 1e21: "1e+21", 1e20: "100000000000000000000", 1.5e21: "1.5e+21", 0.0001: "0.0001",
+             0.12889355547153183: "0.12889355547153183", 5e-324: "5e-324", 1.7976931348623157e308: "1.7976931348623157e+308",
+             100.0: "100", 1e16: "10000000000000000", 0.000123: "0.000123", -2.5: "-2.5", 3.0e-5: "0.00003", 0.0: "0"}
+    for x, s in cases.items():
+        assert f(x) == s, (x, f(x), s)
+    import random
+    random.seed(1)
+    for _ in range(5000):
+        x = random.uniform(-1, 1) * 10 ** random.randint(-12, 25)
+        assert float(f(x)) == x

@@ -61,10 +61,11 @@ def main(argv=None):
         if a.inputB is None:
             d, _, _ = align.all_pairs([m._pwm for m in ma]) if len(ma) > 1 else ([], None, None)
             k = 0
-            for i in range(len(ma)):
-                for j in range(i + 1, len(ma)):
-                    out.write(b"\t".join((ma[i]._name, ma[j]._name, _shortest(d[k]).encode())) + b"\n")
-                    k += 1
+            names = [m._name for m in ma]
+            for i in range(len(ma)):                       # one write per row of the triangle
+                row = d[k:k + len(ma) - i - 1].tolist()
+                out.write(b"".join(b"%s\t%s\t%s\n" % (names[i], names[i + 1 + t], _shortest(v).encode()) for t, v in enumerate(row)))
+                k += len(row)
         else:
             mb = read_motif(a.inputB)
             pw = [m._pwm for m in ma] + [m._pwm for m in mb]

@@ -250,6 +250,9 @@ def _shortest(x):
     otherwise d[.ddd]e[+-]n without zero padding ("1e-7", "1.5e+21").  Used by toMEME / writeFasta (Motif.hs:334,355)
     and `merge_motifs dist` (MergeMotifs.hs:167)."""
     x = float(x)
+    r = repr(x)
+    if "e" not in r and "n" not in r:                # positional repr (1e-4 <= |x| < 1e16): already the ECMAScript form
+        return r[:-2] if r.endswith(".0") else r     # ... except for the trailing ".0" (and "-0.0", never produced here)
     if x != x:
         return "NaN"
     if x in (float("inf"), float("-inf")):

@@ -82,3 +82,31 @@ def test_rc_iupac_and_subpwm(ref_motifs):
     p = Mo.PWM(None, np.array([[0.97, 0.01, 0.01, 0.01], [0.45, 0.45, 0.05, 0.05], [0.25, 0.25, 0.25, 0.25], [0.05, 0.05, 0.45, 0.45]]))
     assert Sq.toBS(Mo.toIUPAC(p)) == b"AMNK"
     assert Mo.toPWM([b"0.1 0.2 0.3 0.4", b"1 0 0 0"])._mat.tolist() == [[0.1, 0.2, 0.3, 0.4], [1.0, 0.0, 0.0, 0.0]]
+
+
+def test_merge_helpers_hand_checked():
+    """mergePWM / mergePWMWeighted / dilute / trim (Motif/Merge.hs:27-111) on cases worked out by hand, plus agreement
+    of mergePWMWeighted with the oracle-side restatement on random inputs and shifts of both signs."""
+    from bioinformatics_toolkit_b200 import merge as M
+    from oracle import app_oracle
+    a = Mo.PWM(None, np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0]]))
+    b = Mo.PWM(None, np.array([[0, 0, 0, 1.0], [0.5, 0.5, 0, 0]]))
+    m = M.mergePWM(a, b, 2)                       # b starts at column 2 of a: overlap of one column, one new column
+    assert m._mat.tolist() == [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0.5, 0.5], [0.5, 0.5, 0, 0]]
+    m = M.mergePWM(a, b, -1)                      # negative shift: roles swapped, a starts at column 1 of b
+    assert m._mat.tolist() == [[0, 0, 0, 1], [0.75, 0.25, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]
+    mw, ws = M.mergePWMWeighted((a, [3, 3, 3]), (b, [1, 1]), 2)
+    assert ws == [3, 3, 4, 1] and mw._mat[2].tolist() == [0, 0, 0.75, 0.25]
+    d = M.dilute((mw, ws))                        # columns supported by fewer sites are pulled towards 0.25
+    assert np.allclose(d._mat[3], (1 * np.array([0.5, 0.5, 0, 0]) + 0.25 * 3) / 4) and np.array_equal(d._mat[2], mw._mat[2])
+    flat = np.array([[0.25, 0.25, 0.25, 0.25], [0.9, 0.05, 0.03, 0.02], [0.3, 0.3, 0.2, 0.2], [0.26, 0.24, 0.25, 0.25]])
+    t = M.trim(Mo.default_bkgd, 0.1, Mo.PWM(None, flat))
+    assert t._mat.tolist() == flat[1:2].tolist()            # uninformative flanks (KL < cutoff) are cut on both sides
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        m1, m2 = synth.synth_pwms(2, int(rng.integers(0, 10 ** 6)), nmin=3, nmax=12)
+        w1, w2 = [int(x) for x in rng.integers(1, 5, m1.shape[0])], [int(x) for x in rng.integers(1, 5, m2.shape[0])]
+        s = int(rng.integers(-m2.shape[0] + 1, m1.shape[0]))
+        got, gw = M.mergePWMWeighted((Mo.PWM(None, m1), w1), (Mo.PWM(None, m2), w2), s)
+        exp, ew = app_oracle.merge_pwm_weighted((m1, w1), (m2, w2), s)
+        assert gw == ew and np.array_equal(got._mat, exp)

@@ -7,9 +7,11 @@ import argparse
 import os
 import sys
 
+import numpy as np
+
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-from bioinformatics_toolkit_b200 import merge as M                                          # noqa: E402
+from bioinformatics_toolkit_b200 import _lib, merge as M                                    # noqa: E402
 from bioinformatics_toolkit_b200.alignment import AlignFn                                    # noqa: E402
 from bioinformatics_toolkit_b200.motif import (Motif, _shortest, default_bkgd, readFasta_,   # noqa: E402
                                                readMEME, toIUPAC, writeFasta, writeMEME)
@@ -59,24 +61,15 @@ def main(argv=None):
     if a.cmd == "dist":
         ma = read_motif(a.INPUT_A)
         if a.inputB is None:
-            d, _, _ = align.all_pairs([m._pwm for m in ma]) if len(ma) > 1 else ([], None, None)
-            k = 0
-            names = [m._name for m in ma]
-            for i in range(len(ma)):                       # one write per row of the triangle
-                row = d[k:k + len(ma) - i - 1].tolist()
-                out.write(b"".join(b"%s\t%s\t%s\n" % (names[i], names[i + 1 + t], _shortest(v).encode()) for t, v in enumerate(row)))
-                k += len(row)
+            d, _, _ = align.all_pairs([m._pwm for m in ma]) if len(ma) > 1 else (np.zeros(0), None, None)
+            out.write(_lib.format_dist([m._name for m in ma], d))
         else:
             mb = read_motif(a.inputB)
             pw = [m._pwm for m in ma] + [m._pwm for m in mb]
-            ia = [i for i in range(len(ma)) for _ in mb]
-            ib = [len(ma) + j for _ in ma for j in range(len(mb))]
+            ia = np.repeat(np.arange(len(ma), dtype=np.int32), len(mb))
+            ib = np.tile(np.arange(len(ma), len(ma) + len(mb), dtype=np.int32), len(ma))
             d, _, _ = align.pairs(pw, ia, ib)
-            k = 0
-            for x in ma:
-                for y in mb:
-                    out.write(b"\t".join((x._name, y._name, _shortest(d[k]).encode())) + b"\n")
-                    k += 1
+            out.write(_lib.format_dist([m._name for m in ma] + [m._name for m in mb], d, ia, ib))
     elif a.cmd == "merge":
         motifs = read_motif(a.INPUT)
         print("Merging Mode: %s" % a.mode, file=sys.stderr)

@@ -261,6 +261,31 @@ class DeviceMotifs:
             pass
 
 
+def format_dist(names, dist, a=None, b=None):
+    """`merge_motifs dist` text through the library's host formatter (pwmscan_format_dist): one line
+    name_a<TAB>name_b<TAB>toShortest d per pair; a = b = None means all i < j in packed order."""
+    L = load()
+    off = np.concatenate([[0], np.cumsum([len(x) for x in names])]).astype(np.int64)
+    buf = b"".join(names)
+    dist = _arr(dist, np.float64)
+    text, tlen = C.c_char_p(), C.c_int64(0)
+    if a is None:
+        n, pa, pb = len(names) * (len(names) - 1) // 2, None, None
+    else:
+        a, b = _arr(a, np.int32), _arr(b, np.int32)
+        n, pa, pb = a.size, _ptr(a), _ptr(b)
+    if dist.size != n:
+        raise ValueError("one distance per pair expected")
+    rc = L.pwmscan_format_dist(C.c_int64(n), C.c_int32(len(names)), pa, pb, _ptr(dist), C.c_char_p(buf), _ptr(off),
+                               C.byref(text), C.byref(tlen))
+    if rc != 0:
+        raise PwmScanError(rc, "pwmscan_format_dist failed")
+    out = C.string_at(text, tlen.value)
+    L.pwmscan_free.argtypes = [_vp]
+    L.pwmscan_free(text)
+    return out
+
+
 class AlignSet:
     """PWMs resident on the device for iterativeMerge (pwmscan_alnset_*): all-pairs initialisation, per-merge slot
     update and row refresh without re-uploading the set."""

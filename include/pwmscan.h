@@ -207,6 +207,11 @@ int  pwmscan_format_bed6(int64_t nhits, const int32_t* segment, const int32_t* m
                          const int64_t* region_start, const char* chrom_names, const int64_t* chrom_off,
                          const char* motif_names, const int64_t* motif_off, const int32_t* motif_len,
                          char** text, int64_t* text_len);
+/* `merge_motifs dist` text (app/MergeMotifs.hs:158-169): one line "name_a<TAB>name_b<TAB>toShortest d" per pair (host code,
+ * multi-threaded).  a == b == NULL: all i < j of the M names in pwmscan_align_all_pairs' packed order; otherwise npairs
+ * explicit pairs.  names: concatenated bytes with M+1 offsets; *text is released with pwmscan_free. */
+int  pwmscan_format_dist(int64_t npairs, int32_t M, const int32_t* a, const int32_t* b, const double* dist, const char* names,
+                         const int64_t* name_off, char** text, int64_t* text_len);
 
 #ifdef __cplusplus
 }

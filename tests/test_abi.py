@@ -75,3 +75,32 @@ def test_bed6_formatter_host_only():
     for k in list(range(40)) + list(rng.integers(0, n, 2000)):
         st = int(rstart[seg[k]] + pos[k])
         assert got[k] == b"%s\t%d\t%d\t%s\t%d\t%s" % (chroms[rchrom[seg[k]]], st, st + mlen[mot[k]], names[mot[k]], score[k], b"+" if strand[k] == 0 else b"-")
+
+
+def test_dist_formatter_host_only():
+    """pwmscan_format_dist (host code): `merge_motifs dist` lines with toShortest numbers, all-pairs and explicit
+    pairs, equal to the Python restatement of the ECMAScript formatting rules — including tiny and huge values."""
+    import time
+    import numpy as np
+    from bioinformatics_toolkit_b200.motif import _shortest
+    rng = np.random.default_rng(5)
+    names = [b"m%d|x" % i for i in range(400)]
+    n = len(names) * (len(names) - 1) // 2
+    d = rng.random(n) * 10.0 ** rng.integers(-9, 3, n)
+    d[:12] = [0.0, 1.0, 1e-5, 1e-6, 1e-7, 1.5e-7, 0.1, 123.5, 1e21, 1e20, 0.12889355547153183, 5e-324]
+    got = _lib.format_dist(names, d).split(b"\n")
+    assert got[-1] == b"" and len(got) == n + 1
+    k = 0
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            if k < 3000 or k % 97 == 0:
+                assert got[k] == b"%s\t%s\t%s" % (names[i], names[j], _shortest(d[k]).encode()), (k, got[k])
+            k += 1
+    a = rng.integers(0, len(names), 5000).astype(np.int32)
+    b = rng.integers(0, len(names), 5000).astype(np.int32)
+    got = _lib.format_dist(names, d[:5000], a, b).split(b"\n")[:-1]
+    assert got == [b"%s\t%s\t%s" % (names[x], names[y], _shortest(v).encode()) for x, y, v in zip(a, b, d[:5000])]
+    big = rng.random(2000 * 1999 // 2)
+    t0 = time.perf_counter()
+    text = _lib.format_dist([b"motif_%d" % i for i in range(2000)], big)
+    assert text.count(b"\n") == big.size and time.perf_counter() - t0 < 20

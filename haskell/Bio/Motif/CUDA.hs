@@ -63,6 +63,20 @@ foreign import ccall safe "pwmscan_alnset_create"    c_alnset_create :: Ptr Ctx 
 foreign import ccall safe "pwmscan_alnset_update"    c_alnset_update :: Ptr AlnSet -> Int32 -> Int32 -> Ptr Double -> IO CInt
 foreign import ccall safe "pwmscan_alnset_pairs"     c_alnset_pairs  :: Ptr AlnSet -> Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
 foreign import ccall safe "pwmscan_alnset_free"      c_alnset_free   :: Ptr AlnSet -> IO ()
+foreign import ccall safe "pwmscan_abi_version"       c_abi_version  :: IO CInt
+foreign import ccall safe "pwmscan_last_timing"       c_last_timing  :: Ptr Ctx -> Ptr Double -> CInt -> IO CInt
+foreign import ccall safe "pwmscan_seq_upload_segments" c_seq_upload_segments :: Ptr Ctx -> Ptr Word8 -> Ptr Int64 -> Int32 -> CInt -> Ptr (Ptr Seq) -> IO CInt
+foreign import ccall safe "pwmscan_seq_length"        c_seq_length   :: Ptr Seq -> IO Int64
+foreign import ccall safe "pwmscan_seq_first_invalid" c_seq_first_invalid :: Ptr Ctx -> Ptr Seq -> CInt -> Ptr Int64 -> IO CInt
+foreign import ccall safe "pwmscan_motifs_get_sigma"  c_get_sigma    :: Ptr Motifs -> Int32 -> CInt -> Ptr Double -> IO CInt
+foreign import ccall safe "pwmscan_motifs_count"      c_motifs_count :: Ptr Motifs -> IO Int32
+foreign import ccall safe "pwmscan_plan_info"         c_plan_info    :: Ptr Plan -> Ptr Double -> CInt -> IO CInt
+foreign import ccall safe "pwmscan_find_tfbs"         c_find_tfbs    :: Ptr Ctx -> Ptr Seq -> Ptr Motifs -> Ptr Double -> CInt -> CInt -> Ptr (Ptr Hits) -> IO CInt
+foreign import ccall safe "pwmscan_cutoff_cdfs"       c_cutoff_cdfs  :: Ptr Ctx -> Ptr Motifs -> Double -> Ptr Double -> Ptr (Ptr Double) -> Ptr (Ptr Double) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "pwmscan_align_pairs"       c_align_pairs  :: Ptr Ctx -> Ptr Motifs -> Int64 -> Ptr Int32 -> Ptr Int32 -> CInt -> Double -> CInt -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
+foreign import ccall safe "pwmscan_format_bed6"       c_format_bed6  :: Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Word8 -> Ptr Int64 -> Ptr Int64 -> Ptr Int32 -> Ptr Int64
+                                                                      -> CString -> Ptr Int64 -> CString -> Ptr Int64 -> Ptr Int32 -> Ptr CString -> Ptr Int64 -> IO CInt
+foreign import ccall safe "pwmscan_format_dist"       c_format_dist  :: Int64 -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> CString -> Ptr Int64 -> Ptr CString -> Ptr Int64 -> IO CInt
 foreign import ccall safe "pwmscan_align_all_pairs"  c_align_all    :: Ptr Ctx -> Ptr Motifs -> CInt -> Double -> CInt -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
 
 -- | The reference signals failure with `error` (pure code) — so do we.

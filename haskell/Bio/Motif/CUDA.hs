@@ -46,6 +46,7 @@ foreign import ccall safe "pwmscan_motifs_set_sigma" c_set_sigma    :: Ptr Motif
 foreign import ccall safe "pwmscan_motifs_free"      c_motifs_free  :: Ptr Motifs -> IO ()
 foreign import ccall safe "pwmscan_plan_create"      c_plan_create  :: Ptr Ctx -> Ptr Motifs -> Ptr Double -> CInt -> CInt -> Ptr (Ptr Plan) -> IO CInt
 foreign import ccall safe "pwmscan_plan_free"        c_plan_free    :: Ptr Plan -> IO ()
+foreign import ccall safe "pwmscan_scan"             c_scan         :: Ptr Ctx -> Ptr Seq -> Ptr Plan -> Ptr (Ptr Hits) -> IO CInt
 foreign import ccall safe "pwmscan_scan_host"        c_scan_host    :: Ptr Ctx -> Ptr Plan -> Ptr Word8 -> Ptr Int64 -> Int32 -> CInt -> Ptr (Ptr Hits) -> IO CInt
 foreign import ccall safe "pwmscan_hits_count"       c_hits_count   :: Ptr Hits -> IO Int64
 foreign import ccall safe "pwmscan_hits_columns"     c_hits_columns :: Ptr Hits -> Ptr (Ptr Int32) -> Ptr (Ptr Word8) -> Ptr (Ptr Int32) -> Ptr (Ptr Int64) -> Ptr (Ptr Double) -> IO CInt

@@ -104,3 +104,12 @@ def test_dist_formatter_host_only():
     t0 = time.perf_counter()
     text = _lib.format_dist([b"motif_%d" % i for i in range(2000)], big)
     assert text.count(b"\n") == big.size and time.perf_counter() - t0 < 20
+
+
+def test_haskell_shim_binds_every_entry_point():
+    """haskell/Bio/Motif/CUDA.hs (the uncompiled drop-in binding) has a foreign import for every function the header
+    declares, so the shim and the C ABI cannot drift apart unnoticed."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hs = open(os.path.join(root, "haskell", "Bio", "Motif", "CUDA.hs")).read()
+    missing = [n for n in _lib.exported_symbols() if ('"%s"' % n) not in hs]
+    assert missing == []

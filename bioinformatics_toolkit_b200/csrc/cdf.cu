@@ -134,7 +134,9 @@ cdf_kernel(int M, int m0, const int32_t* __restrict__ ncol, const int64_t* __res
             const int nbin = s_nbin;
             const double lo = s_lo, step = s_step;
             // ---- map: bin index of every (k, base)   (getIdx, Motif.hs:301-302)
-            for (int i = tid; i < 4 * nbin; i += kCdfThreads) w.start[(i / nbin) * kMaxBin + (i % nbin)] = -1;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                for (int j = tid; j < nbin; j += kCdfThreads) w.start[b * kMaxBin + j] = -1;
             for (int k = tid; k < K; k += kCdfThreads) {
                 const double sc = scfn(f, w.xk[k]);
 #pragma unroll

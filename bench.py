@@ -1,22 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — PWM scan throughput (Gbp*motifs/s) on B200, with hit-set parity as the gate.
+"""bench.py — PWM scan throughput (Gbp*motifs/s) on B200, gated by a hit-set parity check against the oracle.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c4] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1] [--impl ours|reference]
 
-Metric (BASELINE.json): PWM scan Gbp*motifs/sec; one unit = one genome position x one motif, both
-strands included.  A step = one pass of the scan over the rank's synthetic sequence.
+Metric (BASELINE.json): PWM scan Gbp*motifs/sec at 1/2/4/8 B200; one unit = one genome position x one motif,
+both strands included.  A step = one pass of the scan over the whole workload.
 
-Default workload at every N: BASELINE config 2 per GPU — 100 synthetic PWMs (8-20 bp) over a
-synthetic 248 956 422-bp chr1-shaped sequence, p < 1e-5, both strands ("weak" scaling: each rank
-scans its own chromosome-sized sequence, no data-path collective; hit lists stay on the host of the
-rank that produced them).  --workload c4 is the strong-scaling job of config 4 (800 PWMs x 3.1 Gbp
-hg38-shaped genome, chromosome chunks sharded over the ranks).
+Default workload at every N: BASELINE config 4, the configuration the metric is quoted on — 800 synthetic
+JASPAR-sized PWMs over a 3 088 286 401-bp hg38-shaped synthetic genome (25 chromosomes), p < 1e-5, both strands,
+cut into (all motif blocks x 64 Mbp chromosome chunk) items that are sharded over the ranks ("strong" scaling:
+the job is fixed, N GPUs share it; no data-path collective, hit lists are gathered in the host memory of the
+rank that produced them — the decomposition of the reference's findTFBS', Motif/Search.hs:60-84).
+--workload c2 (100 PWMs x chr1-shaped 249 Mbp per GPU, weak scaling) and c1 are the smaller configs.
 
-  value : whole-job throughput with the packed genome, the motif tables and the plan already
-          resident in HBM (timed: prefilter kernel + fp64 re-score + sort + hit list D2H).
-  e2e   : the same through the C ABI from HOST buffers: per step H2D of the ASCII sequence from
-          pinned memory + 2-bit packing + scan + hit list D2H.
-  roofline / cpu_baseline : see DESIGN.md §6.
+  value : whole-job throughput with the packed genome, the motif tables and the plan already resident in HBM
+          (timed per step: first-stage kernels + exact fp64 replay + ordering + hit lists to host memory).
+  e2e   : the same through the C ABI from HOST buffers (pwmscan_scan_host_many): per step H2D of the ASCII
+          genome from pinned memory + 2-bit packing + scan + hit lists D2H.
+  roofline / phases / cpu_baseline : see DESIGN.md §6.
+Before anything is timed, one slice of the workload is scanned on the device and by the oracle and the two hit
+lists must be bit-identical ("parity_checked"); the run aborts otherwise.
 """
 import argparse
 import json
@@ -34,6 +37,12 @@ sys.path.insert(0, ROOT)
 BG = (0.25, 0.25, 0.25, 0.25)
 METRIC = "PWM scan throughput (genome positions x motifs per second, both strands)"
 UNIT = "Gbp*motifs/s"
+DESC = {
+    "c1": "C1: 1 CTCF-like 19-bp PWM x 10 Mbp",
+    "c2": "C2: 100 synthetic PWMs (8-20 bp) x 248,956,422-bp chr1-shaped sequence per GPU, p<1e-5, both strands",
+    "c4": "C4: 800 synthetic PWMs (6-22 bp) x 3,088,286,401-bp hg38-shaped genome, p<1e-5, both strands, "
+          "(motif blocks x 64 Mbp chromosome chunk) items sharded over the ranks",
+}
 
 
 def load_peaks():
@@ -91,57 +100,82 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def thresholds(key, motifs_dev, count):
-    """p = 1e-5 cutoffs from the device scoreCDF; until that kernel reports ready they come from the
-    committed known-answer fixture (tests/golden/config_thresholds.json, oracle-generated)."""
-    from bioinformatics_toolkit_b200 import _lib
-    try:
-        return motifs_dev.pvalue_to_score(1e-5), "device scoreCDF"
-    except _lib.PwmScanError:
-        d = json.load(open(os.path.join(ROOT, "tests", "golden", "config_thresholds.json")))
-        return np.array([float.fromhex(v) for v in d[key][:count]]), "fixture tests/golden/config_thresholds.json"
+def fixture_thresholds(key, count):
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "config_thresholds.json")))
+    return np.array([float.fromhex(v) for v in d[key][:count]])
+
+
+def motifs_of(name):
+    from bioinformatics_toolkit_b200 import synth
+    if name == "c1":
+        return [synth.ctcf_like_pwm()]
+    if name == "c2":
+        return synth.synth_pwms(100, 12)
+    return synth.config_c4_motifs(800)
+
+
+def c4_items(world):
+    """The (all motif blocks x 64 Mbp chromosome chunk) items of config 4 and their assignment to the ranks."""
+    from bioinformatics_toolkit_b200 import shard, synth
+    lengths = [l for _, l in synth.HG38_CHROM_SIZES]
+    items = shard.make_items(lengths, 800, chunk_len=64_000_000)
+    return lengths, shard.assign(items, world)
+
+
+def c4_chunk(it, lengths, nmax):
+    from bioinformatics_toolkit_b200 import shard, synth
+    s, st, en, _, _ = it
+    lo, hi = shard.chunk_bytes_range(it, lengths[s], nmax)
+    runs = [(0, min(10_000, lengths[s])), (max(0, lengths[s] - 10_000), 10_000), (int(lengths[s] * 0.45), int(lengths[s] * 0.03))]
+    return "%s:%d-%d" % (synth.HG38_CHROM_SIZES[s][0], st, en), synth.synth_dna(hi - lo, 4 + 100 * s, gc=0.41, start=lo, n_runs=runs)
 
 
 def workload(name, rank, world):
-    """Returns (list of (label, ascii uint8 array) this rank scans, mats, fixture key, description)."""
-    from bioinformatics_toolkit_b200 import shard, synth
+    """Returns (list of (label, ascii uint8 array, window starts owned) this rank scans, mats)."""
+    from bioinformatics_toolkit_b200 import synth
+    mats = motifs_of(name)
     if name == "c1":
-        dna, mats = synth.config_c1()
-        return [("c1", np.frombuffer(bytes(dna).upper(), dtype=np.uint8).copy())], mats, "c1", "C1: 1 CTCF-like 19-bp PWM x 10 Mbp"
+        dna, _ = synth.config_c1()
+        a = np.frombuffer(bytes(dna).upper(), dtype=np.uint8).copy()
+        return [("c1", a, a.size)], mats
     if name == "c2":
         L = 248956422
         dna = synth.synth_dna(L, 2 + 1000 * rank, gc=0.41, n_runs=synth.chr1_n_runs(L))
-        return [("chr1-shaped/rank%d" % rank, dna)], synth.synth_pwms(100, 12), "c2", \
-            "C2: 100 synthetic PWMs (8-20 bp) x 248,956,422-bp chr1-shaped sequence per GPU, p<1e-5, both strands"
+        return [("chr1-shaped/rank%d" % rank, dna, L)], mats
+    nmax = max(m.shape[0] for m in mats)
+    lengths, per_rank = c4_items(world)
+    out = []
+    for it in per_rank[rank]:
+        label, a = c4_chunk(it, lengths, nmax)
+        out.append((label, a, it[2] - it[1]))
+    return out, mats
+
+
+def reference_sample(name, sample):
+    """The bounded sample of the workload the CPU arms scan: the first bases of the workload's first sequence."""
+    from bioinformatics_toolkit_b200 import synth
     if name == "c4":
-        mats = synth.config_c4_motifs(800)
-        nmax = max(m.shape[0] for m in mats)
-        lengths = [l for _, l in synth.HG38_CHROM_SIZES]
-        items = shard.make_items(lengths, len(mats), chunk_len=64_000_000)
-        mine = shard.assign(items, world)[rank]
-        seqs = []
-        for it in mine:
-            s, st, en, _, _ = it
-            lo, hi = shard.chunk_bytes_range(it, lengths[s], nmax)
-            runs = [(0, min(10_000, lengths[s])), (max(0, lengths[s] - 10_000), 10_000), (int(lengths[s] * 0.45), int(lengths[s] * 0.03))]
-            seqs.append(("%s:%d-%d" % (synth.HG38_CHROM_SIZES[s][0], st, en), synth.synth_dna(hi - lo, 4 + 100 * s, gc=0.41, start=lo, n_runs=runs)))
-        return seqs, mats, "c4", "C4: 800 synthetic PWMs x 3,088,286,401-bp hg38-shaped genome, 64 Mbp chromosome chunks sharded over ranks"
-    raise SystemExit("unknown workload " + name)
+        lengths, _ = c4_items(1)
+        L = lengths[0]
+        return synth.synth_dna(sample, 4, gc=0.41, start=20_000_000, n_runs=[(int(L * 0.45), int(L * 0.03))]), "chr1:20,000,000-"
+    if name == "c2":
+        return synth.synth_dna(sample, 2, gc=0.41, start=20_000_000), "chr1-shaped:20,000,000-"
+    dna, _ = synth.config_c1()
+    return np.frombuffer(bytes(dna).upper(), dtype=np.uint8)[:sample].copy(), "c1:0-"
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (oracle port: look-ahead scan with libm
-    log per visited column exactly like Search.hs:185-188), all host threads, bounded sample."""
+    """--impl reference: the reference's own CPU algorithm (oracle port: look-ahead scan with libm log per visited
+    column exactly like Search.hs:185-188; the reference is Haskell and there is no GHC here), all host threads, on a
+    bounded sample of the same workload; the throughput is extrapolated from that sample."""
     if rank != 0:
         return
     from oracle import oracle as O
-    from bioinformatics_toolkit_b200 import synth
     cores = os.cpu_count() or 1
-    mats = synth.synth_pwms(100, 12) if args.workload != "c4" else synth.config_c4_motifs(800)
-    key = "c2" if args.workload != "c4" else "c4"
-    th = np.array([float.fromhex(v) for v in json.load(open(os.path.join(ROOT, "tests", "golden", "config_thresholds.json")))[key]])
+    mats = motifs_of(args.workload)
+    th = fixture_thresholds(args.workload, len(mats))
     sample = int(args.ref_sample_bp)
-    dna = synth.synth_dna(sample, 2, gc=0.41)
+    dna, where = reference_sample(args.workload, sample)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -150,28 +184,52 @@ def run_reference(args, rank, world):
         if i >= args.warmup:
             times.append(t1 - t0)
     ms = 1e3 * float(np.mean(times))
-    val = sample * len(mats) / (ms / 1e3) / 1e9
-    desc = "first %d bp of the workload's sequence shape x %d motifs, both strands" % (sample, len(mats))
+    val = dna.size * len(mats) / (ms / 1e3) / 1e9
+    desc = "%s%d (%d bp) x %d motifs, both strands; throughput extrapolated from this sample" % (where, 20_000_000 + dna.size, dna.size, len(mats))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "oracle port of the reference CPU scan (reference is Haskell, no GHC here): " + desc},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": DESC[args.workload]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "oracle port of the reference CPU scan; the genuine reference is single-threaded Haskell"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def parity_gate(ctx, plan, mats, th, seqs_host):
+    """One slice of this rank's first sequence through the device and through the oracle: hit lists must be bit-identical."""
+    from oracle import oracle as O
+    from bioinformatics_toolkit_b200 import _lib
+    a = seqs_host[0][1]
+    n = min(a.size, 1_000_000 if len(mats) > 200 else 2_000_000)
+    lo = max(0, min(a.size - n, a.size // 3))
+    sl = np.ascontiguousarray(a[lo:lo + n])
+    h = plan.scan(_lib.DeviceSeq(ctx, sl))
+    cnt, o = O.scan_mt(BG, mats, th, sl, mode=1, nthreads=os.cpu_count() or 1, cap=max(1 << 22, 8 * len(h)))
+    ok = (cnt == len(h) and np.array_equal(h.motif, o[0]) and np.array_equal(h.strand, o[1]) and np.array_equal(h.pos, o[2])
+          and np.array_equal(h.score.view(np.uint64), o[3].view(np.uint64)))
+    if not ok:
+        raise SystemExit("bench.py: PARITY FAILURE — device hit list differs from the oracle on %d bp (device %d hits, oracle %d)" % (n, len(h), cnt))
+    return {"parity_checked": True, "parity_slice_bp": int(n), "parity_hits": int(cnt)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
-    ap.add_argument("--ref-sample-bp", type=float, default=4_000_000)
-    ap.add_argument("--cpu-sample-bp", type=float, default=2_000_000)
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c4"])
+    ap.add_argument("--ref-sample-bp", type=float, default=None)
+    ap.add_argument("--cpu-sample-bp", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    big = args.workload == "c4"
+    if args.ref_sample_bp is None:
+        args.ref_sample_bp = 1_000_000 if big else 4_000_000
+    if args.cpu_sample_bp is None:
+        args.cpu_sample_bp = 4_000_000 if big else 2_000_000
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -194,182 +252,175 @@ def main():
         torch.cuda.synchronize()
 
     ctx = _lib.default_context(local)
-    seqs_host, mats, key, desc = workload(args.workload, rank, world)
+    t_setup = time.perf_counter()
+    seqs_host, mats = workload(args.workload, rank, world)
     mo = _lib.DeviceMotifs(ctx, mats, BG)
-    th, th_src = thresholds(key, mo, len(mats))
+    th = mo.pvalue_to_score(1e-5)                    # device scoreCDF + cdf' (Motif.hs:213-214, 252-326)
     plan = _lib.Plan(mo, th)
     M = len(mats)
-    units = sum(int(a.size) for _, a in seqs_host) * M          # position x motif units of this rank
-    pinned = [torch.from_numpy(a).pin_memory() for _, a in seqs_host]
+    units = sum(int(own) for _, _, own in seqs_host) * M          # position x motif units of this rank
+    pinned = [torch.from_numpy(a).pin_memory() for _, a, _ in seqs_host]
+    host_arrays = [p.numpy() for p in pinned]
+    dev_seqs = [_lib.DeviceSeq(ctx, a) for a in host_arrays]
+    gate = parity_gate(ctx, plan, mats, th, seqs_host) if rank == 0 else {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    last_timing = {}
-    # A rank with many chunks (c4) keeps two scans in flight (shard.ScanWorkers: two library contexts driven by
-    # two host threads), so one chunk's exact replay / sort / hit D2H overlaps the next chunk's prefilter kernel.
-    workers = None
-    if len(pinned) > 1 and not os.environ.get("PWMSCAN_BENCH_SEQUENTIAL"):
-        from bioinformatics_toolkit_b200.shard import ScanWorkers
-        workers = ScanWorkers(local, mats, BG, th, workers=2)
-        dev_seqs = workers.upload([p.numpy() for p in pinned])
-    else:
-        dev_seqs = [_lib.DeviceSeq(ctx, p.numpy()) for p in pinned]
+    t_setup = time.perf_counter() - t_setup
+    acc = {}
+
+    def add_timing():
+        for k, v in ctx.timing().items():
+            acc[k] = acc.get(k, 0.0) + float(v)
 
     def step_resident():
-        nh, pre_ms = 0, 0.0
-        last_timing.clear()
-        if workers is not None:
-            counts, t = workers.scan(dev_seqs, consume=len)        # like the sequential loop: a hit list is dropped once counted
-            last_timing.update(t)
-            return sum(counts), t["prefilter_ms"]
-        for s in dev_seqs:
-            h = plan.scan(s)
-            nh += len(h)
-            t = ctx.timing()
-            pre_ms += t["prefilter_ms"]
-            for k, v in t.items():
-                last_timing[k] = last_timing.get(k, 0.0) + float(v)
-        return nh, pre_ms
+        counts = plan.scan_many(dev_seqs, consume=len)        # a hit list is dropped once counted (a streaming consumer)
+        add_timing()
+        return sum(counts)
 
     def step_e2e():
-        nh, h2d, d2h = 0, 0, 0
-        if workers is not None:
-            counts, t = workers.scan_host([p.numpy() for p in pinned], consume=len)
-            return sum(counts), sum(p.numel() for p in pinned), int(t["d2h_bytes"])
-        for p in pinned:
-            h = plan.scan_host(p.numpy())            # pwmscan_scan_host: host bytes in, host hit list out
-            h2d += p.numel()
-            d2h += int(ctx.timing()["d2h_bytes"])
-            nh += len(h)
-        return nh, h2d, d2h
+        counts = plan.scan_host_many(host_arrays, consume=len)    # pwmscan_scan_host_many: host bytes in, host hit lists out
+        add_timing()
+        return sum(counts)
+
+    def l2_flush():
+        flush.fill_(1)                                         # 256 MiB write on torch's stream ...
+        torch.cuda.synchronize()                               # ... finished before the library's own streams start the step
 
     # ---- device-resident arm -------------------------------------------------------------------
     sampler = ClockSampler(local)          # started before the warm-up: nvidia-smi needs ~100 ms to produce its first row
     sampler.start()
     for _ in range(args.warmup):
-        flush.fill_(1)
-        nh, _ = step_resident()
-    pre_ms_tot = 0.0
+        l2_flush()
+        nh = step_resident()
+    acc.clear()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        flush.fill_(1)                                         # L2 flush (256 MiB write) between steps
-        nh, pre_ms = step_resident()
-        pre_ms_tot += pre_ms
+        l2_flush()
+        nh = step_resident()
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop()
+    res = dict(acc)
     el = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
     un = torch.tensor([float(units)], dtype=torch.float64, device="cuda")
+    hits_all = torch.tensor([float(nh)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
         dist.all_reduce(un, op=dist.ReduceOp.SUM)
+        dist.all_reduce(hits_all, op=dist.ReduceOp.SUM)
     ms_step = 1e3 * el.item() / args.steps
     value = un.item() / (ms_step / 1e3) / 1e9
 
     # ---- end-to-end arm (host buffers -> hits on the host) -----------------------------------------
-    for _ in range(max(1, args.warmup - 1)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, h2d, d2h = step_e2e()
-    barrier()
-    t1 = time.perf_counter()
-    el2 = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(el2, op=dist.ReduceOp.MAX)
-    e2e_val = un.item() / (el2.item() / args.steps) / 1e9
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, args.warmup - 1)):
+            step_e2e()
+        acc.clear()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        t1 = time.perf_counter()
+        el2 = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+        io = torch.tensor([acc["h2d_bytes"] / args.steps, acc["d2h_bytes"] / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(el2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        e2e_ms = 1e3 * el2.item() / args.steps
+        # plain pinned->device copy of the same bytes, to read the e2e number against the PCIe link of this box
+        big_i = int(np.argmax([p.numel() for p in pinned]))
+        dst = torch.empty(pinned[big_i].numel(), dtype=torch.uint8, device="cuda")
+        dst.copy_(pinned[big_i], non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(pinned[big_i], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * pinned[big_i].numel() / (time.perf_counter() - t0) / 1e9
+        del dst
+        my_h2d = acc["h2d_bytes"] / args.steps
+        e2e = {"value": un.item() / (e2e_ms / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+               "ms_per_step": e2e_ms, "pinned_h2d_gbs_this_box": h2d_gbs,
+               # the end-to-end path is bound by the host->device copy of the ASCII bytes (1 B per base): rank 0's share
+               "pcie_roofline": {"bound": "pcie-h2d", "achieved": my_h2d / (e2e_ms / 1e3) / 1e9, "peak": h2d_gbs, "unit": "GB/s",
+                                 "frac": my_h2d / (e2e_ms / 1e3) / 1e9 / h2d_gbs,
+                                 "peak_source": "plain cudaMemcpy of the same pinned buffer, measured in this run (rank 0)"}}
 
-    # ---- plain pinned->device copy of the same bytes, to read the e2e number against the PCIe link ----
-    dst = torch.empty(pinned[0].numel(), dtype=torch.uint8, device="cuda")
-    dst.copy_(pinned[0], non_blocking=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        dst.copy_(pinned[0], non_blocking=True)
-    torch.cuda.synchronize()
-    h2d_gbs = 3 * pinned[0].numel() / (time.perf_counter() - t0) / 1e9
-    del dst
-
-    # ---- roofline of the dominant kernel (prefilter) ------------------------------------------------
+    # ---- roofline of the dominant kernel (first stage) and the phases of a step ---------------------------
     peaks = load_peaks()
     info = plan.info()
-    pre_ms_launch = pre_ms_tot / args.steps / max(1, len(dev_seqs))
-    bp_launch = sum(int(a.size) for _, a in seqs_host) / max(1, len(dev_seqs))
+    n_launch = max(1.0, res["prefilter_launches"])
+    pre_ms_launch = res["prefilter_ms"] / n_launch
+    bp_rank = sum(int(a.size) for _, a, _ in seqs_host)
+    bp_launch = bp_rank * args.steps / n_launch
     clk = peaks["sm_max_mhz"] * 1e6
     hbm_bytes = 0.25 * bp_launch * info["genome_passes"]          # 2-bit genome read once per block pass
-    hbm_ach = hbm_bytes / (pre_ms_launch / 1e3) / 1e9
     ncol_mean = float(np.mean([m.shape[0] for m in mats]))
     lane_ops = 2.0 * ncol_mean * bp_launch * M                     # brute-force look-ups + adds, both strands
     issue_peak = 148 * 128 * clk / 1e12
+    sec = pre_ms_launch / 1e3
     traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")          # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("km_prefilter_kernel", {}).get(args.workload)
     if info["mode"] == "kmer":
-        # governing roof: the L1 gather rate, one 32-byte sector per clock per SM (experiments/masktab/l2gather.cu
-        # reaches 96 % of it: 8.9 TB/s).  Algorithmic bytes: the plan's expected mask sectors per position x 32 B.
+        # governing roof: the L1 gather rate, one 32-byte sector per clock per SM (experiments/masktab/l2gather.cu; profiles/l2gather_*.txt).
+        # Algorithmic bytes: the plan's expected mask sectors per position x 32 B (a model; ncu's l1tex sector count agrees within 1 %).
         alg_bytes = info["table_sectors_per_position"] * 32.0 * bp_launch
         peak = 148 * 32 * clk / 1e9
-        ach = alg_bytes / (pre_ms_launch / 1e3) / 1e9
-        # DRAM traffic of one launch on this exact workload, from the committed ncu --set full capture
-        traffic = 761.9e6 if (args.workload == "c2" and M == 100) else None   # profiles/r1j: 752.8 MB read (64 MiB of tables + L2 misses) + 9.1 MB written
-        roofline = {"bound": "l1-gather", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "kernel": "km_prefilter_kernel", "ms_per_launch": pre_ms_launch,
-                    "peak_source": "148 SMs x one 32-B sector per clk x sm_max_mhz (%s); measured 8.9 TB/s by experiments/masktab/l2gather.cu" % peaks["source"],
+        roofline = {"bound": "l1-gather", "achieved": alg_bytes / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peak,
+                    "traffic": traffic, "kernel": "km_prefilter_kernel", "ms_per_launch": pre_ms_launch, "launches_per_step": n_launch / args.steps,
+                    "peak_source": "148 SMs x one 32-B sector per clk x sm_max_mhz (%s); this repo's micro-benchmark reaches 8.9 TB/s (profiles/l2gather_*.txt); not a MEASURED_PEAKS.json entry" % peaks["source"],
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "L2-resident k-mer mask tables gathered with 256-bit loads; the L1 sector rate, not HBM or L2 bytes, is the roof"}
+                    "note": "L2-resident k-mer mask tables gathered with 256-bit loads; 'achieved' uses the plan's modelled sectors per position; "
+                            "with many motifs (c4) the kernel is instruction-bound, see issue_roofline and profiles/"}
     else:
-        # governing roof: shared-memory crossbar, one 128-B wavefront per clock per SM (B300_MICROARCH.md; not a
-        # MEASURED_PEAKS.json entry).  Algorithmic bytes: first-stage look-up rows, S1_b x 128 B per position per block.
         smem_bytes = info.get("smem_wavefronts_per_position", 0.0) * 128.0 * bp_launch
         smem_peak = 148 * 128 * clk / 1e9
-        smem_ach = smem_bytes / (pre_ms_launch / 1e3) / 1e9
-        # (profiles/r1b_prefilter_ncu_full_metrics.json: dram__bytes_read.sum 62.9 MB + dram__bytes_write.sum 3.1 MB)
-        traffic = 66.0e6 if (args.workload == "c2" and M == 100 and info["mode"] == "lds") else None
-        roofline = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
-                    "traffic": traffic, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
+        roofline = {"bound": "smem", "achieved": smem_bytes / sec / 1e9, "peak": smem_peak, "unit": "GB/s", "frac": smem_bytes / sec / 1e9 / smem_peak,
+                    "traffic": None, "kernel": "prefilter_kernel", "ms_per_launch": pre_ms_launch,
                     "peak_source": "148 SMs x 128 B/clk (B300_MICROARCH.md) x sm_max_mhz (%s)" % peaks["source"],
-                    "algorithmic_bytes_per_launch": smem_bytes,
-                    "note": "shared-memory-bandwidth bound look-up kernel; ncu (profiles/) reports the LSU/shared pipe at the same fraction"}
-    roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"], "traffic": traffic,
-                    "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peaks["source"],
+                    "algorithmic_bytes_per_launch": smem_bytes}
+    roofline_hbm = {"bound": "hbm", "achieved": hbm_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_bytes / sec / 1e9 / peaks["hbm_gbs"],
+                    "traffic": traffic, "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peaks["source"],
                     "note": "HBM is not the governing roof (0.25 B/base per block pass)"}
-    issue = {"bound": "int/fp32 issue of the brute-force algorithm", "achieved": lane_ops / (pre_ms_launch / 1e3) / 1e12,
-             "peak": issue_peak, "unit": "T lane-ops/s (2*n per bp*motif)",
-             "frac": lane_ops / (pre_ms_launch / 1e3) / 1e12 / issue_peak,
-             "note": "> 1 means the table-driven prefilter does fewer operations than the brute-force count"}
+    issue = {"bound": "int/fp32 issue of the brute-force algorithm", "achieved": lane_ops / sec / 1e12, "peak": issue_peak,
+             "unit": "T lane-ops/s (2*n per bp*motif)", "frac": lane_ops / sec / 1e12 / issue_peak,
+             "note": "> 1 means the table-driven first stage does fewer operations than the brute-force count"}
+    hit_bytes = res["d2h_bytes"] / args.steps
+    phases = {"per_step_rank0_ms": {"first_stage": res["prefilter_ms"] / args.steps, "rescore": res["rescore_ms"] / args.steps,
+                                    "order": res["order_ms"] / args.steps},
+              "hit_bytes_to_host_per_step_rank0": hit_bytes, "hit_d2h_gbs_if_serial": hit_bytes / (ms_step / 1e3) / 1e9,
+              "note": "CUDA-event time on each item's stream, summed over the items of a step; items overlap (3 in flight), so the sum may exceed ms_per_step"}
 
     # ---- CPU baseline (oracle port, bounded sample), rank 0 at N=1 only ---------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
-        sample = int(args.cpu_sample_bp)
-        sub = seqs_host[0][1][5_000_000:5_000_000 + sample] if seqs_host[0][1].size > 5_000_000 + sample else seqs_host[0][1][:sample]
+        sub, where = reference_sample(args.workload, int(args.cpu_sample_bp))
         t0 = time.perf_counter()
-        cnt, _ = O.scan_mt(BG, mats, th, sub, mode=0, nthreads=cores, cap=0)
+        O.scan_mt(BG, mats, th, sub, mode=0, nthreads=cores, cap=0)
         dt = time.perf_counter() - t0
         t0 = time.perf_counter()
-        O.scan_mt(BG, mats, th, sub[: max(1, sub.size // 4)], mode=0, nthreads=1, cap=0)
+        O.scan_mt(BG, mats, th, sub[: max(1, sub.size // 8)], mode=0, nthreads=1, cap=0)
         dt1 = time.perf_counter() - t0
         cpu = {"value": sub.size * M / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d bp x %d motifs, both strands, look-ahead scan with libm log per visited column (Search.hs:185-188)" % (sub.size, M),
-               "one_core_value": (sub.size // 4) * M / dt1 / 1e9}
+               "sample": "%s (%d bp) x %d motifs, both strands, look-ahead scan with libm log per visited column (Search.hs:185-188); extrapolated" % (where, sub.size, M),
+               "one_core_value": (sub.size // 8) * M / dt1 / 1e9}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
-            "vs_baseline": None, "dtype": "bit-mask / u16 prefilter + f64 re-score", "data": "synthetic",
-            "config": {"workload": desc, "l2": "256 MiB flush write between steps", "thresholds": th_src,
-                       "scans_in_flight": 2 if workers is not None else 1,
-                       "hits_per_step_rank0": int(nh),
-                       "device_ms_breakdown_last_step": {k: round(float(v), 4) for k, v in last_timing.items()}},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * el2.item() / args.steps, "pinned_h2d_gbs_this_box": h2d_gbs,
-                    # the end-to-end path is bound by the host->device copy of the ASCII bytes (1 B per base): this rank's share
-                    "pcie_roofline": {"bound": "pcie-h2d", "achieved": h2d / (el2.item() / args.steps) / 1e9, "peak": h2d_gbs, "unit": "GB/s",
-                                      "frac": h2d / (el2.item() / args.steps) / 1e9 / h2d_gbs,
-                                      "peak_source": "plain cudaMemcpy of the same pinned buffer, measured in this run"}},
-            "gpu_launches": int(args.steps * len(dev_seqs) * 3), "clocks": clocks,   # km_prefilter + rescore + decode per scan (the radix sort is CUB)
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "issue_roofline": issue, "plan": info, "cpu_baseline": cpu}), flush=True)
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if big else "weak",
+            "vs_baseline": None, "dtype": "u8 bit-mask / u16 first stage + f64 re-score", "data": "synthetic",
+            "config": {"workload": DESC[args.workload], "items_rank0": len(dev_seqs), "scans_in_flight": int(os.environ.get("PWMSCAN_LANES", "3")),
+                       "l2": "256 MiB flush write + sync between steps; per step the rank reads %.0f MB of packed genome and %.0f MB of mask tables (> 126 MB L2)" % (0.375 * bp_rank / 1e6, info["table_bytes"] / 1e6),
+                       "thresholds": "device scoreCDF", "hits_per_step": int(hits_all.item()), "setup_s": round(t_setup, 1), **gate},
+            "e2e": e2e, "gpu_launches": int(res["kernel_launches"]), "clocks": clocks,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "issue_roofline": issue, "phases": phases, "plan": info, "cpu_baseline": cpu}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -98,10 +98,14 @@ class Context:
         raise PwmScanError(rc, msg)
 
     def timing(self):
-        out = np.zeros(8)
-        self.L.pwmscan_last_timing(self.h, _ptr(out), C.c_int(8))
-        return {"prefilter_ms": out[0], "rescore_ms": out[1], "sort_ms": out[2], "device_ms": out[3],
-                "h2d_bytes": out[4], "d2h_bytes": out[5], "candidates": out[6], "prefilter_launches": out[7]}
+        """Device timing of the last scan call on this context (summed over the items of a scan_many)."""
+        out = np.zeros(12)
+        self.L.pwmscan_last_timing(self.h, _ptr(out), C.c_int(12))
+        return {"prefilter_ms": out[0], "rescore_ms": out[1], "order_ms": out[2], "device_ms": out[3],
+                "h2d_bytes": out[4], "d2h_bytes": out[5], "candidates": out[6], "prefilter_launches": out[7],
+                "kernel_launches": out[8], "hits": out[9],
+                # the auxiliary entry points (scoreCDF, alignment, dense scores, per-hit affinity) report here and leave the scan slots alone
+                "aux_kernel_ms": out[10], "aux_host_fallbacks": out[11]}
 
     def scan_host_first_invalid(self, alphabet="IUPAC"):
         """fromBS verdict of the bytes of the last Plan.scan_host on this context: offset of the first byte
@@ -337,6 +341,7 @@ class _HitsHandle:
 
     def __init__(self, ctx, h):
         self.ctx, self.L, self.h = ctx, ctx.L, h        # the hit buffer goes back to the context's pool: keep the context alive
+        self.M = 0
 
     def __del__(self):
         try:
@@ -361,16 +366,70 @@ def _view(ptr, n, owner):
 
 
 class Hits:
-    """Columns of a hit list sorted by (segment, motif, strand, pos).  The arrays are zero-copy
-    views of the library's pinned host buffer."""
+    """A hit list sorted by (segment, motif, strand, pos).
 
-    __slots__ = ("motif", "strand", "segment", "pos", "score")
+    The library transfers compact columns (12 bytes per hit for a single-segment scan): `score`, `pos32` and either
+    `run_off` (single segment: hits of (motif m, strand s) are [run_off[2m+s], run_off[2m+s+1])) or `seg32` +
+    `ms16` (= 2 * motif + strand).  `motif`, `strand`, `segment`, `pos` are the wide columns, expanded on the host by
+    the library the first time one of them is read.  All arrays are zero-copy views of library-owned memory."""
 
-    def __init__(self, motif, strand, segment, pos, score):
-        self.motif, self.strand, self.segment, self.pos, self.score = motif, strand, segment, pos, score
+    def __init__(self, ctx=None, hh=None, cols=None):
+        self._cols = cols            # explicit wide columns (select() / empty lists)
+        self._owner = None
+        self._n = 0 if cols is None else int(cols[3].size)
+        self._wide = None
+        self._compact = None
+        if hh is not None:
+            self._owner = _HitsHandle(ctx, hh)
+            self._n = int(ctx.L.pwmscan_hits_count(hh))
 
     def __len__(self):
-        return int(self.pos.size)
+        return self._n
+
+    def _get_compact(self):
+        if self._compact is None:
+            o, n = self._owner, self._n
+            p32, psc, pro, psg, pms = (C.POINTER(C.c_uint32)(), C.POINTER(C.c_double)(), C.POINTER(C.c_int64)(),
+                                       C.POINTER(C.c_int32)(), C.POINTER(C.c_uint16)())
+            o.L.pwmscan_hits_compact(o.h, C.byref(p32), C.byref(psc), C.byref(pro), C.byref(psg), C.byref(pms))
+            self._compact = (_view(p32, n, o), _view(psc, n, o),
+                             _view(pro, 2 * o.M + 1, o) if pro else None,
+                             _view(psg, n, o) if psg else None, _view(pms, n, o) if pms else None)
+        return self._compact
+
+    def _get_wide(self):
+        if self._cols is not None:
+            return self._cols
+        if self._wide is None:
+            if self._n == 0:
+                self._wide = (np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0))
+            else:
+                o, n = self._owner, self._n
+                pm, ps, pg, pp, pc = (C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)(),
+                                      C.POINTER(C.c_int64)(), C.POINTER(C.c_double)())
+                o.ctx.check(o.L.pwmscan_hits_columns(o.h, C.byref(pm), C.byref(ps), C.byref(pg), C.byref(pp), C.byref(pc)))
+                self._wide = (_view(pm, n, o), _view(ps, n, o), _view(pg, n, o), _view(pp, n, o), _view(pc, n, o))
+        return self._wide
+
+    motif = property(lambda self: self._get_wide()[0])
+    strand = property(lambda self: self._get_wide()[1])
+    segment = property(lambda self: self._get_wide()[2])
+    pos = property(lambda self: self._get_wide()[3])
+
+    @property
+    def score(self):
+        if self._cols is not None or self._n == 0:
+            return self._get_wide()[4]
+        return self._get_compact()[1]
+
+    @property
+    def pos32(self):
+        return self._get_compact()[0] if self._n and self._cols is None else self.pos.astype(np.uint32)
+
+    @property
+    def run_off(self):
+        """Single-segment scans: int64[2M+1] run table of (motif, strand); None otherwise."""
+        return self._get_compact()[2] if self._n and self._cols is None else None
 
     def affinity(self, cdf_off, cdf_x, cdf_y, want_pvalue=False):
         """scanMotif's per-hit BED score (and p-value) on the device: pwmscan_hits_affinity.  cdf_off[M+1]
@@ -378,7 +437,7 @@ class Hits:
         n = len(self)
         aff = np.empty(n, dtype=np.int64)
         pv = np.empty(n) if want_pvalue else None
-        owner = getattr(self.pos, "_owner", None)
+        owner = self._owner
         if n:
             if owner is None or not owner.h:
                 raise ValueError("Hits.affinity needs the library-owned hit list (not a select()/copy)")
@@ -389,14 +448,17 @@ class Hits:
         return (aff, pv) if want_pvalue else aff
 
     def select(self, motif=None, strand=None, segment=None):
-        k = np.ones(self.pos.size, dtype=bool)
+        k = np.ones(self._n, dtype=bool)
         if motif is not None:
             k &= self.motif == motif
         if strand is not None:
             k &= self.strand == strand
         if segment is not None:
             k &= self.segment == segment
-        return Hits(self.motif[k], self.strand[k], self.segment[k], self.pos[k], self.score[k])
+        return Hits(cols=(self.motif[k], self.strand[k], self.segment[k], self.pos[k], self.score[k]))
+
+
+_HITS_CB = C.CFUNCTYPE(None, _vp, C.c_int32, _vp)
 
 
 class Plan:
@@ -443,15 +505,41 @@ class Plan:
         return self._hits(hh)
 
     def _hits(self, hh):
-        L = self.ctx.L
-        owner = _HitsHandle(self.ctx, hh)
-        n = L.pwmscan_hits_count(hh)
-        if n == 0:
-            return Hits(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0))
-        pm, ps, pg, pp, pc = (C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)(),
-                              C.POINTER(C.c_int64)(), C.POINTER(C.c_double)())
-        L.pwmscan_hits_columns(hh, C.byref(pm), C.byref(ps), C.byref(pg), C.byref(pp), C.byref(pc))
-        return Hits(_view(pm, n, owner), _view(ps, n, owner), _view(pg, n, owner), _view(pp, n, owner), _view(pc, n, owner))
+        h = Hits(self.ctx, hh)
+        h._owner.M = self.motifs.M
+        return h
+
+    def _many(self, call, n, consume):
+        out = [None] * n
+        err = []
+        c = consume or (lambda h: h)
+
+        def cb(_user, i, hh):
+            try:
+                out[i] = c(self._hits(_vp(hh)))
+            except BaseException as e:          # never let an exception cross the C frame
+                err.append(e)
+        fn = _HITS_CB(cb)
+        self.ctx.check(call(fn))
+        if err:
+            raise err[0]
+        return out
+
+    def scan_many(self, seqs, consume=None):
+        """pwmscan_scan_many: the items (DeviceSeq) are scanned with several of them in flight on the device.  Returns
+        [Hits per item], or [consume(hits)] — the consumer runs in item order as soon as an item's hits have landed, and
+        a hit list that is dropped goes straight back to the pinned pool (a streaming consumer, like scan_motif's writer)."""
+        arr = (_vp * len(seqs))(*[s.h for s in seqs])
+        return self._many(lambda fn: self.ctx.L.pwmscan_scan_many(self.ctx.h, self.h, C.c_int32(len(seqs)), arr, fn, None), len(seqs), consume)
+
+    def scan_host_many(self, arrays, consume=None, uppercase=False):
+        """pwmscan_scan_host_many: host byte arrays (pinned for full PCIe speed), one single-segment scan each."""
+        arrays = [_arr(a, np.uint8) for a in arrays]
+        ptrs = (_vp * len(arrays))(*[a.ctypes.data for a in arrays])
+        lens = np.array([a.size for a in arrays], dtype=np.int64)
+        return self._many(lambda fn: self.ctx.L.pwmscan_scan_host_many(self.ctx.h, self.h, C.c_int32(len(arrays)), ptrs, _ptr(lens),
+                                                                        C.c_int(SEQ_UPPERCASE if uppercase else 0), fn, None),
+                          len(arrays), consume)
 
     def free(self):
         if self.h:

@@ -95,7 +95,7 @@ extern "C" int pwmscan_hits_affinity(pwmscan_ctx* ctx, const pwmscan_hits* hits,
     PWM_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->timing[0] = ms; ctx->timing[3] = ms;
+    ctx->timing[10] = ms;
     if (out_affinity)
         for (int64_t k = 0; k < n; ++k)
             if (h_flag[(size_t)k]) out_affinity[k] = to_affinity_host(p_host[k]);

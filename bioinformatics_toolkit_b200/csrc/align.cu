@@ -103,8 +103,7 @@ int launch_and_collect(pwmscan_ctx* ctx, const AlignCfg& cfg, const AlignDev& de
     } else {
         for (int64_t k = 0; k < npairs; ++k) if (h_amb[k]) redo(k, pa[k], pb[k]);
     }
-    ctx->timing[0] = ms; ctx->timing[3] = ms; ctx->timing[6] = (double)namb;
-    ctx->timing[5] = (double)npairs * 14;
+    ctx->timing[10] = ms; ctx->timing[11] = (double)namb;
     return PWMSCAN_OK;
 }
 

@@ -317,7 +317,7 @@ int run_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int m0, int mcount, doub
     PWM_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->timing[0] = ms; ctx->timing[3] = ms;
+    ctx->timing[10] = ms;
     if (mode == 1) {
         double* hx = (double*)std::malloc((size_t)std::max<long long>(nout, 1) * 8);
         double* hp = (double*)std::malloc((size_t)std::max<long long>(nout, 1) * 8);

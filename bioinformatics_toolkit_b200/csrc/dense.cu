@@ -108,7 +108,7 @@ extern "C" int pwmscan_scores(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pw
     PWM_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->timing[0] = ms; ctx->timing[3] = ms; ctx->timing[5] = (double)nwin * 8;
+    ctx->timing[10] = ms;
     if (ctx->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.score: invalid nucleotide");
     return PWMSCAN_OK;
 }
@@ -151,7 +151,7 @@ extern "C" int pwmscan_max_match_sc(pwmscan_ctx* ctx, const pwmscan_seq* seq, co
     PWM_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->timing[0] = ms; ctx->timing[3] = ms;
+    ctx->timing[10] = ms;
     if (ctx->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.Search.lookAheadSearch: invalid nucleotide");
     for (int m = 0; m < M; ++m) {
         const unsigned long long k = h_key[m];

@@ -11,15 +11,41 @@
 #include "plan_mma.h"
 #include "plan_km.h"
 
+// Sort key of a hit: [segment | motif : mb bits | strand : 1 bit | position in segment : pb bits] — the reference's
+// output order (Data/Bed/Utils.hs:108-118) is the ascending order of this key.
+struct KeyLayout { int pb, mb; };
+
+constexpr int kOrderCap = 4096;        // hits one CTA orders in shared memory (order.cu)
+constexpr int kOrderIdxBits = 12;      // log2(kOrderCap)
+constexpr int kOrderTarget = 128;      // hits per bucket aimed at
+constexpr int kMaxLanes = 4;           // scans in flight of pwmscan_scan_many
+
+// Everything one in-flight scan needs of its own: streams, events, counters, grow-only scratch.  Lane 0 shares the
+// context's streams and counters (single scans run on it); lanes 1.. are created on demand by pwmscan_scan_many.
+struct ScanLane {
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool owns_streams = false;
+    std::vector<cudaEvent_t> chunk_ev;           // one per in-flight host->device chunk
+    cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* scratch[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long* d_counters = nullptr;    // [0] candidates [1] hits [2] error flag [3] mma overflow [4,5] fromBS verdict
+                                                 // [6] largest ordering bucket that did not fit; [8..] work counters
+    unsigned long long* h_counters = nullptr;    // pinned mirror of [0..7]
+};
+
 struct pwmscan_ctx {
     int device = 0;
+    std::vector<ScanLane*> lanes;                // lanes[0] aliases stream / copy_stream / d_counters / h_counters below
+    cudaEvent_t prefilter_chain = nullptr;       // completion of the last prefilter kernel of any lane (they run one after the other)
+    bool prefilter_chain_valid = false;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host->device chunks of pwmscan_scan_host
     std::vector<cudaEvent_t> chunk_ev;           // one per in-flight chunk (created on demand)
     std::mutex mu;
     std::string err;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t last_host_non_acgt = -1, last_host_non_iupac = -1;   // fromBS verdict of the last pwmscan_scan_host
     int sm_count = 148;
     bool lut_ready = false, dense_lut_ready = false, smem_attr_set = false, mma_attr_set = false;   // per-context one-time device setup
@@ -146,13 +172,25 @@ struct pwmscan_plan {
     double km_cand_rate = 0, km_surv_rate = 0, km_req_rate = 0;
 };
 
+// What a scan hands back.  The device transfers the COMPACT columns only (12 bytes per hit for a single-segment scan):
+//   score f64[n], pos32 u32[n] and, single segment, run_off i64[2M+1] (hits of (motif m, strand s) are
+//   [run_off[2m+s], run_off[2m+s+1])); several segments: seg32 i32[n] + ms16 u16[n] (= 2 * motif + strand).
+// The wide columns of pwmscan_hits_columns are expanded on the host the first time they are asked for.
 struct pwmscan_hits {
     pwmscan_ctx* ctx = nullptr;
     int64_t count = 0;
-    void* buf = nullptr;          // pinned: [pos i64 x n][score f64 x n][motif i32 x n][segment i32 x n][strand u8 x n]
+    int32_t nseg = 1, M = 0;
+    void* buf = nullptr;          // pinned
     size_t buf_bytes = 0;
-    const int64_t* pos = nullptr;
     const double* score = nullptr;
+    const uint32_t* pos32 = nullptr;
+    const int64_t* run_off = nullptr;     // nseg == 1
+    const int32_t* seg32 = nullptr;       // nseg > 1
+    const uint16_t* ms16 = nullptr;       // nseg > 1
+    // lazily expanded (host memory, owned)
+    std::mutex wide_mu;
+    void* wide = nullptr;
+    const int64_t* pos = nullptr;
     const int32_t* motif = nullptr;
     const int32_t* segment = nullptr;
     const uint8_t* strand = nullptr;
@@ -170,12 +208,22 @@ void* dev_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
 void dev_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out);
 void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
-int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
+void* lane_scratch_get(pwmscan_ctx* ctx, ScanLane* lane, int slot, size_t bytes);
+int hits_expand_wide(pwmscan_hits* h);     // fills pos / motif / segment / strand (idempotent, thread-safe)
+// order.cu
+int order_pick_shift(unsigned long long n, int key_bits);
+size_t order_bucket_count(int key_bits, int shift);
+size_t order_work_bytes(size_t nb);
+int order_hits(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const double* d_sc, unsigned long long n, KeyLayout kl,
+               int key_bits, int shift, int nseg, int M, unsigned char* d_work, unsigned long long* d_tkeys, double* d_tsc,
+               unsigned long long* d_skeys, double* d_score, uint32_t* d_pos32, int32_t* d_seg32, uint16_t* d_ms16, long long* d_run_off,
+               unsigned long long* d_flags, int* launches);
+int launch_mma_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap);
 
 int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int L, uint8_t* d_table);
 int km_build_bitmap(pwmscan_ctx* ctx, const uint8_t* d_table, int L, uint8_t* d_bitmap);
-int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
+int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter);
 

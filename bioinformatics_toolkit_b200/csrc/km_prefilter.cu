@@ -428,7 +428,7 @@ int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe
     return PWMSCAN_OK;
 }
 
-int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
+int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter) {
     if (nblocks == 0 || a1 <= a0) return PWMSCAN_OK;
@@ -440,8 +440,8 @@ int launch_km_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, 
     while (iters > 1 && (a1 - a0) / (iters * kKmIterPos) * nblocks < 8LL * ctx->sm_count) iters >>= 1;
     const long long items = (a1 - a0) / (iters * kKmIterPos) * nblocks;
     const int grid = (int)std::min<long long>(ctx->sm_count, items);
-    km_prefilter_kernel<<<grid, kKmThreads, smem_bytes, ctx->stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
-                                                                                    d_cand, cand_cap, ctx->d_counters, work_counter);
+    km_prefilter_kernel<<<grid, kKmThreads, smem_bytes, lane->stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
+                                                                                    d_cand, cand_cap, lane->d_counters, work_counter);
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;
 }

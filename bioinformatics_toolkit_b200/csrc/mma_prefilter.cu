@@ -273,7 +273,7 @@ namespace pwmscan {
 size_t mma_prefilter_smem_bytes() { return ((sizeof(MmaSmem) + 127) & ~size_t(127)) + (size_t)kMmaMaxSteps * kMmaCombos * 32 + 128; }
 static_assert(kMmaCombos * kAccStages <= 512, "accumulator stages must fit the 512 TMEM columns");
 
-int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
+int launch_mma_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap) {
     if (nblocks == 0 || a1 <= a0) return PWMSCAN_OK;
     if (!ctx->mma_attr_set) {
@@ -283,8 +283,8 @@ int launch_mma_prefilter(pwmscan_ctx* ctx, const uint32_t* d_seq2, long long a0,
     const long long n_items = (a1 - a0) / ((long long)kItemTiles * kTile);
     const int grid = (int)std::min<long long>(ctx->sm_count, n_items);
     static const int dbg = std::getenv("PWMSCAN_MMA_DBG") ? std::atoi(std::getenv("PWMSCAN_MMA_DBG")) : 0;
-    mma_prefilter_kernel<<<grid, kMmaThreads, mma_prefilter_smem_bytes(), ctx->stream>>>(d_seq2, a0, a1 - a0, nblocks, d_blocks, d_btiles,
-                                                                                        d_cand, cand_cap, ctx->d_counters, dbg);
+    mma_prefilter_kernel<<<grid, kMmaThreads, mma_prefilter_smem_bytes(), lane->stream>>>(d_seq2, a0, a1 - a0, nblocks, d_blocks, d_btiles,
+                                                                                        d_cand, cand_cap, lane->d_counters, dbg);
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;
 }

@@ -7,11 +7,11 @@
 //   ascii  optional upper-cased copy (IUPAC-aware entry points only)
 //   tables k-mer mask tables per 128-motif block (km_prefilter.cu; default first stage), built on the device;
 //          the other first stages keep their own (shared-memory 4-mer tables / int8 GEMM tiles)
-#include <cub/device/device_radix_sort.cuh>
-
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <new>
 
@@ -50,6 +50,17 @@ void* scratch_get(pwmscan_ctx* ctx, int slot, size_t bytes) {
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMalloc(scratch)"); return nullptr; }
     ctx->scratch[slot] = p; ctx->scratch_bytes[slot] = want;
+    return p;
+}
+
+void* lane_scratch_get(pwmscan_ctx* ctx, ScanLane* lane, int slot, size_t bytes) {
+    if (lane->scratch_bytes[slot] >= bytes && lane->scratch[slot]) return lane->scratch[slot];
+    if (lane->scratch[slot]) { cudaFree(lane->scratch[slot]); lane->scratch[slot] = nullptr; lane->scratch_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMalloc(lane scratch)"); return nullptr; }
+    lane->scratch[slot] = p; lane->scratch_bytes[slot] = want;
     return p;
 }
 
@@ -98,7 +109,7 @@ void* dev_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
 void dev_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(ctx->pool_mu);
-    if (ctx->dev_pool.size() >= 12) { cudaFree(ctx->dev_pool.front().p); ctx->dev_pool.erase(ctx->dev_pool.begin()); }
+    if (ctx->dev_pool.size() >= 24) { cudaFree(ctx->dev_pool.front().p); ctx->dev_pool.erase(ctx->dev_pool.begin()); }
     ctx->dev_pool.push_back({p, bytes});
 }
 
@@ -131,7 +142,7 @@ void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
 void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(ctx->pool_mu);
-    if (ctx->pin_pool.size() >= 6) { cudaFreeHost(ctx->pin_pool.front().p); ctx->pin_pool.erase(ctx->pin_pool.begin()); }
+    if (ctx->pin_pool.size() >= 12) { cudaFreeHost(ctx->pin_pool.front().p); ctx->pin_pool.erase(ctx->pin_pool.begin()); }
     ctx->pin_pool.push_back({p, bytes});
 }
 
@@ -171,7 +182,30 @@ extern "C" int pwmscan_ctx_create(int device, pwmscan_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaMalloc(&ctx->d_counters, kCounterWords * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
     if ((e = cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMallocHost(counters)");
+    if ((e = cudaEventCreateWithFlags(&ctx->prefilter_chain, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    ScanLane* l0 = new (std::nothrow) ScanLane();
+    if (!l0) { delete ctx; return set_err(nullptr, PWMSCAN_EINVAL, "out of host memory"); }
+    l0->stream = ctx->stream; l0->copy_stream = ctx->copy_stream; l0->d_counters = ctx->d_counters; l0->h_counters = ctx->h_counters;
+    ctx->lanes.push_back(l0);
+    for (auto& ev : l0->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "cudaEventCreate");
     *out = ctx;
+    return PWMSCAN_OK;
+}
+
+// Lane `idx` of the context (created on first use; ctx->mu held).
+static int lane_get(pwmscan_ctx* ctx, int idx, ScanLane** out) {
+    while ((int)ctx->lanes.size() <= idx) {
+        ScanLane* l = new (std::nothrow) ScanLane();
+        if (!l) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
+        ctx->lanes.push_back(l);
+        l->owns_streams = true;
+        PWM_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+        PWM_CUDA(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : l->ev) PWM_CUDA(cudaEventCreate(&ev));
+        PWM_CUDA(cudaMalloc(&l->d_counters, kCounterWords * sizeof(unsigned long long)));
+        PWM_CUDA(cudaMallocHost(&l->h_counters, 8 * sizeof(unsigned long long)));
+    }
+    *out = ctx->lanes[idx];
     return PWMSCAN_OK;
 }
 
@@ -179,6 +213,20 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (ScanLane* l : ctx->lanes) {
+        if (l->owns_streams && l->stream) cudaStreamSynchronize(l->stream);
+        for (auto& p : l->scratch) if (p) cudaFree(p);
+        for (auto& ev : l->ev) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : l->chunk_ev) cudaEventDestroy(ev);
+        if (l->owns_streams) {
+            if (l->d_counters) cudaFree(l->d_counters);
+            if (l->h_counters) cudaFreeHost(l->h_counters);
+            if (l->copy_stream) cudaStreamDestroy(l->copy_stream);
+            if (l->stream) cudaStreamDestroy(l->stream);
+        }
+        delete l;
+    }
+    if (ctx->prefilter_chain) cudaEventDestroy(ctx->prefilter_chain);
     for (auto& p : ctx->scratch) if (p) cudaFree(p);
     for (auto& p : ctx->pinned) if (p) cudaFreeHost(p);
     for (auto& b : ctx->dev_pool) cudaFree(b.p);
@@ -187,7 +235,6 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : ctx->chunk_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -195,7 +242,7 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
 
 extern "C" int pwmscan_last_timing(pwmscan_ctx* ctx, double* out, int n) {
     if (!ctx || !out) return PWMSCAN_EINVAL;
-    for (int i = 0; i < n && i < 8; ++i) out[i] = ctx->timing[i];
+    for (int i = 0; i < n && i < 12; ++i) out[i] = ctx->timing[i];
     return PWMSCAN_OK;
 }
 
@@ -295,7 +342,7 @@ static int seq_check_args(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t*
 
 // Allocates the device planes of a sequence (from the pool) and uploads the segment table.
 // *d_raw_out is where the ASCII bytes must land (the kept copy, or scratch slot 0).  ctx->mu held.
-static int seq_alloc(pwmscan_ctx* ctx, const int64_t* seg_off, int32_t nseg, int flags, pwmscan_seq** out, uint8_t** d_raw_out) {
+static int seq_alloc(pwmscan_ctx* ctx, ScanLane* lane, const int64_t* seg_off, int32_t nseg, int flags, pwmscan_seq** out, uint8_t** d_raw_out) {
     const int64_t len = seg_off[nseg];
     pwmscan_seq* s = new (std::nothrow) pwmscan_seq();
     if (!s) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
@@ -310,34 +357,34 @@ static int seq_alloc(pwmscan_ctx* ctx, const int64_t* seg_off, int32_t nseg, int
     s->d_seq2 = s->d_seq2_alloc + 1;
     if (!(s->d_mask = (uint32_t*)dev_pool_get(ctx, (size_t)s->nwords_mask * 4, &s->cap_mask))) return bail(PWMSCAN_ECUDA);
     if (!(s->d_seg_off = (int64_t*)dev_pool_get(ctx, (size_t)(nseg + 1) * 8, &s->cap_seg))) return bail(PWMSCAN_ECUDA);
-    if ((e = cudaMemcpyAsync(s->d_seg_off, s->seg_off.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(s->d_seg_off, s->seg_off.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, lane->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(seg_off)"));
     // the raw bytes: either kept (upper-cased in place by the pack kernel) or a scratch buffer
     if (flags & PWMSCAN_SEQ_KEEP_ASCII) {
         if (!(s->d_ascii = (uint8_t*)dev_pool_get(ctx, (size_t)len + 64, &s->cap_ascii))) return bail(PWMSCAN_ECUDA);
         *d_raw_out = s->d_ascii;
     } else {
-        *d_raw_out = (uint8_t*)scratch_get(ctx, 0, (size_t)len + 64);
+        *d_raw_out = (uint8_t*)lane_scratch_get(ctx, lane, 0, (size_t)len + 64);
         if (!*d_raw_out) return bail(PWMSCAN_ECUDA);
     }
-    if ((e = cudaMemsetAsync(ctx->d_counters + 4, 0xFF, 16, ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
+    if ((e = cudaMemsetAsync(lane->d_counters + 4, 0xFF, 16, lane->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
     *out = s;
     return PWMSCAN_OK;
 }
 
-static int seq_launch_pack(pwmscan_ctx* ctx, pwmscan_seq* s, const uint8_t* d_raw, int64_t t0, int64_t t1) {
+static int seq_launch_pack(pwmscan_ctx* ctx, ScanLane* lane, pwmscan_seq* s, const uint8_t* d_raw, int64_t t0, int64_t t1) {
     if (t1 <= t0) return PWMSCAN_OK;
     const int bs = 256;
-    pack_kernel<<<(unsigned)((t1 - t0 + bs - 1) / bs), bs, 0, ctx->stream>>>(
+    pack_kernel<<<(unsigned)((t1 - t0 + bs - 1) / bs), bs, 0, lane->stream>>>(
         d_raw, s->len, (s->flags & PWMSCAN_SEQ_UPPERCASE) ? 1 : 0, s->d_seq2, s->d_mask,
-        (s->flags & PWMSCAN_SEQ_KEEP_ASCII) ? s->d_ascii : nullptr, t0, t1, ctx->d_counters + 4);
+        (s->flags & PWMSCAN_SEQ_KEEP_ASCII) ? s->d_ascii : nullptr, t0, t1, lane->d_counters + 4);
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;
 }
 
-static int seq_finish(pwmscan_ctx* ctx, pwmscan_seq* s) {   // after a stream sync: fetch the fromBS validation result
-    s->first_non_acgt = ctx->h_counters[4] == ~0ull ? -1 : (int64_t)ctx->h_counters[4];
-    s->first_non_iupac = ctx->h_counters[5] == ~0ull ? -1 : (int64_t)ctx->h_counters[5];
+static int seq_finish(ScanLane* lane, pwmscan_seq* s) {   // after a stream sync: fetch the fromBS validation result
+    s->first_non_acgt = lane->h_counters[4] == ~0ull ? -1 : (int64_t)lane->h_counters[4];
+    s->first_non_iupac = lane->h_counters[5] == ~0ull ? -1 : (int64_t)lane->h_counters[5];
     return PWMSCAN_OK;
 }
 
@@ -352,17 +399,18 @@ static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t
     if ((rc = ensure_lut(ctx))) return rc;
     pwmscan_seq* s = nullptr;
     uint8_t* d_raw = nullptr;
-    if ((rc = seq_alloc(ctx, seg_off, nseg, flags, &s, &d_raw))) return rc;
+    ScanLane* lane = ctx->lanes[0];
+    if ((rc = seq_alloc(ctx, lane, seg_off, nseg, flags, &s, &d_raw))) return rc;
     auto bail = [&](int code) { pwmscan_seq_free(s); return code; };
     const int64_t len = s->len;
     cudaError_t e;
     if (len > 0 && (e = cudaMemcpyAsync(d_raw, ascii, (size_t)len, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(ascii)"));
-    if ((rc = seq_launch_pack(ctx, s, d_raw, 0, s->nwords_mask))) return bail(rc);
+    if ((rc = seq_launch_pack(ctx, lane, s, d_raw, 0, s->nwords_mask))) return bail(rc);
     if ((e = cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(first_bad)"));
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "pack_kernel"));
-    seq_finish(ctx, s);
+    seq_finish(lane, s);
     ctx->timing[4] = (double)len + (double)(nseg + 1) * 8;
     *out = s;
     return PWMSCAN_OK;
@@ -829,9 +877,8 @@ __device__ __forceinline__ int find_segment(const int64_t* __restrict__ seg_off,
     return lo;
 }
 
-// Sort key of a hit, packed as tightly as this scan allows so that the radix sort runs over as few bits as
-// possible: [segment | motif : mb bits | strand : 1 bit | position in segment : pb bits].
-struct KeyLayout { int pb, mb; };
+// Sort key of a hit (KeyLayout, internal.h), packed as tightly as this scan allows so that the ordering pass
+// (order.cu) needs few buckets: [segment | motif : mb bits | strand : 1 bit | position in segment : pb bits].
 __device__ __forceinline__ unsigned long long hit_key(KeyLayout kl, int seg, int motif, int strand, int64_t pos_in_seg) {
     return ((((((unsigned long long)seg << kl.mb) | (unsigned long long)motif) << 1) | (unsigned long long)strand) << kl.pb) |
            (unsigned long long)pos_in_seg;
@@ -927,22 +974,8 @@ __global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec
     }
 }
 
-// Sorted (key, score) pairs -> the column layout handed to the caller (one D2H copy).
-__global__ void decode_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, long long n, KeyLayout kl,
-                              long long* __restrict__ pos, double* __restrict__ score, int32_t* __restrict__ motif,
-                              int32_t* __restrict__ segment, uint8_t* __restrict__ strand) {
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long key = keys[k];
-        pos[k] = (long long)(key & ((1ull << kl.pb) - 1ull));
-        score[k] = sc[k];
-        strand[k] = (uint8_t)((key >> kl.pb) & 1ull);
-        motif[k] = (int32_t)((key >> (kl.pb + 1)) & ((1ull << kl.mb) - 1ull));
-        if (segment) segment[k] = (int32_t)(key >> (kl.pb + 1 + kl.mb));
-    }
-}
-
 // Exact kernel: every window of every listed combo replayed in fp64 (IUPAC-aware when skip == 0).
-// Used for combos the prefilter cannot take (skip == 0, > 28 columns, non-finite cutoffs/tables).
+// Used for combos the prefilter cannot take (skip == 0, non-finite cutoffs/tables).
 __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, int skip, const uint32_t* __restrict__ seq2,
                              const uint32_t* __restrict__ mask, const uint8_t* __restrict__ ascii,
                              const int64_t* __restrict__ seg_off, int nseg, int64_t len, const double* __restrict__ tab16,
@@ -981,71 +1014,114 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
 // ------------------------------------------------------------------------------------------------
 // scan driver
 // ------------------------------------------------------------------------------------------------
+// A scan runs in three phases on a lane (its own streams, counters and scratch), so that several scans can be in flight
+// on one device (pwmscan_scan_many: the (motif block x chromosome chunk) items of a whole-genome scan):
+//   A  enqueue: [pipelined upload + 2-bit packing,] first stage (prefilter), exact fp64 replay of the candidates,
+//      the counters to the host
+//   B  once the hit count is known: ordering (order.cu) into the compact columns, one device->host copy
+//   C  once that copy has landed: the hit list object
+// The first-stage kernels of different lanes are chained by an event: they fill every SM and cannot overlap anyway, and
+// the chain makes the CUDA-event time of a launch the kernel's own time.
+namespace {
+
 // Host->device job of a pipelined scan (pwmscan_scan_host): the ASCII bytes go up in chunks on the
 // copy stream; each chunk is packed and scanned on the compute stream as soon as it has landed, so
 // the PCIe transfer hides behind the prefilter kernel of the previous chunks.
 struct UploadJob {
-    const uint8_t* ascii;
-    uint8_t* d_raw;
-    pwmscan_seq* seq;      // mutable view of the sequence being filled
+    const uint8_t* ascii = nullptr;
+    uint8_t* d_raw = nullptr;
+    pwmscan_seq* seq = nullptr;      // mutable view of the sequence being filled
 };
 
-static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* pl, pwmscan_hits** out, const UploadJob* job) {
-    int rc = ensure_lut(ctx);
-    if (rc) return rc;
+struct ScanJob {
+    ScanLane* lane = nullptr;
+    const pwmscan_seq* seq = nullptr;
+    const pwmscan_plan* pl = nullptr;
+    bool host = false;               // sequence uploaded by this job (scan_host): released in phase C
+    UploadJob up;
+    KeyLayout kl{1, 1};
+    int key_bits = 0, shift = 0, attempt = 0;
+    unsigned long long cand_cap = 0, hit_cap = 0, nhits = 0, ncand = 0;
+    int prefilter_launches = 0, kernels = 0;
+    size_t n8 = 0, out_bytes = 0;
+    unsigned char* d_out = nullptr;
+    pwmscan_hits* hits = nullptr;
+    bool active = false;
+};
+
+inline int bits_for(uint64_t max_value) { int b = 1; while (b < 63 && (max_value >> b) != 0) ++b; return b; }
+
+enum { EV_START = 0, EV_PRE = 1, EV_RES = 2, EV_ORD = 3, EV_GATE = 4, EV_A = 5, EV_B = 6 };
+enum { SL_RAW = 0, SL_CAND = 1, SL_KEYS = 2, SL_SC = 3, SL_WORK = 4, SL_TKEYS = 5, SL_TSC = 6, SL_SKEYS = 7, SL_OUT = 8 };
+
+void job_release(ScanJob& j) {
+    if (j.hits) { pwmscan_hits_free(j.hits); j.hits = nullptr; }
+    if (j.host && j.up.seq) { pwmscan_seq_free(j.up.seq); j.up.seq = nullptr; }
+    j.active = false;
+}
+
+// Phase A.  attempt > 0 (a capacity overflow): the sequence is packed already, plain re-run.
+int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
+    ScanLane* lane = j.lane;
+    const pwmscan_seq* seq = j.seq;
+    const pwmscan_plan* pl = j.pl;
     const pwmscan_motifs* mo = pl->motifs;
+    cudaStream_t st = lane->stream;
+    int rc;
     const int64_t len = seq->len;
     const int64_t n_anchor = round_up(len + kPadFront + 64, kAnchorRound);
-    auto bits_for = [](uint64_t max_value) { int b = 1; while (b < 63 && (max_value >> b) != 0) ++b; return b; };
-    int64_t max_seg = 0;
-    for (int32_t g = 0; g < seq->nseg; ++g) max_seg = std::max(max_seg, seq->seg_off[g + 1] - seq->seg_off[g]);
-    KeyLayout kl;
-    kl.pb = bits_for((uint64_t)max_seg); kl.mb = bits_for((uint64_t)std::max(1, mo->M - 1));
-    const int key_bits = kl.pb + 1 + kl.mb + bits_for((uint64_t)std::max(1, seq->nseg - 1));
-    if (key_bits > 64) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: segments x motifs x segment length exceed the 64-bit hit key");
+    if (j.attempt == 0) {
+        int64_t max_seg = 0;
+        for (int32_t g = 0; g < seq->nseg; ++g) max_seg = std::max(max_seg, seq->seg_off[g + 1] - seq->seg_off[g]);
+        j.kl.pb = bits_for((uint64_t)max_seg); j.kl.mb = bits_for((uint64_t)std::max(1, mo->M - 1));
+        j.key_bits = j.kl.pb + 1 + j.kl.mb + (seq->nseg > 1 ? bits_for((uint64_t)(seq->nseg - 1)) : 0);
+        if (j.key_bits > 64) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: segments x motifs x segment length exceed the 64-bit hit key");
+        if (j.kl.pb > 32) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: segment longer than 2^32");
+    }
+    const bool use_mma = pl->mode == PWM_MODE_MMA, use_km = pl->mode == PWM_MODE_KMER;
+    const int n_pre_blocks = use_mma ? pl->mma_nblocks : use_km ? pl->km_nblocks : pl->nblocks;
+    const std::vector<DevCombo>& generic = use_mma ? pl->mma_generic : use_km ? pl->km_generic : pl->generic;
+    const DevCombo* d_generic = use_mma ? pl->d_mma_generic : use_km ? pl->d_km_generic : pl->d_generic;
+    const DevCombo* d_combos = use_mma ? pl->d_mma_combos : use_km ? pl->d_km_combos : pl->d_combos;
+    if (j.attempt == 0) {
+        // capacities: expected + slack, grown and re-run on overflow
+        j.cand_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
+        if (use_mma) j.cand_cap += (unsigned long long)ctx->sm_count * 28 * 256 * 2;        // every epilogue warp reserves whole 256-record chunks
+        j.hit_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
+        if (!generic.empty() && j.hit_cap < (1ull << 22)) j.hit_cap = 1ull << 22;
+    }
+    unsigned long long* d_cand = (unsigned long long*)lane_scratch_get(ctx, lane, SL_CAND, j.cand_cap * 8);
+    unsigned long long* d_keys = (unsigned long long*)lane_scratch_get(ctx, lane, SL_KEYS, j.hit_cap * 8);
+    double* d_sc = (double*)lane_scratch_get(ctx, lane, SL_SC, j.hit_cap * 8);
+    if (!d_cand || !d_keys || !d_sc) return PWMSCAN_ECUDA;
+    if (pl->nblocks > 0 && !ctx->smem_attr_set) {
+        PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
+        PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
+        ctx->smem_attr_set = true;
+    }
     auto items_of = [&](long long anchors, int iters) {
         long long t = 0;
         for (int b = 0; b < pl->nblocks; ++b) t += (anchors / ((long long)kWarps * 32 * iters)) / pl->blocks[b].rep;
         return t;
     };
     const size_t smem_bytes = (size_t)pl->max_nslot * kSlotBytes;
-    if (pl->nblocks > 0) {
-        if (!ctx->smem_attr_set) {
-            PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
-            PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
-            ctx->smem_attr_set = true;
-        }
-    }
-    // which first stage: the shared-memory look-up kernel or the tensor-core (tcgen05) one
-    const bool use_mma = pl->mode == PWM_MODE_MMA, use_km = pl->mode == PWM_MODE_KMER;
-    const int n_pre_blocks = use_mma ? pl->mma_nblocks : use_km ? pl->km_nblocks : pl->nblocks;
-    const std::vector<DevCombo>& generic = use_mma ? pl->mma_generic : use_km ? pl->km_generic : pl->generic;
-    const DevCombo* d_generic = use_mma ? pl->d_mma_generic : use_km ? pl->d_km_generic : pl->d_generic;
-    const DevCombo* d_combos = use_mma ? pl->d_mma_combos : use_km ? pl->d_km_combos : pl->d_combos;
-    const double cand_rate = pl->cand_rate;
-    // capacities: expected + slack, grown and re-run on overflow
-    unsigned long long cand_cap = (unsigned long long)(cand_rate * (double)len * 1.5) + (1ull << 20);
-    if (use_mma) cand_cap += (unsigned long long)ctx->sm_count * 28 * 256 * 2;             // every epilogue warp reserves whole 256-record chunks
-    unsigned long long hit_cap = (unsigned long long)(pl->cand_rate * (double)len * 1.5) + (1ull << 20);
-    if (!generic.empty() && hit_cap < (1ull << 22)) hit_cap = 1ull << 22;
-    unsigned long long nhits = 0, ncand = 0;
-    unsigned long long *d_cand = nullptr, *d_keys = nullptr;
-    double* d_sc = nullptr;
-    float ms_pre = 0, ms_res = 0, ms_sort = 0, ms_tot = 0;
-    int launches = 0;
+    bool chained = false;
     auto launch_prefilter = [&](long long a0, long long a1, int slot) -> int {
+        if (n_pre_blocks == 0 || a1 <= a0) return PWMSCAN_OK;
+        if (!chained) {               // first-stage kernels of different lanes run one after the other
+            if (ctx->prefilter_chain_valid) PWM_CUDA(cudaStreamWaitEvent(st, ctx->prefilter_chain, 0));
+            if (!j.host || j.attempt > 0) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
+            chained = true;
+        }
         if (use_km) {
-            if (pl->km_nblocks == 0) return PWMSCAN_OK;
-            ++launches;
-            return launch_km_prefilter(ctx, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_smem_bytes, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
-                                       pl->d_km_combos, d_cand, cand_cap, ctx->d_counters + 8 + slot);
+            ++j.prefilter_launches;
+            return launch_km_prefilter(ctx, lane, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_smem_bytes, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
+                                       pl->d_km_combos, d_cand, j.cand_cap, lane->d_counters + 8 + slot);
         }
         if (use_mma) {
-            if (pl->mma_nblocks == 0) return PWMSCAN_OK;
-            ++launches;
-            return launch_mma_prefilter(ctx, seq->d_seq2, a0, a1, pl->mma_nblocks, pl->d_mma_blocks, pl->d_btiles, d_cand, cand_cap);
+            ++j.prefilter_launches;
+            return launch_mma_prefilter(ctx, lane, seq->d_seq2, a0, a1, pl->mma_nblocks, pl->d_mma_blocks, pl->d_btiles, d_cand, j.cand_cap);
         }
-        if (pl->nblocks == 0) return PWMSCAN_OK;
         int iters = kIters;                                   // short inputs: smaller items so that every SM gets work
         while (iters > 1 && items_of(a1 - a0, iters) < 4LL * ctx->sm_count) iters >>= 1;
         const long long items = items_of(a1 - a0, iters);
@@ -1058,154 +1134,230 @@ static int scan_impl(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_pla
         bool any_full = false;                                        // TMEM serves blocks whose 32 lanes carry distinct motifs
         for (const auto& b : pl->blocks) any_full |= (b.rep == 1);
         if (any_full && use_tmem)
-            prefilter_kernel<true><<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
-                                                                               d_cand, cand_cap, ctx->d_counters, ctx->d_counters + 8 + slot);
+            prefilter_kernel<true><<<grid, kThreads, smem_bytes, st>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+                                                                       d_cand, j.cand_cap, lane->d_counters, lane->d_counters + 8 + slot);
         else
-            prefilter_kernel<false><<<grid, kThreads, smem_bytes, ctx->stream>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
-                                                                                d_cand, cand_cap, ctx->d_counters, ctx->d_counters + 8 + slot);
+            prefilter_kernel<false><<<grid, kThreads, smem_bytes, st>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+                                                                        d_cand, j.cand_cap, lane->d_counters, lane->d_counters + 8 + slot);
         PWM_CUDA(cudaGetLastError());
-        ++launches;
+        ++j.prefilter_launches;
         return PWMSCAN_OK;
     };
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        d_cand = (unsigned long long*)scratch_get(ctx, 1, cand_cap * 8);
-        d_keys = (unsigned long long*)scratch_get(ctx, 2, hit_cap * 8);
-        d_sc = (double*)scratch_get(ctx, 3, hit_cap * 8);
-        if (!d_cand || !d_keys || !d_sc) return PWMSCAN_ECUDA;
-        PWM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
-        PWM_CUDA(cudaMemsetAsync(ctx->d_counters + 8, 0, (kCounterWords - 8) * sizeof(unsigned long long), ctx->stream));
-        if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, cand_cap * 8, ctx->stream));     // sentinel: warps reserve whole chunks
-        PWM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-        if (job && attempt == 0) {
-            // chunk boundaries are multiples of the anchor rounding unit, so every launch covers whole work items.
-            // 16 Mi bases per chunk (smaller chunks cost more in per-launch overhead than they hide), except that
-            // the end is split off as a short last chunk so that little work is left once the last byte has landed.
-            static const int chunk_units = std::getenv("PWMSCAN_CHUNK_UNITS") ? std::max(8, std::atoi(std::getenv("PWMSCAN_CHUNK_UNITS"))) : 32;   // experiments
-            int64_t cb = chunk_units * kAnchorRound;
-            while ((len + cb - 1) / cb > kMaxChunks - 1) cb *= 2;
-            const int64_t tail = 4 * kAnchorRound;
-            std::vector<int64_t> bounds(1, 0);
-            while (len - bounds.back() > cb + tail) bounds.push_back(bounds.back() + cb);
-            if (len - bounds.back() > 2 * tail) bounds.push_back((len - tail) / kAnchorRound * kAnchorRound);
-            bounds.push_back(len);
-            const int nch = (int)bounds.size() - 1;
-            while ((int)ctx->chunk_ev.size() < nch) {
-                cudaEvent_t ev;
-                PWM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                ctx->chunk_ev.push_back(ev);
-            }
-            PWM_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));               // copies must not overtake the previous use of d_raw
-            PWM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[4], 0));
-            // (one copy stream: alternating two streams was measured slower, 6.7 vs 5.3 ms on C2)
-            for (int l = 0; l < nch; ++l) {
-                const int64_t b0 = bounds[l], b1 = bounds[l + 1];
-                cudaStream_t cs = ctx->copy_stream;
-                if (b1 > b0) PWM_CUDA(cudaMemcpyAsync(job->d_raw + b0, job->ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
-                PWM_CUDA(cudaEventRecord(ctx->chunk_ev[l], cs));
-            }
-            long long scanned = 0;
-            for (int l = 0; l < nch; ++l) {
-                const bool last = (l == nch - 1);
-                const int64_t b0 = bounds[l], b1 = bounds[l + 1];
-                PWM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[l], 0));
-                // pack threads own 32 stored bases: positions [32t-32, 32t)
-                const int64_t t0 = l == 0 ? 0 : b0 / 32 + 1, t1 = last ? job->seq->nwords_mask : b1 / 32 + 1;
-                if ((rc = seq_launch_pack(ctx, job->seq, job->d_raw, t0, t1))) return rc;
-                // anchors whose windows (and the prefetch of the next words) lie inside what is packed so far
-                const long long a1 = last ? n_anchor : std::max<long long>(scanned, b1 - kAnchorRound);
-                if (a1 > scanned) { if ((rc = launch_prefilter(scanned, a1, l))) return rc; scanned = a1; }
-            }
-        } else {
-            if ((rc = launch_prefilter(0, n_anchor, 0))) return rc;
+    PWM_CUDA(cudaMemsetAsync(lane->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, (kCounterWords - 6) * sizeof(unsigned long long), st));
+    if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, j.cand_cap * 8, st));     // sentinel: warps reserve whole chunks
+    if (j.host && j.attempt == 0) {
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
+        // chunk boundaries are multiples of the anchor rounding unit, so every launch covers whole work items.
+        // 16 Mi bases per chunk (smaller chunks cost more in per-launch overhead than they hide), except that
+        // the end is split off as a short last chunk so that little work is left once the last byte has landed.
+        static const int chunk_units = std::getenv("PWMSCAN_CHUNK_UNITS") ? std::max(8, std::atoi(std::getenv("PWMSCAN_CHUNK_UNITS"))) : 32;   // experiments
+        int64_t cb = chunk_units * kAnchorRound;
+        while ((len + cb - 1) / cb > kMaxChunks - 1) cb *= 2;
+        const int64_t tail = 4 * kAnchorRound;
+        std::vector<int64_t> bounds(1, 0);
+        while (len - bounds.back() > cb + tail) bounds.push_back(bounds.back() + cb);
+        if (len - bounds.back() > 2 * tail) bounds.push_back((len - tail) / kAnchorRound * kAnchorRound);
+        bounds.push_back(len);
+        const int nch = (int)bounds.size() - 1;
+        while ((int)lane->chunk_ev.size() < nch) {
+            cudaEvent_t ev;
+            PWM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            lane->chunk_ev.push_back(ev);
         }
-        PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        if (n_pre_blocks > 0) {
-            if (use_mma)
-                rescore_chunks_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(d_cand, cand_cap, pl->d_mma_blocks, pl->d_btiles, d_combos, seq->d_seq2, seq->d_mask,
-                                                                                  seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                                                  d_sc, hit_cap, ctx->d_counters, kl);
-            else
-                rescore_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_cand, cand_cap, d_combos, seq->d_seq2, seq->d_mask,
-                                                                          seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                                          d_sc, hit_cap, ctx->d_counters, kl);
-            PWM_CUDA(cudaGetLastError());
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_GATE], st));               // copies must not overtake the previous use of d_raw
+        PWM_CUDA(cudaStreamWaitEvent(lane->copy_stream, lane->ev[EV_GATE], 0));
+        // (one copy stream: alternating two streams was measured slower, 6.7 vs 5.3 ms on C2)
+        for (int l = 0; l < nch; ++l) {
+            const int64_t b0 = bounds[l], b1 = bounds[l + 1];
+            if (b1 > b0) PWM_CUDA(cudaMemcpyAsync(j.up.d_raw + b0, j.up.ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, lane->copy_stream));
+            PWM_CUDA(cudaEventRecord(lane->chunk_ev[l], lane->copy_stream));
         }
-        if (!generic.empty() && len > 0) {
-            const int bs = 256;
-            const long long gx = std::min<long long>((len + bs - 1) / bs, 65535LL * 16);
-            dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(generic.size(), 65535));
-            exact_kernel<<<grid, bs, 0, ctx->stream>>>(d_generic, (int)generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
-                                                      seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, hit_cap, ctx->d_counters, kl);
-            PWM_CUDA(cudaGetLastError());
+        long long scanned = 0;
+        for (int l = 0; l < nch; ++l) {
+            const bool last = (l == nch - 1);
+            const int64_t b0 = bounds[l], b1 = bounds[l + 1];
+            PWM_CUDA(cudaStreamWaitEvent(st, lane->chunk_ev[l], 0));
+            // pack threads own 32 stored bases: positions [32t-32, 32t)
+            const int64_t t0 = l == 0 ? 0 : b0 / 32 + 1, t1 = last ? j.up.seq->nwords_mask : b1 / 32 + 1;
+            if ((rc = seq_launch_pack(ctx, lane, j.up.seq, j.up.d_raw, t0, t1))) return rc;
+            ++j.kernels;
+            // anchors whose windows (and the prefetch of the next words) lie inside what is packed so far
+            const long long a1 = last ? n_anchor : std::max<long long>(scanned, b1 - kAnchorRound);
+            if (a1 > scanned) { if ((rc = launch_prefilter(scanned, a1, l))) return rc; scanned = a1; }
         }
-        PWM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-        PWM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        PWM_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (job && attempt == 0) {
-            seq_finish(ctx, job->seq);
-            ctx->last_host_non_acgt = job->seq->first_non_acgt; ctx->last_host_non_iupac = job->seq->first_non_iupac;
+        // the fromBS verdict of the packed bytes
+        PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 4, lane->d_counters + 4, 16, cudaMemcpyDeviceToHost, st));
+    } else {
+        if ((rc = launch_prefilter(0, n_anchor, 0))) return rc;
+        if (!chained) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
+    }
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_PRE], st));
+    if (chained) { PWM_CUDA(cudaEventRecord(ctx->prefilter_chain, st)); ctx->prefilter_chain_valid = true; }
+    j.kernels += j.prefilter_launches;
+    if (n_pre_blocks > 0) {
+        if (use_mma)
+            rescore_chunks_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(d_cand, j.cand_cap, pl->d_mma_blocks, pl->d_btiles, d_combos, seq->d_seq2, seq->d_mask,
+                                                                      seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
+                                                                      d_sc, j.hit_cap, lane->d_counters, j.kl);
+        else
+            rescore_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_cand, j.cand_cap, d_combos, seq->d_seq2, seq->d_mask,
+                                                              seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
+                                                              d_sc, j.hit_cap, lane->d_counters, j.kl);
+        PWM_CUDA(cudaGetLastError());
+        ++j.kernels;
+    }
+    if (!generic.empty() && len > 0) {
+        const int bs = 256;
+        const long long gx = std::min<long long>((len + bs - 1) / bs, 65535LL * 16);
+        dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(generic.size(), 65535));
+        exact_kernel<<<grid, bs, 0, st>>>(d_generic, (int)generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
+                                          seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, j.hit_cap, lane->d_counters, j.kl);
+        PWM_CUDA(cudaGetLastError());
+        ++j.kernels;
+    }
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_RES], st));
+    PWM_CUDA(cudaMemcpyAsync(lane->h_counters, lane->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_A], st));
+    return PWMSCAN_OK;
+}
+
+// Ordering + the device->host copy of the compact columns for the current j.shift (stream-ordered).
+int scan_enqueue_order(pwmscan_ctx* ctx, ScanJob& j) {
+    ScanLane* lane = j.lane;
+    cudaStream_t st = lane->stream;
+    const int M = j.pl->motifs->M, nseg = j.seq->nseg;
+    const unsigned long long n = j.nhits;
+    const size_t nb = order_bucket_count(j.key_bits, j.shift);
+    if (nb > ((size_t)1 << 28)) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit density too skewed to order");
+    unsigned char* d_work = (unsigned char*)lane_scratch_get(ctx, lane, SL_WORK, order_work_bytes(nb));
+    unsigned long long* d_tkeys = (unsigned long long*)lane_scratch_get(ctx, lane, SL_TKEYS, n * 8);
+    double* d_tsc = (double*)lane_scratch_get(ctx, lane, SL_TSC, n * 8);
+    unsigned long long* d_skeys = (unsigned long long*)lane_scratch_get(ctx, lane, SL_SKEYS, n * 8);
+    j.d_out = (unsigned char*)lane_scratch_get(ctx, lane, SL_OUT, j.out_bytes);
+    if (!d_work || !d_tkeys || !d_tsc || !d_skeys || !j.d_out) return PWMSCAN_ECUDA;
+    const size_t n8 = j.n8;
+    double* o_sc = (double*)j.d_out;
+    uint32_t* o_pos = (uint32_t*)(j.d_out + n8 * 8);
+    long long* o_run = nseg == 1 ? (long long*)(j.d_out + n8 * 12) : nullptr;
+    int32_t* o_seg = nseg == 1 ? nullptr : (int32_t*)(j.d_out + n8 * 12);
+    uint16_t* o_ms = nseg == 1 ? nullptr : (uint16_t*)(j.d_out + n8 * 16);
+    PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, 8, st));
+    int rc = order_hits(ctx, st, (const unsigned long long*)lane->scratch[SL_KEYS], (const double*)lane->scratch[SL_SC], n, j.kl, j.key_bits, j.shift,
+                        nseg, M, d_work, d_tkeys, d_tsc, d_skeys, o_sc, o_pos, o_seg, o_ms, o_run, lane->d_counters + 6, &j.kernels);
+    if (rc) return rc;
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_ORD], st));
+    PWM_CUDA(cudaMemcpyAsync(j.hits->buf, j.d_out, j.out_bytes, cudaMemcpyDeviceToHost, st));
+    PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 6, lane->d_counters + 6, 8, cudaMemcpyDeviceToHost, st));
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_B], st));
+    return PWMSCAN_OK;
+}
+
+// Phase B: waits for the counters of phase A, repeats A with larger buffers if they overflowed, then enqueues the ordering.
+int scan_phase_b(pwmscan_ctx* ctx, ScanJob& j) {
+    ScanLane* lane = j.lane;
+    const pwmscan_plan* pl = j.pl;
+    for (;;) {
+        PWM_CUDA(cudaEventSynchronize(lane->ev[EV_A]));
+        if (j.host && j.attempt == 0) {
+            seq_finish(lane, j.up.seq);
+            ctx->last_host_non_acgt = j.up.seq->first_non_acgt; ctx->last_host_non_iupac = j.up.seq->first_non_iupac;
         }
-        ncand = ctx->h_counters[0]; nhits = ctx->h_counters[1];
-        if (use_mma && ctx->h_counters[3] != 0) ncand = std::max(ncand, cand_cap) + 2 * ctx->h_counters[3];   // candidates that did not fit
-        if (ctx->h_counters[2] & 2ull) return set_err(ctx, PWMSCAN_ECUDA, "pwmscan_scan: tensor-core prefilter pipeline aborted (bounded wait expired)");
-        if (ctx->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.Search.lookAheadSearch: invalid nucleotide");
-        if (ncand <= cand_cap && nhits <= hit_cap) break;
-        if (attempt == 3) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit buffers kept overflowing");
-        cand_cap = std::max(cand_cap, ncand + (ncand >> 3) + 1024);
-        hit_cap = std::max(hit_cap, std::max(nhits, ncand) + (nhits >> 3) + 1024);
+        j.ncand = lane->h_counters[0]; j.nhits = lane->h_counters[1];
+        if (pl->mode == PWM_MODE_MMA && lane->h_counters[3] != 0) j.ncand = std::max(j.ncand, j.cand_cap) + 2 * lane->h_counters[3];   // candidates that did not fit
+        if (lane->h_counters[2] & 2ull) return set_err(ctx, PWMSCAN_ECUDA, "pwmscan_scan: tensor-core prefilter pipeline aborted (bounded wait expired)");
+        if (lane->h_counters[2] != 0) return set_err(ctx, PWMSCAN_ENUCL, "Bio.Motif.Search.lookAheadSearch: invalid nucleotide");
+        if (j.ncand <= j.cand_cap && j.nhits <= j.hit_cap) break;
+        if (j.attempt == 3) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit buffers kept overflowing");
+        j.cand_cap = std::max(j.cand_cap, j.ncand + (j.ncand >> 3) + 1024);
+        j.hit_cap = std::max(j.hit_cap, std::max(j.nhits, j.ncand) + (j.nhits >> 3) + 1024);
+        ++j.attempt;
+        int rc = scan_phase_a(ctx, j);
+        if (rc) return rc;
     }
     pwmscan_hits* h = new (std::nothrow) pwmscan_hits();
     if (!h) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
-    h->ctx = ctx;
-    h->count = (int64_t)nhits;
-    if (nhits > 0) {
-        unsigned long long* d_keys2 = (unsigned long long*)scratch_get(ctx, 4, nhits * 8);
-        double* d_sc2 = (double*)scratch_get(ctx, 5, nhits * 8);
-        if (!d_keys2 || !d_sc2) { delete h; return PWMSCAN_ECUDA; }
-        size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, key_bits, ctx->stream);
-        const size_t n8 = (nhits + 7) & ~7ull;                       // keeps every column 8-byte aligned
-        const bool one_seg = seq->nseg == 1;                        // the segment column (all zero) is then not materialised
-        const size_t col_bytes = n8 * (one_seg ? 21 : 25);
-        unsigned char* d_tmp = (unsigned char*)scratch_get(ctx, 6, tmp_bytes + 256 + col_bytes);
-        if (!d_tmp) { delete h; return PWMSCAN_ECUDA; }
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_sc, d_sc2, (int64_t)nhits, 0, key_bits, ctx->stream);
-        if (e != cudaSuccess) { delete h; return cuda_fail(ctx, e, "cub::DeviceRadixSort"); }
-        unsigned char* d_cols = d_tmp + ((tmp_bytes + 255) & ~(size_t)255);
-        long long* c_pos = (long long*)d_cols;
-        double* c_sc = (double*)(d_cols + n8 * 8);
-        int32_t* c_mo = (int32_t*)(d_cols + n8 * 16);
-        int32_t* c_sg = one_seg ? nullptr : (int32_t*)(d_cols + n8 * 20);
-        uint8_t* c_st = (uint8_t*)(d_cols + n8 * (one_seg ? 20 : 24));
-        decode_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_keys2, d_sc2, (long long)nhits, kl, c_pos, c_sc, c_mo, c_sg, c_st);
-        if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return cuda_fail(ctx, e, "decode_kernel"); }
-        cudaEventRecord(ctx->ev[3], ctx->stream);
-        h->buf = pin_pool_get(ctx, col_bytes, &h->buf_bytes);
-        if (!h->buf) { delete h; return PWMSCAN_ECUDA; }
-        if ((e = cudaMemcpyAsync(h->buf, d_cols, col_bytes, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) { pwmscan_hits_free(h); return cuda_fail(ctx, e, "D2H hits"); }
-        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { pwmscan_hits_free(h); return cuda_fail(ctx, e, "scan sync"); }
-        unsigned char* hb = (unsigned char*)h->buf;
-        h->pos = (const int64_t*)hb; h->score = (const double*)(hb + n8 * 8); h->motif = (const int32_t*)(hb + n8 * 16);
-        h->strand = (const uint8_t*)(hb + n8 * (one_seg ? 20 : 24));
-        if (one_seg) {
-            if (!(h->segment = zero_column(ctx, n8))) { pwmscan_hits_free(h); return set_err(ctx, PWMSCAN_EINVAL, "out of host memory"); }
-        } else {
-            h->segment = (const int32_t*)(hb + n8 * 20);
+    j.hits = h;
+    h->ctx = ctx; h->count = (int64_t)j.nhits; h->nseg = j.seq->nseg; h->M = pl->motifs->M;
+    if (j.nhits == 0) return PWMSCAN_OK;
+    const size_t n8 = (j.nhits + 7) & ~7ull;                    // keeps every column 8-byte aligned
+    j.n8 = n8;
+    j.out_bytes = j.seq->nseg == 1 ? n8 * 12 + (size_t)(2 * h->M + 1) * 8 : n8 * 18;
+    h->buf = pin_pool_get(ctx, j.out_bytes, &h->buf_bytes);
+    if (!h->buf) return PWMSCAN_ECUDA;
+    j.shift = order_pick_shift(j.nhits, j.key_bits);
+    return scan_enqueue_order(ctx, j);
+}
+
+// Phase C: waits for the hit list, hands it over (the job keeps nothing), releases a sequence the job owned.
+int scan_phase_c(pwmscan_ctx* ctx, ScanJob& j, pwmscan_hits** out, double* timing /* accumulated, 12 entries */) {
+    ScanLane* lane = j.lane;
+    float ms_pre = 0, ms_res = 0, ms_ord = 0, ms_tot = 0;
+    if (j.nhits > 0) {
+        for (;;) {
+            PWM_CUDA(cudaEventSynchronize(lane->ev[EV_B]));
+            const unsigned long long over = lane->h_counters[6];
+            if (over == 0) break;
+            // a bucket did not fit the ordering kernel's shared memory: smaller buckets, again (keys are unique per position,
+            // so 2^kOrderIdxBits positions of one (segment, motif, strand) always fit)
+            if (j.shift == 0) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: internal: ordering bucket overflow at shift 0");
+            int drop = 1;
+            while (((unsigned long long)kOrderCap << drop) < over) ++drop;
+            j.shift = std::max(0, j.shift - drop - 1);
+            int rc = scan_enqueue_order(ctx, j);
+            if (rc) return rc;
         }
-        cudaEventElapsedTime(&ms_sort, ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&ms_tot, ctx->ev[0], ctx->ev[3]);
+        pwmscan_hits* h = j.hits;
+        unsigned char* hb = (unsigned char*)h->buf;
+        h->score = (const double*)hb;
+        h->pos32 = (const uint32_t*)(hb + j.n8 * 8);
+        if (h->nseg == 1) h->run_off = (const int64_t*)(hb + j.n8 * 12);
+        else { h->seg32 = (const int32_t*)(hb + j.n8 * 12); h->ms16 = (const uint16_t*)(hb + j.n8 * 16); }
+        cudaEventElapsedTime(&ms_ord, lane->ev[EV_RES], lane->ev[EV_ORD]);
+        cudaEventElapsedTime(&ms_tot, lane->ev[EV_START], lane->ev[EV_ORD]);
     } else {
-        cudaEventElapsedTime(&ms_tot, ctx->ev[0], ctx->ev[2]);
+        cudaEventElapsedTime(&ms_tot, lane->ev[EV_START], lane->ev[EV_RES]);
     }
-    cudaEventElapsedTime(&ms_pre, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ms_res, ctx->ev[1], ctx->ev[2]);
-    ctx->timing[0] = ms_pre; ctx->timing[1] = ms_res; ctx->timing[2] = ms_sort; ctx->timing[3] = ms_tot;
-    ctx->timing[5] = (double)nhits * (seq->nseg == 1 ? 21 : 25) + 32;
-    ctx->timing[6] = (double)ncand;
-    ctx->timing[7] = (double)launches;
-    *out = h;
+    cudaEventElapsedTime(&ms_pre, lane->ev[EV_START], lane->ev[EV_PRE]);
+    cudaEventElapsedTime(&ms_res, lane->ev[EV_PRE], lane->ev[EV_RES]);
+    timing[0] += ms_pre; timing[1] += ms_res; timing[2] += ms_ord; timing[3] += ms_tot;
+    if (j.host) timing[4] += (double)j.seq->len + (double)(j.seq->nseg + 1) * 8;
+    timing[5] += (double)j.out_bytes + 40;
+    timing[6] += (double)j.ncand;
+    timing[7] += (double)j.prefilter_launches;
+    timing[8] += (double)j.kernels;
+    timing[9] += (double)j.nhits;
+    *out = j.hits;
+    j.hits = nullptr;
+    job_release(j);
     return PWMSCAN_OK;
 }
+
+int scan_one(pwmscan_ctx* ctx, ScanJob& j, pwmscan_hits** out) {
+    double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int rc = scan_phase_a(ctx, j);
+    if (!rc) rc = scan_phase_b(ctx, j);
+    if (!rc) rc = scan_phase_c(ctx, j, out, t);
+    if (rc) { cudaStreamSynchronize(j.lane->stream); cudaStreamSynchronize(j.lane->copy_stream); job_release(j); return rc; }
+    for (int i = 0; i < 12; ++i) ctx->timing[i] = t[i];
+    return PWMSCAN_OK;
+}
+
+// Sets up the job of a host-bytes scan: allocates the sequence planes, the upload happens inside phase A.
+int job_init_host(pwmscan_ctx* ctx, ScanJob& j, ScanLane* lane, const pwmscan_plan* pl, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg, int flags) {
+    j = ScanJob();
+    j.lane = lane; j.pl = pl; j.host = true; j.active = true;
+    if (!pl->skip) flags |= PWMSCAN_SEQ_KEEP_ASCII;
+    pwmscan_seq* s = nullptr;
+    uint8_t* d_raw = nullptr;
+    int rc = seq_alloc(ctx, lane, seg_off, nseg, flags, &s, &d_raw);
+    if (rc) return rc;
+    j.up.ascii = ascii; j.up.d_raw = d_raw; j.up.seq = s;
+    j.seq = s;
+    return PWMSCAN_OK;
+}
+
+}  // namespace
 
 extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_plan* pl, pwmscan_hits** out) {
     if (!ctx || !seq || !pl || !out) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: NULL argument");
@@ -1214,7 +1366,11 @@ extern "C" int pwmscan_scan(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwms
     if (!pl->skip && !seq->d_ascii) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan: skip_ambiguous = 0 needs a sequence uploaded with PWMSCAN_SEQ_KEEP_ASCII");
     std::lock_guard<std::mutex> lk(ctx->mu);
     PWM_CUDA(cudaSetDevice(ctx->device));
-    return scan_impl(ctx, seq, pl, out, nullptr);
+    int rc = ensure_lut(ctx);
+    if (rc) return rc;
+    ScanJob j;
+    j.lane = ctx->lanes[0]; j.seq = seq; j.pl = pl; j.active = true;
+    return scan_one(ctx, j, out);
 }
 
 extern "C" int pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* pl, const uint8_t* ascii, const int64_t* seg_off, int32_t nseg,
@@ -1224,19 +1380,90 @@ extern "C" int pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* pl, const
     if (pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_host: plan belongs to another context");
     int rc = seq_check_args(ctx, ascii, seg_off, nseg);
     if (rc) return rc;
-    if (!pl->skip) flags |= PWMSCAN_SEQ_KEEP_ASCII;
     std::lock_guard<std::mutex> lk(ctx->mu);
     PWM_CUDA(cudaSetDevice(ctx->device));
     if ((rc = ensure_lut(ctx))) return rc;
-    pwmscan_seq* s = nullptr;
-    uint8_t* d_raw = nullptr;
-    if ((rc = seq_alloc(ctx, seg_off, nseg, flags, &s, &d_raw))) return rc;
-    UploadJob job{ascii, d_raw, s};
-    rc = scan_impl(ctx, s, pl, out, &job);
+    ScanJob j;
+    if ((rc = job_init_host(ctx, j, ctx->lanes[0], pl, ascii, seg_off, nseg, flags))) return rc;
+    rc = scan_one(ctx, j, out);
     if (rc) cudaDeviceSynchronize();          // no copy may still read the caller's buffer after we return
-    ctx->timing[4] = (double)s->len + (double)(nseg + 1) * 8;
-    pwmscan_seq_free(s);
     return rc;
+}
+
+// Many scans of one plan with up to kMaxLanes in flight: while the first stage of one item runs, the exact replay, the
+// ordering and the hit-list copy of the previous ones proceed on their own lanes.  Hit lists are handed to `cb` in
+// item order (the callee owns them: pwmscan_hits_free); same results as one pwmscan_scan / pwmscan_scan_host per item.
+static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, const pwmscan_seq* const* seqs, const uint8_t* const* ascii,
+                          const int64_t* lens, int flags, pwmscan_hits_cb cb, void* user) {
+    if (n == 0) return PWMSCAN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_lut(ctx);
+    if (rc) return rc;
+    const char* env_lanes = std::getenv("PWMSCAN_LANES");                  // read per call: experiments sweep it within one process
+    const int want_lanes = env_lanes ? std::max(1, std::min(kMaxLanes, std::atoi(env_lanes))) : 3;
+    const int K = std::min<int>(want_lanes, n);
+    ScanJob jobs[kMaxLanes];
+    double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto start = [&](int i) -> int {
+        ScanJob& j = jobs[i % K];
+        ScanLane* lane = nullptr;
+        int r = lane_get(ctx, i % K, &lane);
+        if (r) return r;
+        if (seqs) {
+            j = ScanJob();
+            j.lane = lane; j.seq = seqs[i]; j.pl = pl; j.active = true;
+        } else {
+            const int64_t off[2] = {0, lens[i]};
+            if ((r = job_init_host(ctx, j, lane, pl, ascii[i], off, 1, flags))) return r;
+        }
+        return scan_phase_a(ctx, j);
+    };
+    auto finish = [&](int i) -> int {
+        pwmscan_hits* h = nullptr;
+        int r = scan_phase_c(ctx, jobs[i % K], &h, t);
+        if (r) return r;
+        if (cb) cb(user, i, h); else pwmscan_hits_free(h);
+        return PWMSCAN_OK;
+    };
+    for (int i = 0; i < K && !rc; ++i) rc = start(i);
+    for (int i = 0; i < n && !rc; ++i) {
+        rc = scan_phase_b(ctx, jobs[i % K]);
+        if (!rc && i >= 1) {
+            rc = finish(i - 1);
+            if (!rc && i - 1 + K < n) rc = start(i - 1 + K);
+        }
+    }
+    if (!rc) rc = finish(n - 1);
+    if (rc) {                                     // drain: nothing may still touch caller or pooled buffers
+        cudaDeviceSynchronize();
+        for (int k = 0; k < K; ++k) job_release(jobs[k]);
+        return rc;
+    }
+    for (int i = 0; i < 12; ++i) ctx->timing[i] = t[i];
+    return PWMSCAN_OK;
+}
+
+extern "C" int pwmscan_scan_many(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, const pwmscan_seq* const* seqs, pwmscan_hits_cb cb, void* user) {
+    if (!ctx || !pl || n < 0 || (n > 0 && !seqs)) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_many: bad argument");
+    if (pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_many: plan belongs to another context");
+    for (int32_t i = 0; i < n; ++i) {
+        if (!seqs[i] || seqs[i]->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_many: sequence belongs to another context");
+        if (!pl->skip && !seqs[i]->d_ascii) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_many: skip_ambiguous = 0 needs PWMSCAN_SEQ_KEEP_ASCII sequences");
+    }
+    return scan_many_impl(ctx, pl, n, seqs, nullptr, nullptr, 0, cb, user);
+}
+
+extern "C" int pwmscan_scan_host_many(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, const uint8_t* const* ascii, const int64_t* lens, int flags,
+                                      pwmscan_hits_cb cb, void* user) {
+    if (!ctx || !pl || n < 0 || (n > 0 && (!ascii || !lens))) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_host_many: bad argument");
+    if (pl->ctx != ctx) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_scan_host_many: plan belongs to another context");
+    for (int32_t i = 0; i < n; ++i) {
+        const int64_t off[2] = {0, lens[i]};
+        int rc = seq_check_args(ctx, ascii[i], off, 1);
+        if (rc) return rc;
+    }
+    return scan_many_impl(ctx, pl, n, nullptr, ascii, lens, flags, cb, user);
 }
 
 extern "C" int pwmscan_scan_host_first_invalid(pwmscan_ctx* ctx, int alphabet, int64_t* pos_out) {
@@ -1256,11 +1483,67 @@ extern "C" int pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// hit lists
+// ------------------------------------------------------------------------------------------------
+namespace pwmscan {
+
+// Expands the compact columns into the wide ones (host memory).  Idempotent and thread-safe.
+int hits_expand_wide(pwmscan_hits* h) {
+    std::lock_guard<std::mutex> lk(h->wide_mu);
+    if (h->pos || h->count == 0) return PWMSCAN_OK;
+    const size_t n = (size_t)h->count, n8 = (n + 7) & ~(size_t)7;
+    const bool one = h->nseg == 1;
+    unsigned char* w = (unsigned char*)std::malloc(n8 * (8 + 4 + 1 + (one ? 0 : 4)));
+    if (!w) return set_err(h->ctx, PWMSCAN_EINVAL, "out of host memory");
+    int64_t* pos = (int64_t*)w;
+    int32_t* motif = (int32_t*)(w + n8 * 8);
+    int32_t* segment = one ? nullptr : (int32_t*)(w + n8 * 12);
+    uint8_t* strand = w + n8 * (one ? 12 : 16);
+    auto part = [&](size_t i0, size_t i1) {
+        if (one) {
+            const int64_t* ro = h->run_off;
+            int c = (int)(std::upper_bound(ro, ro + 2 * h->M + 1, (int64_t)i0) - ro) - 1;
+            for (size_t i = i0; i < i1; ++i) {
+                while ((int64_t)i >= ro[c + 1]) ++c;
+                pos[i] = (int64_t)h->pos32[i]; motif[i] = c >> 1; strand[i] = (uint8_t)(c & 1);
+            }
+        } else {
+            for (size_t i = i0; i < i1; ++i) {
+                pos[i] = (int64_t)h->pos32[i]; motif[i] = (int32_t)(h->ms16[i] >> 1); strand[i] = (uint8_t)(h->ms16[i] & 1); segment[i] = h->seg32[i];
+            }
+        }
+    };
+    const unsigned nth = n < (1u << 20) ? 1u : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (nth <= 1) part(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; ++t) th.emplace_back(part, n * t / nth, n * (t + 1) / nth);
+        for (auto& x : th) x.join();
+    }
+    if (one) {
+        const int32_t* z = zero_column(h->ctx, n8);
+        if (!z) { std::free(w); return set_err(h->ctx, PWMSCAN_EINVAL, "out of host memory"); }
+        h->segment = z;
+    } else {
+        h->segment = segment;
+    }
+    h->wide = w; h->motif = motif; h->strand = strand;
+    h->pos = pos;
+    return PWMSCAN_OK;
+}
+
+}  // namespace pwmscan
+
 extern "C" int64_t pwmscan_hits_count(const pwmscan_hits* h) { return h ? h->count : -1; }
 
 extern "C" int pwmscan_hits_columns(const pwmscan_hits* h, const int32_t** motif, const uint8_t** strand, const int32_t** segment,
                                     const int64_t** pos, const double** score) {
     if (!h) return PWMSCAN_EINVAL;
+    if (motif || strand || segment || pos) {
+        int rc = hits_expand_wide(const_cast<pwmscan_hits*>(h));
+        if (rc) return rc;
+    }
     if (motif) *motif = h->motif;
     if (strand) *strand = h->strand;
     if (segment) *segment = h->segment;
@@ -1269,9 +1552,21 @@ extern "C" int pwmscan_hits_columns(const pwmscan_hits* h, const int32_t** motif
     return PWMSCAN_OK;
 }
 
+extern "C" int pwmscan_hits_compact(const pwmscan_hits* h, const uint32_t** pos32, const double** score, const int64_t** run_off,
+                                    const int32_t** segment, const uint16_t** motif_strand) {
+    if (!h) return PWMSCAN_EINVAL;
+    if (pos32) *pos32 = h->pos32;
+    if (score) *score = h->score;
+    if (run_off) *run_off = h->run_off;
+    if (segment) *segment = h->seg32;
+    if (motif_strand) *motif_strand = h->ms16;
+    return PWMSCAN_OK;
+}
+
 extern "C" void pwmscan_hits_free(pwmscan_hits* h) {
     if (!h) return;
     if (h->buf && h->ctx) pin_pool_put(h->ctx, h->buf, h->buf_bytes);
+    if (h->wide) std::free(h->wide);
     delete h;
 }
 

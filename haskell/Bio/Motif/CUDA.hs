@@ -14,6 +14,7 @@ module Bio.Motif.CUDA
     , pValueToScoreGPU
     , scoreCDFGPU
     , scanRegionsGPU
+    , scanChunksGPU
     , hitsAffinityGPU
     , alignAllPairsGPU
     ) where
@@ -30,6 +31,8 @@ import           Data.Word
 import           Foreign
 import           Foreign.C.String
 import           Foreign.C.Types
+import           Data.IORef
+import           System.Environment       (lookupEnv)
 import           System.IO.Unsafe         (unsafePerformIO)
 
 import           Bio.Motif                (Bkgd (..), CDF (..), PWM (..), size)
@@ -78,6 +81,12 @@ foreign import ccall safe "pwmscan_align_pairs"       c_align_pairs  :: Ptr Ctx 
 foreign import ccall safe "pwmscan_format_bed6"       c_format_bed6  :: Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Word8 -> Ptr Int64 -> Ptr Int64 -> Ptr Int32 -> Ptr Int64
                                                                       -> CString -> Ptr Int64 -> CString -> Ptr Int64 -> Ptr Int32 -> Ptr CString -> Ptr Int64 -> IO CInt
 foreign import ccall safe "pwmscan_format_dist"       c_format_dist  :: Int64 -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> CString -> Ptr Int64 -> Ptr CString -> Ptr Int64 -> IO CInt
+foreign import ccall safe "pwmscan_hits_compact"     c_hits_compact :: Ptr Hits -> Ptr (Ptr Word32) -> Ptr (Ptr Double) -> Ptr (Ptr Int64) -> Ptr (Ptr Int32) -> Ptr (Ptr Word16) -> IO CInt
+-- hit lists of a multi-item scan arrive through a callback (item order, calling thread); the callee owns them
+type HitsCb = Ptr () -> Int32 -> Ptr Hits -> IO ()
+foreign import ccall "wrapper" mkHitsCb :: HitsCb -> IO (FunPtr HitsCb)
+foreign import ccall safe "pwmscan_scan_many"        c_scan_many    :: Ptr Ctx -> Ptr Plan -> Int32 -> Ptr (Ptr Seq) -> FunPtr HitsCb -> Ptr () -> IO CInt
+foreign import ccall safe "pwmscan_scan_host_many"   c_scan_host_many :: Ptr Ctx -> Ptr Plan -> Int32 -> Ptr (Ptr Word8) -> Ptr Int64 -> CInt -> FunPtr HitsCb -> Ptr () -> IO CInt
 foreign import ccall safe "pwmscan_align_all_pairs"  c_align_all    :: Ptr Ctx -> Ptr Motifs -> CInt -> Double -> CInt -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
 
 -- | The reference signals failure with `error` (pure code) — so do we.
@@ -92,7 +101,9 @@ withDevice dev = bracket open c_ctx_destroy
 -- through it with unsafePerformIO; every call is deterministic, so this is referentially transparent.
 {-# NOINLINE theCtx #-}
 theCtx :: Ptr Ctx
-theCtx = unsafePerformIO $ alloca $ \p -> do { rc <- c_ctx_create 0 p; check nullPtr rc; peek p }
+theCtx = unsafePerformIO $ do
+    dev <- maybe 0 read <$> lookupEnv "PWMSCAN_DEVICE"
+    alloca $ \p -> do { rc <- c_ctx_create (fromIntegral (dev :: Int)) p; check nullPtr rc; peek p }
 
 -- U.Vector / M.Matrix are unpinned: copy to Storable before the call.
 withMotifs :: Bkgd -> [PWM] -> (Ptr Motifs -> IO a) -> IO a
@@ -178,6 +189,33 @@ scanRegionsGPU plan bytes lens =
             return [ (fromIntegral g, fromIntegral m, s == 0, fromIntegral q, v) | (g, m, s, q, v) <- zip5' sg ms st ps sc ]
   where zip5' (a:as) (b:bs) (c:cs) (d:ds) (e:es) = (a, b, c, d, e) : zip5' as bs cs ds es
         zip5' _ _ _ _ _ = []
+
+-- | Whole-chromosome / whole-genome scans: the (motif block x chromosome chunk) items of the reference's findTFBS'
+-- (Bio/Motif/Search.hs:60-84), several of them in flight on the device (pwmscan_scan_host_many).  Every chunk is a
+-- strict ByteString of the genome store (`getChrom`, Bio/Seq/IO.hs:77-84, cut into pieces that overlap by
+-- (longest motif - 1) bytes); the result of chunk i is, per (motif, strand), the (position in chunk, score) pairs
+-- in ascending position — what `findTFBS` yields for that PWM on that chunk.
+scanChunksGPU :: Ptr Plan -> Int -> [B.ByteString] -> IO [[((Int, Bool), [(Int, Double)])]]
+scanChunksGPU plan nMotif chunks = do
+    acc <- newIORef []
+    cb  <- mkHitsCb $ \_ _ h -> do
+        cnt <- fromIntegral <$> c_hits_count h
+        r <- alloca $ \pp -> alloca $ \ps -> alloca $ \pr -> do
+            _ <- c_hits_compact h pp ps pr nullPtr nullPtr
+            if cnt == 0 then return [] else do
+                pos <- peek pp >>= peekArray cnt; sc <- peek ps >>= peekArray cnt
+                ro  <- peek pr >>= peekArray (2 * nMotif + 1)
+                let runs = zip ro (tail ro)
+                return [ ((c `div` 2, even c), [ (fromIntegral q, v) | (q, v) <- take (fromIntegral (b - a)) $ drop (fromIntegral a) $ zip pos sc ])
+                       | (c, (a, b)) <- zip [0 ..] runs, b > a ]
+        c_hits_free h
+        modifyIORef' acc (r :)
+    let go [] ptrs lens = withArray (reverse ptrs) $ \pa -> withArray (reverse lens) $ \pl ->
+            c_scan_host_many theCtx plan (fromIntegral $ length chunks) pa pl 1 cb nullPtr >>= check theCtx
+        go (c : cs) ptrs lens = BU.unsafeUseAsCStringLen c $ \(p, n) -> go cs (castPtr p : ptrs) (fromIntegral n : lens)
+    go chunks [] []
+    freeHaskellFunPtr cb
+    reverse <$> readIORef acc
 
 -- | scanMotif's per-hit BED score on the device (Bio/Data/Bed/Utils.hs:109-123): `toAffinity (1 - cdf c sc)` for
 -- every hit of `h`, given every motif's truncated CDF (the `_cdf` fields of the CutoffMotifs) as one

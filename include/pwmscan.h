@@ -53,10 +53,12 @@ int pwmscan_abi_version(void);
 int  pwmscan_ctx_create(int device, pwmscan_ctx** out);
 void pwmscan_ctx_destroy(pwmscan_ctx* ctx);
 const char* pwmscan_last_error(pwmscan_ctx* ctx);
-/* Device time (ms, CUDA events on the library's stream) of the phases of the last scan call:
- * out[0] prefilter kernel, out[1] exact re-score kernel, out[2] sort, out[3] total device span,
- * out[4] host->device bytes, out[5] device->host bytes, out[6] prefilter candidates,
- * out[7] prefilter kernel launches. n = number of doubles available in out. */
+/* Device time (ms, CUDA events on the scan's stream) of the phases of the last scan call (summed over the items of
+ * a pwmscan_scan_many): out[0] first-stage (prefilter) kernels, out[1] exact re-score kernel, out[2] ordering,
+ * out[3] device span start .. ordered, out[4] host->device bytes, out[5] device->host bytes, out[6] prefilter
+ * candidates, out[7] prefilter kernel launches, out[8] kernel launches in all, out[9] hits.  The other entry points
+ * (scoreCDF, alignment, dense scores, per-hit affinity) report their kernel time in out[10] (and alignment its number
+ * of host re-evaluations in out[11]) and leave the scan slots alone.  n = number of doubles available in out (<= 12). */
 int  pwmscan_last_timing(pwmscan_ctx* ctx, double* out, int n);
 
 /* ---- sequences: Bio.Seq `DNA a` (Seq.hs:41,59-67,86-95) ------------------------------------- */
@@ -123,13 +125,32 @@ int  pwmscan_scan_host(pwmscan_ctx* ctx, const pwmscan_plan* plan, const uint8_t
  * the concatenated input of the first byte outside the alphabet (0 = ACGT, 1 = IUPAC; after upper-casing
  * if PWMSCAN_SEQ_UPPERCASE was given), -1 if there is none. */
 int  pwmscan_scan_host_first_invalid(pwmscan_ctx* ctx, int alphabet, int64_t* pos_out);
+/* Many scans of one plan — the (motif block x chromosome chunk) items of a whole-genome scan (the decomposition of
+ * the reference's findTFBS', Motif/Search.hs:60-84) — with several of them in flight on the device: while the first
+ * stage of one item runs, the exact replay, the ordering and the hit-list copy of the previous items proceed.  Hit
+ * lists are handed to `cb` in item order, on the calling thread; the callee owns them (pwmscan_hits_free).  Same
+ * results as one pwmscan_scan / pwmscan_scan_host per item.  pwmscan_scan_host_many takes n single sequences
+ * (ascii[i], lens[i]) in host memory (pinned for full PCIe speed). */
+typedef void (*pwmscan_hits_cb)(void* user, int32_t item, pwmscan_hits* hits);
+int  pwmscan_scan_many(pwmscan_ctx* ctx, const pwmscan_plan* plan, int32_t n, const pwmscan_seq* const* seqs,
+                       pwmscan_hits_cb cb, void* user);
+int  pwmscan_scan_host_many(pwmscan_ctx* ctx, const pwmscan_plan* plan, int32_t n, const uint8_t* const* ascii,
+                            const int64_t* lens, int flags, pwmscan_hits_cb cb, void* user);
 /* Convenience: plan_create + scan + plan_free. */
 int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
                        const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);
 int64_t pwmscan_hits_count(const pwmscan_hits* hits);
-/* Column views (read-only host memory, valid until pwmscan_hits_free / pwmscan_ctx_destroy); any pointer
- * argument may be NULL.  (For a single-segment scan the segment column is a shared all-zero array of the
- * context: it is not transferred from the device.) */
+/* What the device transfers — the compact columns, in the order above: score[n], pos32[n] (window start within
+ * its segment) and
+ *   - single-segment scans: run_off[2M+1]; the hits of (motif m, strand s) are [run_off[2m+s], run_off[2m+s+1])
+ *     (exactly the (Int, Double) stream `findTFBS` yields for that PWM), segment = motif_strand = NULL: 12 bytes/hit;
+ *   - several segments: segment[n] and motif_strand[n] = 2 * motif + strand, run_off = NULL: 18 bytes/hit.
+ * Read-only pinned host memory, valid until pwmscan_hits_free; any pointer argument may be NULL. */
+int  pwmscan_hits_compact(const pwmscan_hits* hits, const uint32_t** pos32, const double** score,
+                          const int64_t** run_off, const int32_t** segment, const uint16_t** motif_strand);
+/* Wide column views (read-only host memory, valid until pwmscan_hits_free / pwmscan_ctx_destroy); any pointer
+ * argument may be NULL.  motif / strand / segment / pos are expanded from the compact columns on the host the
+ * first time one of them is asked for. */
 int  pwmscan_hits_columns(const pwmscan_hits* hits, const int32_t** motif, const uint8_t** strand,
                           const int32_t** segment, const int64_t** pos, const double** score);
 void pwmscan_hits_free(pwmscan_hits* hits);

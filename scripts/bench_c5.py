@@ -48,14 +48,14 @@ def main():
     t0 = time.perf_counter()
     th = mo8.pvalue_to_score(1e-5)
     t_cdf = time.perf_counter() - t0
-    cdf_kernel_ms = ctx.timing()["prefilter_ms"]
+    cdf_kernel_ms = ctx.timing()["aux_kernel_ms"]
     t0 = time.perf_counter()
     for m in m800[:20]:
         O.pvalue_to_score(1e-5, BG, m)
     t_cdf_or = (time.perf_counter() - t0) / 20
     print(json.dumps({"config": "C5 all-vs-all alignment of %d PWMs (%d pairs), jsd/expPenal 0.05/l1" % (M, npair),
-                      "align_call_s": t_all, "align_kernel_ms": tm["prefilter_ms"], "pairs_per_s": npair / t_all,
-                      "host_reevaluated_pairs": int(tm["candidates"]), "parity_pairs_checked": nchk, "parity_ok": bool(ok),
+                      "align_call_s": t_all, "align_kernel_ms": tm["aux_kernel_ms"], "pairs_per_s": npair / t_all,
+                      "host_reevaluated_pairs": int(tm["aux_host_fallbacks"]), "parity_pairs_checked": nchk, "parity_ok": bool(ok),
                       "oracle_pairs_per_s_1core": nchk / t_or,
                       "cdf_800_motifs_call_s": t_cdf, "cdf_kernel_ms": cdf_kernel_ms, "oracle_cdf_s_per_motif_1core": t_cdf_or}))
     assert ok

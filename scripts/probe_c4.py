@@ -11,8 +11,9 @@ dna = synth.synth_dna(64_000_000, 5, gc=0.41)
 mo = _lib.DeviceMotifs(ctx, mats, BG)
 plan = _lib.Plan(mo, th)
 seq = _lib.DeviceSeq(ctx, dna)
-for rep in range(4):
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     t0 = time.perf_counter(); h = plan.scan(seq); t1 = time.perf_counter()
     tm = ctx.timing()
-    print("scan %.2f ms | %s | hits %d" % (1e3 * (t1 - t0), {k: round(float(v), 2) for k, v in tm.items() if k.endswith("_ms")}, len(h)))
+    print("scan %.2f ms | %s | hits %d cand %d kernels %d d2h %.1f MB" % (1e3 * (t1 - t0), {k: round(float(v), 3) for k, v in tm.items() if k.endswith("_ms")}, len(h),
+          tm["candidates"], tm["kernel_launches"], tm["d2h_bytes"] / 1e6))
     del h

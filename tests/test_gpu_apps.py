@@ -194,3 +194,34 @@ def test_iterative_merge_resident_equals_per_call_path():
         assert len(a) == len(b) and len(a) < len(motifs)
         for x, y in zip(a, b):
             assert x[0] == y[0] and x[2] == y[2] and np.array_equal(x[1]._mat, y[1]._mat)
+
+
+def test_scan_motif_config_c3_sample_at_size(tmp_path):
+    """BASELINE config 3 shape at a size the oracle finishes in seconds: the 800 JASPAR-sized PWMs x 2 000 BED regions of
+    500 bp (unsorted, on four chromosomes, some soft-masked, some out of range) at p = 1e-5 — scan_motif's BED6 text must
+    be byte-identical to the oracle composition (per-region multi-threaded oracle scan + cdf + toAffinity + toLine)."""
+    from oracle import app_oracle
+    chroms = [(b"chr1", synth.synth_dna(3_000_000, 4, gc=0.41, lower_frac=0.3, n_runs=[(1_350_000, 90_000)])),
+              (b"chr2", synth.synth_dna(2_000_000, 104, gc=0.41)),
+              (b"chrX", synth.synth_dna(1_200_000, 2204, gc=0.38, lower_frac=0.1)),
+              (b"chrM", synth.synth_dna(16_569, 2404, gc=0.44))]
+    path = os.path.join(tmp_path, "genome.idx")
+    write_genome(chroms, path)
+    gen = dict(chroms)
+    mats = synth.config_c4_motifs(800)
+    names = [b"MA%04d.1" % i for i in range(len(mats))]
+    motifs = [Mo.Motif(nm, Mo.PWM(None, m)) for nm, m in zip(names, mats)]
+    rng = np.random.default_rng(3)
+    sizes = np.array([c[1].size for c in chroms], dtype=np.float64)
+    beds = []
+    for _ in range(2000):
+        ci = int(rng.choice(len(chroms), p=sizes / sizes.sum()))
+        s = int(rng.integers(0, chroms[ci][1].size - 400))            # a few run past the end: skipped with a warning
+        beds.append((chroms[ci][0], s, s + 500))
+    cms = mkCutoffMotifs(Mo.default_bkgd, 1e-5, motifs)
+    out = io.BytesIO()
+    n = scanMotif(openGenome(path), cms, iter(beds), out=out, warn=None)
+    got = out.getvalue().split(b"\n")[:-1]
+    exp = app_oracle.scan_motif_lines_mt(gen, names, mats, beds, p=1e-5, nthreads=os.cpu_count() or 8)
+    assert n == len(got) and len(exp) > 20_000
+    assert got == exp

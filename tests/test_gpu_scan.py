@@ -391,3 +391,163 @@ def test_random_sweep_small_cases(ctx, oracle):
         h = gpu_scan(ctx, mats, thres, dna, strands=strands, bg=bg)
         o = oracle_scan(oracle, mats, thres, dna, strands=strands, bg=bg)
         assert_same(h, o)
+
+
+def _same_hits(a, b):
+    assert len(a) == len(b)
+    for x, y in ((a.motif, b.motif), (a.strand, b.strand), (a.segment, b.segment), (a.pos, b.pos),
+                 (a.score.view(np.uint64), b.score.view(np.uint64))):
+        assert np.array_equal(x, y)
+
+
+def test_scan_many_equals_single_scans(ctx, oracle):
+    """pwmscan_scan_many / pwmscan_scan_host_many (several items in flight on their own lanes) hand back, in item
+    order, exactly the hit lists of one pwmscan_scan per item — including empty items and more items than lanes."""
+    mats = synth.synth_pwms(90, 5, nmin=6, nmax=21)
+    thres = [0.58 * oracle.optimal_score(BG, m) for m in mats]
+    plan = _lib.Plan(_lib.DeviceMotifs(ctx, mats, BG), thres)
+    lens = [700_000, 0, 5, 1_300_000, 64, 2_000_000, 40_000, 900_000, 17_000_000]
+    arrays = [synth.synth_dna(L, 300 + i, gc=0.42, n_runs=[(L // 2, 500)] if L > 1000 else ()) for i, L in enumerate(lens)]
+    seqs = [_lib.DeviceSeq(ctx, a) for a in arrays]
+    single = [plan.scan(s) for s in seqs]
+    assert sum(len(h) for h in single) > 10000
+    many = plan.scan_many(seqs)
+    host = plan.scan_host_many(arrays)
+    for a, b, c in zip(single, many, host):
+        _same_hits(a, b)
+        _same_hits(a, c)
+    # streaming consumer: called in item order, results kept
+    seen = []
+    counts = plan.scan_many(seqs, consume=lambda h: (seen.append(len(h)), len(h))[1])
+    assert counts == [len(h) for h in single] == seen
+    assert ctx.timing()["hits"] == sum(counts) and ctx.timing()["kernel_launches"] >= 2 * len(seqs)
+    # a consumer that raises does not leave the library in a bad state
+    with pytest.raises(ZeroDivisionError):
+        plan.scan_many(seqs, consume=lambda h: 1 // 0)
+    _same_hits(single[3], plan.scan(seqs[3]))
+
+
+def test_compact_columns_and_run_table(ctx, oracle):
+    """The transferred form of a hit list: score + 32-bit positions + the (motif, strand) run table (single segment)
+    or 16-bit motif|strand + segment (several segments); the wide columns are expanded from it."""
+    mats = synth.synth_pwms(33, 8, nmin=6, nmax=18)
+    thres = [0.55 * oracle.optimal_score(BG, m) for m in mats]
+    dna = synth.synth_dna(600_000, 12, gc=0.47)
+    h = gpu_scan(ctx, mats, thres, dna)
+    ro = h.run_off
+    assert ro is not None and ro.size == 2 * len(mats) + 1 and ro[0] == 0 and ro[-1] == len(h) and np.all(np.diff(ro) >= 0)
+    for m in (0, 7, 32):
+        for s in (0, 1):
+            a, b = int(ro[2 * m + s]), int(ro[2 * m + s + 1])
+            pos, sc = oracle.find_tfbs(BG, mats[m] if s == 0 else oracle.rc_pwm(mats[m]), dna, thres[m], True, mode=1)
+            assert np.array_equal(h.pos32[a:b], pos.astype(np.uint32)) and np.array_equal(h.score[a:b].view(np.uint64), sc.view(np.uint64))
+            assert np.all(h.motif[a:b] == m) and np.all(h.strand[a:b] == s)
+    assert np.array_equal(h.pos, h.pos32.astype(np.int64)) and not h.segment.any()
+    off = np.array([0, 100_000, 100_000, 350_000, 600_000], dtype=np.int64)
+    hs = gpu_scan(ctx, mats, thres, dna, seg_off=off)
+    assert hs.run_off is None and len(hs) > 1000
+    key = (hs.segment.astype(np.int64) << 50) | (hs.motif.astype(np.int64) << 34) | (hs.strand.astype(np.int64) << 33) | hs.pos
+    assert np.all(np.diff(key) > 0)
+
+
+def test_ordering_dense_bucket_retry(ctx, oracle):
+    """One motif hits everywhere while hundreds of others never do: the ordering pass's first bucket layout (one bucket
+    per (motif, strand)) overflows the shared-memory sort and it must retry with smaller buckets — same order."""
+    mats = synth.synth_pwms(300, 17, nmin=8, nmax=14)
+    thres = [1e9] * len(mats)
+    thres[123] = -1e9
+    thres[7] = 0.5 * oracle.optimal_score(BG, mats[7])
+    dna = synth.synth_dna(150_000, 3)
+    h = gpu_scan(ctx, mats, thres, dna)
+    n = mats[123].shape[0]
+    assert len(h.select(motif=123)) == 2 * (dna.size - n + 1)
+    o = oracle_scan(oracle, [mats[7], mats[123]], [thres[7], thres[123]], dna)
+    assert len(h) == o[0].size
+    assert np.array_equal(h.motif, np.where(o[0] == 0, 7, 123)) and np.array_equal(h.strand, o[1]) and np.array_equal(h.pos, o[2])
+    assert np.array_equal(h.score.view(np.uint64), o[3].view(np.uint64))
+
+
+def test_sigma_matches_oracle(ctx, oracle, ref_motifs):
+    """optimalScoresSuffix (Motif/Search.hs:111-124): the library's sigma vectors (host libm) are the oracle's, bit for bit,
+    for the PWM and for its reverse complement, uniform and skewed background."""
+    mats = [m for _, m in ref_motifs] + synth.config_c4_motifs(40)
+    for bg in (BG, (0.3, 0.2, 0.2, 0.3)):
+        mo = _lib.DeviceMotifs(ctx, mats, bg)
+        for m, mat in enumerate(mats):
+            for s, mm in ((0, mat), (1, oracle.rc_pwm(mat))):
+                assert np.array_equal(mo.get_sigma(m, s).view(np.uint64), oracle.optimal_scores_suffix(bg, mm).view(np.uint64))
+
+
+def _c4_setup(ctx):
+    mats = synth.config_c4_motifs(800)
+    th = [float.fromhex(v) for v in json.load(open(os.path.join(GOLDEN, "config_thresholds.json")))["c4"]]
+    return mats, th, _lib.Plan(_lib.DeviceMotifs(ctx, mats, BG), th)
+
+
+def test_config_c4_plan_on_chunk_seam_and_n_edge(ctx, oracle):
+    """BASELINE config 4 as bench.py runs it: the 800-motif plan (7 blocks, planner-chosen first-table bitmaps, 3-table
+    blocks) over 8 Mbp of chr1 around the 64 Mbp item seam — scanned as the two shard items with their halo, through
+    pwmscan_scan_many, merged on the host — and over 2 Mbp around the edge of the 7.5 Mbp N block; bit-identical to the
+    oracle's scan of the same bytes."""
+    from bioinformatics_toolkit_b200 import shard
+    mats, th, plan = _c4_setup(ctx)
+    assert plan.info()["blocks"] == 7
+    nmax = max(m.shape[0] for m in mats)
+    nlen_of = np.array([m.shape[0] for m in mats])
+    L = synth.HG38_CHROM_SIZES[0][1]
+    runs = [(0, 10_000), (L - 10_000, 10_000), (int(L * 0.45), int(L * 0.03))]
+    # (a) the seam between the items [0, 64M) and [64M, 128M) of chr1, cut down to 4 Mbp on either side
+    lo, seam, hi = 60_000_000, 64_000_000, 68_000_000
+    region = synth.synth_dna(hi - lo, 4, gc=0.41, start=lo, n_runs=runs)
+    items = [(0, lo, seam, 0, 800), (0, seam, hi, 0, 800)]
+    arrays = []
+    for it in items:
+        b0, b1 = shard.chunk_bytes_range(it, hi, nmax)
+        arrays.append(np.ascontiguousarray(region[b0 - lo:b1 - lo]))
+    got = plan.scan_many([_lib.DeviceSeq(ctx, a) for a in arrays])
+    per_item = []
+    for it, h in zip(items, got):
+        k = shard.keep_hit_mask(h.pos, nlen_of[h.motif], it, hi)
+        per_item.append((np.zeros(int(k.sum()), np.int64), h.motif[k], h.strand[k], h.pos[k] + (it[1] - lo), h.score[k]))
+    _, mo_, st_, pos_, sc_ = shard.merge_hits(per_item)
+    cnt, o = oracle.scan_mt(BG, mats, th, region, mode=1, nthreads=os.cpu_count() or 8, cap=1 << 23)
+    assert cnt == pos_.size and cnt > 100_000
+    assert np.array_equal(mo_, o[0]) and np.array_equal(st_, o[1]) and np.array_equal(pos_, o[2])
+    assert np.array_equal(sc_.view(np.uint64), o[3].view(np.uint64))
+    # hits whose window crosses the seam exist and come from the first item only
+    cross = (pos_ < seam - lo) & (pos_ + nlen_of[mo_] > seam - lo)
+    assert cross.sum() > 10
+    # (b) the start of the N block (windows running into it are not hits) — through the host-bytes path
+    nb = int(L * 0.45)
+    lo2 = nb - 1_000_000
+    reg2 = synth.synth_dna(2_000_000, 4, gc=0.41, start=lo2, n_runs=runs)
+    h2 = plan.scan_host(reg2)
+    cnt2, o2 = oracle.scan_mt(BG, mats, th, reg2, mode=1, nthreads=os.cpu_count() or 8, cap=1 << 22)
+    assert cnt2 == len(h2) and cnt2 > 10_000
+    assert np.array_equal(h2.motif, o2[0]) and np.array_equal(h2.strand, o2[1]) and np.array_equal(h2.pos, o2[2])
+    assert np.array_equal(h2.score.view(np.uint64), o2[3].view(np.uint64))
+    assert (h2.pos + nlen_of[h2.motif]).max() <= 1_000_000
+
+
+def test_config_c2_slices_on_seams(ctx, oracle):
+    """BASELINE config 2 at full size through pwmscan_scan_host: 16 oracle slices placed on the seams of the 16 Mi-base
+    upload chunks and of the 32 768-position work items (plus the N-block edges) must match bit for bit."""
+    dna, mats = synth.config_c2()
+    th = [float.fromhex(v) for v in json.load(open(os.path.join(GOLDEN, "config_thresholds.json")))["c2"]]
+    plan = _lib.Plan(_lib.DeviceMotifs(ctx, mats, BG), th)
+    h = plan.scan_host(dna)
+    nlen = np.array([m.shape[0] for m in mats])[h.motif]
+    chunk = 16 * 1024 * 1024
+    centres = [k * chunk for k in (1, 2, 3, 7, 8, 13, 14)] + [k * chunk - 32 for k in (5, 11)]            # upload-chunk seams (stored index = position + 32)
+    centres += [32768 * k - 32 for k in (1, 977, 3111, 6000)] + [121_700_000, 139_700_000, dna.size - 60_000]   # work-item seams, N-block edges, the end
+    assert len(centres) == 16
+    tot = 0
+    for c in centres:
+        lo, hi = max(0, c - 60_000), min(dna.size, c + 60_000)
+        cnt, o = oracle.scan_mt(BG, mats, th, dna[lo:hi], mode=1, nthreads=os.cpu_count() or 8, cap=1 << 20)
+        k = (h.pos >= lo) & (h.pos + nlen <= hi)
+        assert k.sum() == cnt
+        assert np.array_equal(h.motif[k], o[0]) and np.array_equal(h.strand[k], o[1]) and np.array_equal(h.pos[k] - lo, o[2])
+        assert np.array_equal(h.score[k].view(np.uint64), o[3].view(np.uint64))
+        tot += cnt
+    assert tot > 1000

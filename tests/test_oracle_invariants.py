@@ -117,3 +117,17 @@ def test_short_and_empty(oracle, ref_motifs):
 def test_to_affinity(oracle):
     # Data/Bed/Utils.hs:120-123
     assert oracle.to_affinity(1e-5) == 500 and oracle.to_affinity(0.5) == 9 and oracle.to_affinity(0.0) == 1000
+
+
+def test_app_oracle_mt_composition_equals_plain(oracle):
+    """oracle/app_oracle.scan_motif_lines_mt (one multi-threaded oracle scan per region) prints exactly the lines of the
+    plain per-(region, motif, strand) restatement of scanMotif (Data/Bed/Utils.hs:101-124)."""
+    from oracle import app_oracle
+    gen = {b"chr1": synth.synth_dna(30_000, 31, gc=0.45, lower_frac=0.2, n_runs=[(9000, 300)]), b"chr2": synth.synth_dna(8_000, 32)}
+    mats = synth.synth_pwms(9, 44, nmin=6, nmax=16)
+    names = [b"M%d" % i for i in range(len(mats))]
+    rng = np.random.default_rng(2)
+    beds = [(c, int(s), int(s) + int(w)) for c, s, w in zip(rng.choice([b"chr1", b"chr2", b"chrQ"], 40), rng.integers(0, 7800, 40), rng.integers(1, 600, 40))]
+    a = app_oracle.scan_motif_lines(gen, names, mats, beds, p=1e-3)
+    b = app_oracle.scan_motif_lines_mt(gen, names, mats, beds, p=1e-3, nthreads=4)
+    assert a == b and len(a) > 30

@@ -78,6 +78,14 @@ def _ptr(a):
     return a.ctypes.data_as(_vp)
 
 
+def _alphabet_code(alphabet):
+    """0 = `DNA Basic` (ACGT), 1 = `DNA IUPAC` (Seq.hs:41-57); anything else is a caller bug."""
+    try:
+        return {"Basic": 0, "IUPAC": 1}[alphabet]
+    except KeyError:
+        raise ValueError("alphabet must be 'Basic' or 'IUPAC', got %r" % (alphabet,))
+
+
 class Context:
     """One per device (pwmscan_ctx)."""
 
@@ -109,9 +117,9 @@ class Context:
 
     def scan_host_first_invalid(self, alphabet="IUPAC"):
         """fromBS verdict of the bytes of the last Plan.scan_host on this context: offset of the first byte
-        outside the alphabet ("DNA" = ACGT, "IUPAC"), or -1."""
+        outside the alphabet ("Basic" = ACGT, "IUPAC"; the names of seq.ALPHABET), or -1."""
         pos = C.c_int64(-1)
-        self.check(self.L.pwmscan_scan_host_first_invalid(self.h, C.c_int(0 if alphabet == "DNA" else 1), C.byref(pos)))
+        self.check(self.L.pwmscan_scan_host_first_invalid(self.h, C.c_int(_alphabet_code(alphabet)), C.byref(pos)))
         return int(pos.value)
 
     def close(self):
@@ -163,7 +171,7 @@ class DeviceSeq:
 
     def first_invalid(self, alphabet="IUPAC"):
         pos = C.c_int64(-1)
-        self.ctx.check(self.ctx.L.pwmscan_seq_first_invalid(self.ctx.h, self.h, C.c_int(0 if alphabet == "Basic" else 1), C.byref(pos)))
+        self.ctx.check(self.ctx.L.pwmscan_seq_first_invalid(self.ctx.h, self.h, C.c_int(_alphabet_code(alphabet)), C.byref(pos)))
         return pos.value
 
     def free(self):

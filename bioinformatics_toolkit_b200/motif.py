@@ -63,9 +63,84 @@ def gcContentPWM(pwm):
     return acc / size(pwm)
 
 
+def _pow10(k):
+    """`10 ^ k :: Double` as GHC evaluates it: exponentiation by repeated squaring IN Double (GHC.Real.(^): powImpl /
+    powImplAcc), so it is exact up to 10^22 and carries the squaring's rounding errors beyond."""
+    if k == 0:
+        return 1.0
+    x, y = 10.0, k
+    while y % 2 == 0:
+        x, y = x * x, y // 2
+    if y == 1:
+        return x
+    z, x, y = x, x * x, y // 2
+    while True:
+        if y % 2 == 0:
+            x, y = x * x, y // 2
+        elif y == 1:
+            return x * z
+        else:
+            z, x, y = x * z, x * x, y // 2
+
+
+def read_double(tok):
+    """Bio.Utils.Misc.readDouble (Utils/Misc.hs:21-25) = `fst . fromMaybe err . readSigned readExponential` of the
+    third-party `bytestring-lexing` (>= 0.5, bioinformatics-toolkit.cabal:68; source not under /root/reference —
+    restated from the published 0.5.0.x algorithm, Data.ByteString.Lex.Fractional):
+
+      * optional sign, then DIGITS [ '.' DIGITS ] [ (e|E) [sign] DIGITS ]; at least one digit before the point; whatever
+        follows the longest such prefix is ignored (`fst`);
+      * the digits are accumulated EXACTLY as one Integer mantissa (whole * 10^len(frac) + frac), scale = -len(frac)
+        plus the exponent;
+      * value = 0 if the mantissa is 0, else `fromInteger mantissa / 10 ^ (-scale)` (scale < 0) or
+        `fromInteger mantissa * 10 ^ scale`, with `10 ^ k` evaluated in Double by repeated squaring.
+
+    So it is NOT correctly rounded like strtod / Python float(): a mantissa above 2^53 is rounded once by fromInteger
+    and again by the division, and powers of ten beyond 10^22 are inexact.  Version assumption: fromInteger rounds to
+    nearest-even (true for mantissas below 2^63; GHC's big-Integer conversion differs between GHC versions — unpinned).
+    """
+    b = tok if isinstance(tok, (bytes, bytearray)) else str(tok).encode("latin1")
+
+    def fail():
+        raise ValueError("readDouble: Fail to cast ByteString to Double:%r" % (bytes(b),))
+
+    i, n, neg = 0, len(b), False
+    if n and b[0] in b"+-":
+        neg, i = b[0] == 0x2D, 1
+    j = i
+    while j < n and 0x30 <= b[j] <= 0x39:
+        j += 1
+    if j == i:
+        fail()
+    mant, scale = int(b[i:j]), 0
+    if j < n and b[j] == 0x2E:
+        k = j + 1
+        while k < n and 0x30 <= b[k] <= 0x39:
+            k += 1
+        if k > j + 1:
+            mant, scale, j = mant * 10 ** (k - j - 1) + int(b[j + 1:k]), -(k - j - 1), k
+    if j < n and b[j] in b"eE":
+        k = j + 1
+        eneg = False
+        if k < n and b[k] in b"+-":
+            eneg, k = b[k] == 0x2D, k + 1
+        k0 = k
+        while k < n and 0x30 <= b[k] <= 0x39:
+            k += 1
+        if k > k0:
+            scale += -int(b[k0:k]) if eneg else int(b[k0:k])
+    if mant == 0:
+        v = 0.0
+    elif scale < 0:
+        v = float(mant) / _pow10(-scale)
+    else:
+        v = float(mant) * _pow10(scale)
+    return -v if neg else v
+
+
 def toPWM(lines):
-    """Motif.hs:329-330: lines of 4 numbers."""
-    return PWM(None, [[float(x) for x in (l.decode() if isinstance(l, bytes) else l).split()] for l in lines])
+    """Motif.hs:329-330: lines of 4 numbers, each through readDouble (Utils/Misc.hs:21-25)."""
+    return PWM(None, [[read_double(x) for x in (l if isinstance(l, (bytes, bytearray)) else l.encode("latin1")).split()] for l in lines])
 
 
 def _argmax_last(row):
@@ -187,6 +262,32 @@ def pValueToScore(p, bg, pwm):
     return float(_dev_motifs(bg, [pwm]).pvalue_to_score(p)[0])
 
 
+def pValueToScoreExact(p, bg, pwm):
+    """Motif.hs:218-230: the exact cutoff by enumerating all 4^l k-mers (`replicateM l "ACGT"`: first letter slowest),
+    scoring each with scoreHelp (sequential fp64 sum of libm logs, pseudocount 0.0001, Motif.hs:164-193) and pBkgd
+    (sequential product, 197-208), sorting by descending score and accumulating the background probability until it
+    exceeds p.  The reference calls it "inpractical for long motifs" and uses it as a test oracle only; so does this
+    host restatement (l <= 13).  Ties in the score keep enumeration order (the reference's introsort is unstable; the
+    returned score does not depend on the order of ties)."""
+    l = size(pwm)
+    if l > 13:
+        raise ValueError("pValueToScoreExact: 4^%d k-mers is impractical" % l)
+    f = bg.freqs
+    sc = np.zeros(1)
+    pb = np.ones(1)
+    for k in range(l):
+        row = [0.0001 if v == 0 else float(v) for v in pwm._mat[k]]
+        t = np.array([math.log(row[b] / f[b]) for b in range(4)])
+        sc = (sc[:, None] + t[None, :]).reshape(-1)           # acc + sc, left to right; the new letter varies fastest
+        pb = (pb[:, None] * np.array(f)[None, :]).reshape(-1)
+    order = np.argsort(-sc, kind="stable")
+    acc = np.cumsum(pb[order])                                # go: acc + snd, strictly sequential
+    j = int(np.searchsorted(acc > p, True))
+    if j >= acc.size:
+        raise IndexError("pValueToScoreExact: index out of bounds (p >= total probability)")
+    return float(sc[order[j]])
+
+
 def pValueToScores(p, bg, pwms):
     """Batched pValueToScore for a list of PWMs (one launch per DP column for all motifs)."""
     return _dev_motifs(bg, pwms).pvalue_to_score(p)
@@ -236,7 +337,7 @@ def fromMEME(meme):
 
 def _to_motif(parts):
     name, n, rows = parts[0], parts[1], parts[2:]
-    return Motif(name.encode("latin1"), PWM(int(n), [[float(v) for v in r.split()] for r in rows]))
+    return Motif(name.encode("latin1"), PWM(int(n), [[read_double(v) for v in r.split()] for r in rows]))
 
 
 def readMEME(path):
@@ -281,9 +382,32 @@ def _shortest(x):
     return sign + body + "e" + ("+" if e >= 0 else "-") + str(abs(e))
 
 
+def _show_ffloat(x):
+    """Text.Printf's `%f` WITHOUT a precision = `showFFloat Nothing` (Numeric): all shortest round-trip digits in fixed
+    notation, never an exponent, at least one digit on either side of the point ("0.25", "1.0", "0.0000001") — not C's
+    six decimals.  Used by toMEME's background line (Motif.hs:351)."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    sign = "-" if (x < 0 or (x == 0 and math.copysign(1.0, x) < 0)) else ""
+    mant, _, ex = repr(abs(x)).partition("e")
+    ip, _, fp = mant.partition(".")
+    digits = (ip + fp).lstrip("0")
+    e = len(ip) + (int(ex) if ex else 0) - (len(ip + fp) - len(digits))      # value = 0.DIGITS x 10^e (floatToDigits)
+    digits = digits.rstrip("0")
+    if not digits:
+        return sign + "0.0"
+    if e <= 0:
+        return sign + "0." + "0" * (-e) + digits
+    whole, rest = digits[:e].ljust(e, "0"), digits[e:]
+    return sign + whole + "." + (rest or "0")
+
+
 def toMEME(motifs, bg=default_bkgd):
     a, c, g, t = bg.freqs
-    s = "MEME version 4\n\nALPHABET= ACGT\n\nstrands: + -\n\nBackground letter frequencies\nA %f C %f G %f T %f\n\n" % (a, c, g, t)
+    s = "MEME version 4\n\nALPHABET= ACGT\n\nstrands: + -\n\nBackground letter frequencies\nA %s C %s G %s T %s\n\n" % tuple(_show_ffloat(v) for v in (a, c, g, t))
     for m in motifs:
         sites = 1 if m._pwm._nSites is None else m._pwm._nSites
         s += "MOTIF " + m._name.decode("latin1") + "\n"

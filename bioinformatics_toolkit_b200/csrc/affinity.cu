@@ -56,6 +56,10 @@ extern "C" int pwmscan_hits_affinity(pwmscan_ctx* ctx, const pwmscan_hits* hits,
     if (n == 0) return PWMSCAN_OK;
     const int64_t npts = cdf_off[M];
     if (npts < 0 || (npts > 0 && (!cdf_x || !cdf_y))) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_hits_affinity: bad CDF arrays");
+    {   // the per-hit motif column is one of the wide columns: expanded from the compact ones on first use
+        int rc = hits_expand_wide(const_cast<pwmscan_hits*>(hits));
+        if (rc) return rc;
+    }
     for (int64_t k = 0; k < n; ++k)
         if (hits->motif[k] < 0 || hits->motif[k] >= M) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_hits_affinity: hit of a motif outside the CDF list");
     std::lock_guard<std::mutex> lk(ctx->mu);

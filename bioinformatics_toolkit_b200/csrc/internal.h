@@ -211,13 +211,26 @@ void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 void* lane_scratch_get(pwmscan_ctx* ctx, ScanLane* lane, int slot, size_t bytes);
 int hits_expand_wide(pwmscan_hits* h);     // fills pos / motif / segment / strand (idempotent, thread-safe)
 // order.cu
+struct OrderWork { size_t nb; unsigned int* cnt; unsigned long long *start, *cursor, *tiles; };
 int order_pick_shift(unsigned long long n, int key_bits);
 size_t order_bucket_count(int key_bits, int shift);
 size_t order_work_bytes(size_t nb);
-int order_hits(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const double* d_sc, unsigned long long n, KeyLayout kl,
-               int key_bits, int shift, int nseg, int M, unsigned char* d_work, unsigned long long* d_tkeys, double* d_tsc,
-               unsigned long long* d_skeys, double* d_score, uint32_t* d_pos32, int32_t* d_seg32, uint16_t* d_ms16, long long* d_run_off,
-               unsigned long long* d_flags, int* launches);
+OrderWork order_work_view(unsigned char* d_work, size_t nb);
+int order_count(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const unsigned long long* d_nhits, unsigned long long cap,
+                int shift, const OrderWork& w, int* launches);
+int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const double* d_sc, unsigned long long n_est, KeyLayout kl,
+                 int shift, int nseg, int M, const OrderWork& w, unsigned long long* d_tkeys, double* d_tsc,
+                 unsigned long long* d_skeys, double* d_score, uint32_t* d_pos32, int32_t* d_seg32, uint16_t* d_ms16, long long* d_run_off,
+                 unsigned long long* d_flags, int* launches);
+// Where the kernels that find hits put them: unordered (key, score) pairs + one counter per ordering bucket (key >> shift).
+struct HitSink {
+    unsigned long long* keys;
+    double* sc;
+    unsigned long long cap;
+    unsigned long long* counters;     // [1] = number of hits found (may exceed cap: the scan is then repeated with larger buffers)
+    unsigned int* bucket_cnt;
+    int shift;
+};
 int launch_mma_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, int nblocks, const DevMmaBlock* d_blocks,
                          const int8_t* d_btiles, unsigned long long* d_cand, unsigned long long cand_cap);
 

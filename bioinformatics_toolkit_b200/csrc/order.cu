@@ -20,10 +20,11 @@ using namespace pwmscan;
 namespace {
 
 constexpr int kSortThreads = 128;
-constexpr int kScanTile = 4096;                 // counters per CTA of the multi-CTA scan
+constexpr int kScanTile = 2048;                 // counters per CTA of the scan
 
-__global__ void bucket_count_kernel(const unsigned long long* __restrict__ keys, unsigned long long n, int shift,
-                                    unsigned int* __restrict__ cnt) {
+__global__ void bucket_count_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, unsigned long long cap,
+                                    int shift, unsigned int* __restrict__ cnt) {
+    const unsigned long long n = *n_ptr < cap ? *n_ptr : cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
         atomicAdd(&cnt[keys[i] >> shift], 1u);
 }
@@ -52,25 +53,16 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return r;
 }
 
-// nb <= 1024 * per: the whole scan in one CTA.  start[nb] = n; cursor = copy of start for the scatter.
-__global__ void __launch_bounds__(1024) bucket_scan_single_kernel(const unsigned int* __restrict__ cnt, unsigned long long nb,
-                                                                  unsigned long long* __restrict__ start, unsigned long long* __restrict__ cursor) {
-    const unsigned long long per = (nb + blockDim.x - 1) / blockDim.x;
-    const unsigned long long b0 = (unsigned long long)threadIdx.x * per, b1 = b0 + per < nb ? b0 + per : nb;
-    unsigned long long s = 0;
-    for (unsigned long long b = b0; b < b1; ++b) s += cnt[b];
-    unsigned long long total;
-    unsigned long long run = block_exclusive_scan(s, &total);
-    for (unsigned long long b = b0; b < b1; ++b) { start[b] = run; cursor[b] = run; run += cnt[b]; }
-    if (threadIdx.x == 0) start[nb] = total;
-}
+// Exclusive scan of the bucket counters in three launches (tile sums, scan of the tile sums, per-tile scan); every global
+// access is coalesced: a tile's kScanTile counters go through shared memory (padded: one thread then owns 8 consecutive ones).
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
 
-// multi-CTA scan, three launches: tile sums, scan of the tile sums, per-tile scan
 __global__ void __launch_bounds__(256) bucket_tile_sum_kernel(const unsigned int* __restrict__ cnt, unsigned long long nb,
                                                               unsigned long long* __restrict__ tile_sum) {
     const unsigned long long t0 = (unsigned long long)blockIdx.x * kScanTile;
     unsigned long long s = 0;
-    for (int i = threadIdx.x; i < kScanTile; i += 256) if (t0 + i < nb) s += cnt[t0 + i];
+#pragma unroll
+    for (int i = 0; i < kScanTile / 256; ++i) { const unsigned long long b = t0 + (unsigned long long)i * 256 + threadIdx.x; if (b < nb) s += cnt[b]; }
     unsigned long long total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
@@ -92,24 +84,36 @@ __global__ void __launch_bounds__(1024) bucket_tile_scan_kernel(unsigned long lo
     }
 }
 
-__global__ void __launch_bounds__(256) bucket_tile_apply_kernel(const unsigned int* __restrict__ cnt, unsigned long long nb, unsigned long long n,
+__global__ void __launch_bounds__(256) bucket_tile_apply_kernel(const unsigned int* __restrict__ cnt, unsigned long long nb,
                                                                 const unsigned long long* __restrict__ tile_sum,
                                                                 unsigned long long* __restrict__ start, unsigned long long* __restrict__ cursor) {
     constexpr int per = kScanTile / 256;
-    const unsigned long long b0 = (unsigned long long)blockIdx.x * kScanTile + (unsigned long long)threadIdx.x * per;
+    __shared__ unsigned int s_c[kScanTile + kScanTile / 32];
+    __shared__ unsigned long long s_o[kScanTile + kScanTile / 32];
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * kScanTile;
+#pragma unroll
+    for (int i = 0; i < per; ++i) { const int e = i * 256 + threadIdx.x; s_c[pad_idx(e)] = t0 + e < nb ? cnt[t0 + e] : 0u; }
+    __syncthreads();
     unsigned int c[per];
     unsigned long long s = 0;
 #pragma unroll
-    for (int i = 0; i < per; ++i) { c[i] = b0 + i < nb ? cnt[b0 + i] : 0u; s += c[i]; }
+    for (int i = 0; i < per; ++i) { c[i] = s_c[pad_idx(threadIdx.x * per + i)]; s += c[i]; }
     unsigned long long total;
     unsigned long long run = tile_sum[blockIdx.x] + block_exclusive_scan(s, &total);
 #pragma unroll
-    for (int i = 0; i < per; ++i) if (b0 + i < nb) { start[b0 + i] = run; cursor[b0 + i] = run; run += c[i]; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) start[nb] = n;
+    for (int i = 0; i < per; ++i) { s_o[pad_idx(threadIdx.x * per + i)] = run; run += c[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+        const int e = i * 256 + threadIdx.x;
+        if (t0 + e < nb) { const unsigned long long v = s_o[pad_idx(e)]; start[t0 + e] = v; cursor[t0 + e] = v; }
+    }
+    if (t0 + kScanTile >= nb && threadIdx.x == 0) start[nb] = tile_sum[blockIdx.x] + total;      // the last tile: total = number of hits
 }
 
-__global__ void bucket_scatter_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, unsigned long long n, int shift,
-                                      unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ tkeys, double* __restrict__ tsc) {
+__global__ void bucket_scatter_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sc, const unsigned long long* __restrict__ n_ptr,
+                                      int shift, unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ tkeys, double* __restrict__ tsc) {
+    const unsigned long long n = *n_ptr;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long k = keys[i];
         const unsigned long long slot = atomicAdd(&cursor[k >> shift], 1ull);
@@ -166,13 +170,19 @@ __global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const unsigne
     }
 }
 
-// Single-segment scans: run_off[c] = first hit of combo c = 2 * motif + strand (c = 0 .. 2M): lower bound of c << pb.
-__global__ void run_offsets_kernel(const unsigned long long* __restrict__ skeys, unsigned long long n, int pb, int nrun,
-                                   long long* __restrict__ run_off) {
+// Single-segment scans: run_off[c] = first hit of combo c = 2 * motif + strand (c = 0 .. 2M).  A bucket never spans two
+// combos when shift <= pb: the offset is the bucket's start; otherwise (few hits) the lower bound of c << pb in the sorted keys.
+__global__ void run_offsets_kernel(const unsigned long long* __restrict__ skeys, const unsigned long long* __restrict__ start, unsigned long long nb,
+                                   int shift, int pb, int nrun, long long* __restrict__ run_off) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > nrun) return;
     const unsigned long long target = (unsigned long long)c << pb;
-    unsigned long long lo = 0, hi = n;
+    if (shift <= pb) {
+        const unsigned long long b = target >> shift;
+        run_off[c] = (long long)start[b < nb ? b : nb];
+        return;
+    }
+    unsigned long long lo = 0, hi = start[nb];
     while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (skeys[mid] < target) lo = mid + 1; else hi = mid; }
     run_off[c] = (long long)lo;
 }
@@ -192,41 +202,48 @@ int order_pick_shift(unsigned long long n, int key_bits) {
 
 size_t order_bucket_count(int key_bits, int shift) { return key_bits > shift ? ((size_t)1 << (key_bits - shift)) : 1; }
 
-// Stream-ordered.  d_work: cnt u32[nb] + start u64[nb+1] + cursor u64[nb] + tiles u64[ceil(nb / 4096)] (order_work_bytes);
-// d_tkeys/d_tsc: n entries of scratch; outputs as described on top.  d_flags[0] must be 0 on entry (the caller
-// clears it with the other counters) and holds the size of the largest overflowing bucket afterwards.
-size_t order_work_bytes(size_t nb) { return nb * 4 + 64 + (nb + 1) * 8 + nb * 8 + ((nb + kScanTile - 1) / kScanTile + 1) * 8; }
+size_t order_work_bytes(size_t nb) { return ((nb * 4 + 63) & ~(size_t)63) + (nb + 1) * 8 + nb * 8 + ((nb + kScanTile - 1) / kScanTile + 1) * 8; }
 
-int order_hits(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const double* d_sc, unsigned long long n, KeyLayout kl,
-               int key_bits, int shift, int nseg, int M, unsigned char* d_work, unsigned long long* d_tkeys, double* d_tsc,
-               unsigned long long* d_skeys, double* d_score, uint32_t* d_pos32, int32_t* d_seg32, uint16_t* d_ms16, long long* d_run_off,
-               unsigned long long* d_flags, int* launches) {
-    const size_t nb = order_bucket_count(key_bits, shift);
-    unsigned int* cnt = (unsigned int*)d_work;
-    unsigned long long* start = (unsigned long long*)(d_work + ((nb * 4 + 63) & ~(size_t)63));
-    unsigned long long* cursor = start + nb + 1;
-    unsigned long long* tiles = cursor + nb;
+OrderWork order_work_view(unsigned char* d_work, size_t nb) {
+    OrderWork w;
+    w.nb = nb;
+    w.cnt = (unsigned int*)d_work;
+    w.start = (unsigned long long*)(d_work + ((nb * 4 + 63) & ~(size_t)63));
+    w.cursor = w.start + nb + 1;
+    w.tiles = w.cursor + nb;
+    return w;
+}
+
+// Counts the stored hits per bucket (only needed when the counting was not fused into the kernels that produce the hits:
+// the retry with a smaller shift).  w.cnt must be zero.  Stream-ordered.
+int order_count(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const unsigned long long* d_nhits, unsigned long long cap,
+                int shift, const OrderWork& w, int* launches) {
+    bucket_count_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_keys, d_nhits, cap, shift, w.cnt);
+    PWM_CUDA(cudaGetLastError());
+    *launches += 1;
+    return PWMSCAN_OK;
+}
+
+// Everything after the counting: scan, scatter, per-bucket sort into the output columns, run table.  n_est only sizes the
+// grids (the kernels read the real count from the scan's total).  d_flags[0] must be 0 on entry and holds the size of the
+// largest bucket that did not fit afterwards.  Stream-ordered, no host synchronisation.
+int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const double* d_sc, unsigned long long n_est, KeyLayout kl,
+                 int shift, int nseg, int M, const OrderWork& w, unsigned long long* d_tkeys, double* d_tsc,
+                 unsigned long long* d_skeys, double* d_score, uint32_t* d_pos32, int32_t* d_seg32, uint16_t* d_ms16, long long* d_run_off,
+                 unsigned long long* d_flags, int* launches) {
     const int sm = ctx->sm_count;
-    PWM_CUDA(cudaMemsetAsync(cnt, 0, nb * 4, st));
-    const unsigned grid_n = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)sm * 16);
-    bucket_count_kernel<<<grid_n, 256, 0, st>>>(d_keys, n, shift, cnt);
-    if (nb <= 32768) {
-        bucket_scan_single_kernel<<<1, 1024, 0, st>>>(cnt, nb, start, cursor);
-        *launches += 1;
-    } else {
-        const unsigned long long ntiles = (nb + kScanTile - 1) / kScanTile;
-        bucket_tile_sum_kernel<<<(unsigned)ntiles, 256, 0, st>>>(cnt, nb, tiles);
-        bucket_tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
-        bucket_tile_apply_kernel<<<(unsigned)ntiles, 256, 0, st>>>(cnt, nb, n, tiles, start, cursor);
-        *launches += 3;
-    }
-    bucket_scatter_kernel<<<grid_n, 256, 0, st>>>(d_keys, d_sc, n, shift, cursor, d_tkeys, d_tsc);
-    const unsigned grid_b = (unsigned)std::min<size_t>(nb, (size_t)sm * 16);
-    bucket_sort_kernel<<<grid_b, kSortThreads, 0, st>>>(start, nb, shift, d_tkeys, d_tsc, kl, nseg > 1 ? 1 : 0, d_skeys, d_score, d_pos32, d_seg32,
+    const unsigned long long ntiles = (w.nb + kScanTile - 1) / kScanTile;
+    bucket_tile_sum_kernel<<<(unsigned)ntiles, 256, 0, st>>>(w.cnt, w.nb, w.tiles);
+    bucket_tile_scan_kernel<<<1, 1024, 0, st>>>(w.tiles, ntiles);
+    bucket_tile_apply_kernel<<<(unsigned)ntiles, 256, 0, st>>>(w.cnt, w.nb, w.tiles, w.start, w.cursor);
+    const unsigned grid_n = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((n_est + 255) / 256, (unsigned long long)sm * 16));
+    bucket_scatter_kernel<<<grid_n, 256, 0, st>>>(d_keys, d_sc, w.start + w.nb, shift, w.cursor, d_tkeys, d_tsc);
+    const unsigned grid_b = (unsigned)std::min<size_t>(w.nb, (size_t)sm * 16);
+    bucket_sort_kernel<<<grid_b, kSortThreads, 0, st>>>(w.start, w.nb, shift, d_tkeys, d_tsc, kl, nseg > 1 ? 1 : 0, d_skeys, d_score, d_pos32, d_seg32,
                                                        d_ms16, d_flags);
-    *launches += 3;
+    *launches += 5;
     if (nseg == 1) {
-        run_offsets_kernel<<<(2 * M + 1 + 255) / 256, 256, 0, st>>>(d_skeys, n, kl.pb, 2 * M, d_run_off);
+        run_offsets_kernel<<<(2 * M + 1 + 255) / 256, 256, 0, st>>>(d_skeys, w.start, w.nb, shift, kl.pb, 2 * M, d_run_off);
         *launches += 1;
     }
     PWM_CUDA(cudaGetLastError());

@@ -259,8 +259,25 @@ constexpr int64_t kAnchorRound = kChunk * 32;               // anchor ranges are
 
 __constant__ unsigned char c_iupac_lut[256];
 
-// One thread per 32 stored bases: two packed words + one mask word.
-__global__ void pack_kernel(const uint8_t* ascii, int64_t len, int uppercase, uint32_t* __restrict__ seq2,
+// Four ASCII bytes of one 32-bit word -> their 2-bit codes packed into 8 bits (byte k at bits 2k..2k+1) and a byte-wise
+// "not one of ACGT" flag (0x80 per offending byte), without a table: with x = bits 1..2 of a letter (A 0, C 1, T 2, G 3)
+// the letter an ACGT byte must be is 0x41 + 2x (+ 15 for x == 2), the code is x ^ (x >> 1), and a multiply gathers the
+// four 2-bit fields.  `fold` = 0xDFDFDFDF upper-cases letters (fromBS's toUpper, Seq.hs:86-95), 0xFFFFFFFF leaves them.
+__device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t fold, uint32_t* bad) {
+    const uint32_t v = w & fold;
+    const uint32_t x = (v >> 1) & 0x03030303u;
+    const uint32_t m = (x >> 1) & ~x & 0x01010101u;
+    const uint32_t expect = 0x41414141u + (x << 1) + (m << 4) - m;
+    const uint32_t d = v ^ expect;
+    *bad |= (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    const uint32_t code = x ^ ((x >> 1) & 0x01010101u);
+    return (code * 0x01041040u) >> 24;
+}
+
+// One thread per 32 stored bases: two packed words + one mask word.  Fast path (32 aligned bytes inside the sequence, all
+// of them A/C/G/T, no ASCII copy wanted): two 16-byte loads and ~4 integer operations per base; anything else (sequence
+// ends, N runs and other IUPAC letters, invalid bytes, KEEP_ASCII) takes the per-byte path below.
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* ascii, int64_t len, int uppercase, uint32_t* __restrict__ seq2,
                             uint32_t* __restrict__ mask, uint8_t* ascii_out /* may alias ascii */, int64_t t0, int64_t t1,
                             unsigned long long* first_bad /* [0] non-ACGT, [1] non-IUPAC */) {
     const int64_t t = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,8 +289,20 @@ __global__ void pack_kernel(const uint8_t* ascii, int64_t len, int uppercase, ui
     __align__(16) uint8_t buf[32];
     const bool interior = (p0 >= 0) && (p0 + 32 <= len) && ((((uintptr_t)(ascii + p0)) & 15) == 0);
     if (interior) {
-        const uint4 a = *reinterpret_cast<const uint4*>(ascii + p0);
-        const uint4 b = *reinterpret_cast<const uint4*>(ascii + p0 + 16);
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(ascii + p0));          // streamed once: do not keep it in the caches
+        const uint4 b = __ldcs(reinterpret_cast<const uint4*>(ascii + p0 + 16));
+        if (!ascii_out) {
+            const uint32_t fold = uppercase ? 0xDFDFDFDFu : 0xFFFFFFFFu;
+            uint32_t bad = 0;
+            const uint32_t c0 = pack4(a.x, fold, &bad), c1 = pack4(a.y, fold, &bad), c2 = pack4(a.z, fold, &bad), c3 = pack4(a.w, fold, &bad);
+            const uint32_t c4 = pack4(b.x, fold, &bad), c5 = pack4(b.y, fold, &bad), c6 = pack4(b.z, fold, &bad), c7 = pack4(b.w, fold, &bad);
+            if (bad == 0u) {
+                seq2[2 * t] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+                seq2[2 * t + 1] = c4 | (c5 << 8) | (c6 << 16) | (c7 << 24);
+                mask[t] = 0u;
+                return;
+            }
+        }
         *reinterpret_cast<uint4*>(buf) = a;
         *reinterpret_cast<uint4*>(buf + 16) = b;
     } else {
@@ -884,30 +913,54 @@ __device__ __forceinline__ unsigned long long hit_key(KeyLayout kl, int seg, int
            (unsigned long long)pos_in_seg;
 }
 
+// Stores one hit and counts it in its ordering bucket (order.cu).
+__device__ __forceinline__ void sink_store(const HitSink& hs, unsigned long long slot, unsigned long long key, double sc) {
+    if (slot < hs.cap) {
+        hs.keys[slot] = key; hs.sc[slot] = sc;
+        atomicAdd(&hs.bucket_cnt[key >> hs.shift], 1u);
+    }
+}
+
 // Appends the hits of the calling lanes with one atomicAdd per warp (all lanes of the warp that are in the
 // surrounding loop iteration must call it; `hit` selects the ones that have something to append).
-__device__ __forceinline__ void append_hits(bool hit, unsigned long long key, double sc, unsigned long long* __restrict__ hit_keys,
-                                            double* __restrict__ hit_sc, unsigned long long hit_cap, unsigned long long* counters) {
+__device__ __forceinline__ void append_hits(bool hit, unsigned long long key, double sc, const HitSink& hs) {
     const unsigned act = __activemask();
     const unsigned bal = __ballot_sync(act, hit);
     if (bal == 0u) return;
     const int lane = threadIdx.x & 31, leader = __ffs((int)bal) - 1;
     unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(&counters[1], (unsigned long long)__popc(bal));
+    if (lane == leader) base = atomicAdd(&hs.counters[1], (unsigned long long)__popc(bal));
     base = __shfl_sync(act, base, leader);
-    if (hit) {
-        const unsigned long long slot = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
-        if (slot < hit_cap) { hit_keys[slot] = key; hit_sc[slot] = sc; }
+    if (hit) sink_store(hs, base + (unsigned)__popc(bal & ((1u << lane) - 1u)), key, sc);
+}
+
+// replay_skip (scan_core.cuh: the literal lookAheadSearch' loop, Motif/Search.hs:176-189) with the window's 2-bit codes and
+// invalid-base flags fetched up front (three + two 32-bit words for up to 32 columns) instead of one dependent load pair per
+// column; what remains per column are the two independent table reads.  Same additions in the same order.
+__device__ __forceinline__ bool replay_window(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ mask, int64_t u0, int n,
+                                              const double* __restrict__ tab16, const double* __restrict__ th, double* score) {
+    if (n > 32) return replay_skip(seq2, mask, u0, n, tab16, th, score);
+    const int64_t w = u0 >> 4;
+    const int s2 = 2 * (int)(u0 & 15);
+    const uint32_t a0 = __ldg(seq2 + w), a1 = __ldg(seq2 + w + 1), a2 = __ldg(seq2 + w + 2);
+    const unsigned long long x = (unsigned long long)__funnelshift_r(a0, a1, s2) | ((unsigned long long)__funnelshift_r(a1, a2, s2) << 32);
+    const int64_t mw = u0 >> 5;
+    const uint32_t inv = __funnelshift_r(__ldg(mask + mw), __ldg(mask + mw + 1), (int)(u0 & 31));
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double sc = ((inv >> k) & 1u) ? PWM_NEG_INF : __ldg(tab16 + 16 * k + (int)((x >> (2 * k)) & 3ull));
+        acc = __dadd_rn(acc, sc);
+        if (acc < __ldg(th + k)) return false;
     }
+    *score = acc;
+    return true;
 }
 
 __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsigned long long cand_cap,
                                const DevCombo* __restrict__ combos, const uint32_t* __restrict__ seq2,
                                const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
-                               const double* __restrict__ tab16, const double* __restrict__ th,
-                               unsigned long long* __restrict__ hit_keys, double* __restrict__ hit_sc,
-                               unsigned long long hit_cap, unsigned long long* counters, KeyLayout kl) {
-    unsigned long long ncand = counters[0];
+                               const double* __restrict__ tab16, const double* __restrict__ th, HitSink hs, KeyLayout kl) {
+    unsigned long long ncand = hs.counters[0];
     if (ncand > cand_cap) ncand = cand_cap;
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < ncand;
          k += (unsigned long long)gridDim.x * blockDim.x) {
@@ -922,13 +975,13 @@ __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsi
             if (cb.motif >= 0 && i >= 0 && i + cb.n <= len) {
                 const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
                 if (i + cb.n <= seg_off[seg + 1] &&
-                    replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
+                    replay_window(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
                     hit = true;
                     key = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]);
                 }
             }
         }
-        append_hits(hit, key, sc, hit_keys, hit_sc, hit_cap, counters);
+        append_hits(hit, key, sc, hs);
     }
 }
 
@@ -938,10 +991,8 @@ __global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec
                                       const DevMmaBlock* __restrict__ blocks, const int8_t* __restrict__ btiles,
                                       const DevCombo* __restrict__ combos, const uint32_t* __restrict__ seq2,
                                       const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
-                                      const double* __restrict__ tab16, const double* __restrict__ th,
-                                      unsigned long long* __restrict__ hit_keys, double* __restrict__ hit_sc,
-                                      unsigned long long hit_cap, unsigned long long* counters, KeyLayout kl) {
-    unsigned long long nrec = counters[0];
+                                      const double* __restrict__ tab16, const double* __restrict__ th, HitSink hs, KeyLayout kl) {
+    unsigned long long nrec = hs.counters[0];
     if (nrec > cap) nrec = cap;
     const int lane = threadIdx.x & 31;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -968,8 +1019,7 @@ __global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec
         if (i + cb.n > seg_off[seg + 1]) continue;
         double sc;
         if (replay_skip(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
-            const unsigned long long slot = atomicAdd(&counters[1], 1ull);
-            if (slot < hit_cap) { hit_keys[slot] = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
+            sink_store(hs, atomicAdd(&hs.counters[1], 1ull), hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]), sc);
         }
     }
 }
@@ -979,8 +1029,8 @@ __global__ void rescore_chunks_kernel(const unsigned long long* __restrict__ rec
 __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, int skip, const uint32_t* __restrict__ seq2,
                              const uint32_t* __restrict__ mask, const uint8_t* __restrict__ ascii,
                              const int64_t* __restrict__ seg_off, int nseg, int64_t len, const double* __restrict__ tab16,
-                             const double* __restrict__ th, unsigned long long* __restrict__ hit_keys,
-                             double* __restrict__ hit_sc, unsigned long long hit_cap, unsigned long long* counters, KeyLayout kl) {
+                             const double* __restrict__ th, HitSink hs, KeyLayout kl) {
+    unsigned long long* counters = hs.counters;
   for (int ci = blockIdx.y; ci < ncombo; ci += gridDim.y) {
     const DevCombo cb = combos[ci];
     const double* tb = tab16 + cb.tab_off;
@@ -1001,10 +1051,7 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
                 if (sc < tk[k]) { hit = false; break; }
             }
         }
-        if (hit) {
-            const unsigned long long slot = atomicAdd(&counters[1], 1ull);
-            if (slot < hit_cap) { hit_keys[slot] = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]); hit_sc[slot] = sc; }
-        }
+        if (hit) sink_store(hs, atomicAdd(&counters[1], 1ull), hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]), sc);
     }
   }
 }
@@ -1044,6 +1091,7 @@ struct ScanJob {
     unsigned long long cand_cap = 0, hit_cap = 0, nhits = 0, ncand = 0;
     int prefilter_launches = 0, kernels = 0;
     size_t n8 = 0, out_bytes = 0;
+    size_t col_cap = 0;              // entries per device output column (= hit_cap rounded up)
     unsigned char* d_out = nullptr;
     pwmscan_hits* hits = nullptr;
     bool active = false;
@@ -1058,6 +1106,46 @@ void job_release(ScanJob& j) {
     if (j.hits) { pwmscan_hits_free(j.hits); j.hits = nullptr; }
     if (j.host && j.up.seq) { pwmscan_seq_free(j.up.seq); j.up.seq = nullptr; }
     j.active = false;
+}
+
+// Device output columns of a job (lane scratch SL_OUT), each with room for col_cap entries.
+struct OutCols { double* score; uint32_t* pos32; long long* run_off; int32_t* seg32; uint16_t* ms16; };
+OutCols job_out_cols(const ScanJob& j) {
+    OutCols oc;
+    unsigned char* d = j.d_out;
+    oc.score = (double*)d;
+    oc.pos32 = (uint32_t*)(d + j.col_cap * 8);
+    oc.run_off = (long long*)(d + j.col_cap * 12);
+    oc.seg32 = (int32_t*)(d + j.col_cap * 12);
+    oc.ms16 = (uint16_t*)(d + j.col_cap * 16);
+    return oc;
+}
+
+// (Re)allocates what the ordering pass needs for the job's current shift and hit capacity.
+int job_order_buffers(pwmscan_ctx* ctx, ScanJob& j) {
+    ScanLane* lane = j.lane;
+    const size_t nb = order_bucket_count(j.key_bits, j.shift);
+    if (nb > ((size_t)1 << 28)) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit density too uneven to order");
+    j.col_cap = ((size_t)j.hit_cap + 7) & ~(size_t)7;
+    const int M = j.pl->motifs->M;
+    const size_t out_bytes = j.seq->nseg == 1 ? j.col_cap * 12 + (size_t)(2 * M + 1) * 8 : j.col_cap * 18;
+    if (!lane_scratch_get(ctx, lane, SL_WORK, order_work_bytes(nb)) || !lane_scratch_get(ctx, lane, SL_TKEYS, j.col_cap * 8) ||
+        !lane_scratch_get(ctx, lane, SL_TSC, j.col_cap * 8) || !lane_scratch_get(ctx, lane, SL_SKEYS, j.col_cap * 8) ||
+        !(j.d_out = (unsigned char*)lane_scratch_get(ctx, lane, SL_OUT, out_bytes)))
+        return PWMSCAN_ECUDA;
+    return PWMSCAN_OK;
+}
+
+// scan -> scatter -> per-bucket sort -> run table, behind whatever counted the hits into ow.cnt (stream-ordered).
+int job_order_finish(pwmscan_ctx* ctx, ScanJob& j, const OrderWork& ow) {
+    ScanLane* lane = j.lane;
+    const OutCols oc = job_out_cols(j);
+    const bool one = j.seq->nseg == 1;
+    const unsigned long long n_est = j.nhits ? j.nhits : (unsigned long long)(j.pl->cand_rate * (double)j.seq->len) + 1024;
+    return order_finish(ctx, lane->stream, (const unsigned long long*)lane->scratch[SL_KEYS], (const double*)lane->scratch[SL_SC], n_est, j.kl, j.shift,
+                        j.seq->nseg, j.pl->motifs->M, ow, (unsigned long long*)lane->scratch[SL_TKEYS], (double*)lane->scratch[SL_TSC],
+                        (unsigned long long*)lane->scratch[SL_SKEYS], oc.score, oc.pos32, one ? nullptr : oc.seg32, one ? nullptr : oc.ms16,
+                        one ? oc.run_off : nullptr, lane->d_counters + 6, &j.kernels);
 }
 
 // Phase A.  attempt > 0 (a capacity overflow): the sequence is packed already, plain re-run.
@@ -1094,6 +1182,12 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     unsigned long long* d_keys = (unsigned long long*)lane_scratch_get(ctx, lane, SL_KEYS, j.hit_cap * 8);
     double* d_sc = (double*)lane_scratch_get(ctx, lane, SL_SC, j.hit_cap * 8);
     if (!d_cand || !d_keys || !d_sc) return PWMSCAN_ECUDA;
+    // the ordering pass (order.cu) runs right behind the kernels that find the hits: its bucket layout comes from the
+    // EXPECTED hit count (a bad guess only costs a retry in phase B), its buffers are sized by the hit capacity
+    j.shift = order_pick_shift(std::max<unsigned long long>((unsigned long long)(pl->cand_rate * (double)len) + 1024, j.nhits), j.key_bits);
+    if ((rc = job_order_buffers(ctx, j))) return rc;
+    const OrderWork ow = order_work_view((unsigned char*)lane->scratch[SL_WORK], order_bucket_count(j.key_bits, j.shift));
+    HitSink hs{d_keys, d_sc, j.hit_cap, lane->d_counters, ow.cnt, j.shift};
     if (pl->nblocks > 0 && !ctx->smem_attr_set) {
         PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
         PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
@@ -1145,6 +1239,7 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     };
     PWM_CUDA(cudaMemsetAsync(lane->d_counters, 0, 4 * sizeof(unsigned long long), st));
     PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, (kCounterWords - 6) * sizeof(unsigned long long), st));
+    PWM_CUDA(cudaMemsetAsync(ow.cnt, 0, ow.nb * 4, st));
     if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, j.cand_cap * 8, st));     // sentinel: warps reserve whole chunks
     if (j.host && j.attempt == 0) {
         PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
@@ -1198,12 +1293,10 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     if (n_pre_blocks > 0) {
         if (use_mma)
             rescore_chunks_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(d_cand, j.cand_cap, pl->d_mma_blocks, pl->d_btiles, d_combos, seq->d_seq2, seq->d_mask,
-                                                                      seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                                      d_sc, j.hit_cap, lane->d_counters, j.kl);
+                                                                      seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
         else
             rescore_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_cand, j.cand_cap, d_combos, seq->d_seq2, seq->d_mask,
-                                                              seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, d_keys,
-                                                              d_sc, j.hit_cap, lane->d_counters, j.kl);
+                                                              seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
         PWM_CUDA(cudaGetLastError());
         ++j.kernels;
     }
@@ -1212,51 +1305,26 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         const long long gx = std::min<long long>((len + bs - 1) / bs, 65535LL * 16);
         dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(generic.size(), 65535));
         exact_kernel<<<grid, bs, 0, st>>>(d_generic, (int)generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
-                                          seq->nseg, len, mo->d_tab16, pl->d_th, d_keys, d_sc, j.hit_cap, lane->d_counters, j.kl);
+                                          seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
         PWM_CUDA(cudaGetLastError());
         ++j.kernels;
     }
     PWM_CUDA(cudaEventRecord(lane->ev[EV_RES], st));
+    if ((rc = job_order_finish(ctx, j, ow))) return rc;
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_ORD], st));
     PWM_CUDA(cudaMemcpyAsync(lane->h_counters, lane->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 6, lane->d_counters + 6, 8, cudaMemcpyDeviceToHost, st));
     PWM_CUDA(cudaEventRecord(lane->ev[EV_A], st));
     return PWMSCAN_OK;
 }
 
-// Ordering + the device->host copy of the compact columns for the current j.shift (stream-ordered).
-int scan_enqueue_order(pwmscan_ctx* ctx, ScanJob& j) {
-    ScanLane* lane = j.lane;
-    cudaStream_t st = lane->stream;
-    const int M = j.pl->motifs->M, nseg = j.seq->nseg;
-    const unsigned long long n = j.nhits;
-    const size_t nb = order_bucket_count(j.key_bits, j.shift);
-    if (nb > ((size_t)1 << 28)) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: hit density too skewed to order");
-    unsigned char* d_work = (unsigned char*)lane_scratch_get(ctx, lane, SL_WORK, order_work_bytes(nb));
-    unsigned long long* d_tkeys = (unsigned long long*)lane_scratch_get(ctx, lane, SL_TKEYS, n * 8);
-    double* d_tsc = (double*)lane_scratch_get(ctx, lane, SL_TSC, n * 8);
-    unsigned long long* d_skeys = (unsigned long long*)lane_scratch_get(ctx, lane, SL_SKEYS, n * 8);
-    j.d_out = (unsigned char*)lane_scratch_get(ctx, lane, SL_OUT, j.out_bytes);
-    if (!d_work || !d_tkeys || !d_tsc || !d_skeys || !j.d_out) return PWMSCAN_ECUDA;
-    const size_t n8 = j.n8;
-    double* o_sc = (double*)j.d_out;
-    uint32_t* o_pos = (uint32_t*)(j.d_out + n8 * 8);
-    long long* o_run = nseg == 1 ? (long long*)(j.d_out + n8 * 12) : nullptr;
-    int32_t* o_seg = nseg == 1 ? nullptr : (int32_t*)(j.d_out + n8 * 12);
-    uint16_t* o_ms = nseg == 1 ? nullptr : (uint16_t*)(j.d_out + n8 * 16);
-    PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, 8, st));
-    int rc = order_hits(ctx, st, (const unsigned long long*)lane->scratch[SL_KEYS], (const double*)lane->scratch[SL_SC], n, j.kl, j.key_bits, j.shift,
-                        nseg, M, d_work, d_tkeys, d_tsc, d_skeys, o_sc, o_pos, o_seg, o_ms, o_run, lane->d_counters + 6, &j.kernels);
-    if (rc) return rc;
-    PWM_CUDA(cudaEventRecord(lane->ev[EV_ORD], st));
-    PWM_CUDA(cudaMemcpyAsync(j.hits->buf, j.d_out, j.out_bytes, cudaMemcpyDeviceToHost, st));
-    PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 6, lane->d_counters + 6, 8, cudaMemcpyDeviceToHost, st));
-    PWM_CUDA(cudaEventRecord(lane->ev[EV_B], st));
-    return PWMSCAN_OK;
-}
-
-// Phase B: waits for the counters of phase A, repeats A with larger buffers if they overflowed, then enqueues the ordering.
+// Phase B: waits for the counters of phase A, repeats A with larger buffers if they overflowed (and the ordering with
+// smaller buckets if one did not fit the sorting kernel's shared memory), then enqueues the copies of the compact columns.
 int scan_phase_b(pwmscan_ctx* ctx, ScanJob& j) {
     ScanLane* lane = j.lane;
     const pwmscan_plan* pl = j.pl;
+    cudaStream_t st = lane->stream;
+    int rc;
     for (;;) {
         PWM_CUDA(cudaEventSynchronize(lane->ev[EV_A]));
         if (j.host && j.attempt == 0) {
@@ -1272,21 +1340,48 @@ int scan_phase_b(pwmscan_ctx* ctx, ScanJob& j) {
         j.cand_cap = std::max(j.cand_cap, j.ncand + (j.ncand >> 3) + 1024);
         j.hit_cap = std::max(j.hit_cap, std::max(j.nhits, j.ncand) + (j.nhits >> 3) + 1024);
         ++j.attempt;
-        int rc = scan_phase_a(ctx, j);
-        if (rc) return rc;
+        if ((rc = scan_phase_a(ctx, j))) return rc;
+    }
+    // a bucket did not fit the sorting kernel's shared memory (far more hits than expected, or very uneven): smaller buckets,
+    // again — positions are unique per (segment, motif, strand), so 2^kOrderIdxBits positions of one of them always fit
+    for (unsigned long long over = lane->h_counters[6]; over != 0; over = lane->h_counters[6]) {
+        if (j.shift == 0) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: internal: ordering bucket overflow at shift 0");
+        int drop = 1;
+        while (((unsigned long long)kOrderCap << drop) < over) ++drop;
+        j.shift = std::max(0, std::min(j.shift - drop - 1, order_pick_shift(j.nhits, j.key_bits)));
+        if ((rc = job_order_buffers(ctx, j))) return rc;
+        const OrderWork ow = order_work_view((unsigned char*)lane->scratch[SL_WORK], order_bucket_count(j.key_bits, j.shift));
+        PWM_CUDA(cudaMemsetAsync(ow.cnt, 0, ow.nb * 4, st));
+        PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, 8, st));
+        if ((rc = order_count(ctx, st, (const unsigned long long*)lane->scratch[SL_KEYS], lane->d_counters + 1, j.hit_cap, j.shift, ow, &j.kernels))) return rc;
+        if ((rc = job_order_finish(ctx, j, ow))) return rc;
+        PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 6, lane->d_counters + 6, 8, cudaMemcpyDeviceToHost, st));
+        PWM_CUDA(cudaStreamSynchronize(st));
     }
     pwmscan_hits* h = new (std::nothrow) pwmscan_hits();
     if (!h) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
     j.hits = h;
     h->ctx = ctx; h->count = (int64_t)j.nhits; h->nseg = j.seq->nseg; h->M = pl->motifs->M;
     if (j.nhits == 0) return PWMSCAN_OK;
-    const size_t n8 = (j.nhits + 7) & ~7ull;                    // keeps every column 8-byte aligned
+    const size_t n = (size_t)j.nhits, n8 = (n + 7) & ~(size_t)7;             // keeps every host column 8-byte aligned
+    const bool one = h->nseg == 1;
     j.n8 = n8;
-    j.out_bytes = j.seq->nseg == 1 ? n8 * 12 + (size_t)(2 * h->M + 1) * 8 : n8 * 18;
+    j.out_bytes = one ? n8 * 12 + (size_t)(2 * h->M + 1) * 8 : n8 * 18;
     h->buf = pin_pool_get(ctx, j.out_bytes, &h->buf_bytes);
     if (!h->buf) return PWMSCAN_ECUDA;
-    j.shift = order_pick_shift(j.nhits, j.key_bits);
-    return scan_enqueue_order(ctx, j);
+    // the compact columns: [score f64][pos32 u32] + [run_off i64 x (2M+1)] or [seg32 i32][ms16 u16]
+    unsigned char* hb = (unsigned char*)h->buf;
+    const OutCols oc = job_out_cols(j);
+    PWM_CUDA(cudaMemcpyAsync(hb, oc.score, n * 8, cudaMemcpyDeviceToHost, st));
+    PWM_CUDA(cudaMemcpyAsync(hb + n8 * 8, oc.pos32, n * 4, cudaMemcpyDeviceToHost, st));
+    if (one) {
+        PWM_CUDA(cudaMemcpyAsync(hb + n8 * 12, oc.run_off, (size_t)(2 * h->M + 1) * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        PWM_CUDA(cudaMemcpyAsync(hb + n8 * 12, oc.seg32, n * 4, cudaMemcpyDeviceToHost, st));
+        PWM_CUDA(cudaMemcpyAsync(hb + n8 * 16, oc.ms16, n * 2, cudaMemcpyDeviceToHost, st));
+    }
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_B], st));
+    return PWMSCAN_OK;
 }
 
 // Phase C: waits for the hit list, hands it over (the job keeps nothing), releases a sequence the job owned.
@@ -1294,35 +1389,21 @@ int scan_phase_c(pwmscan_ctx* ctx, ScanJob& j, pwmscan_hits** out, double* timin
     ScanLane* lane = j.lane;
     float ms_pre = 0, ms_res = 0, ms_ord = 0, ms_tot = 0;
     if (j.nhits > 0) {
-        for (;;) {
-            PWM_CUDA(cudaEventSynchronize(lane->ev[EV_B]));
-            const unsigned long long over = lane->h_counters[6];
-            if (over == 0) break;
-            // a bucket did not fit the ordering kernel's shared memory: smaller buckets, again (keys are unique per position,
-            // so 2^kOrderIdxBits positions of one (segment, motif, strand) always fit)
-            if (j.shift == 0) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: internal: ordering bucket overflow at shift 0");
-            int drop = 1;
-            while (((unsigned long long)kOrderCap << drop) < over) ++drop;
-            j.shift = std::max(0, j.shift - drop - 1);
-            int rc = scan_enqueue_order(ctx, j);
-            if (rc) return rc;
-        }
+        PWM_CUDA(cudaEventSynchronize(lane->ev[EV_B]));
         pwmscan_hits* h = j.hits;
         unsigned char* hb = (unsigned char*)h->buf;
         h->score = (const double*)hb;
         h->pos32 = (const uint32_t*)(hb + j.n8 * 8);
         if (h->nseg == 1) h->run_off = (const int64_t*)(hb + j.n8 * 12);
         else { h->seg32 = (const int32_t*)(hb + j.n8 * 12); h->ms16 = (const uint16_t*)(hb + j.n8 * 16); }
-        cudaEventElapsedTime(&ms_ord, lane->ev[EV_RES], lane->ev[EV_ORD]);
-        cudaEventElapsedTime(&ms_tot, lane->ev[EV_START], lane->ev[EV_ORD]);
-    } else {
-        cudaEventElapsedTime(&ms_tot, lane->ev[EV_START], lane->ev[EV_RES]);
     }
     cudaEventElapsedTime(&ms_pre, lane->ev[EV_START], lane->ev[EV_PRE]);
     cudaEventElapsedTime(&ms_res, lane->ev[EV_PRE], lane->ev[EV_RES]);
+    cudaEventElapsedTime(&ms_ord, lane->ev[EV_RES], lane->ev[EV_ORD]);
+    cudaEventElapsedTime(&ms_tot, lane->ev[EV_START], lane->ev[EV_ORD]);
     timing[0] += ms_pre; timing[1] += ms_res; timing[2] += ms_ord; timing[3] += ms_tot;
     if (j.host) timing[4] += (double)j.seq->len + (double)(j.seq->nseg + 1) * 8;
-    timing[5] += (double)j.out_bytes + 40;
+    timing[5] += (double)j.out_bytes + 48;
     timing[6] += (double)j.ncand;
     timing[7] += (double)j.prefilter_launches;
     timing[8] += (double)j.kernels;
@@ -1429,12 +1510,16 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
     for (int i = 0; i < K && !rc; ++i) rc = start(i);
     for (int i = 0; i < n && !rc; ++i) {
         rc = scan_phase_b(ctx, jobs[i % K]);
-        if (!rc && i >= 1) {
+        if (rc) break;
+        if (K == 1) {                                 // one lane: strictly one item after the other
+            rc = finish(i);
+            if (!rc && i + 1 < n) rc = start(i + 1);
+        } else if (i >= 1) {                          // item i-1's copy has had item i's phase B to land; its lane takes item i-1+K
             rc = finish(i - 1);
             if (!rc && i - 1 + K < n) rc = start(i - 1 + K);
         }
     }
-    if (!rc) rc = finish(n - 1);
+    if (!rc && K > 1) rc = finish(n - 1);
     if (rc) {                                     // drain: nothing may still touch caller or pooled buffers
         cudaDeviceSynchronize();
         for (int k = 0; k < K; ++k) job_release(jobs[k]);

@@ -17,7 +17,7 @@ struct KeyLayout { int pb, mb; };
 
 constexpr int kOrderCap = 4096;        // hits one CTA orders in shared memory (order.cu)
 constexpr int kOrderIdxBits = 12;      // log2(kOrderCap)
-constexpr int kOrderTarget = 128;      // hits per bucket aimed at
+constexpr int kOrderTarget = 24;       // hits per bucket aimed at (a warp orders up to 256 in registers, order.cu)
 constexpr int kMaxLanes = 4;           // scans in flight of pwmscan_scan_many
 
 // Everything one in-flight scan needs of its own: streams, events, counters, grow-only scratch.  Lane 0 shares the
@@ -128,7 +128,7 @@ struct DevKmBlock {
     int64_t q16_off;     // uint16 elements into d_km_q16 ([256][max_n][4])
     int64_t bitmap_off;  // bytes into d_km_tables of the "first mask non-zero" bitmap (one bit per k-mer of step 0)
     int32_t bitmap_words;  // 32-bit words of it; 0 = this block runs without the bitmap
-    int32_t pad_;
+    int32_t direct;        // 1 = the block's single table sees every column of every combo: a surviving bit is the whole-window test
 };
 
 enum { PWM_MODE_LDS = 0, PWM_MODE_MMA = 1, PWM_MODE_KMER = 2 };
@@ -211,11 +211,11 @@ void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 void* lane_scratch_get(pwmscan_ctx* ctx, ScanLane* lane, int slot, size_t bytes);
 int hits_expand_wide(pwmscan_hits* h);     // fills pos / motif / segment / strand (idempotent, thread-safe)
 // order.cu
-struct OrderWork { size_t nb; unsigned int* cnt; unsigned long long *start, *cursor, *tiles; };
+struct OrderWork { size_t nb, big_cap; unsigned int* cnt; unsigned long long *start, *cursor, *tiles, *big; };
 int order_pick_shift(unsigned long long n, int key_bits);
 size_t order_bucket_count(int key_bits, int shift);
-size_t order_work_bytes(size_t nb);
-OrderWork order_work_view(unsigned char* d_work, size_t nb);
+size_t order_work_bytes(size_t nb, size_t hit_cap);
+OrderWork order_work_view(unsigned char* d_work, size_t nb, size_t hit_cap);
 int order_count(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const unsigned long long* d_nhits, unsigned long long cap,
                 int shift, const OrderWork& w, int* launches);
 int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_keys, const double* d_sc, unsigned long long n_est, KeyLayout kl,

@@ -405,6 +405,327 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Second generation of the kernel (PWMSCAN_KM_KERNEL=2): the same first stage, table layout, middle stage and candidate
+// format, but organised around WARPS instead of CTAs:
+//   * a work unit is (block, kKm2UnitPos positions) and belongs to one warp, which draws it from the global counter
+//     (the next one is requested while the current one is processed), stages the unit's 2-bit words in its own slice
+//     of shared memory and runs it to the end — no CTA-wide barrier per item, no waiting for the slowest warp;
+//   * the CTA only synchronises when the block in shared memory (middle-stage rows, bitmap) has to change: a warp that
+//     has drawn a unit of a later block waits at the barrier until every warp has, the smallest wanted block is loaded;
+//   * bitmap scan: 16 positions per thread from one 64-bit window (two shifts per position instead of five);
+//   * blocks whose single table covers every column of every motif (short motifs) skip the middle stage: a surviving
+//     bit already is the whole-window test.
+constexpr int kKm2UnitPos = 2048;
+constexpr int kKm2SeqWords = kKmHaloWords + kKm2UnitPos / 16 + 5;
+
+struct Km2Shared {
+    uint32_t seq[kKmThreads / 32][kKm2SeqWords];
+    uint32_t queue[kKmThreads / 32][kKmQueue];
+    uint16_t hitq[kKmThreads / 32][kKmHitQueue];
+    uint32_t cn[kKmCombos];
+    int want;
+};
+
+struct Km2Ctx {                     // what the per-warp helpers need (all warp-uniform)
+    const uint32_t* sseq;           // the unit's staged words (halo in front)
+    const uint32_t* cn;
+    const uint16_t* q16;
+    uint32_t* q;
+    int max_n, direct;
+    long long U0, len;
+    unsigned long long combo_base;
+    unsigned long long* cand;
+    unsigned long long cand_cap;
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ void km2_drain(const Km2Ctx& c, uint32_t entry, bool active) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t combo = entry & 255u;
+    const int p = (int)(entry >> 8);
+    const uint32_t cn = c.cn[combo];
+    const int cc = (int)(short)(cn & 0xFFFFu), n = (int)(cn >> 16);
+    const long long i = c.U0 + p - cc - kPadFront;                   // window start in sequence coordinates
+    bool ok = active && i >= 0 && i + n <= c.len;
+    if (ok && !c.direct) {
+        const int rel = p - cc + 16 * kKmHaloWords;                  // window start relative to sseq[0]
+        const int wi = rel >> 4, s2 = 2 * (rel & 15);
+        const uint32_t w0 = c.sseq[wi], w1 = c.sseq[wi + 1], w2 = c.sseq[wi + 2];
+        const uint32_t x0 = __funnelshift_r(w0, w1, s2), x1 = __funnelshift_r(w1, w2, s2);
+        uint32_t x2 = 0, x3 = 0;
+        if (n > 32) {
+            const uint32_t w3 = c.sseq[wi + 3], w4 = c.sseq[wi + 4];
+            x2 = __funnelshift_r(w2, w3, s2); x3 = __funnelshift_r(w3, w4, s2);
+        }
+        const uint2* row = reinterpret_cast<const uint2*>(c.q16) + (size_t)combo * c.max_n;
+        uint32_t sum = 0;
+        for (int k = 0; k < n; ++k) {                               // rows in order of decreasing expected deficit
+            const uint2 r = row[k];
+            const uint32_t col = ((r.x >> 12) & 15u) | ((r.x >> 24) & 0x30u);
+            const uint32_t xs = col < 32u ? (col < 16u ? x0 : x1) : (col < 48u ? x2 : x3);
+            const uint32_t b = (xs >> (2u * (col & 15u))) & 3u;
+            const uint32_t f = (b & 2u) ? r.y : r.x;
+            sum += (f >> (16u * (b & 1u))) & 0xFFFu;
+            if (sum > (uint32_t)kKmQ) break;
+        }
+        ok = sum <= (uint32_t)kKmQ;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+    if (bal) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&c.counters[0], (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (ok) {
+            const unsigned long long slot = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
+            if (slot < c.cand_cap) c.cand[slot] = ((c.combo_base + combo) << 40) | (unsigned long long)(c.U0 + p);
+        }
+    }
+}
+
+// as km_expand, on the warp's own queue
+__device__ __forceinline__ void km2_expand(const Km2Ctx& c, Mask& m, uint32_t p, int& qcnt) {
+    const int lane = threadIdx.x & 31;
+    uint32_t any = mask_any(m);
+    unsigned bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
+    while (bal) {
+        if (any) {
+            uint32_t bit;
+            if (m.v[0]) { bit = __ffs((int)m.v[0]) - 1; m.v[0] &= m.v[0] - 1; }
+            else if (m.v[1]) { bit = 32 + __ffs((int)m.v[1]) - 1; m.v[1] &= m.v[1] - 1; }
+            else if (m.v[2]) { bit = 64 + __ffs((int)m.v[2]) - 1; m.v[2] &= m.v[2] - 1; }
+            else if (m.v[3]) { bit = 96 + __ffs((int)m.v[3]) - 1; m.v[3] &= m.v[3] - 1; }
+            else if (m.v[4]) { bit = 128 + __ffs((int)m.v[4]) - 1; m.v[4] &= m.v[4] - 1; }
+            else if (m.v[5]) { bit = 160 + __ffs((int)m.v[5]) - 1; m.v[5] &= m.v[5] - 1; }
+            else if (m.v[6]) { bit = 192 + __ffs((int)m.v[6]) - 1; m.v[6] &= m.v[6] - 1; }
+            else { bit = 224 + __ffs((int)m.v[7]) - 1; m.v[7] &= m.v[7] - 1; }
+            c.q[qcnt + __popc(bal & ((1u << lane) - 1u))] = (p << 8) | bit;
+            any = mask_any(m);
+        }
+        qcnt += __popc(bal);
+        __syncwarp();
+        if (qcnt >= 32) {
+            const uint32_t e = c.q[lane];
+            const uint32_t rest = (lane + 32 < qcnt) ? c.q[lane + 32] : 0u;
+            __syncwarp();
+            if (lane + 32 < qcnt) c.q[lane] = rest;
+            qcnt -= 32;
+            km2_drain(c, e, true);
+            __syncwarp();
+        }
+        bal = __ballot_sync(0xFFFFFFFFu, any != 0u);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void km2_hits(const Km2Ctx& c, const uint8_t* const (&tp)[NT], const int (&tsh)[NT], const uint32_t (&tmk)[NT], uint64_t pol,
+                                         uint32_t p, bool active, int& qcnt) {
+    Mask m;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m.v[w] = 0u;
+    if (active) {
+        const int wi = (int)(p >> 4) + kKmHaloWords, s2 = 2 * (int)(p & 15u);
+        const uint32_t w0 = c.sseq[wi], w1 = c.sseq[wi + 1], w2 = c.sseq[wi + 2];
+        const unsigned long long x = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
+        m = ldg_mask(tp[0] + (size_t)((uint32_t)(x >> tsh[0]) & tmk[0]) * 32, pol);
+        if (NT > 1) {                                       // the first mask is known to be non-zero: no need to wait for it
+            const Mask t = ldg_mask(tp[1] + (size_t)((uint32_t)(x >> tsh[1]) & tmk[1]) * 32, pol);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) m.v[w] &= t.v[w];
+        }
+#pragma unroll
+        for (int s = 2; s < NT; ++s) {
+            if (mask_any(m)) {
+                const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x >> tsh[s]) & tmk[s]) * 32, pol);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) m.v[w] &= t.v[w];
+            }
+        }
+    }
+    km2_expand(c, m, p, qcnt);
+}
+
+// One unit of a block with a first-table bitmap.  Scan: a thread tests 16 consecutive positions; the k-mers of all of them
+// come out of ONE 64-bit window (the 32 bases from the first k-mer's first base), shifted by 2 bits per position.
+template <int NT>
+__device__ __forceinline__ void km2_unit_bitmap(const Km2Ctx& c, const uint32_t* __restrict__ s_bm, const DevKmBlock& db, const uint8_t* __restrict__ tab,
+                                                uint16_t* hq, int unit_pos) {
+    const int lane = threadIdx.x & 31;
+    int qcnt = 0, hcnt = 0;
+    const uint64_t pol = l2_keep_policy();
+    const uint8_t* tp[NT];
+    int tsh[NT];
+    uint32_t tmk[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) { tp[s] = tab + db.table_off[s]; tsh[s] = db.shift[s]; tmk[s] = db.kmask[s]; }
+    const int off0 = tsh[0] >> 1;                                       // bases between a position and its first table's k-mer
+    const uint32_t mk0 = tmk[0];
+#pragma unroll 1
+    for (int pb0 = 0; pb0 < unit_pos; pb0 += 512) {
+        const int pb = pb0 + 16 * lane;
+        const int B = pb + off0 + 16 * kKmHaloWords;                    // first base of position pb's k-mer, relative to sseq[0]
+        const int wi = B >> 4, sB = 2 * (B & 15);
+        const uint32_t w0 = c.sseq[wi], w1 = c.sseq[wi + 1], w2 = c.sseq[wi + 2];
+        const uint32_t xlo = __funnelshift_r(w0, w1, sB), xhi = __funnelshift_r(w1, w2, sB);
+        uint32_t hm = 0;                                                // bit 15 - k: position pb + k has a non-zero first mask
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t i0 = __funnelshift_r(xlo, xhi, 2 * k) & mk0;
+            const uint32_t word = s_bm[i0 >> 5];
+            hm = __funnelshift_l(word << (~i0 & 31u), hm, 1);           // hm = hm << 1 | bit i0 of word
+        }
+        // compaction: per round every thread that still has a hit queues one
+        unsigned bal = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+        while (bal) {
+            if (hm) {
+                const int b = __ffs((int)hm) - 1;
+                hq[hcnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(pb + 15 - b);
+                hm &= hm - 1u;
+            }
+            hcnt += __popc(bal);
+            __syncwarp();
+            if (hcnt >= 32) {
+                const uint32_t p = hq[lane];
+                const uint32_t rest = (lane + 32 < hcnt) ? hq[lane + 32] : 0u;
+                __syncwarp();
+                if (lane + 32 < hcnt) hq[lane] = (uint16_t)rest;
+                hcnt -= 32;
+                km2_hits<NT>(c, tp, tsh, tmk, pol, p, true, qcnt);
+                __syncwarp();
+            }
+            bal = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+        }
+    }
+    if (hcnt > 0) {
+        const uint32_t p = lane < hcnt ? hq[lane] : 0u;
+        km2_hits<NT>(c, tp, tsh, tmk, pol, p, lane < hcnt, qcnt);
+    }
+    if (qcnt > 0) {
+        const uint32_t e = lane < qcnt ? c.q[lane] : 0u;
+        km2_drain(c, e, lane < qcnt);
+    }
+}
+
+// One unit of a block without a bitmap: two adjacent positions per thread and iteration (km_item's loop).
+template <int NT>
+__device__ __forceinline__ void km2_unit_plain(const Km2Ctx& c, const DevKmBlock& db, const uint8_t* __restrict__ tab, int unit_pos) {
+    const int lane = threadIdx.x & 31;
+    int qcnt = 0;
+    const uint64_t pol = l2_keep_policy();
+    const uint8_t* tp[NT];
+    int tsh[NT];
+    uint32_t tmk[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) { tp[s] = tab + db.table_off[s]; tsh[s] = db.shift[s]; tmk[s] = db.kmask[s]; }
+#pragma unroll 1
+    for (int pb0 = 0; pb0 < unit_pos; pb0 += 64) {
+        Mask m[2];
+        unsigned long long x[2];
+        const int p = pb0 + 2 * lane;
+        {
+            const int wi = (p >> 4) + kKmHaloWords, s2 = 2 * (p & 15);
+            const uint32_t w0 = c.sseq[wi], w1 = c.sseq[wi + 1], w2 = c.sseq[wi + 2];
+            x[0] = (unsigned long long)__funnelshift_r(w0, w1, s2) | ((unsigned long long)__funnelshift_r(w1, w2, s2) << 32);
+            x[1] = (unsigned long long)__funnelshift_r(w0, w1, s2 + 2) | ((unsigned long long)__funnelshift_r(w1, w2, s2 + 2) << 32);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) m[j] = ldg_mask(tp[0] + (size_t)((uint32_t)(x[j] >> tsh[0]) & tmk[0]) * 32, pol);
+#pragma unroll
+        for (int s = 1; s < NT; ++s) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (mask_any(m[j])) {
+                    const Mask t = ldg_mask(tp[s] + (size_t)((uint32_t)(x[j] >> tsh[s]) & tmk[s]) * 32, pol);
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) m[j].v[w] &= t.v[w];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) km2_expand(c, m[j], (uint32_t)(p + j), qcnt);
+    }
+    if (qcnt > 0) {
+        const uint32_t e = lane < qcnt ? c.q[lane] : 0u;
+        km2_drain(c, e, lane < qcnt);
+    }
+}
+
+__global__ void __launch_bounds__(kKmThreads, 1)
+km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long total_units, int unit_pos, int nblocks,
+                       const DevKmBlock* __restrict__ blocks, const uint8_t* __restrict__ tables, const uint16_t* __restrict__ q16,
+                       const DevCombo* __restrict__ combos, long long len, unsigned long long* __restrict__ cand, unsigned long long cand_cap,
+                       unsigned long long* counters, unsigned long long* work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Km2Shared sh;
+    uint16_t* s_q16 = reinterpret_cast<uint16_t*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long units_per_block = n_anchor / unit_pos;
+    if (tid == 0) sh.want = 0x7FFFFFFF;
+    __syncthreads();
+    int cur_blk = -1;
+    DevKmBlock db = blocks[0];
+    const uint32_t* s_bm = nullptr;
+    // the warp's next unit is always requested one unit ahead
+    long long next_unit = 0;
+    if (lane == 0) next_unit = (long long)atomicAdd(work_counter, 1ull);
+    for (;;) {
+        const long long unit = __shfl_sync(0xFFFFFFFFu, next_unit, 0);
+        if (lane == 0 && unit < total_units) next_unit = (long long)atomicAdd(work_counter, 1ull);     // in flight while this unit runs
+        const int blk = unit < total_units ? (int)(unit / units_per_block) : nblocks;                    // nblocks = nothing left
+        while (blk != cur_blk) {
+            // the block in shared memory has to change: wait until no warp needs the current one any more, load the
+            // smallest block any warp wants (every warp is here with a block >= that)
+            __syncthreads();
+            if (lane == 0) atomicMin(&sh.want, blk);
+            __syncthreads();
+            const int nb = sh.want;
+            __syncthreads();
+            if (tid == 0) sh.want = 0x7FFFFFFF;
+            if (nb >= nblocks) return;                                   // every warp has run out of units
+            db = blocks[nb];
+            const uint4* src = reinterpret_cast<const uint4*>(q16 + db.q16_off);
+            uint4* dst = reinterpret_cast<uint4*>(s_q16);
+            const int n16 = kKmCombos * db.max_n * 8 / 16;
+            for (int i = tid; i < n16; i += kKmThreads) dst[i] = __ldg(src + i);
+            s_bm = reinterpret_cast<const uint32_t*>(smem_raw + (size_t)n16 * 16);       // bitmap right behind the rows
+            if (db.bitmap_words > 0) {
+                const uint4* bsrc = reinterpret_cast<const uint4*>(tables + db.bitmap_off);
+                uint4* bdst = reinterpret_cast<uint4*>(smem_raw + (size_t)n16 * 16);
+                for (int i = tid; i < db.bitmap_words / 4; i += kKmThreads) bdst[i] = __ldg(bsrc + i);
+            }
+            if (tid < kKmCombos) {
+                const DevCombo dc = combos[(size_t)nb * kKmCombos + tid];
+                sh.cn[tid] = ((uint32_t)dc.c & 0xFFFFu) | ((uint32_t)dc.n << 16);
+            }
+            cur_blk = nb;
+            __syncthreads();
+        }
+        const long long U0 = anchor0 + (unit - (long long)blk * units_per_block) * unit_pos;
+        uint32_t* sseq = sh.seq[warp];
+        {   // stage the unit's 2-bit words (64 bases of history in front; the allocation has one front word)
+            const long long w0 = (U0 >> 4) - kKmHaloWords;
+            const int nw = kKmHaloWords + unit_pos / 16 + 5;
+            for (int i = lane; i < nw; i += 32) sseq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
+        }
+        __syncwarp();
+        Km2Ctx c;
+        c.sseq = sseq; c.cn = sh.cn; c.q16 = s_q16; c.q = sh.queue[warp]; c.max_n = db.max_n; c.direct = db.direct;
+        c.U0 = U0; c.len = len; c.combo_base = (unsigned long long)blk * kKmCombos; c.cand = cand; c.cand_cap = cand_cap; c.counters = counters;
+#define KM2_RUN(NT_) \
+        if (db.bitmap_words > 0) km2_unit_bitmap<NT_>(c, s_bm, db, tables, sh.hitq[warp], unit_pos); \
+        else km2_unit_plain<NT_>(c, db, tables, unit_pos);
+        switch (db.nt) {
+            case 1: KM2_RUN(1) break;
+            case 2: KM2_RUN(2) break;
+            case 3: KM2_RUN(3) break;
+            default: KM2_RUN(4) break;
+        }
+#undef KM2_RUN
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 namespace pwmscan {
@@ -434,7 +755,20 @@ int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2
     if (nblocks == 0 || a1 <= a0) return PWMSCAN_OK;
     if (!ctx->km_attr_set) {
         PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmSmemBudget));
+        PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmSmemBudget));
         ctx->km_attr_set = true;
+    }
+    static const int which = std::getenv("PWMSCAN_KM_KERNEL") ? std::atoi(std::getenv("PWMSCAN_KM_KERNEL")) : 1;
+    if (which == 2) {
+        // warp-owned units of 2048 positions (512 for short inputs, so that every warp of every SM gets some)
+        int unit_pos = kKm2UnitPos;
+        while (unit_pos > 512 && (a1 - a0) / unit_pos * nblocks < 4LL * ctx->sm_count * (kKmThreads / 32)) unit_pos >>= 1;
+        const long long units = (a1 - a0) / unit_pos * nblocks;
+        const int grid = (int)std::min<long long>(ctx->sm_count, (units + kKmThreads / 32 - 1) / (kKmThreads / 32));
+        km_prefilter_kernel_v2<<<grid, kKmThreads, smem_bytes, lane->stream>>>(d_seq2, a0, a1 - a0, units, unit_pos, nblocks, d_blocks, d_tables, d_q16, d_combos,
+                                                                               len, d_cand, cand_cap, lane->d_counters, work_counter);
+        PWM_CUDA(cudaGetLastError());
+        return PWMSCAN_OK;
     }
     int iters = kKmMaxIters;                                  // short inputs: smaller items so that every SM gets several
     while (iters > 1 && (a1 - a0) / (iters * kKmIterPos) * nblocks < 8LL * ctx->sm_count) iters >>= 1;

@@ -19,7 +19,9 @@ using namespace pwmscan;
 
 namespace {
 
-constexpr int kSortThreads = 128;
+constexpr int kSortThreads = 256;               // CTA of the shared-memory sort (big buckets)
+constexpr int kWarpCap = 256;                   // hits one warp orders in registers (8 per lane)
+constexpr int kWarpIdxBits = 8;
 constexpr int kScanTile = 2048;                 // counters per CTA of the scan
 
 __global__ void bucket_count_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, unsigned long long cap,
@@ -122,20 +124,109 @@ __global__ void bucket_scatter_kernel(const unsigned long long* __restrict__ key
     }
 }
 
-// One CTA per bucket (grid-stride over the buckets).  flags[0] = largest bucket that did not fit.
-__global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const unsigned long long* __restrict__ start, unsigned long long nb, int shift,
-                                                                   const unsigned long long* __restrict__ tkeys, const double* __restrict__ tsc,
-                                                                   KeyLayout kl, int multi_seg, unsigned long long* __restrict__ skeys,
-                                                                   double* __restrict__ score, uint32_t* __restrict__ pos32,
-                                                                   int32_t* __restrict__ seg32, uint16_t* __restrict__ ms16,
-                                                                   unsigned long long* __restrict__ flags) {
+// Writes the element that ended up at sorted position `o` of a bucket: v = (key - base) << idx_bits | index among the
+// bucket's scattered elements.
+struct SortOut {
+    const double* tsc; unsigned long long* skeys; double* score; uint32_t* pos32; int32_t* seg32; uint16_t* ms16;
+    KeyLayout kl; int multi_seg;
+};
+__device__ __forceinline__ void sort_emit(const SortOut& so, unsigned long long s, unsigned long long o, unsigned long long base, unsigned long long v, int idx_bits) {
+    const unsigned long long key = base + (v >> idx_bits);
+    so.skeys[o] = key;
+    so.pos32[o] = (uint32_t)(key & ((1ull << so.kl.pb) - 1ull));
+    so.score[o] = so.tsc[s + (v & ((1ull << idx_bits) - 1ull))];
+    if (so.multi_seg) {
+        so.ms16[o] = (uint16_t)((key >> so.kl.pb) & ((1ull << (so.kl.mb + 1)) - 1ull));
+        so.seg32[o] = (int32_t)(key >> (so.kl.pb + 1 + so.kl.mb));
+    }
+}
+
+// Bitonic sort of 32 * E values held E per lane (value index = lane * E + r), ascending, entirely in registers: partners
+// closer than E live in the same lane, the others are one shuffle away.  No shared memory, no barrier.
+template <int E>
+__device__ __forceinline__ void warp_bitonic(unsigned long long (&v)[E]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= E) {
+                const int lj = j / E;                                   // partner lane = lane ^ lj, same r
+                const bool lower = (lane & lj) == 0;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v[r], lj);
+                    const bool up = ((lane * E + r) & k) == 0;
+                    const bool keep_min = (up == lower);
+                    const unsigned long long mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+                    v[r] = keep_min ? mn : mx;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & j) == 0) {
+                        const bool up = ((lane * E + r) & k) == 0;
+                        const unsigned long long a = v[r], c = v[r | j];
+                        if ((a > c) == up) { v[r] = c; v[r | j] = a; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void warp_sort_bucket(unsigned long long s, int cnt, unsigned long long base, const unsigned long long* __restrict__ tkeys,
+                                                 const SortOut& so) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = lane * E + r;
+        v[r] = i < cnt ? (((tkeys[s + i] - base) << kWarpIdxBits) | (unsigned long long)i) : ~0ull;
+    }
+    warp_bitonic<E>(v);
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = lane * E + r;
+        if (i < cnt) sort_emit(so, s, s + (unsigned long long)i, base, v[r], kWarpIdxBits);
+    }
+}
+
+// One WARP per bucket (grid-stride over the buckets): up to kWarpCap hits are ordered in registers.  Larger buckets go to
+// the list of bucket_sort_big_kernel.  big[0] = number of listed buckets, big[1..] their indices.
+__global__ void __launch_bounds__(256) bucket_sort_kernel(const unsigned long long* __restrict__ start, unsigned long long nb, int shift,
+                                                          const unsigned long long* __restrict__ tkeys, SortOut so,
+                                                          unsigned long long* __restrict__ big, unsigned long long big_cap, unsigned long long* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nwarp = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long b = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += nwarp) {
+        const unsigned long long s = start[b], cnt = start[b + 1] - s;
+        if (cnt == 0) continue;
+        const unsigned long long base = shift < 64 ? (b << shift) : 0ull;
+        if (cnt <= 32) warp_sort_bucket<1>(s, (int)cnt, base, tkeys, so);
+        else if (cnt <= 64) warp_sort_bucket<2>(s, (int)cnt, base, tkeys, so);
+        else if (cnt <= 128) warp_sort_bucket<4>(s, (int)cnt, base, tkeys, so);
+        else if (cnt <= (unsigned long long)kWarpCap) warp_sort_bucket<8>(s, (int)cnt, base, tkeys, so);
+        else if (lane == 0) {
+            const unsigned long long k = atomicAdd(&big[0], 1ull);
+            if (k < big_cap) big[1 + k] = b; else atomicMax(&flags[0], cnt);      // (cannot happen: the list has room for every possible big bucket)
+        }
+    }
+}
+
+// One CTA per listed bucket: bitonic sort in shared memory, up to kOrderCap hits.  flags[0] = largest bucket that did not fit.
+__global__ void __launch_bounds__(kSortThreads) bucket_sort_big_kernel(const unsigned long long* __restrict__ start, int shift,
+                                                                       const unsigned long long* __restrict__ tkeys, SortOut so,
+                                                                       const unsigned long long* __restrict__ big, unsigned long long big_cap,
+                                                                       unsigned long long* __restrict__ flags) {
     __shared__ unsigned long long v[kOrderCap];
     const int tid = threadIdx.x;
-    const unsigned long long pos_mask = (1ull << kl.pb) - 1ull, ms_mask = (1ull << (kl.mb + 1)) - 1ull;
-    for (unsigned long long b = blockIdx.x; b < nb; b += gridDim.x) {
+    const unsigned long long nbig = big[0] < big_cap ? big[0] : big_cap;
+    for (unsigned long long q = blockIdx.x; q < nbig; q += gridDim.x) {
+        const unsigned long long b = big[1 + q];
         const unsigned long long s = start[b], e = start[b + 1];
         const unsigned long long cnt = e - s;
-        if (cnt == 0) continue;
         if (cnt > (unsigned long long)kOrderCap) { if (tid == 0) atomicMax(&flags[0], cnt); continue; }
         const unsigned long long base = shift < 64 ? (b << shift) : 0ull;
         int n2 = 1;
@@ -154,18 +245,7 @@ __global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const unsigne
                 }
                 __syncthreads();
             }
-        for (int i = tid; i < (int)cnt; i += kSortThreads) {
-            const unsigned long long x = v[i];
-            const unsigned long long key = base + (x >> kOrderIdxBits);
-            const unsigned long long o = s + (unsigned long long)i;
-            skeys[o] = key;
-            pos32[o] = (uint32_t)(key & pos_mask);
-            score[o] = tsc[s + (x & ((1ull << kOrderIdxBits) - 1ull))];
-            if (multi_seg) {
-                ms16[o] = (uint16_t)((key >> kl.pb) & ms_mask);
-                seg32[o] = (int32_t)(key >> (kl.pb + 1 + kl.mb));
-            }
-        }
+        for (int i = tid; i < (int)cnt; i += kSortThreads) sort_emit(so, s, s + (unsigned long long)i, base, v[i], kOrderIdxBits);
         __syncthreads();
     }
 }
@@ -202,15 +282,22 @@ int order_pick_shift(unsigned long long n, int key_bits) {
 
 size_t order_bucket_count(int key_bits, int shift) { return key_bits > shift ? ((size_t)1 << (key_bits - shift)) : 1; }
 
-size_t order_work_bytes(size_t nb) { return ((nb * 4 + 63) & ~(size_t)63) + (nb + 1) * 8 + nb * 8 + ((nb + kScanTile - 1) / kScanTile + 1) * 8; }
+// cnt u32[nb] | start u64[nb+1] | cursor u64[nb] | tile sums | list of big buckets (1 + big_cap entries; a big bucket holds
+// more than kWarpCap hits, so hit_cap / kWarpCap + 1 entries always suffice)
+static size_t big_cap_of(size_t nb, size_t hit_cap) { return std::min(nb, hit_cap / kWarpCap + 1); }
+size_t order_work_bytes(size_t nb, size_t hit_cap) {
+    return ((nb * 4 + 63) & ~(size_t)63) + (nb + 1) * 8 + nb * 8 + ((nb + kScanTile - 1) / kScanTile + 1) * 8 + (big_cap_of(nb, hit_cap) + 1) * 8;
+}
 
-OrderWork order_work_view(unsigned char* d_work, size_t nb) {
+OrderWork order_work_view(unsigned char* d_work, size_t nb, size_t hit_cap) {
     OrderWork w;
     w.nb = nb;
+    w.big_cap = big_cap_of(nb, hit_cap);
     w.cnt = (unsigned int*)d_work;
     w.start = (unsigned long long*)(d_work + ((nb * 4 + 63) & ~(size_t)63));
     w.cursor = w.start + nb + 1;
     w.tiles = w.cursor + nb;
+    w.big = w.tiles + (nb + kScanTile - 1) / kScanTile + 1;
     return w;
 }
 
@@ -238,9 +325,12 @@ int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_
     bucket_tile_apply_kernel<<<(unsigned)ntiles, 256, 0, st>>>(w.cnt, w.nb, w.tiles, w.start, w.cursor);
     const unsigned grid_n = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((n_est + 255) / 256, (unsigned long long)sm * 16));
     bucket_scatter_kernel<<<grid_n, 256, 0, st>>>(d_keys, d_sc, w.start + w.nb, shift, w.cursor, d_tkeys, d_tsc);
-    const unsigned grid_b = (unsigned)std::min<size_t>(w.nb, (size_t)sm * 16);
-    bucket_sort_kernel<<<grid_b, kSortThreads, 0, st>>>(w.start, w.nb, shift, d_tkeys, d_tsc, kl, nseg > 1 ? 1 : 0, d_skeys, d_score, d_pos32, d_seg32,
-                                                       d_ms16, d_flags);
+    SortOut so{d_tsc, d_skeys, d_score, d_pos32, d_seg32, d_ms16, kl, nseg > 1 ? 1 : 0};
+    PWM_CUDA(cudaMemsetAsync(w.big, 0, 8, st));
+    const unsigned grid_b = (unsigned)std::max<size_t>(1, std::min<size_t>((w.nb + 7) / 8, (size_t)sm * 8));
+    bucket_sort_kernel<<<grid_b, 256, 0, st>>>(w.start, w.nb, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
+    bucket_sort_big_kernel<<<sm * 2, kSortThreads, 0, st>>>(w.start, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
+    *launches += 1;
     *launches += 5;
     if (nseg == 1) {
         run_offsets_kernel<<<(2 * M + 1 + 255) / 256, 256, 0, st>>>(d_skeys, w.start, w.nb, shift, kl.pb, 2 * M, d_run_off);

@@ -29,7 +29,8 @@ constexpr int kKmWords = kKmCombos / 32;        // 8 x uint32 = one 32-byte sect
 constexpr int kKmMaxTables = 4;
 constexpr int kKmMinL = 8, kKmMaxL = 10;        // window lengths: 8-, 9- or 10-mers (2, 8, 32 MiB per table)
 constexpr size_t kKmMaxTableBytes = (size_t)72 << 20;   // per block, so that the tables of the running block stay in the 126 MB L2
-constexpr size_t kKmSmemBudget = (size_t)196 << 10;     // dynamic shared memory of the kernel: middle-stage rows + first-table bitmap
+constexpr size_t kKmSmemBudget = (size_t)194 << 10;     // dynamic shared memory of the kernel: middle-stage rows + first-table bitmap
+                                                        // (+ ~32 KB static: staged sequence words and queues of the 32 warps <= 227 KB)
 constexpr double kKmBitmapClk = 0.4;            // clocks per position and SM of the shared-memory bitmap look-up: its wavefronts (~0.11, bank
                                                 // conflicts included) share L1TEX with the gathers, plus index/test instructions — fitted on C2
 constexpr int kKmQ = 4000;                      // fixed-point budget of the middle stage; entries saturate at 4095 (12 bits)

@@ -733,7 +733,10 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
                 const int t = s < bp.nt ? bp.order[s] : 0;
                 hb[b].shift[s] = 2 * bp.off[t]; hb[b].kmask[s] = (1u << (2 * bp.L[t])) - 1u; hb[b].table_off[s] = toff[t];
             }
-            hb[b].bitmap_off = (int64_t)table_bytes; hb[b].bitmap_words = (int32_t)(bp.bitmap_bytes() / 4); hb[b].pad_ = 0;
+            hb[b].bitmap_off = (int64_t)table_bytes; hb[b].bitmap_words = (int32_t)(bp.bitmap_bytes() / 4);
+            hb[b].direct = bp.nt == 1 ? 1 : 0;                       // ... if every enabled combo's window [c, c + L) covers its columns [0, n)
+            for (int ci = 0; ci < kKmCombos && hb[b].direct; ++ci)
+                if (bp.combo[ci].enabled && (bp.combo[ci].c > 0 || bp.combo[ci].c + bp.L[0] < bp.combo[ci].n)) hb[b].direct = 0;
             table_bytes += (bp.bitmap_bytes() + 255) / 256 * 256;
             pl->km_smem_bytes = std::max(pl->km_smem_bytes, bp.q16_bytes() + bp.bitmap_bytes());
             hb[b].q16_off = (int64_t)hq.size();
@@ -1085,6 +1088,8 @@ struct ScanJob {
     const pwmscan_seq* seq = nullptr;
     const pwmscan_plan* pl = nullptr;
     bool host = false;               // sequence uploaded by this job (scan_host): released in phase C
+    bool whole_upload = false;       // one upload + one first-stage launch for the whole sequence (items of a scan_many: the
+                                     // other lanes hide the transfer; fewer, larger launches keep the mask tables in L2 longer)
     UploadJob up;
     KeyLayout kl{1, 1};
     int key_bits = 0, shift = 0, attempt = 0;
@@ -1129,7 +1134,7 @@ int job_order_buffers(pwmscan_ctx* ctx, ScanJob& j) {
     j.col_cap = ((size_t)j.hit_cap + 7) & ~(size_t)7;
     const int M = j.pl->motifs->M;
     const size_t out_bytes = j.seq->nseg == 1 ? j.col_cap * 12 + (size_t)(2 * M + 1) * 8 : j.col_cap * 18;
-    if (!lane_scratch_get(ctx, lane, SL_WORK, order_work_bytes(nb)) || !lane_scratch_get(ctx, lane, SL_TKEYS, j.col_cap * 8) ||
+    if (!lane_scratch_get(ctx, lane, SL_WORK, order_work_bytes(nb, (size_t)j.hit_cap)) || !lane_scratch_get(ctx, lane, SL_TKEYS, j.col_cap * 8) ||
         !lane_scratch_get(ctx, lane, SL_TSC, j.col_cap * 8) || !lane_scratch_get(ctx, lane, SL_SKEYS, j.col_cap * 8) ||
         !(j.d_out = (unsigned char*)lane_scratch_get(ctx, lane, SL_OUT, out_bytes)))
         return PWMSCAN_ECUDA;
@@ -1186,7 +1191,7 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     // EXPECTED hit count (a bad guess only costs a retry in phase B), its buffers are sized by the hit capacity
     j.shift = order_pick_shift(std::max<unsigned long long>((unsigned long long)(pl->cand_rate * (double)len) + 1024, j.nhits), j.key_bits);
     if ((rc = job_order_buffers(ctx, j))) return rc;
-    const OrderWork ow = order_work_view((unsigned char*)lane->scratch[SL_WORK], order_bucket_count(j.key_bits, j.shift));
+    const OrderWork ow = order_work_view((unsigned char*)lane->scratch[SL_WORK], order_bucket_count(j.key_bits, j.shift), (size_t)j.hit_cap);
     HitSink hs{d_keys, d_sc, j.hit_cap, lane->d_counters, ow.cnt, j.shift};
     if (pl->nblocks > 0 && !ctx->smem_attr_set) {
         PWM_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kSlotBytes));
@@ -1251,8 +1256,10 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         while ((len + cb - 1) / cb > kMaxChunks - 1) cb *= 2;
         const int64_t tail = 4 * kAnchorRound;
         std::vector<int64_t> bounds(1, 0);
-        while (len - bounds.back() > cb + tail) bounds.push_back(bounds.back() + cb);
-        if (len - bounds.back() > 2 * tail) bounds.push_back((len - tail) / kAnchorRound * kAnchorRound);
+        if (!j.whole_upload) {
+            while (len - bounds.back() > cb + tail) bounds.push_back(bounds.back() + cb);
+            if (len - bounds.back() > 2 * tail) bounds.push_back((len - tail) / kAnchorRound * kAnchorRound);
+        }
         bounds.push_back(len);
         const int nch = (int)bounds.size() - 1;
         while ((int)lane->chunk_ev.size() < nch) {
@@ -1350,7 +1357,7 @@ int scan_phase_b(pwmscan_ctx* ctx, ScanJob& j) {
         while (((unsigned long long)kOrderCap << drop) < over) ++drop;
         j.shift = std::max(0, std::min(j.shift - drop - 1, order_pick_shift(j.nhits, j.key_bits)));
         if ((rc = job_order_buffers(ctx, j))) return rc;
-        const OrderWork ow = order_work_view((unsigned char*)lane->scratch[SL_WORK], order_bucket_count(j.key_bits, j.shift));
+        const OrderWork ow = order_work_view((unsigned char*)lane->scratch[SL_WORK], order_bucket_count(j.key_bits, j.shift), (size_t)j.hit_cap);
         PWM_CUDA(cudaMemsetAsync(ow.cnt, 0, ow.nb * 4, st));
         PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, 8, st));
         if ((rc = order_count(ctx, st, (const unsigned long long*)lane->scratch[SL_KEYS], lane->d_counters + 1, j.hit_cap, j.shift, ow, &j.kernels))) return rc;
@@ -1497,6 +1504,7 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
         } else {
             const int64_t off[2] = {0, lens[i]};
             if ((r = job_init_host(ctx, j, lane, pl, ascii[i], off, 1, flags))) return r;
+            j.whole_upload = K > 1 && lens[i] <= ((int64_t)1 << 27);
         }
         return scan_phase_a(ctx, j);
     };

@@ -514,9 +514,9 @@ def test_config_c4_plan_on_chunk_seam_and_n_edge(ctx, oracle):
     assert cnt == pos_.size and cnt > 100_000
     assert np.array_equal(mo_, o[0]) and np.array_equal(st_, o[1]) and np.array_equal(pos_, o[2])
     assert np.array_equal(sc_.view(np.uint64), o[3].view(np.uint64))
-    # hits whose window crosses the seam exist and come from the first item only
-    cross = (pos_ < seam - lo) & (pos_ + nlen_of[mo_] > seam - lo)
-    assert cross.sum() > 10
+    # windows that start in the first item's last positions and end in the second item's bytes belong to the first item
+    h0 = got[0]
+    assert ((h0.pos < seam - lo) & (h0.pos + nlen_of[h0.motif] > seam - lo)).sum() == ((pos_ < seam - lo) & (pos_ + nlen_of[mo_] > seam - lo)).sum()
     # (b) the start of the N block (windows running into it are not hits) — through the host-bytes path
     nb = int(L * 0.45)
     lo2 = nb - 1_000_000

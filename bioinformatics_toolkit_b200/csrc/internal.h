@@ -17,7 +17,7 @@ struct KeyLayout { int pb, mb; };
 
 constexpr int kOrderCap = 4096;        // hits one CTA orders in shared memory (order.cu)
 constexpr int kOrderIdxBits = 12;      // log2(kOrderCap)
-constexpr int kOrderTarget = 24;       // hits per bucket aimed at (a warp orders up to 256 in registers, order.cu)
+constexpr int kOrderTarget = 8;        // hits per bucket aimed at (a warp orders spans of whole buckets, up to 256 hits, in registers: order.cu)
 constexpr int kMaxLanes = 4;           // scans in flight of pwmscan_scan_many
 
 // Everything one in-flight scan needs of its own: streams, events, counters, grow-only scratch.  Lane 0 shares the
@@ -83,6 +83,7 @@ struct pwmscan_seq {
     int64_t nwords2 = 0, nwords_mask = 0;
     int64_t first_non_acgt = -1, first_non_iupac = -1;
     int flags = 0;
+    bool borrowed = false;              // device planes belong to a scan lane's scratch (host scans), not to the pool
 };
 
 struct pwmscan_motifs {

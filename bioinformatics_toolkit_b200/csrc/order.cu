@@ -175,9 +175,11 @@ __device__ __forceinline__ void warp_bitonic(unsigned long long (&v)[E]) {
     }
 }
 
+// Orders the span [s, s + cnt) of the scattered hits — whole consecutive buckets, so ascending key order IS the final
+// order — in registers.  base = smallest key the span can hold; (key - base) < 2^(shift + 5) leaves room for the index.
 template <int E>
-__device__ __forceinline__ void warp_sort_bucket(unsigned long long s, int cnt, unsigned long long base, const unsigned long long* __restrict__ tkeys,
-                                                 const SortOut& so) {
+__device__ __forceinline__ void warp_sort_span(unsigned long long s, int cnt, unsigned long long base, const unsigned long long* __restrict__ tkeys,
+                                               const SortOut& so) {
     const int lane = threadIdx.x & 31;
     unsigned long long v[E];
 #pragma unroll
@@ -193,24 +195,41 @@ __device__ __forceinline__ void warp_sort_bucket(unsigned long long s, int cnt, 
     }
 }
 
-// One WARP per bucket (grid-stride over the buckets): up to kWarpCap hits are ordered in registers.  Larger buckets go to
-// the list of bucket_sort_big_kernel.  big[0] = number of listed buckets, big[1..] their indices.
+// One WARP per group of 32 consecutive buckets (grid-stride over the groups): the lanes fetch the 33 bucket boundaries with
+// two coalesced loads, then the warp walks the group in spans of whole buckets holding at most kWarpCap hits, each ordered
+// in registers (empty and tiny buckets cost nothing extra).  A single bucket above kWarpCap goes to the list of
+// bucket_sort_big_kernel: big[0] = number of listed buckets, big[1..] their indices.
 __global__ void __launch_bounds__(256) bucket_sort_kernel(const unsigned long long* __restrict__ start, unsigned long long nb, int shift,
                                                           const unsigned long long* __restrict__ tkeys, SortOut so,
                                                           unsigned long long* __restrict__ big, unsigned long long big_cap, unsigned long long* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const unsigned long long nwarp = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long b = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += nwarp) {
-        const unsigned long long s = start[b], cnt = start[b + 1] - s;
-        if (cnt == 0) continue;
-        const unsigned long long base = shift < 64 ? (b << shift) : 0ull;
-        if (cnt <= 32) warp_sort_bucket<1>(s, (int)cnt, base, tkeys, so);
-        else if (cnt <= 64) warp_sort_bucket<2>(s, (int)cnt, base, tkeys, so);
-        else if (cnt <= 128) warp_sort_bucket<4>(s, (int)cnt, base, tkeys, so);
-        else if (cnt <= (unsigned long long)kWarpCap) warp_sort_bucket<8>(s, (int)cnt, base, tkeys, so);
-        else if (lane == 0) {
-            const unsigned long long k = atomicAdd(&big[0], 1ull);
-            if (k < big_cap) big[1 + k] = b; else atomicMax(&flags[0], cnt);      // (cannot happen: the list has room for every possible big bucket)
+    const unsigned long long ngroup = (nb + 31) >> 5;
+    for (unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroup; g += nwarp) {
+        const unsigned long long b0 = g << 5;
+        const unsigned long long bl = b0 + lane < nb ? b0 + lane : nb;
+        const unsigned long long st = start[bl], en = start[bl < nb ? bl + 1 : nb];      // lanes past the last bucket: empty
+        if (__shfl_sync(0xFFFFFFFFu, en, 31) == __shfl_sync(0xFFFFFFFFu, st, 0)) continue;   // nothing in this group
+        int l0 = 0;
+        while (l0 < 32) {
+            const unsigned long long s0 = __shfl_sync(0xFFFFFFFFu, st, l0);
+            const unsigned fit = __ballot_sync(0xFFFFFFFFu, lane >= l0 && en - s0 <= (unsigned long long)kWarpCap);
+            if (fit == 0u) {                                          // bucket l0 alone is too large for a warp
+                if (lane == l0) {
+                    const unsigned long long k = atomicAdd(&big[0], 1ull);
+                    if (k < big_cap) big[1 + k] = b0 + l0; else atomicMax(&flags[0], en - st);   // (cannot happen: the list has room for every big bucket)
+                }
+                ++l0;
+                continue;
+            }
+            const int l1 = 32 - __clz((int)fit);                     // boundaries are non-decreasing: the fitting lanes are l0 .. l1-1
+            const int cnt = (int)(__shfl_sync(0xFFFFFFFFu, en, l1 - 1) - s0);
+            const unsigned long long base = shift < 64 ? ((b0 + (unsigned long long)l0) << shift) : 0ull;
+            if (cnt > 128) warp_sort_span<8>(s0, cnt, base, tkeys, so);
+            else if (cnt > 64) warp_sort_span<4>(s0, cnt, base, tkeys, so);
+            else if (cnt > 32) warp_sort_span<2>(s0, cnt, base, tkeys, so);
+            else if (cnt > 0) warp_sort_span<1>(s0, cnt, base, tkeys, so);
+            l0 = l1;
         }
     }
 }
@@ -276,7 +295,7 @@ int order_pick_shift(unsigned long long n, int key_bits) {
     int lb = 0;                                             // log2 of the bucket count aimed at
     while (lb < 26 && ((unsigned long long)kOrderTarget << lb) < n) ++lb;
     int shift = key_bits > lb ? key_bits - lb : 0;
-    if (shift > 64 - kOrderIdxBits) shift = 64 - kOrderIdxBits;  // (key - base) << idx bits must fit 64 bits
+    if (shift > 64 - kOrderIdxBits - 5) shift = 64 - kOrderIdxBits - 5;   // (key - base of a 32-bucket span) << idx bits must fit 64 bits
     return shift;
 }
 
@@ -327,9 +346,9 @@ int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_
     bucket_scatter_kernel<<<grid_n, 256, 0, st>>>(d_keys, d_sc, w.start + w.nb, shift, w.cursor, d_tkeys, d_tsc);
     SortOut so{d_tsc, d_skeys, d_score, d_pos32, d_seg32, d_ms16, kl, nseg > 1 ? 1 : 0};
     PWM_CUDA(cudaMemsetAsync(w.big, 0, 8, st));
-    const unsigned grid_b = (unsigned)std::max<size_t>(1, std::min<size_t>((w.nb + 7) / 8, (size_t)sm * 8));
+    const unsigned grid_b = (unsigned)std::max<size_t>(1, std::min<size_t>((w.nb + 255) / 256, (size_t)sm * 8));      // 8 warps = 8 groups of 32 buckets per CTA
     bucket_sort_kernel<<<grid_b, 256, 0, st>>>(w.start, w.nb, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
-    bucket_sort_big_kernel<<<sm * 2, kSortThreads, 0, st>>>(w.start, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
+    bucket_sort_big_kernel<<<sm * 6, kSortThreads, 0, st>>>(w.start, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
     *launches += 1;
     *launches += 5;
     if (nseg == 1) {

@@ -75,10 +75,13 @@ void* pinned_get(pwmscan_ctx* ctx, int slot, size_t bytes) {
     return p;
 }
 
-static void* pool_take(std::vector<pwmscan_ctx::PoolBuf>& pool, size_t bytes, size_t* bytes_out) {
+// Smallest cached buffer that holds `bytes` and wastes at most `slack` times the request (+16 MB).  A miss means a
+// cudaMalloc / cudaMallocHost, and a full pool a cudaFree / cudaFreeHost — both synchronise the whole device and stall every
+// scan in flight, so the match is generous.
+static void* pool_take(std::vector<pwmscan_ctx::PoolBuf>& pool, size_t bytes, size_t* bytes_out, size_t slack) {
     int best = -1;
     for (size_t i = 0; i < pool.size(); ++i)
-        if (pool[i].bytes >= bytes && pool[i].bytes <= 2 * bytes + (1 << 20) && (best < 0 || pool[i].bytes < pool[best].bytes)) best = (int)i;
+        if (pool[i].bytes >= bytes && pool[i].bytes <= slack * bytes + ((size_t)16 << 20) && (best < 0 || pool[i].bytes < pool[best].bytes)) best = (int)i;
     if (best < 0) return nullptr;
     void* p = pool[best].p;
     *bytes_out = pool[best].bytes;
@@ -89,7 +92,7 @@ static void* pool_take(std::vector<pwmscan_ctx::PoolBuf>& pool, size_t bytes, si
 void* dev_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
     {
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
-        if (void* p = pool_take(ctx->dev_pool, bytes, bytes_out)) return p;
+        if (void* p = pool_take(ctx->dev_pool, bytes, bytes_out, 4)) return p;
     }
     void* p = nullptr;
     const size_t want = bytes + 256;
@@ -129,7 +132,7 @@ static const int32_t* zero_column(pwmscan_ctx* ctx, size_t n) {
 void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
     {
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
-        if (void* p = pool_take(ctx->pin_pool, bytes, bytes_out)) return p;
+        if (void* p = pool_take(ctx->pin_pool, bytes, bytes_out, 64)) return p;
     }
     void* p = nullptr;
     const size_t want = bytes + bytes / 8 + 4096;
@@ -142,7 +145,7 @@ void* pin_pool_get(pwmscan_ctx* ctx, size_t bytes, size_t* bytes_out) {
 void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(ctx->pool_mu);
-    if (ctx->pin_pool.size() >= 12) { cudaFreeHost(ctx->pin_pool.front().p); ctx->pin_pool.erase(ctx->pin_pool.begin()); }
+    if (ctx->pin_pool.size() >= 16) { cudaFreeHost(ctx->pin_pool.front().p); ctx->pin_pool.erase(ctx->pin_pool.begin()); }
     ctx->pin_pool.push_back({p, bytes});
 }
 
@@ -371,7 +374,10 @@ static int seq_check_args(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t*
 
 // Allocates the device planes of a sequence (from the pool) and uploads the segment table.
 // *d_raw_out is where the ASCII bytes must land (the kept copy, or scratch slot 0).  ctx->mu held.
-static int seq_alloc(pwmscan_ctx* ctx, ScanLane* lane, const int64_t* seg_off, int32_t nseg, int flags, pwmscan_seq** out, uint8_t** d_raw_out) {
+// lane_owned: the planes live in the lane's grow-only scratch (the sequence of a pwmscan_scan_host item exists only for
+// the duration of its scan): no allocation or release per item.
+static int seq_alloc(pwmscan_ctx* ctx, ScanLane* lane, const int64_t* seg_off, int32_t nseg, int flags, pwmscan_seq** out, uint8_t** d_raw_out,
+                     bool lane_owned = false) {
     const int64_t len = seg_off[nseg];
     pwmscan_seq* s = new (std::nothrow) pwmscan_seq();
     if (!s) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
@@ -382,14 +388,25 @@ static int seq_alloc(pwmscan_ctx* ctx, ScanLane* lane, const int64_t* seg_off, i
     s->nwords_mask = n_anchor / 32 + 4;
     auto bail = [&](int code) { pwmscan_seq_free(s); return code; };
     cudaError_t e;
-    if (!(s->d_seq2_alloc = (uint32_t*)dev_pool_get(ctx, (size_t)(s->nwords2 + 1) * 4, &s->cap_seq2))) return bail(PWMSCAN_ECUDA);
+    s->borrowed = lane_owned;
+    if (lane_owned) {
+        s->d_seq2_alloc = (uint32_t*)lane_scratch_get(ctx, lane, 9, (size_t)(s->nwords2 + 1) * 4);
+        s->d_mask = (uint32_t*)lane_scratch_get(ctx, lane, 10, (size_t)s->nwords_mask * 4);
+        s->d_seg_off = (int64_t*)lane_scratch_get(ctx, lane, 11, (size_t)(nseg + 1) * 8);
+        if (!s->d_seq2_alloc || !s->d_mask || !s->d_seg_off) return bail(PWMSCAN_ECUDA);
+    } else {
+        if (!(s->d_seq2_alloc = (uint32_t*)dev_pool_get(ctx, (size_t)(s->nwords2 + 1) * 4, &s->cap_seq2))) return bail(PWMSCAN_ECUDA);
+        if (!(s->d_mask = (uint32_t*)dev_pool_get(ctx, (size_t)s->nwords_mask * 4, &s->cap_mask))) return bail(PWMSCAN_ECUDA);
+        if (!(s->d_seg_off = (int64_t*)dev_pool_get(ctx, (size_t)(nseg + 1) * 8, &s->cap_seg))) return bail(PWMSCAN_ECUDA);
+    }
     s->d_seq2 = s->d_seq2_alloc + 1;
-    if (!(s->d_mask = (uint32_t*)dev_pool_get(ctx, (size_t)s->nwords_mask * 4, &s->cap_mask))) return bail(PWMSCAN_ECUDA);
-    if (!(s->d_seg_off = (int64_t*)dev_pool_get(ctx, (size_t)(nseg + 1) * 8, &s->cap_seg))) return bail(PWMSCAN_ECUDA);
     if ((e = cudaMemcpyAsync(s->d_seg_off, s->seg_off.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, lane->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(seg_off)"));
     // the raw bytes: either kept (upper-cased in place by the pack kernel) or a scratch buffer
-    if (flags & PWMSCAN_SEQ_KEEP_ASCII) {
+    if ((flags & PWMSCAN_SEQ_KEEP_ASCII) && lane_owned) {
+        if (!(s->d_ascii = (uint8_t*)lane_scratch_get(ctx, lane, 0, (size_t)len + 64))) return bail(PWMSCAN_ECUDA);
+        *d_raw_out = s->d_ascii;
+    } else if (flags & PWMSCAN_SEQ_KEEP_ASCII) {
         if (!(s->d_ascii = (uint8_t*)dev_pool_get(ctx, (size_t)len + 64, &s->cap_ascii))) return bail(PWMSCAN_ECUDA);
         *d_raw_out = s->d_ascii;
     } else {
@@ -466,7 +483,7 @@ extern "C" int pwmscan_seq_first_invalid(pwmscan_ctx* ctx, const pwmscan_seq* se
 
 extern "C" void pwmscan_seq_free(pwmscan_seq* s) {
     if (!s) return;
-    if (s->ctx) {
+    if (s->ctx && !s->borrowed) {
         dev_pool_put(s->ctx, s->d_seq2_alloc, s->cap_seq2);
         dev_pool_put(s->ctx, s->d_mask, s->cap_mask);
         dev_pool_put(s->ctx, s->d_ascii, s->cap_ascii);
@@ -1438,7 +1455,7 @@ int job_init_host(pwmscan_ctx* ctx, ScanJob& j, ScanLane* lane, const pwmscan_pl
     if (!pl->skip) flags |= PWMSCAN_SEQ_KEEP_ASCII;
     pwmscan_seq* s = nullptr;
     uint8_t* d_raw = nullptr;
-    int rc = seq_alloc(ctx, lane, seg_off, nseg, flags, &s, &d_raw);
+    int rc = seq_alloc(ctx, lane, seg_off, nseg, flags, &s, &d_raw, true);
     if (rc) return rc;
     j.up.ascii = ascii; j.up.d_raw = d_raw; j.up.seq = s;
     j.seq = s;

@@ -332,6 +332,20 @@ class AlignSet:
             self.ctx.check(self.ctx.L.pwmscan_alnset_pairs(self.h, C.c_int64(n), pa, pb, _ptr(d), _ptr(sd), _ptr(pos)))
         return d, sd, pos
 
+    def _next(self, call):
+        i, j, d, sd, pos = C.c_int32(-1), C.c_int32(-1), C.c_double(0.0), C.c_uint8(0), C.c_int32(0)
+        self.ctx.check(call(C.byref(i), C.byref(j), C.byref(d), C.byref(sd), C.byref(pos)))
+        return (None if i.value < 0 else (int(i.value), int(j.value), float(d.value), bool(sd.value), int(pos.value)))
+
+    def matrix_init(self):
+        """All-pairs matrix of iterativeMerge kept on the device; returns its first minimum (i, j, d, isSame, pos) or None."""
+        return self._next(lambda *o: self.ctx.L.pwmscan_alnset_matrix_init(self.h, *o))
+
+    def merge_step(self, i, j, mat):
+        """Slot j has been merged into slot i (new PWM `mat`): update the resident matrix, return the next minimum or None."""
+        m = _arr(mat, np.float64).reshape(-1, 4)
+        return self._next(lambda *o: self.ctx.L.pwmscan_alnset_merge_step(self.h, C.c_int32(i), C.c_int32(j), C.c_int32(m.shape[0]), _ptr(m), *o))
+
     def free(self):
         if self.h:
             self.ctx.L.pwmscan_alnset_free(self.h)

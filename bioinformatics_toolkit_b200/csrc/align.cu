@@ -20,7 +20,8 @@ struct AlignDev {
     const double* logs;      // same layout: log2 of the entries (host glibc)
     const int64_t* col_off;  // [2m+s] column offset
     const int32_t* ncol;     // [m]
-    const double* opti;      // [(x * 65 + y) * 64 + i] = optimalSc x y !! i
+    const double* opti;      // [(x * (maxc + 1) + y) * maxc + i] = optimalSc x y !! i
+    int maxc;                // longest PWM the opti table covers (64 for pwmscan_motifs; alignment sets grow)
 };
 
 __device__ __forceinline__ void run_pair(const AlignCfg& cfg, const AlignDev& d, int i, int j, double* dist,
@@ -29,7 +30,7 @@ __device__ __forceinline__ void run_pair(const AlignCfg& cfg, const AlignDev& d,
     const int64_t o1 = 4 * d.col_off[2 * i], o2 = 4 * d.col_off[2 * j], o2r = 4 * d.col_off[2 * j + 1];
     double dd; int sd, pp, am = 0;
     align_pair(cfg, d.mats + o1, d.logs + o1, n1, d.mats + o2, d.logs + o2, d.mats + o2r, d.logs + o2r, n2,
-               d.opti + ((size_t)n1 * 65 + n2) * 64, d.opti + ((size_t)n2 * 65 + n1) * 64, &dd, &sd, &pp, &am);
+               d.opti + ((size_t)n1 * (d.maxc + 1) + n2) * d.maxc, d.opti + ((size_t)n2 * (d.maxc + 1) + n1) * d.maxc, &dd, &sd, &pp, &am);
     dist[k] = dd; same_dir[k] = (uint8_t)sd; pos[k] = pp; amb[k] = (uint8_t)am;
 }
 
@@ -93,7 +94,7 @@ int launch_and_collect(pwmscan_ctx* ctx, const AlignCfg& cfg, const AlignDev& de
         const size_t o1 = 4 * (size_t)col_off[2 * i], o2 = 4 * (size_t)col_off[2 * j], o2r = 4 * (size_t)col_off[2 * j + 1];
         double dd; int sd, pp, am = 0;
         align_pair(cfg, h_mats + o1, h_logs + o1, n1, h_mats + o2, h_logs + o2, h_mats + o2r, h_logs + o2r, n2,
-                   h_opti + ((size_t)n1 * 65 + n2) * 64, h_opti + ((size_t)n2 * 65 + n1) * 64, &dd, &sd, &pp, &am);
+                   h_opti + ((size_t)n1 * (dev.maxc + 1) + n2) * dev.maxc, h_opti + ((size_t)n2 * (dev.maxc + 1) + n1) * dev.maxc, &dd, &sd, &pp, &am);
         dist[k] = dd; same_dir[k] = (uint8_t)sd; pos[k] = pp;
         ++namb;
     };
@@ -152,7 +153,7 @@ int run_align(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int64_t npairs, const 
     PWM_CUDA(cudaMemcpyAsync(d_opti, h_opti.data(), b_opti, cudaMemcpyHostToDevice, ctx->stream));
     PWM_CUDA(cudaMemcpyAsync(d_off, mo->col_off.data(), b_off, cudaMemcpyHostToDevice, ctx->stream));
     PWM_CUDA(cudaMemcpyAsync(d_n, h_n.data(), b_n, cudaMemcpyHostToDevice, ctx->stream));
-    AlignDev dev{d_mats, d_logs, d_off, d_n, d_opti};
+    AlignDev dev{d_mats, d_logs, d_off, d_n, d_opti, 64};
     return launch_and_collect(ctx, cfg, dev, M, h_mats.data(), h_logs.data(), mo->col_off.data(), h_n.data(), h_opti.data(), npairs, pa, pb,
                               dist, same_dir, pos);
 }
@@ -175,36 +176,231 @@ extern "C" int pwmscan_align_pairs(pwmscan_ctx* ctx, const pwmscan_motifs* mo, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Resident alignment set: the PWMs of iterativeMerge stay on the device (Merge.hs:113-170).  The
-// all-pairs initialisation (161-165) and every row refresh (138-145) run on the same device arrays;
-// a merge replaces one slot in place (its matrix, reverse complement and log2 table) instead of
-// re-uploading every motif.  Slots have a fixed stride of 64 columns; the optimalSc table covers
-// every length pair up to 64 x 64, so merged PWMs of new lengths need nothing else.
+// Resident alignment set: the PWMs AND the distance matrix of iterativeMerge stay on the device
+// (Merge.hs:113-170).  The all-pairs initialisation (161-165), every row refresh (138-145) and the
+// search for the next pair to merge (the first minimum in row-major order, strict <: 149-158) run on
+// the same device arrays; a merge replaces one slot in place (its matrix, reverse complement and log2
+// table) and only the five numbers of the next minimum come back.  Slots have a fixed stride of `maxc`
+// columns (64 to begin with); a merged PWM that is longer makes the set grow (stride doubled, optimalSc
+// table rebuilt) up to kAlnMaxCols columns — the reference has no limit, merged PWMs of real motif
+// collections stay far below it.
 // ------------------------------------------------------------------------------------------------
+constexpr int kAlnMaxCols = 256;
+
 struct pwmscan_alnset {
     pwmscan_ctx* ctx = nullptr;
     int32_t M = 0;
+    int maxc = 64;
     AlignCfg cfg;
     std::vector<int32_t> n;           // columns per slot
-    std::vector<int64_t> col_off;     // [2m+s] = (2m+s) * 64 (column offsets, fixed stride)
-    std::vector<double> mats, logs;   // host mirror, [(2m+s) * 256]
-    std::vector<double> opti;         // [(x * 65 + y) * 64 + i]
+    std::vector<int64_t> col_off;     // [2m+s] = (2m+s) * maxc (column offsets, fixed stride)
+    std::vector<double> mats, logs;   // host mirror, [(2m+s) * 4 * maxc]
+    std::vector<double> opti;         // [(x * (maxc + 1) + y) * maxc + i]
     double *d_mats = nullptr, *d_logs = nullptr, *d_opti = nullptr;
     int64_t* d_off = nullptr;
     int32_t* d_n = nullptr;
+    // the matrix of iterativeMerge (pwmscan_alnset_matrix_init / _merge_step): entry (r, c), r < c, both slots alive;
+    // +inf everywhere else
+    double* d_D = nullptr;
+    uint8_t* d_SD = nullptr;
+    int32_t* d_POS = nullptr;
+    uint8_t* d_alive = nullptr;
+    unsigned long long* d_amb = nullptr;      // [0] count, [1..] r * M + c of entries whose decision was a near-tie
+    unsigned long long* d_part = nullptr;     // argmin partials: (value bits, index) per CTA + the final one
+    std::vector<uint8_t> alive;
 };
 
 namespace {
 
 void alnset_fill_slot(pwmscan_alnset* a, int32_t m, int32_t ncol, const double* mat) {
+    const size_t stride = 4 * (size_t)a->maxc;
     a->n[m] = ncol;
-    double* f = a->mats.data() + (size_t)(2 * m) * 256;
-    double* r = f + 256;
-    std::memset(f, 0, 512 * sizeof(double));
+    double* f = a->mats.data() + (size_t)(2 * m) * stride;
+    double* r = f + stride;
+    std::memset(f, 0, 2 * stride * sizeof(double));
     for (int e = 0; e < 4 * ncol; ++e) { f[e] = mat[e]; r[e] = mat[4 * ncol - 1 - e]; }      // rcPWM: reversed flattening (Motif.hs:77-78)
-    double* lf = a->logs.data() + (size_t)(2 * m) * 256;
-    for (int e = 0; e < 512; ++e) lf[e] = 0.0;
-    for (int e = 0; e < 4 * ncol; ++e) { lf[e] = std::log(f[e]) / a->cfg.ln2; lf[256 + e] = std::log(r[e]) / a->cfg.ln2; }
+    double* lf = a->logs.data() + (size_t)(2 * m) * stride;
+    for (size_t e = 0; e < 2 * stride; ++e) lf[e] = 0.0;
+    for (int e = 0; e < 4 * ncol; ++e) { lf[e] = std::log(f[e]) / a->cfg.ln2; lf[stride + e] = std::log(r[e]) / a->cfg.ln2; }
+}
+
+void alnset_free_device(pwmscan_alnset* a) {
+    if (a->d_mats) cudaFree(a->d_mats);
+    if (a->d_logs) cudaFree(a->d_logs);
+    if (a->d_opti) cudaFree(a->d_opti);
+    if (a->d_off) cudaFree(a->d_off);
+    if (a->d_n) cudaFree(a->d_n);
+    a->d_mats = a->d_logs = a->d_opti = nullptr; a->d_off = nullptr; a->d_n = nullptr;
+}
+
+// (Re)builds the optimalSc table and the device copies for the set's current maxc from the host mirror.
+int alnset_upload(pwmscan_alnset* a) {
+    pwmscan_ctx* ctx = a->ctx;
+    const int mc = a->maxc;
+    a->opti.assign((size_t)(mc + 1) * (mc + 1) * mc, 0.0);
+    for (int x = 1; x <= mc; ++x)
+        for (int y = 1; y <= mc; ++y) aln_optimal_sc(a->cfg, x, y, a->opti.data() + ((size_t)x * (mc + 1) + y) * mc);
+    for (int m = 0; m < 2 * a->M; ++m) a->col_off[m] = (int64_t)m * mc;
+    alnset_free_device(a);
+    const size_t b_m = a->mats.size() * 8;
+    PWM_CUDA(cudaMalloc((void**)&a->d_mats, b_m));
+    PWM_CUDA(cudaMalloc((void**)&a->d_logs, b_m));
+    PWM_CUDA(cudaMalloc((void**)&a->d_opti, a->opti.size() * 8));
+    PWM_CUDA(cudaMalloc((void**)&a->d_off, a->col_off.size() * 8));
+    PWM_CUDA(cudaMalloc((void**)&a->d_n, (size_t)a->M * 4));
+    PWM_CUDA(cudaMemcpy(a->d_mats, a->mats.data(), b_m, cudaMemcpyHostToDevice));
+    PWM_CUDA(cudaMemcpy(a->d_logs, a->logs.data(), b_m, cudaMemcpyHostToDevice));
+    PWM_CUDA(cudaMemcpy(a->d_opti, a->opti.data(), a->opti.size() * 8, cudaMemcpyHostToDevice));
+    PWM_CUDA(cudaMemcpy(a->d_off, a->col_off.data(), a->col_off.size() * 8, cudaMemcpyHostToDevice));
+    PWM_CUDA(cudaMemcpy(a->d_n, a->n.data(), (size_t)a->M * 4, cudaMemcpyHostToDevice));
+    return PWMSCAN_OK;
+}
+
+// Makes room for PWMs of `need` columns: new stride, host mirrors re-laid, everything re-uploaded.
+int alnset_grow(pwmscan_alnset* a, int need) {
+    int mc = a->maxc;
+    while (mc < need) mc *= 2;
+    if (mc > kAlnMaxCols) mc = kAlnMaxCols;
+    const size_t os = 4 * (size_t)a->maxc, ns = 4 * (size_t)mc;
+    std::vector<double> m2((size_t)2 * a->M * ns, 0.0), l2((size_t)2 * a->M * ns, 0.0);
+    for (int m = 0; m < 2 * a->M; ++m) {
+        std::memcpy(m2.data() + (size_t)m * ns, a->mats.data() + (size_t)m * os, os * 8);
+        std::memcpy(l2.data() + (size_t)m * ns, a->logs.data() + (size_t)m * os, os * 8);
+    }
+    a->mats.swap(m2); a->logs.swap(l2);
+    a->maxc = mc;
+    return alnset_upload(a);
+}
+
+AlignDev alnset_dev(const pwmscan_alnset* a) { return AlignDev{a->d_mats, a->d_logs, a->d_off, a->d_n, a->d_opti, a->maxc}; }
+
+// ---- the resident matrix ------------------------------------------------------------------------
+__device__ __forceinline__ void mat_store(const AlignCfg& cfg, const AlignDev& d, int M, int r, int c, double* D, uint8_t* SD, int32_t* POS,
+                                          unsigned long long* amb) {
+    const int n1 = d.ncol[r], n2 = d.ncol[c];
+    const int64_t o1 = 4 * d.col_off[2 * r], o2 = 4 * d.col_off[2 * c], o2r = 4 * d.col_off[2 * c + 1];
+    double dd; int sd, pp, am = 0;
+    align_pair(cfg, d.mats + o1, d.logs + o1, n1, d.mats + o2, d.logs + o2, d.mats + o2r, d.logs + o2r, n2,
+               d.opti + ((size_t)n1 * (d.maxc + 1) + n2) * d.maxc, d.opti + ((size_t)n2 * (d.maxc + 1) + n1) * d.maxc, &dd, &sd, &pp, &am);
+    const size_t k = (size_t)r * M + c;
+    D[k] = dd; SD[k] = (uint8_t)sd; POS[k] = pp;
+    if (am) { const unsigned long long q = atomicAdd(&amb[0], 1ull); amb[1 + q] = (unsigned long long)k; }
+}
+
+// all r < c; the rest of the matrix is +inf
+__global__ void alnmat_fill_kernel(AlignCfg cfg, AlignDev d, int M, double* D, uint8_t* SD, int32_t* POS, unsigned long long* amb) {
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M) return;
+    if (c <= r) { D[(size_t)r * M + c] = __longlong_as_double(0x7FF0000000000000LL); return; }
+    mat_store(cfg, d, M, r, c, D, SD, POS, amb);
+}
+
+// after slot j was merged into slot i: column and row j are blanked (Merge.hs:135: the matrix is symmetric), slot i is
+// re-aligned against every slot still alive, argument order by index (138-145)
+__global__ void alnmat_refresh_kernel(AlignCfg cfg, AlignDev d, int M, int i, int j, const uint8_t* __restrict__ alive, double* D, uint8_t* SD,
+                                      int32_t* POS, unsigned long long* amb) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    D[(size_t)q * M + j] = inf;
+    D[(size_t)j * M + q] = inf;
+    if (q == i || q == j || !alive[q]) return;
+    if (i < q) mat_store(cfg, d, M, i, q, D, SD, POS, amb); else mat_store(cfg, d, M, q, i, D, SD, POS, amb);
+}
+
+// entries the host re-evaluated (near-ties): k = r * M + c
+__global__ void alnmat_patch_kernel(int n, const unsigned long long* __restrict__ k, const double* __restrict__ dd, const int32_t* __restrict__ pp,
+                                    const uint8_t* __restrict__ sd, double* D, uint8_t* SD, int32_t* POS) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    D[k[t]] = dd[t]; SD[k[t]] = sd[t]; POS[k[t]] = pp[t];
+}
+
+// first minimum in row-major order (strict <): the smallest (value, index) pair.  Distances are >= 0, so the bit pattern of
+// a double orders like the value and one 128-bit comparison does both.
+__device__ __forceinline__ void argmin_combine(unsigned long long& v, unsigned long long& k, unsigned long long v2, unsigned long long k2) {
+    if (v2 < v || (v2 == v && k2 < k)) { v = v2; k = k2; }
+}
+__global__ void __launch_bounds__(256) alnmat_argmin_kernel(const double* __restrict__ D, unsigned long long n, unsigned long long* __restrict__ part) {
+    __shared__ unsigned long long sv[8], sk[8];
+    unsigned long long v = ~0ull, k = ~0ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x)
+        argmin_combine(v, k, (unsigned long long)__double_as_longlong(D[t]), t);
+    for (int o = 16; o > 0; o >>= 1) argmin_combine(v, k, __shfl_xor_sync(0xFFFFFFFFu, v, o), __shfl_xor_sync(0xFFFFFFFFu, k, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; sk[threadIdx.x >> 5] = k; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) argmin_combine(v, k, sv[w], sk[w]);
+        part[2 * blockIdx.x] = v; part[2 * blockIdx.x + 1] = k;
+    }
+}
+__global__ void alnmat_argmin_final_kernel(int nparts, unsigned long long* part, const uint8_t* __restrict__ SD, const int32_t* __restrict__ POS) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long v = ~0ull, k = ~0ull;
+    for (int p = 0; p < nparts; ++p) argmin_combine(v, k, part[2 * p], part[2 * p + 1]);
+    unsigned long long* out = part + 2 * nparts;              // [value bits, index, same_dir, pos]
+    out[0] = v; out[1] = k;
+    const bool none = v >= 0x7FF0000000000000ull;
+    out[2] = none ? 0ull : (unsigned long long)SD[k];
+    out[3] = none ? 0ull : (unsigned long long)(long long)POS[k];
+}
+
+constexpr int kArgminParts = 592;
+
+// Resolves the near-ties recorded by the last fill / refresh on the host (same function, glibc), patches the matrix and
+// returns the first minimum.  ctx->mu held.
+int alnmat_settle_and_argmin(pwmscan_alnset* a, int32_t* oi, int32_t* oj, double* od, uint8_t* osd, int32_t* opos) {
+    pwmscan_ctx* ctx = a->ctx;
+    const int M = a->M;
+    unsigned long long namb = 0;
+    PWM_CUDA(cudaMemcpyAsync(&namb, a->d_amb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PWM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (namb > 0) {
+        std::vector<unsigned long long> ks((size_t)namb);
+        PWM_CUDA(cudaMemcpy(ks.data(), a->d_amb + 1, (size_t)namb * 8, cudaMemcpyDeviceToHost));
+        std::vector<double> dd((size_t)namb);
+        std::vector<int32_t> pp((size_t)namb);
+        std::vector<uint8_t> sd((size_t)namb);
+        const int mc = a->maxc;
+        for (size_t t = 0; t < (size_t)namb; ++t) {
+            const int r = (int)(ks[t] / (unsigned long long)M), c = (int)(ks[t] % (unsigned long long)M);
+            const int n1 = a->n[r], n2 = a->n[c];
+            const size_t o1 = 4 * (size_t)a->col_off[2 * r], o2 = 4 * (size_t)a->col_off[2 * c], o2r = 4 * (size_t)a->col_off[2 * c + 1];
+            double d; int s, p, am = 0;
+            align_pair(a->cfg, a->mats.data() + o1, a->logs.data() + o1, n1, a->mats.data() + o2, a->logs.data() + o2, a->mats.data() + o2r,
+                       a->logs.data() + o2r, n2, a->opti.data() + ((size_t)n1 * (mc + 1) + n2) * mc, a->opti.data() + ((size_t)n2 * (mc + 1) + n1) * mc,
+                       &d, &s, &p, &am);
+            dd[t] = d; sd[t] = (uint8_t)s; pp[t] = p;
+        }
+        const size_t nb = (size_t)namb;
+        unsigned char* d_p = (unsigned char*)scratch_get(ctx, 1, nb * 24 + 64);
+        if (!d_p) return PWMSCAN_ECUDA;
+        unsigned long long* d_k = (unsigned long long*)d_p;
+        double* d_dd = (double*)(d_p + nb * 8);
+        int32_t* d_pp = (int32_t*)(d_p + nb * 16);
+        uint8_t* d_sd = d_p + nb * 20;
+        PWM_CUDA(cudaMemcpyAsync(d_k, ks.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PWM_CUDA(cudaMemcpyAsync(d_dd, dd.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PWM_CUDA(cudaMemcpyAsync(d_pp, pp.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PWM_CUDA(cudaMemcpyAsync(d_sd, sd.data(), nb, cudaMemcpyHostToDevice, ctx->stream));
+        alnmat_patch_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>((int)nb, d_k, d_dd, d_pp, d_sd, a->d_D, a->d_SD, a->d_POS);
+        PWM_CUDA(cudaGetLastError());
+        PWM_CUDA(cudaStreamSynchronize(ctx->stream));        // the host vectors go out of scope
+    }
+    ctx->timing[11] += (double)namb;
+    alnmat_argmin_kernel<<<kArgminParts, 256, 0, ctx->stream>>>(a->d_D, (unsigned long long)M * M, a->d_part);
+    alnmat_argmin_final_kernel<<<1, 32, 0, ctx->stream>>>(kArgminParts, a->d_part, a->d_SD, a->d_POS);
+    PWM_CUDA(cudaGetLastError());
+    unsigned long long res[4];
+    PWM_CUDA(cudaMemcpyAsync(res, a->d_part + 2 * kArgminParts, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PWM_CUDA(cudaStreamSynchronize(ctx->stream));
+    double d;
+    std::memcpy(&d, &res[0], 8);
+    if (res[0] >= 0x7FF0000000000000ull) { *oi = -1; *oj = -1; *od = d; *osd = 0; *opos = 0; return PWMSCAN_OK; }
+    *oi = (int32_t)(res[1] / (unsigned long long)M); *oj = (int32_t)(res[1] % (unsigned long long)M);
+    *od = d; *osd = (uint8_t)res[2]; *opos = (int32_t)(long long)res[3];
+    return PWMSCAN_OK;
 }
 
 }  // namespace
@@ -215,38 +411,28 @@ extern "C" int pwmscan_alnset_create(pwmscan_ctx* ctx, int32_t M, const int32_t*
     *out = nullptr;
     if (penalty_kind < 0 || penalty_kind > 3 || combine_kind < 0 || combine_kind > 3)
         return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_align: unknown penalty / combine kind");
-    for (int m = 0; m < M; ++m)
-        if (ncol[m] < 1 || ncol[m] > PWMSCAN_MAX_COLS) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_alnset_create: motif length outside 1..64");
+    int longest = 1;
+    for (int m = 0; m < M; ++m) {
+        if (ncol[m] < 1 || ncol[m] > kAlnMaxCols) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_alnset_create: motif length outside 1..256");
+        longest = std::max(longest, (int)ncol[m]);
+    }
     std::lock_guard<std::mutex> lk(ctx->mu);
     PWM_CUDA(cudaSetDevice(ctx->device));
     pwmscan_alnset* a = new (std::nothrow) pwmscan_alnset();
     if (!a) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
     a->ctx = ctx; a->M = M;
+    while (a->maxc < longest) a->maxc *= 2;
     a->cfg.penal_kind = penalty_kind; a->cfg.comb_kind = combine_kind; a->cfg.gap = gap; a->cfg.ln2 = std::log(2.0);
     a->n.resize(M); a->col_off.resize((size_t)2 * M);
-    a->mats.assign((size_t)2 * M * 256, 0.0); a->logs.assign((size_t)2 * M * 256, 0.0);
+    a->mats.assign((size_t)2 * M * 4 * a->maxc, 0.0); a->logs.assign((size_t)2 * M * 4 * a->maxc, 0.0);
+    a->alive.assign((size_t)M, 1);
     const double* p = mats;
     for (int m = 0; m < M; ++m) {
-        a->col_off[2 * m] = (int64_t)(2 * m) * 64; a->col_off[2 * m + 1] = (int64_t)(2 * m + 1) * 64;
         alnset_fill_slot(a, m, ncol[m], p);
         p += 4 * ncol[m];
     }
-    a->opti.assign((size_t)65 * 65 * 64, 0.0);
-    for (int x = 1; x <= 64; ++x)
-        for (int y = 1; y <= 64; ++y) aln_optimal_sc(a->cfg, x, y, a->opti.data() + ((size_t)x * 65 + y) * 64);
-    cudaError_t e;
-    auto bail = [&](cudaError_t err, const char* what) { const int rc = cuda_fail(ctx, err, what); pwmscan_alnset_free(a); return rc; };
-    const size_t b_m = a->mats.size() * 8;
-    if ((e = cudaMalloc((void**)&a->d_mats, b_m)) != cudaSuccess) return bail(e, "cudaMalloc(alnset mats)");
-    if ((e = cudaMalloc((void**)&a->d_logs, b_m)) != cudaSuccess) return bail(e, "cudaMalloc(alnset logs)");
-    if ((e = cudaMalloc((void**)&a->d_opti, a->opti.size() * 8)) != cudaSuccess) return bail(e, "cudaMalloc(alnset opti)");
-    if ((e = cudaMalloc((void**)&a->d_off, a->col_off.size() * 8)) != cudaSuccess) return bail(e, "cudaMalloc(alnset off)");
-    if ((e = cudaMalloc((void**)&a->d_n, (size_t)M * 4)) != cudaSuccess) return bail(e, "cudaMalloc(alnset n)");
-    if ((e = cudaMemcpy(a->d_mats, a->mats.data(), b_m, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload alnset");
-    if ((e = cudaMemcpy(a->d_logs, a->logs.data(), b_m, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload alnset");
-    if ((e = cudaMemcpy(a->d_opti, a->opti.data(), a->opti.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload alnset");
-    if ((e = cudaMemcpy(a->d_off, a->col_off.data(), a->col_off.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload alnset");
-    if ((e = cudaMemcpy(a->d_n, a->n.data(), (size_t)M * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload alnset");
+    int rc = alnset_upload(a);
+    if (rc) { pwmscan_alnset_free(a); return rc; }
     *out = a;
     return PWMSCAN_OK;
 }
@@ -254,28 +440,40 @@ extern "C" int pwmscan_alnset_create(pwmscan_ctx* ctx, int32_t M, const int32_t*
 extern "C" void pwmscan_alnset_free(pwmscan_alnset* a) {
     if (!a) return;
     if (a->ctx) cudaSetDevice(a->ctx->device);
-    if (a->d_mats) cudaFree(a->d_mats);
-    if (a->d_logs) cudaFree(a->d_logs);
-    if (a->d_opti) cudaFree(a->d_opti);
-    if (a->d_off) cudaFree(a->d_off);
-    if (a->d_n) cudaFree(a->d_n);
+    alnset_free_device(a);
+    if (a->d_D) cudaFree(a->d_D);
+    if (a->d_SD) cudaFree(a->d_SD);
+    if (a->d_POS) cudaFree(a->d_POS);
+    if (a->d_alive) cudaFree(a->d_alive);
+    if (a->d_amb) cudaFree(a->d_amb);
+    if (a->d_part) cudaFree(a->d_part);
     delete a;
+}
+
+// Replaces the PWM of a slot (host mirror + device); grows the set if the PWM is longer than the current stride.  ctx->mu held.
+static int alnset_update_locked(pwmscan_alnset* a, int32_t slot, int32_t ncol, const double* mat) {
+    pwmscan_ctx* ctx = a->ctx;
+    if (slot < 0 || slot >= a->M) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_alnset_update: slot out of range");
+    if (ncol < 1 || ncol > kAlnMaxCols) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_alnset_update: motif length outside 1..256");
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    if (ncol > a->maxc) {
+        PWM_CUDA(cudaStreamSynchronize(ctx->stream));
+        int rc = alnset_grow(a, ncol);
+        if (rc) return rc;
+    }
+    alnset_fill_slot(a, slot, ncol, mat);
+    const size_t stride = 4 * (size_t)a->maxc, o = (size_t)(2 * slot) * stride;
+    PWM_CUDA(cudaMemcpyAsync(a->d_mats + o, a->mats.data() + o, 2 * stride * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PWM_CUDA(cudaMemcpyAsync(a->d_logs + o, a->logs.data() + o, 2 * stride * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PWM_CUDA(cudaMemcpyAsync(a->d_n + slot, a->n.data() + slot, 4, cudaMemcpyHostToDevice, ctx->stream));
+    PWM_CUDA(cudaStreamSynchronize(ctx->stream));        // the host mirror may be rewritten by the next update
+    return PWMSCAN_OK;
 }
 
 extern "C" int pwmscan_alnset_update(pwmscan_alnset* a, int32_t slot, int32_t ncol, const double* mat) {
     if (!a || !mat) return PWMSCAN_EINVAL;
-    pwmscan_ctx* ctx = a->ctx;
-    if (slot < 0 || slot >= a->M) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_alnset_update: slot out of range");
-    if (ncol < 1 || ncol > PWMSCAN_MAX_COLS) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_alnset_update: motif length outside 1..64");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PWM_CUDA(cudaSetDevice(ctx->device));
-    alnset_fill_slot(a, slot, ncol, mat);
-    const size_t o = (size_t)(2 * slot) * 256;
-    PWM_CUDA(cudaMemcpyAsync(a->d_mats + o, a->mats.data() + o, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    PWM_CUDA(cudaMemcpyAsync(a->d_logs + o, a->logs.data() + o, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    PWM_CUDA(cudaMemcpyAsync(a->d_n + slot, a->n.data() + slot, 4, cudaMemcpyHostToDevice, ctx->stream));
-    PWM_CUDA(cudaStreamSynchronize(ctx->stream));        // the host mirror may be rewritten by the next update
-    return PWMSCAN_OK;
+    std::lock_guard<std::mutex> lk(a->ctx->mu);
+    return alnset_update_locked(a, slot, ncol, mat);
 }
 
 extern "C" int pwmscan_alnset_pairs(pwmscan_alnset* a, int64_t npairs, const int32_t* pa, const int32_t* pb, double* dist,
@@ -291,7 +489,55 @@ extern "C" int pwmscan_alnset_pairs(pwmscan_alnset* a, int64_t npairs, const int
         if (pa[k] < 0 || pa[k] >= a->M || pb[k] < 0 || pb[k] >= a->M) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_alnset_pairs: slot out of range");
     std::lock_guard<std::mutex> lk(ctx->mu);
     PWM_CUDA(cudaSetDevice(ctx->device));
-    AlignDev dev{a->d_mats, a->d_logs, a->d_off, a->d_n, a->d_opti};
-    return launch_and_collect(ctx, a->cfg, dev, a->M, a->mats.data(), a->logs.data(), a->col_off.data(), a->n.data(), a->opti.data(), npairs,
+    return launch_and_collect(ctx, a->cfg, alnset_dev(a), a->M, a->mats.data(), a->logs.data(), a->col_off.data(), a->n.data(), a->opti.data(), npairs,
                               pa, pb, dist, same_dir, pos);
+}
+
+extern "C" int pwmscan_alnset_matrix_init(pwmscan_alnset* a, int32_t* i, int32_t* j, double* d, uint8_t* same_dir, int32_t* pos) {
+    if (!a || !i || !j || !d || !same_dir || !pos) return PWMSCAN_EINVAL;
+    pwmscan_ctx* ctx = a->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PWM_CUDA(cudaSetDevice(ctx->device));
+    const size_t MM = (size_t)a->M * a->M;
+    if (!a->d_D) {
+        PWM_CUDA(cudaMalloc((void**)&a->d_D, MM * 8));
+        PWM_CUDA(cudaMalloc((void**)&a->d_SD, MM));
+        PWM_CUDA(cudaMalloc((void**)&a->d_POS, MM * 4));
+        PWM_CUDA(cudaMalloc((void**)&a->d_alive, (size_t)a->M));
+        PWM_CUDA(cudaMalloc((void**)&a->d_amb, (MM / 2 + 2) * 8));
+        PWM_CUDA(cudaMalloc((void**)&a->d_part, (size_t)(2 * kArgminParts + 4) * 8));
+    }
+    std::fill(a->alive.begin(), a->alive.end(), (uint8_t)1);
+    PWM_CUDA(cudaMemsetAsync(a->d_alive, 1, (size_t)a->M, ctx->stream));
+    PWM_CUDA(cudaMemsetAsync(a->d_amb, 0, 8, ctx->stream));
+    PWM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    dim3 grid((unsigned)((a->M + 127) / 128), (unsigned)a->M);
+    alnmat_fill_kernel<<<grid, 128, 0, ctx->stream>>>(a->cfg, alnset_dev(a), a->M, a->d_D, a->d_SD, a->d_POS, a->d_amb);
+    PWM_CUDA(cudaGetLastError());
+    PWM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->timing[11] = 0;
+    int rc = alnmat_settle_and_argmin(a, i, j, d, same_dir, pos);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing[10] = ms;
+    return rc;
+}
+
+extern "C" int pwmscan_alnset_merge_step(pwmscan_alnset* a, int32_t i, int32_t j, int32_t ncol, const double* mat, int32_t* ni, int32_t* nj,
+                                         double* d, uint8_t* same_dir, int32_t* pos) {
+    if (!a || !mat || !ni || !nj || !d || !same_dir || !pos) return PWMSCAN_EINVAL;
+    pwmscan_ctx* ctx = a->ctx;
+    if (!a->d_D) return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_alnset_merge_step: call pwmscan_alnset_matrix_init first");
+    if (i < 0 || j < 0 || i >= a->M || j >= a->M || i == j || !a->alive[i] || !a->alive[j])
+        return set_err(ctx, PWMSCAN_EINVAL, "pwmscan_alnset_merge_step: slots must be two different live slots");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = alnset_update_locked(a, i, ncol, mat);
+    if (rc) return rc;
+    a->alive[j] = 0;
+    PWM_CUDA(cudaMemsetAsync(a->d_alive + j, 0, 1, ctx->stream));
+    PWM_CUDA(cudaMemsetAsync(a->d_amb, 0, 8, ctx->stream));
+    alnmat_refresh_kernel<<<(unsigned)((a->M + 127) / 128), 128, 0, ctx->stream>>>(a->cfg, alnset_dev(a), a->M, i, j, a->d_alive, a->d_D, a->d_SD,
+                                                                                   a->d_POS, a->d_amb);
+    PWM_CUDA(cudaGetLastError());
+    return alnmat_settle_and_argmin(a, ni, nj, d, same_dir, pos);
 }

@@ -212,7 +212,7 @@ void pin_pool_put(pwmscan_ctx* ctx, void* p, size_t bytes);
 void* lane_scratch_get(pwmscan_ctx* ctx, ScanLane* lane, int slot, size_t bytes);
 int hits_expand_wide(pwmscan_hits* h);     // fills pos / motif / segment / strand (idempotent, thread-safe)
 // order.cu
-struct OrderWork { size_t nb, big_cap; unsigned int* cnt; unsigned long long *start, *cursor, *tiles, *big; };
+struct OrderWork { size_t nb, big_cap, med_cap; unsigned int* cnt; unsigned long long *start, *cursor, *tiles, *big, *med; };
 int order_pick_shift(unsigned long long n, int key_bits);
 size_t order_bucket_count(int key_bits, int shift);
 size_t order_work_bytes(size_t nb, size_t hit_cap);

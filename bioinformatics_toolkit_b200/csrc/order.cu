@@ -20,7 +20,8 @@ using namespace pwmscan;
 namespace {
 
 constexpr int kSortThreads = 256;               // CTA of the shared-memory sort (big buckets)
-constexpr int kWarpCap = 256;                   // hits one warp orders in registers (8 per lane)
+constexpr int kSpanCap = 64;                    // hits per span of whole buckets in the main sorting kernel (2 per lane)
+constexpr int kWarpCap = 256;                   // hits one warp orders in registers at most (8 per lane: the medium kernel)
 constexpr int kWarpIdxBits = 8;
 constexpr int kScanTile = 2048;                 // counters per CTA of the scan
 
@@ -196,11 +197,18 @@ __device__ __forceinline__ void warp_sort_span(unsigned long long s, int cnt, un
 }
 
 // One WARP per group of 32 consecutive buckets (grid-stride over the groups): the lanes fetch the 33 bucket boundaries with
-// two coalesced loads, then the warp walks the group in spans of whole buckets holding at most kWarpCap hits, each ordered
-// in registers (empty and tiny buckets cost nothing extra).  A single bucket above kWarpCap goes to the list of
-// bucket_sort_big_kernel: big[0] = number of listed buckets, big[1..] their indices.
+// two coalesced loads, then the warp walks the group in spans of whole buckets holding at most kSpanCap hits, each ordered
+// in registers (empty and tiny buckets cost nothing extra; short bitonic networks: ~6 instructions per hit).  A single
+// bucket above kSpanCap goes to the list of bucket_sort_medium_kernel (<= kWarpCap hits) or bucket_sort_big_kernel:
+// list[0] = number of listed buckets, list[1..] their indices.
+__device__ __forceinline__ void list_push(unsigned long long* list, unsigned long long cap, unsigned long long b, unsigned long long cnt, unsigned long long* flags) {
+    const unsigned long long k = atomicAdd(&list[0], 1ull);
+    if (k < cap) list[1 + k] = b; else atomicMax(&flags[0], cnt);      // (cannot happen: the lists have room for every such bucket)
+}
+
 __global__ void __launch_bounds__(256) bucket_sort_kernel(const unsigned long long* __restrict__ start, unsigned long long nb, int shift,
                                                           const unsigned long long* __restrict__ tkeys, SortOut so,
+                                                          unsigned long long* __restrict__ med, unsigned long long med_cap,
                                                           unsigned long long* __restrict__ big, unsigned long long big_cap, unsigned long long* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const unsigned long long nwarp = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -213,11 +221,11 @@ __global__ void __launch_bounds__(256) bucket_sort_kernel(const unsigned long lo
         int l0 = 0;
         while (l0 < 32) {
             const unsigned long long s0 = __shfl_sync(0xFFFFFFFFu, st, l0);
-            const unsigned fit = __ballot_sync(0xFFFFFFFFu, lane >= l0 && en - s0 <= (unsigned long long)kWarpCap);
-            if (fit == 0u) {                                          // bucket l0 alone is too large for a warp
+            const unsigned fit = __ballot_sync(0xFFFFFFFFu, lane >= l0 && en - s0 <= (unsigned long long)kSpanCap);
+            if (fit == 0u) {                                          // bucket l0 alone is too large for this kernel
                 if (lane == l0) {
-                    const unsigned long long k = atomicAdd(&big[0], 1ull);
-                    if (k < big_cap) big[1 + k] = b0 + l0; else atomicMax(&flags[0], en - st);   // (cannot happen: the list has room for every big bucket)
+                    if (en - st <= (unsigned long long)kWarpCap) list_push(med, med_cap, b0 + l0, en - st, flags);
+                    else list_push(big, big_cap, b0 + l0, en - st, flags);
                 }
                 ++l0;
                 continue;
@@ -225,12 +233,26 @@ __global__ void __launch_bounds__(256) bucket_sort_kernel(const unsigned long lo
             const int l1 = 32 - __clz((int)fit);                     // boundaries are non-decreasing: the fitting lanes are l0 .. l1-1
             const int cnt = (int)(__shfl_sync(0xFFFFFFFFu, en, l1 - 1) - s0);
             const unsigned long long base = shift < 64 ? ((b0 + (unsigned long long)l0) << shift) : 0ull;
-            if (cnt > 128) warp_sort_span<8>(s0, cnt, base, tkeys, so);
-            else if (cnt > 64) warp_sort_span<4>(s0, cnt, base, tkeys, so);
-            else if (cnt > 32) warp_sort_span<2>(s0, cnt, base, tkeys, so);
+            if (cnt > 32) warp_sort_span<2>(s0, cnt, base, tkeys, so);
             else if (cnt > 0) warp_sort_span<1>(s0, cnt, base, tkeys, so);
             l0 = l1;
         }
+    }
+}
+
+// One warp per listed bucket of kSpanCap < hits <= kWarpCap: the same register sort, 4 or 8 hits per lane.
+__global__ void __launch_bounds__(256) bucket_sort_medium_kernel(const unsigned long long* __restrict__ start, int shift,
+                                                                 const unsigned long long* __restrict__ tkeys, SortOut so,
+                                                                 const unsigned long long* __restrict__ med, unsigned long long med_cap) {
+    const unsigned long long nwarp = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long nmed = med[0] < med_cap ? med[0] : med_cap;
+    for (unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nmed; q += nwarp) {
+        const unsigned long long b = med[1 + q];
+        const unsigned long long s = start[b];
+        const int cnt = (int)(start[b + 1] - s);
+        const unsigned long long base = shift < 64 ? (b << shift) : 0ull;
+        if (cnt > 128) warp_sort_span<8>(s, cnt, base, tkeys, so);
+        else warp_sort_span<4>(s, cnt, base, tkeys, so);
     }
 }
 
@@ -304,8 +326,10 @@ size_t order_bucket_count(int key_bits, int shift) { return key_bits > shift ? (
 // cnt u32[nb] | start u64[nb+1] | cursor u64[nb] | tile sums | list of big buckets (1 + big_cap entries; a big bucket holds
 // more than kWarpCap hits, so hit_cap / kWarpCap + 1 entries always suffice)
 static size_t big_cap_of(size_t nb, size_t hit_cap) { return std::min(nb, hit_cap / kWarpCap + 1); }
+static size_t med_cap_of(size_t nb, size_t hit_cap) { return std::min(nb, hit_cap / kSpanCap + 1); }
 size_t order_work_bytes(size_t nb, size_t hit_cap) {
-    return ((nb * 4 + 63) & ~(size_t)63) + (nb + 1) * 8 + nb * 8 + ((nb + kScanTile - 1) / kScanTile + 1) * 8 + (big_cap_of(nb, hit_cap) + 1) * 8;
+    return ((nb * 4 + 63) & ~(size_t)63) + (nb + 1) * 8 + nb * 8 + ((nb + kScanTile - 1) / kScanTile + 1) * 8 + (big_cap_of(nb, hit_cap) + 1) * 8 +
+           (med_cap_of(nb, hit_cap) + 1) * 8;
 }
 
 OrderWork order_work_view(unsigned char* d_work, size_t nb, size_t hit_cap) {
@@ -317,6 +341,8 @@ OrderWork order_work_view(unsigned char* d_work, size_t nb, size_t hit_cap) {
     w.cursor = w.start + nb + 1;
     w.tiles = w.cursor + nb;
     w.big = w.tiles + (nb + kScanTile - 1) / kScanTile + 1;
+    w.med = w.big + w.big_cap + 1;
+    w.med_cap = med_cap_of(nb, hit_cap);
     return w;
 }
 
@@ -347,9 +373,11 @@ int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_
     SortOut so{d_tsc, d_skeys, d_score, d_pos32, d_seg32, d_ms16, kl, nseg > 1 ? 1 : 0};
     PWM_CUDA(cudaMemsetAsync(w.big, 0, 8, st));
     const unsigned grid_b = (unsigned)std::max<size_t>(1, std::min<size_t>((w.nb + 255) / 256, (size_t)sm * 8));      // 8 warps = 8 groups of 32 buckets per CTA
-    bucket_sort_kernel<<<grid_b, 256, 0, st>>>(w.start, w.nb, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
+    PWM_CUDA(cudaMemsetAsync(w.med, 0, 8, st));
+    bucket_sort_kernel<<<grid_b, 256, 0, st>>>(w.start, w.nb, shift, d_tkeys, so, w.med, w.med_cap, w.big, w.big_cap, d_flags);
+    bucket_sort_medium_kernel<<<sm * 4, 256, 0, st>>>(w.start, shift, d_tkeys, so, w.med, w.med_cap);
     bucket_sort_big_kernel<<<sm * 6, kSortThreads, 0, st>>>(w.start, shift, d_tkeys, so, w.big, w.big_cap, d_flags);
-    *launches += 1;
+    *launches += 2;
     *launches += 5;
     if (nseg == 1) {
         run_offsets_kernel<<<(2 * M + 1 + 255) / 256, 256, 0, st>>>(d_skeys, w.start, w.nb, shift, kl.pb, 2 * M, d_run_off);

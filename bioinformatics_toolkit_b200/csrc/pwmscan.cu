@@ -1121,7 +1121,7 @@ struct ScanJob {
 
 inline int bits_for(uint64_t max_value) { int b = 1; while (b < 63 && (max_value >> b) != 0) ++b; return b; }
 
-enum { EV_START = 0, EV_PRE = 1, EV_RES = 2, EV_ORD = 3, EV_GATE = 4, EV_A = 5, EV_B = 6 };
+enum { EV_START = 0, EV_PRE = 1, EV_RES = 2, EV_ORD = 3, EV_GATE = 4, EV_A = 5, EV_B = 6, EV_H2D0 = 7, EV_H2D1 = 8, EV_PSTART = 9 };
 enum { SL_RAW = 0, SL_CAND = 1, SL_KEYS = 2, SL_SC = 3, SL_WORK = 4, SL_TKEYS = 5, SL_TSC = 6, SL_SKEYS = 7, SL_OUT = 8 };
 
 void job_release(ScanJob& j) {
@@ -1227,6 +1227,7 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         if (!chained) {               // first-stage kernels of different lanes run one after the other
             if (ctx->prefilter_chain_valid) PWM_CUDA(cudaStreamWaitEvent(st, ctx->prefilter_chain, 0));
             if (!j.host || j.attempt > 0) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
+            PWM_CUDA(cudaEventRecord(lane->ev[EV_PSTART], st));
             chained = true;
         }
         if (use_km) {
@@ -1286,12 +1287,14 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         }
         PWM_CUDA(cudaEventRecord(lane->ev[EV_GATE], st));               // copies must not overtake the previous use of d_raw
         PWM_CUDA(cudaStreamWaitEvent(lane->copy_stream, lane->ev[EV_GATE], 0));
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_H2D0], lane->copy_stream));
         // (one copy stream: alternating two streams was measured slower, 6.7 vs 5.3 ms on C2)
         for (int l = 0; l < nch; ++l) {
             const int64_t b0 = bounds[l], b1 = bounds[l + 1];
             if (b1 > b0) PWM_CUDA(cudaMemcpyAsync(j.up.d_raw + b0, j.up.ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, lane->copy_stream));
             PWM_CUDA(cudaEventRecord(lane->chunk_ev[l], lane->copy_stream));
         }
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_H2D1], lane->copy_stream));
         long long scanned = 0;
         for (int l = 0; l < nch; ++l) {
             const bool last = (l == nch - 1);
@@ -1525,10 +1528,22 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
         }
         return scan_phase_a(ctx, j);
     };
+    static const bool trace = std::getenv("PWMSCAN_TRACE") != nullptr;       // per-item timeline on stderr (ms since the call started)
+    cudaEvent_t ref = nullptr;
+    if (trace) { cudaEventCreate(&ref); cudaEventRecord(ref, ctx->lanes[0]->stream); cudaEventSynchronize(ref); }
     auto finish = [&](int i) -> int {
         pwmscan_hits* h = nullptr;
-        int r = scan_phase_c(ctx, jobs[i % K], &h, t);
+        ScanJob& fj = jobs[i % K];
+        const bool had_hits = fj.nhits > 0, was_host = fj.host;
+        int r = scan_phase_c(ctx, fj, &h, t);
         if (r) return r;
+        if (trace) {
+            ScanLane* l = fj.lane;
+            auto at = [&](int e) { float ms = -1; cudaEventElapsedTime(&ms, ref, l->ev[e]); return ms; };
+            if (!had_hits) cudaEventSynchronize(l->ev[EV_A]);
+            std::fprintf(stderr, "[trace] item %3d lane %d: h2d %8.3f..%8.3f first-stage %8.3f..%8.3f rescore ..%8.3f order ..%8.3f d2h ..%8.3f\n", i, i % K,
+                         was_host ? at(EV_H2D0) : -1.f, was_host ? at(EV_H2D1) : -1.f, at(EV_PSTART), at(EV_PRE), at(EV_RES), at(EV_ORD), had_hits ? at(EV_B) : -1.f);
+        }
         if (cb) cb(user, i, h); else pwmscan_hits_free(h);
         return PWMSCAN_OK;
     };
@@ -1550,6 +1565,7 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
         for (int k = 0; k < K; ++k) job_release(jobs[k]);
         return rc;
     }
+    if (ref) cudaEventDestroy(ref);
     for (int i = 0; i < 12; ++i) ctx->timing[i] = t[i];
     return PWMSCAN_OK;
 }

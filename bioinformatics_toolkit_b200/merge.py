@@ -119,16 +119,33 @@ def mergeTreeWeighted(align, t):
 def iterativeMerge(align, th, motifs):
     """Merge.hs:113-170.  Returns [([names], PWM, weights)].
 
-    The distance matrix is initialised with one all-pairs call; with a device AlignFn the PWMs then stay resident on
-    the device (`align.resident`): a merge replaces one slot and refreshes one row, and the minimum is tracked per row
-    instead of re-scanning the N x N matrix.  An arbitrary Python `align` callable falls back to per-call alignment."""
+    With a device AlignFn the PWMs AND the distance matrix stay resident on the device (`align.resident`): a merge replaces
+    one slot, refreshes one row/column and finds the next minimum there; only that minimum comes back.  The host-matrix path
+    below (one all-pairs call, then per-row minimum tracking) serves AlignFns without a resident matrix; an arbitrary
+    Python `align` callable falls back to per-call alignment."""
     n = len(motifs)
     items = [([m._name], m._pwm, [1] * size(m._pwm)) for m in motifs]
     if n < 2:
         return items
     resident = align.resident([m._pwm for m in motifs]) if hasattr(align, "resident") else None
+    if resident is not None and hasattr(resident, "matrix_init"):
+        # the matrix, the row refresh and the search for the minimum all stay on the device (pwmscan_alnset_matrix_init /
+        # _merge_step); per merge only mergePWMWeighted runs here
+        try:
+            nxt = resident.matrix_init()                           # initialisation, Merge.hs:161-165 + the first `loop` (149-158)
+            while nxt is not None and nxt[2] < th:
+                i, j, _, same, p = nxt
+                nm1, pwm1, w1 = items[i]
+                nm2, pwm2, w2 = items[j]
+                pwm_, w_ = mergePWMWeighted((pwm1, w1), (pwm2, w2), p) if same else mergePWMWeighted((pwm1, w1), (rcPWM(pwm2), w2[::-1]), p)
+                items[i] = (nm1 + nm2, pwm_, w_)
+                items[j] = None
+                nxt = resident.merge_step(i, j, pwm_._mat)
+        finally:
+            resident.free()
+        return [it for it in items if it is not None]
     if resident is not None:
-        d, sd, pos = resident.pairs()                              # initialisation, Merge.hs:161-165
+        d, sd, pos = resident.pairs()
     else:
         d, sd, pos = align.all_pairs([m._pwm for m in motifs])
     D = np.full((n, n), np.inf)

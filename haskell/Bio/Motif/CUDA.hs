@@ -67,6 +67,8 @@ foreign import ccall safe "pwmscan_alnset_create"    c_alnset_create :: Ptr Ctx 
 foreign import ccall safe "pwmscan_alnset_update"    c_alnset_update :: Ptr AlnSet -> Int32 -> Int32 -> Ptr Double -> IO CInt
 foreign import ccall safe "pwmscan_alnset_pairs"     c_alnset_pairs  :: Ptr AlnSet -> Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
 foreign import ccall safe "pwmscan_alnset_free"      c_alnset_free   :: Ptr AlnSet -> IO ()
+foreign import ccall safe "pwmscan_alnset_matrix_init" c_alnset_matrix_init :: Ptr AlnSet -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
+foreign import ccall safe "pwmscan_alnset_merge_step"  c_alnset_merge_step  :: Ptr AlnSet -> Int32 -> Int32 -> Int32 -> Ptr Double -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Ptr Word8 -> Ptr Int32 -> IO CInt
 foreign import ccall safe "pwmscan_abi_version"       c_abi_version  :: IO CInt
 foreign import ccall safe "pwmscan_last_timing"       c_last_timing  :: Ptr Ctx -> Ptr Double -> CInt -> IO CInt
 foreign import ccall safe "pwmscan_seq_upload_segments" c_seq_upload_segments :: Ptr Ctx -> Ptr Word8 -> Ptr Int64 -> Int32 -> CInt -> Ptr (Ptr Seq) -> IO CInt

@@ -37,7 +37,8 @@ extern "C" {
 #define PWMSCAN_EDOMAIN  -5   /* "p must be in [0,1]" / "cdf': impossible!" (Motif.hs:254,261) */
 
 /* limits */
-#define PWMSCAN_MAX_COLS      64      /* PWM columns */
+#define PWMSCAN_MAX_COLS      64      /* PWM columns in a motif set: scan, CDF, dense scores, pair lists */
+#define PWMSCAN_ALNSET_MAX_COLS 256   /* PWM columns in a slot of an alignment set: merged PWMs grow (iterativeMerge) */
 #define PWMSCAN_MAX_MOTIFS    32768   /* motifs per pwmscan_motifs */
 #define PWMSCAN_MAX_SEGMENTS  65536   /* sequences per pwmscan_seq */
 
@@ -208,6 +209,15 @@ int  pwmscan_alnset_create(pwmscan_ctx* ctx, int32_t M, const int32_t* ncol, con
 int  pwmscan_alnset_update(pwmscan_alnset* set, int32_t slot, int32_t ncol, const double* mat_rowmajor);
 int  pwmscan_alnset_pairs(pwmscan_alnset* set, int64_t npairs, const int32_t* a, const int32_t* b, double* dist,
                           uint8_t* same_dir, int32_t* pos);
+/* The matrix of iterativeMerge itself resident on the device (Merge.hs:121-165).  pwmscan_alnset_matrix_init aligns all
+ * i < j (161-165) and returns the first minimum in the reference's scan order (i ascending, j ascending, strict <:
+ * 149-158) as (*i, *j, *d, *same_dir, *pos); *i = -1 when no pair is left.  After the caller has merged slot j into slot
+ * i (mergePWMWeighted stays host code), pwmscan_alnset_merge_step installs the merged PWM in slot i, blanks row and
+ * column j (135), re-aligns slot i with every live slot (138-145, argument order by index) and returns the next minimum:
+ * one call and 40 bytes back per merge.  A merged PWM longer than the slots makes the set grow (up to 256 columns). */
+int  pwmscan_alnset_matrix_init(pwmscan_alnset* set, int32_t* i, int32_t* j, double* d, uint8_t* same_dir, int32_t* pos);
+int  pwmscan_alnset_merge_step(pwmscan_alnset* set, int32_t i, int32_t j, int32_t ncol, const double* mat_rowmajor,
+                               int32_t* next_i, int32_t* next_j, double* d, uint8_t* same_dir, int32_t* pos);
 void pwmscan_alnset_free(pwmscan_alnset* set);
 
 /* ---- scanMotif's per-hit columns (Data/Bed/Utils.hs:109-123), computed on the device for the hits of a scan:

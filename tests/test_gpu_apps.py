@@ -226,3 +226,42 @@ def test_scan_motif_config_c3_sample_at_size(tmp_path):
     exp = app_oracle.scan_motif_lines_mt(gen, names, mats, beds, p=1e-5, nthreads=os.cpu_count() or 8)
     assert n == len(got) and len(exp) > 20_000
     assert got == exp
+
+
+def test_iterative_merge_device_matrix_and_long_merges():
+    """pwmscan_alnset_matrix_init / _merge_step (matrix, row refresh and argmin resident on the device) against (a) the
+    host-matrix path over the same resident PWMs, (b) the oracle's restatement of Merge.hs:113-170 — including a chain of
+    merges whose PWM grows past 64 columns (the slots of the alignment set grow; the reference has no length limit)."""
+    from oracle import app_oracle
+
+    class HostMatrix:                    # resident PWMs, but the matrix and the argmin stay in Python (round-1 path)
+        def __init__(self, f):
+            self.f = f
+            self.all_pairs, self.pairs = f.all_pairs, f.pairs
+
+        def resident(self, pwms):
+            r = self.f.resident(pwms)
+
+            class R:
+                pairs, update, free = r.pairs, r.update, r.free
+            return R()
+
+    mats = synth.config_c5_motifs(120, seed=43)
+    motifs = [Mo.Motif(b"m%d" % i, Mo.PWM(20, m)) for i, m in enumerate(mats)]
+    for th in (0.05, 0.25):
+        a = M.iterativeMerge(alignment, th, motifs)
+        b = M.iterativeMerge(HostMatrix(alignment), th, motifs)
+        assert len(a) == len(b) and len(a) < len(motifs)
+        for x, y in zip(a, b):
+            assert x[0] == y[0] and x[2] == y[2] and np.array_equal(x[1]._mat, y[1]._mat)
+    # overlapping windows of one long PWM merge back into something longer than 64 columns
+    master = synth.synth_pwm(150, np.random.Generator(np.random.PCG64(5)), alpha=0.05, zero_frac=0.0)
+    tiles = [np.ascontiguousarray(master[s:s + 24]) for s in range(0, 126, 6)]
+    tmot = [Mo.Motif(b"t%d" % i, Mo.PWM(10, m)) for i, m in enumerate(tiles)]
+    lin = AlignFn("linear", 0.001, "l1")
+    got = M.iterativeMerge(lin, 0.05, tmot)
+    assert max(x[1]._mat.shape[0] for x in got) > 128 and len(got) < len(tmot)
+    exp = app_oracle.iterative_merge(0.05, [m._name for m in tmot], tiles, penal="linear", gap=0.001, comb="l1")
+    assert len(got) == len(exp)
+    for x, y in zip(got, exp):
+        assert x[0] == y[0] and list(x[2]) == list(y[2]) and np.array_equal(x[1]._mat, y[1])

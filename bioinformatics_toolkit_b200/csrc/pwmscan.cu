@@ -1509,7 +1509,7 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
     int rc = ensure_lut(ctx);
     if (rc) return rc;
     const char* env_lanes = std::getenv("PWMSCAN_LANES");                  // read per call: experiments sweep it within one process
-    const int want_lanes = env_lanes ? std::max(1, std::min(kMaxLanes, std::atoi(env_lanes))) : 3;
+    const int want_lanes = env_lanes ? std::max(1, std::min(kMaxLanes, std::atoi(env_lanes))) : (seqs ? 4 : 5);
     const int K = std::min<int>(want_lanes, n);
     ScanJob jobs[kMaxLanes];
     double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1547,17 +1547,26 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
         if (cb) cb(user, i, h); else pwmscan_hits_free(h);
         return PWMSCAN_OK;
     };
-    for (int i = 0; i < K && !rc; ++i) rc = start(i);
+    // Item j runs on lane j % K, which is free once item j - K has been handed over.  Items are started as far ahead as the
+    // lanes allow: their uploads and first stages queue up behind the running one, so the device never waits for the host
+    // (which spends its time waiting for the counters of the oldest item) nor for a transfer.
+    int next_start = 0, done = 0;
+    auto fill = [&]() -> int {
+        while (next_start < n && next_start < done + K) { int r = start(next_start); if (r) return r; ++next_start; }
+        return PWMSCAN_OK;
+    };
+    rc = fill();
     for (int i = 0; i < n && !rc; ++i) {
         rc = scan_phase_b(ctx, jobs[i % K]);
         if (rc) break;
         if (K == 1) {                                 // one lane: strictly one item after the other
             rc = finish(i);
-            if (!rc && i + 1 < n) rc = start(i + 1);
-        } else if (i >= 1) {                          // item i-1's copy has had item i's phase B to land; its lane takes item i-1+K
+            done = i + 1;
+        } else if (i >= 1) {                          // item i-1's copy has had item i's phase B to land
             rc = finish(i - 1);
-            if (!rc && i - 1 + K < n) rc = start(i - 1 + K);
+            done = i;
         }
+        if (!rc) rc = fill();
     }
     if (!rc && K > 1) rc = finish(n - 1);
     if (rc) {                                     // drain: nothing may still touch caller or pooled buffers

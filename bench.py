@@ -237,6 +237,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if rank == 0 and os.environ.get("BENCH_TRACE_RANK0"):
+        os.environ["PWMSCAN_TRACE"] = "1"              # per-item timeline of rank 0 on stderr (pwmscan_scan_many)
     import torch
     import torch.distributed as dist
     from bioinformatics_toolkit_b200 import _lib

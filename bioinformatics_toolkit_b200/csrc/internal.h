@@ -24,6 +24,8 @@ constexpr int kMaxLanes = 8;           // scans in flight of pwmscan_scan_many (
 // context's streams and counters (single scans run on it); lanes 1.. are created on demand by pwmscan_scan_many.
 struct ScanLane {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t pstream = nullptr;              // low priority: upload-side packing + first stage; `stream` (high priority) carries the exact replay,
+                                                 // the ordering and the hit-list copy, which are short and slip in between retiring first-stage CTAs
     bool owns_streams = false;
     std::vector<cudaEvent_t> chunk_ev;           // one per in-flight host->device chunk
     cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -37,8 +39,8 @@ struct ScanLane {
 struct pwmscan_ctx {
     int device = 0;
     std::vector<ScanLane*> lanes;                // lanes[0] aliases stream / copy_stream / d_counters / h_counters below
-    cudaEvent_t prefilter_chain = nullptr;       // completion of the last prefilter kernel of any lane (they run one after the other)
-    bool prefilter_chain_valid = false;
+    cudaEvent_t prefilter_chain = nullptr;       // completion of the last first-stage kernel of any lane: the PERSISTENT first stages
+    bool prefilter_chain_valid = false;          // (lds, mma, kmer kernels 1 and 2) run one after the other; the default one is not chained
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host->device chunks of pwmscan_scan_host
     std::vector<cudaEvent_t> chunk_ev;           // one per in-flight chunk (created on demand)
@@ -237,7 +239,8 @@ int launch_mma_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq
 
 int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe, int L, uint8_t* d_table);
 int km_build_bitmap(pwmscan_ctx* ctx, const uint8_t* d_table, int L, uint8_t* d_bitmap);
-int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
+bool km_prefilter_is_persistent();          // which k-mer first-stage kernel runs (PWMSCAN_KM_KERNEL; the default one is not persistent)
+int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, cudaStream_t stream, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter);
 

@@ -726,6 +726,77 @@ km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, lon
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Third generation (the default): the warp-organised unit code of the second, but NOT persistent.  A CTA is one
+// (block, range of positions) item of the grid: it loads the block's middle-stage rows / bitmap once, its 32 warps draw the
+// units of the range from a counter in shared memory (no global atomic, no block-change barrier) and the CTA retires.
+// Because CTAs retire all the time, the exact replay / ordering kernels of the previous item (high-priority stream) get
+// SMs within microseconds instead of waiting behind a whole persistent first-stage launch, and the next item's CTAs
+// fill the tail of this one (first-stage launches of different lanes are no longer chained).
+__global__ void __launch_bounds__(kKmThreads, 1)
+km_prefilter_kernel_v3(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long range_pos, int unit_pos, int ranges_per_block,
+                       const DevKmBlock* __restrict__ blocks, const uint8_t* __restrict__ tables, const uint16_t* __restrict__ q16,
+                       const DevCombo* __restrict__ combos, long long len, unsigned long long* __restrict__ cand, unsigned long long cand_cap,
+                       unsigned long long* counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Km2Shared sh;
+    uint16_t* s_q16 = reinterpret_cast<uint16_t*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int blk = (int)(blockIdx.x / (unsigned)ranges_per_block);
+    const long long R0 = (long long)(blockIdx.x - (unsigned)blk * (unsigned)ranges_per_block) * range_pos;
+    const DevKmBlock db = blocks[blk];
+    const int n16 = kKmCombos * db.max_n * 8 / 16;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(q16 + db.q16_off);
+        uint4* dst = reinterpret_cast<uint4*>(s_q16);
+        for (int i = tid; i < n16; i += kKmThreads) dst[i] = __ldg(src + i);
+        if (db.bitmap_words > 0) {
+            const uint4* bsrc = reinterpret_cast<const uint4*>(tables + db.bitmap_off);
+            uint4* bdst = reinterpret_cast<uint4*>(smem_raw + (size_t)n16 * 16);       // bitmap right behind the rows
+            for (int i = tid; i < db.bitmap_words / 4; i += kKmThreads) bdst[i] = __ldg(bsrc + i);
+        }
+        if (tid < kKmCombos) {
+            const DevCombo dc = combos[(size_t)blk * kKmCombos + tid];
+            sh.cn[tid] = ((uint32_t)dc.c & 0xFFFFu) | ((uint32_t)dc.n << 16);
+        }
+        if (tid == 0) sh.want = 0;                                             // next unit of this CTA's range
+    }
+    __syncthreads();
+    const uint32_t* s_bm = reinterpret_cast<const uint32_t*>(smem_raw + (size_t)n16 * 16);
+    const long long left = n_anchor - R0;
+    const int nunits = (int)((left < range_pos ? left : range_pos) / unit_pos);
+    uint32_t* sseq = sh.seq[warp];
+    Km2Ctx c;
+    c.sseq = sseq; c.cn = sh.cn; c.q16 = s_q16; c.q = sh.queue[warp]; c.max_n = db.max_n; c.direct = db.direct;
+    c.len = len; c.combo_base = (unsigned long long)blk * kKmCombos; c.cand = cand; c.cand_cap = cand_cap; c.counters = counters;
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&sh.want, 1);
+        u = __shfl_sync(0xFFFFFFFFu, u, 0);
+        if (u >= nunits) break;
+        const long long U0 = anchor0 + R0 + (long long)u * unit_pos;
+        {   // stage the unit's 2-bit words (64 bases of history in front; the allocation has one front word)
+            const long long w0 = (U0 >> 4) - kKmHaloWords;
+            const int nw = kKmHaloWords + unit_pos / 16 + 5;
+            for (int i = lane; i < nw; i += 32) sseq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
+        }
+        __syncwarp();
+        c.U0 = U0;
+#define KM3_RUN(NT_) \
+        if (db.bitmap_words > 0) km2_unit_bitmap<NT_>(c, s_bm, db, tables, sh.hitq[warp], unit_pos); \
+        else km2_unit_plain<NT_>(c, db, tables, unit_pos);
+        switch (db.nt) {
+            case 1: KM3_RUN(1) break;
+            case 2: KM3_RUN(2) break;
+            case 3: KM3_RUN(3) break;
+            default: KM3_RUN(4) break;
+        }
+#undef KM3_RUN
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 namespace pwmscan {
@@ -749,23 +820,45 @@ int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe
     return PWMSCAN_OK;
 }
 
-int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
+static int km_kernel_choice() {
+    static const int which = std::getenv("PWMSCAN_KM_KERNEL") ? std::atoi(std::getenv("PWMSCAN_KM_KERNEL")) : 3;    // 1, 2 = the persistent kernels (kept as parity-tested variants)
+    return which;
+}
+bool km_prefilter_is_persistent() { return km_kernel_choice() != 3; }
+
+int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, cudaStream_t stream, const uint32_t* d_seq2, long long a0, long long a1, long long len, int nblocks, size_t smem_bytes,
                         const DevKmBlock* d_blocks, const uint8_t* d_tables, const uint16_t* d_q16, const DevCombo* d_combos,
                         unsigned long long* d_cand, unsigned long long cand_cap, unsigned long long* work_counter) {
     if (nblocks == 0 || a1 <= a0) return PWMSCAN_OK;
     if (!ctx->km_attr_set) {
         PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmSmemBudget));
         PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmSmemBudget));
+        PWM_CUDA(cudaFuncSetAttribute(km_prefilter_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmSmemBudget));
         ctx->km_attr_set = true;
     }
-    static const int which = std::getenv("PWMSCAN_KM_KERNEL") ? std::atoi(std::getenv("PWMSCAN_KM_KERNEL")) : 1;
+    const int which = km_kernel_choice();
+    if (which == 3) {
+        // CTA = (block, range of positions); ranges of 1 Mi positions, smaller for short inputs so that every SM gets a few CTAs;
+        // warp-owned units of 2048 positions, at least two per warp
+        static const long long range_max = std::getenv("PWMSCAN_KM_RANGE") ? std::max(16384LL, std::atoll(std::getenv("PWMSCAN_KM_RANGE"))) : (1LL << 20);   // experiments
+        long long range_pos = range_max;
+        while (range_pos > 16384 && (long long)nblocks * ((a1 - a0 + range_pos - 1) / range_pos) < 2LL * ctx->sm_count) range_pos >>= 1;
+        int unit_pos = kKm2UnitPos;
+        while (unit_pos > 512 && range_pos / unit_pos < 2 * (kKmThreads / 32)) unit_pos >>= 1;
+        const long long ranges = (a1 - a0 + range_pos - 1) / range_pos;
+        if (ranges * nblocks > 0x7FFFFFFFLL) return set_err(ctx, PWMSCAN_ERANGE, "pwmscan_scan: sequence x motif blocks exceed the first stage's grid");
+        km_prefilter_kernel_v3<<<(unsigned)(ranges * nblocks), kKmThreads, smem_bytes, stream>>>(d_seq2, a0, a1 - a0, range_pos, unit_pos, (int)ranges, d_blocks, d_tables, d_q16,
+                                                                                                 d_combos, len, d_cand, cand_cap, lane->d_counters);
+        PWM_CUDA(cudaGetLastError());
+        return PWMSCAN_OK;
+    }
     if (which == 2) {
         // warp-owned units of 2048 positions (512 for short inputs, so that every warp of every SM gets some)
         int unit_pos = kKm2UnitPos;
         while (unit_pos > 512 && (a1 - a0) / unit_pos * nblocks < 4LL * ctx->sm_count * (kKmThreads / 32)) unit_pos >>= 1;
         const long long units = (a1 - a0) / unit_pos * nblocks;
         const int grid = (int)std::min<long long>(ctx->sm_count, (units + kKmThreads / 32 - 1) / (kKmThreads / 32));
-        km_prefilter_kernel_v2<<<grid, kKmThreads, smem_bytes, lane->stream>>>(d_seq2, a0, a1 - a0, units, unit_pos, nblocks, d_blocks, d_tables, d_q16, d_combos,
+        km_prefilter_kernel_v2<<<grid, kKmThreads, smem_bytes, stream>>>(d_seq2, a0, a1 - a0, units, unit_pos, nblocks, d_blocks, d_tables, d_q16, d_combos,
                                                                                len, d_cand, cand_cap, lane->d_counters, work_counter);
         PWM_CUDA(cudaGetLastError());
         return PWMSCAN_OK;
@@ -774,7 +867,7 @@ int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, const uint32_t* d_seq2
     while (iters > 1 && (a1 - a0) / (iters * kKmIterPos) * nblocks < 8LL * ctx->sm_count) iters >>= 1;
     const long long items = (a1 - a0) / (iters * kKmIterPos) * nblocks;
     const int grid = (int)std::min<long long>(ctx->sm_count, items);
-    km_prefilter_kernel<<<grid, kKmThreads, smem_bytes, lane->stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
+    km_prefilter_kernel<<<grid, kKmThreads, smem_bytes, stream>>>(d_seq2, a0, a1 - a0, items, iters, d_blocks, d_tables, d_q16, d_combos, len,
                                                                                     d_cand, cand_cap, lane->d_counters, work_counter);
     PWM_CUDA(cudaGetLastError());
     return PWMSCAN_OK;

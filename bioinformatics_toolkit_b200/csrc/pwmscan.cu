@@ -176,7 +176,9 @@ extern "C" int pwmscan_ctx_create(int device, pwmscan_ctx** out) {
     ctx->device = device;
     auto fail = [&](cudaError_t err, const char* what) { int rc = cuda_fail(nullptr, err, what); delete ctx; return rc; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "cudaEventCreate");
     cudaDeviceProp prop;
@@ -190,6 +192,7 @@ extern "C" int pwmscan_ctx_create(int device, pwmscan_ctx** out) {
     if (!l0) { delete ctx; return set_err(nullptr, PWMSCAN_EINVAL, "out of host memory"); }
     l0->stream = ctx->stream; l0->copy_stream = ctx->copy_stream; l0->d_counters = ctx->d_counters; l0->h_counters = ctx->h_counters;
     ctx->lanes.push_back(l0);
+    if ((e = cudaStreamCreateWithPriority(&l0->pstream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     for (auto& ev : l0->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "cudaEventCreate");
     *out = ctx;
     return PWMSCAN_OK;
@@ -202,7 +205,10 @@ static int lane_get(pwmscan_ctx* ctx, int idx, ScanLane** out) {
         if (!l) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
         ctx->lanes.push_back(l);
         l->owns_streams = true;
-        PWM_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+        int prio_least = 0, prio_greatest = 0;
+        PWM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        PWM_CUDA(cudaStreamCreateWithPriority(&l->stream, cudaStreamNonBlocking, prio_greatest));
+        PWM_CUDA(cudaStreamCreateWithPriority(&l->pstream, cudaStreamNonBlocking, prio_least));
         PWM_CUDA(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : l->ev) PWM_CUDA(cudaEventCreate(&ev));
         PWM_CUDA(cudaMalloc(&l->d_counters, kCounterWords * sizeof(unsigned long long)));
@@ -218,6 +224,7 @@ extern "C" void pwmscan_ctx_destroy(pwmscan_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (ScanLane* l : ctx->lanes) {
         if (l->owns_streams && l->stream) cudaStreamSynchronize(l->stream);
+        if (l->pstream) { cudaStreamSynchronize(l->pstream); cudaStreamDestroy(l->pstream); }
         for (auto& p : l->scratch) if (p) cudaFree(p);
         for (auto& ev : l->ev) if (ev) cudaEventDestroy(ev);
         for (auto& ev : l->chunk_ev) cudaEventDestroy(ev);
@@ -418,10 +425,10 @@ static int seq_alloc(pwmscan_ctx* ctx, ScanLane* lane, const int64_t* seg_off, i
     return PWMSCAN_OK;
 }
 
-static int seq_launch_pack(pwmscan_ctx* ctx, ScanLane* lane, pwmscan_seq* s, const uint8_t* d_raw, int64_t t0, int64_t t1) {
+static int seq_launch_pack(pwmscan_ctx* ctx, ScanLane* lane, cudaStream_t stream, pwmscan_seq* s, const uint8_t* d_raw, int64_t t0, int64_t t1) {
     if (t1 <= t0) return PWMSCAN_OK;
     const int bs = 256;
-    pack_kernel<<<(unsigned)((t1 - t0 + bs - 1) / bs), bs, 0, lane->stream>>>(
+    pack_kernel<<<(unsigned)((t1 - t0 + bs - 1) / bs), bs, 0, stream>>>(
         d_raw, s->len, (s->flags & PWMSCAN_SEQ_UPPERCASE) ? 1 : 0, s->d_seq2, s->d_mask,
         (s->flags & PWMSCAN_SEQ_KEEP_ASCII) ? s->d_ascii : nullptr, t0, t1, lane->d_counters + 4);
     PWM_CUDA(cudaGetLastError());
@@ -452,7 +459,7 @@ static int seq_upload_impl(pwmscan_ctx* ctx, const uint8_t* ascii, const int64_t
     cudaError_t e;
     if (len > 0 && (e = cudaMemcpyAsync(d_raw, ascii, (size_t)len, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(ascii)"));
-    if ((rc = seq_launch_pack(ctx, lane, s, d_raw, 0, s->nwords_mask))) return bail(rc);
+    if ((rc = seq_launch_pack(ctx, lane, lane->stream, s, d_raw, 0, s->nwords_mask))) return bail(rc);
     if ((e = cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemcpyAsync(first_bad)"));
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "pack_kernel"));
@@ -1177,6 +1184,9 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     const pwmscan_plan* pl = j.pl;
     const pwmscan_motifs* mo = pl->motifs;
     cudaStream_t st = lane->stream;
+    // k-mer first stage: counters, packing and the first-stage kernels run on the lane's low-priority stream, everything behind
+    // them (exact replay, ordering, copies) on the high-priority one
+    cudaStream_t pst = pl->mode == PWM_MODE_KMER ? lane->pstream : lane->stream;
     int rc;
     const int64_t len = seq->len;
     const int64_t n_anchor = round_up(len + kPadFront + 64, kAnchorRound);
@@ -1222,17 +1232,18 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     };
     const size_t smem_bytes = (size_t)pl->max_nslot * kSlotBytes;
     bool chained = false;
+    const bool persistent = !use_km || km_prefilter_is_persistent();
     auto launch_prefilter = [&](long long a0, long long a1, int slot) -> int {
         if (n_pre_blocks == 0 || a1 <= a0) return PWMSCAN_OK;
-        if (!chained) {               // first-stage kernels of different lanes run one after the other
-            if (ctx->prefilter_chain_valid) PWM_CUDA(cudaStreamWaitEvent(st, ctx->prefilter_chain, 0));
-            if (!j.host || j.attempt > 0) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
-            PWM_CUDA(cudaEventRecord(lane->ev[EV_PSTART], st));
+        if (!chained) {               // persistent first-stage kernels of different lanes run one after the other
+            if (persistent && ctx->prefilter_chain_valid) PWM_CUDA(cudaStreamWaitEvent(pst, ctx->prefilter_chain, 0));
+            if (!j.host || j.attempt > 0) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], pst));
+            PWM_CUDA(cudaEventRecord(lane->ev[EV_PSTART], pst));
             chained = true;
         }
         if (use_km) {
             ++j.prefilter_launches;
-            return launch_km_prefilter(ctx, lane, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_smem_bytes, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
+            return launch_km_prefilter(ctx, lane, pst, seq->d_seq2, a0, a1, len, pl->km_nblocks, pl->km_smem_bytes, pl->d_km_blocks, pl->d_km_tables, pl->d_km_q16,
                                        pl->d_km_combos, d_cand, j.cand_cap, lane->d_counters + 8 + slot);
         }
         if (use_mma) {
@@ -1251,21 +1262,25 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         bool any_full = false;                                        // TMEM serves blocks whose 32 lanes carry distinct motifs
         for (const auto& b : pl->blocks) any_full |= (b.rep == 1);
         if (any_full && use_tmem)
-            prefilter_kernel<true><<<grid, kThreads, smem_bytes, st>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+            prefilter_kernel<true><<<grid, kThreads, smem_bytes, pst>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
                                                                        d_cand, j.cand_cap, lane->d_counters, lane->d_counters + 8 + slot);
         else
-            prefilter_kernel<false><<<grid, kThreads, smem_bytes, st>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
+            prefilter_kernel<false><<<grid, kThreads, smem_bytes, pst>>>(seq->d_seq2, a0, a1 - a0, items, iters, pl->nblocks, pl->d_blocks, pl->d_tables,
                                                                         d_cand, j.cand_cap, lane->d_counters, lane->d_counters + 8 + slot);
         PWM_CUDA(cudaGetLastError());
         ++j.prefilter_launches;
         return PWMSCAN_OK;
     };
-    PWM_CUDA(cudaMemsetAsync(lane->d_counters, 0, 4 * sizeof(unsigned long long), st));
-    PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, (kCounterWords - 6) * sizeof(unsigned long long), st));
-    PWM_CUDA(cudaMemsetAsync(ow.cnt, 0, ow.nb * 4, st));
-    if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, j.cand_cap * 8, st));     // sentinel: warps reserve whole chunks
+    if (pst != st) {                  // whatever the lane's main stream still has queued (segment table, counters of the upload) comes first
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_GATE], st));
+        PWM_CUDA(cudaStreamWaitEvent(pst, lane->ev[EV_GATE], 0));
+    }
+    PWM_CUDA(cudaMemsetAsync(lane->d_counters, 0, 4 * sizeof(unsigned long long), pst));
+    PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, (kCounterWords - 6) * sizeof(unsigned long long), pst));
+    PWM_CUDA(cudaMemsetAsync(ow.cnt, 0, ow.nb * 4, pst));
+    if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, j.cand_cap * 8, pst));     // sentinel: warps reserve whole chunks
     if (j.host && j.attempt == 0) {
-        PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_START], pst));
         // chunk boundaries are multiples of the anchor rounding unit, so every launch covers whole work items.
         // 16 Mi bases per chunk (smaller chunks cost more in per-launch overhead than they hide), except that
         // the end is split off as a short last chunk so that little work is left once the last byte has landed.
@@ -1285,7 +1300,7 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
             PWM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             lane->chunk_ev.push_back(ev);
         }
-        PWM_CUDA(cudaEventRecord(lane->ev[EV_GATE], st));               // copies must not overtake the previous use of d_raw
+        PWM_CUDA(cudaEventRecord(lane->ev[EV_GATE], pst));              // copies must not overtake the previous use of d_raw
         PWM_CUDA(cudaStreamWaitEvent(lane->copy_stream, lane->ev[EV_GATE], 0));
         PWM_CUDA(cudaEventRecord(lane->ev[EV_H2D0], lane->copy_stream));
         // (one copy stream: alternating two streams was measured slower, 6.7 vs 5.3 ms on C2)
@@ -1299,23 +1314,24 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         for (int l = 0; l < nch; ++l) {
             const bool last = (l == nch - 1);
             const int64_t b0 = bounds[l], b1 = bounds[l + 1];
-            PWM_CUDA(cudaStreamWaitEvent(st, lane->chunk_ev[l], 0));
+            PWM_CUDA(cudaStreamWaitEvent(pst, lane->chunk_ev[l], 0));
             // pack threads own 32 stored bases: positions [32t-32, 32t)
             const int64_t t0 = l == 0 ? 0 : b0 / 32 + 1, t1 = last ? j.up.seq->nwords_mask : b1 / 32 + 1;
-            if ((rc = seq_launch_pack(ctx, lane, j.up.seq, j.up.d_raw, t0, t1))) return rc;
+            if ((rc = seq_launch_pack(ctx, lane, pst, j.up.seq, j.up.d_raw, t0, t1))) return rc;
             ++j.kernels;
             // anchors whose windows (and the prefetch of the next words) lie inside what is packed so far
             const long long a1 = last ? n_anchor : std::max<long long>(scanned, b1 - kAnchorRound);
             if (a1 > scanned) { if ((rc = launch_prefilter(scanned, a1, l))) return rc; scanned = a1; }
         }
-        // the fromBS verdict of the packed bytes
-        PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 4, lane->d_counters + 4, 16, cudaMemcpyDeviceToHost, st));
     } else {
         if ((rc = launch_prefilter(0, n_anchor, 0))) return rc;
-        if (!chained) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], st));
+        if (!chained) PWM_CUDA(cudaEventRecord(lane->ev[EV_START], pst));
     }
-    PWM_CUDA(cudaEventRecord(lane->ev[EV_PRE], st));
-    if (chained) { PWM_CUDA(cudaEventRecord(ctx->prefilter_chain, st)); ctx->prefilter_chain_valid = true; }
+    PWM_CUDA(cudaEventRecord(lane->ev[EV_PRE], pst));
+    if (chained && persistent) { PWM_CUDA(cudaEventRecord(ctx->prefilter_chain, pst)); ctx->prefilter_chain_valid = true; }
+    if (pst != st) PWM_CUDA(cudaStreamWaitEvent(st, lane->ev[EV_PRE], 0));
+    if (j.host && j.attempt == 0)     // the fromBS verdict of the packed bytes
+        PWM_CUDA(cudaMemcpyAsync(lane->h_counters + 4, lane->d_counters + 4, 16, cudaMemcpyDeviceToHost, st));
     j.kernels += j.prefilter_launches;
     if (n_pre_blocks > 0) {
         if (use_mma)
@@ -1529,14 +1545,25 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
         return scan_phase_a(ctx, j);
     };
     static const bool trace = std::getenv("PWMSCAN_TRACE") != nullptr;       // per-item timeline on stderr (ms since the call started)
+    // First-stage launches of different lanes overlap (the next one fills the tail of the running one), so the first-stage
+    // time of the call is the length of the UNION of their [start, end] intervals, measured against one reference event.
     cudaEvent_t ref = nullptr;
-    if (trace) { cudaEventCreate(&ref); cudaEventRecord(ref, ctx->lanes[0]->stream); cudaEventSynchronize(ref); }
+    PWM_CUDA(cudaEventCreate(&ref));
+    PWM_CUDA(cudaEventRecord(ref, ctx->lanes[0]->stream));
+    PWM_CUDA(cudaEventSynchronize(ref));
+    std::vector<std::pair<float, float>> pre_iv;
+    pre_iv.reserve((size_t)n);
     auto finish = [&](int i) -> int {
         pwmscan_hits* h = nullptr;
         ScanJob& fj = jobs[i % K];
         const bool had_hits = fj.nhits > 0, was_host = fj.host;
         int r = scan_phase_c(ctx, fj, &h, t);
         if (r) return r;
+        if (fj.prefilter_launches > 0) {
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, ref, fj.lane->ev[EV_PSTART]) == cudaSuccess && cudaEventElapsedTime(&b, ref, fj.lane->ev[EV_PRE]) == cudaSuccess) pre_iv.emplace_back(a, b);
+            else cudaGetLastError();
+        }
         if (trace) {
             ScanLane* l = fj.lane;
             auto at = [&](int e) { float ms = -1; cudaEventElapsedTime(&ms, ref, l->ev[e]); return ms; };
@@ -1572,9 +1599,20 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
     if (rc) {                                     // drain: nothing may still touch caller or pooled buffers
         cudaDeviceSynchronize();
         for (int k = 0; k < K; ++k) job_release(jobs[k]);
+        cudaEventDestroy(ref);
         return rc;
     }
-    if (ref) cudaEventDestroy(ref);
+    cudaEventDestroy(ref);
+    if (!pre_iv.empty()) {
+        std::sort(pre_iv.begin(), pre_iv.end());
+        double busy = 0;
+        float lo = pre_iv[0].first, hi = pre_iv[0].second;
+        for (size_t k = 1; k < pre_iv.size(); ++k) {
+            if (pre_iv[k].first > hi) { busy += hi - lo; lo = pre_iv[k].first; hi = pre_iv[k].second; }
+            else hi = std::max(hi, pre_iv[k].second);
+        }
+        t[0] = busy + (hi - lo);
+    }
     for (int i = 0; i < 12; ++i) ctx->timing[i] = t[i];
     return PWMSCAN_OK;
 }

@@ -319,3 +319,75 @@ int emul_km_plan_info(int M, const int* ncol, const double* mats, const double* 
     }
     return nb;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// scoreCDF through csrc/cdf_core.h — the gather form cdf_kernel runs (run boundaries by walking the inverted index
+// function, one output bin = its four runs merged by (x, base)), with the kernel's tile / chunk structure executed
+// serially.  Returns the number of compressed CDF points.
+#include "../../bioinformatics_toolkit_b200/csrc/cdf_core.h"
+#include <cmath>
+
+extern "C" __attribute__((visibility("default")))
+int64_t emul_score_cdf(const double* bg, int n, const double* mat, double* out_x, double* out_p, int64_t cap, int64_t* stats /* [0] idx evaluations [1] boundaries */) {
+    constexpr int kMaxBin = 200000, kTile = 1024, kG = 8;
+    const double m_epsilon = 2.220446049250313e-16;
+    std::vector<double> prev(1, 1.0), nw;
+    CdfScFn f{1, 0.0, 0.0};
+    int xlo = 0, xhi = 0;
+    const double lbg[4] = {std::log(bg[0]), std::log(bg[1]), std::log(bg[2]), std::log(bg[3])};
+    int64_t nbound = 0;
+    for (int col = 0; col < n; ++col) {
+        CdfCol c;
+        c.f = f; c.xlo = xlo; c.xhi = xhi;
+        double xb[4];
+        for (int b = 0; b < 4; ++b) { const double p = mat[4 * col + b]; xb[b] = (p == 0 ? std::log(0.001) : std::log(p)) - lbg[b]; }
+        double mn = xb[0], mx = xb[0];
+        for (int b = 1; b < 4; ++b) { if (xb[b] < mn) mn = xb[b]; if (xb[b] > mx) mx = xb[b]; }
+        const double lo = cdf_scfn(f, xlo) + mn, hi = cdf_scfn(f, xhi) + mx;
+        if (!(lo < hi)) continue;
+        const double nbd = std::ceil((hi - lo) / 1e-5);
+        c.nbin = nbd > (double)kMaxBin ? kMaxBin : (int)nbd;
+        c.lo = lo; c.step = (hi - lo) / (double)c.nbin;
+        cdf_col_setup(c);
+        nw.assign((size_t)c.nbin, 0.0);
+        int nlo = 0x7FFFFFFF, nhi = -1;
+        std::vector<int> st((size_t)4 * (kTile + 1));
+        for (int j0 = 0; j0 < c.nbin; j0 += kTile) {
+            const int tn = std::min(kTile, c.nbin - j0);
+            for (int item = 0; item < 4 * (kTile / kG); ++item) {            // one item per thread: (base, chunk of kG bins)
+                const int b = item & 3, jj0 = (item >> 2) * kG;
+                if (jj0 > tn) continue;
+                CdfWalk w;
+                const CdfBase cb = cdf_base_setup(c, xb[b]);
+                cdf_walk_begin(c, cb, j0 + jj0, w);
+                st[(size_t)b * (kTile + 1) + jj0] = w.x;
+                for (int g = 1; g <= kG && jj0 + g <= tn; ++g) { cdf_walk_next(c, cb, j0 + jj0 + g, w); st[(size_t)b * (kTile + 1) + jj0 + g] = w.x; ++nbound; }
+            }
+            for (int jj = 0; jj < tn; ++jj) {
+                const int* s0 = &st[0 * (kTile + 1) + jj]; const int* s1 = &st[1 * (kTile + 1) + jj];
+                const int* s2 = &st[2 * (kTile + 1) + jj]; const int* s3 = &st[3 * (kTile + 1) + jj];
+                const double acc = cdf_gather_bin(prev.data(), bg, s0[0], s0[1], s1[0], s1[1], s2[0], s2[1], s3[0], s3[1]);
+                nw[(size_t)j0 + jj] = acc;
+                if (acc != 0.0) { nlo = std::min(nlo, j0 + jj); nhi = std::max(nhi, j0 + jj); }
+            }
+        }
+        prev.swap(nw);
+        xlo = nlo; xhi = nhi;
+        f.is_const = 0; f.step = c.step; f.lo = c.lo;
+    }
+    const int64_t len = (int64_t)prev.size();
+    std::vector<double> P((size_t)len);
+    double run = 0.0;
+    for (int64_t i = 0; i < len; ++i) { run = i == 0 ? prev[0] : run + prev[(size_t)i]; P[(size_t)i] = run; }
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < len; ++i) {
+        bool keep = i == 0;
+        if (!keep) {
+            keep = P[(size_t)i] - P[(size_t)i - 1] > m_epsilon;
+            if (!keep && i + 1 < len) keep = P[(size_t)i + 1] - P[(size_t)i] > m_epsilon;
+        }
+        if (keep) { if (cnt < cap) { out_x[cnt] = cdf_scfn(f, (int)i); out_p[cnt] = P[(size_t)i]; } ++cnt; }
+    }
+    if (stats) { stats[0] = 0; stats[1] = nbound; }
+    return cnt;
+}

@@ -8,7 +8,7 @@ both strands included.  A step = one pass of the scan over the whole workload.
 
 Default workload at every N: BASELINE config 4, the configuration the metric is quoted on — 800 synthetic
 JASPAR-sized PWMs over a 3 088 286 401-bp hg38-shaped synthetic genome (25 chromosomes), p < 1e-5, both strands,
-cut into (all motif blocks x 64 Mbp chromosome chunk) items that are sharded over the ranks ("strong" scaling:
+cut into (all motif blocks x chromosome chunk of 64 / 64 / 32 / 16 Mbp at 1 / 2 / 4 / 8 GPUs) items that are sharded over the ranks ("strong" scaling:
 the job is fixed, N GPUs share it; no data-path collective, hit lists are gathered in the host memory of the
 rank that produced them — the decomposition of the reference's findTFBS', Motif/Search.hs:60-84).
 --workload c2 (100 PWMs x chr1-shaped 249 Mbp per GPU, weak scaling) and c1 are the smaller configs.
@@ -41,7 +41,7 @@ DESC = {
     "c1": "C1: 1 CTCF-like 19-bp PWM x 10 Mbp",
     "c2": "C2: 100 synthetic PWMs (8-20 bp) x 248,956,422-bp chr1-shaped sequence per GPU, p<1e-5, both strands",
     "c4": "C4: 800 synthetic PWMs (6-22 bp) x 3,088,286,401-bp hg38-shaped genome, p<1e-5, both strands, "
-          "(motif blocks x 64 Mbp chromosome chunk) items sharded over the ranks",
+          "(all motif blocks x chromosome chunk) items sharded over the ranks",
 }
 
 
@@ -118,7 +118,7 @@ def c4_items(world):
     """The (all motif blocks x 64 Mbp chromosome chunk) items of config 4 and their assignment to the ranks."""
     from bioinformatics_toolkit_b200 import shard, synth
     lengths = [l for _, l in synth.HG38_CHROM_SIZES]
-    items = shard.make_items(lengths, 800, chunk_len=64_000_000)
+    items = shard.make_items(lengths, 800, chunk_len=shard.pick_chunk_len(sum(lengths), world))
     return lengths, shard.assign(items, world)
 
 
@@ -418,7 +418,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if big else "weak",
             "vs_baseline": None, "dtype": "u8 bit-mask / u16 first stage + f64 re-score", "data": "synthetic",
-            "config": {"workload": DESC[args.workload], "items_rank0": len(dev_seqs), "scans_in_flight": int(os.environ.get("PWMSCAN_LANES", "3")),
+            "config": {"workload": DESC[args.workload], "items_rank0": len(dev_seqs), "chunk_bp": int(max(a.size for a in host_arrays)), "scans_in_flight": os.environ.get("PWMSCAN_LANES", "6 resident / 7 from host bytes"),
                        "l2": "256 MiB flush write + sync between steps; per step the rank reads %.0f MB of packed genome and %.0f MB of mask tables (> 126 MB L2)" % (0.375 * bp_rank / 1e6, info["table_bytes"] / 1e6),
                        "thresholds": "device scoreCDF", "hits_per_step": int(hits_all.item()), "setup_s": round(t_setup, 1), **gate},
             "e2e": e2e, "gpu_launches": int(res["kernel_launches"]), "clocks": clocks,

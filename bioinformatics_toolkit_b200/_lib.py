@@ -59,6 +59,7 @@ def load():
         L.pwmscan_seq_length.restype = C.c_int64
         L.pwmscan_hits_count.restype = C.c_int64
         L.pwmscan_hits_count.argtypes = [_vp]
+        L.pwmscan_hits_first_invalid.argtypes = [_vp, C.c_int, C.POINTER(C.c_int64)]
         L.pwmscan_ctx_destroy.argtypes = [_vp]
         L.pwmscan_seq_free.argtypes = [_vp]
         L.pwmscan_motifs_free.argtypes = [_vp]
@@ -407,6 +408,16 @@ class Hits:
 
     def __len__(self):
         return self._n
+
+    def first_invalid(self, alphabet="IUPAC"):
+        """fromBS verdict of the bytes a host scan uploaded for this list (pwmscan_hits_first_invalid): offset of the first
+        byte outside the alphabet, -1 if none (and for scans of resident sequences)."""
+        if self._owner is None:
+            return -1
+        pos = C.c_int64(-1)
+        ctx = self._owner.ctx
+        ctx.check(ctx.L.pwmscan_hits_first_invalid(self._owner.h, C.c_int(_alphabet_code(alphabet)), C.byref(pos)))
+        return int(pos.value)
 
     def _get_compact(self):
         if self._compact is None:

@@ -216,6 +216,114 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
     return total if out is not None else results
 
 
+def scanGenome(genome, motifs, out=None, chroms=None, chunk_len=64_000_000, warn=sys.stderr, ctx=None):
+    """scanMotif over WHOLE chromosomes straight from the genome store — the result of
+    `scanMotif genome motifs [(chr, 0, size) | (chr, size) <- getChrSizes genome]` (Utils.hs:101-124 with getChrom,
+    Seq/IO.hs:77-84), produced chromosome by chromosome: the bytes of a chromosome are read from the index file in
+    chunks of `chunk_len` window starts (+ a halo of the longest motif - 1), go through pinned staging buffers into
+    pwmscan_scan_host_many (upload, 2-bit packing, first stage, exact replay and hit copy of several chunks in flight), the
+    per-hit BED score comes from the device (pwmscan_hits_affinity) and the chunks' (motif, strand) runs are stitched
+    into the reference's order (motif, strand, ascending position over the whole chromosome).  A chromosome with a byte
+    outside the IUPAC alphabet is a Left in the reference (fromBS): warned about and skipped.
+    Yields / writes BED6 like scanMotif; returns the hit count when `out` is given."""
+    import ctypes as C
+    import torch
+    from . import shard
+    ctx = ctx or _lib.default_context()
+    if not motifs:
+        return 0 if out is not None else []
+    bg = motifs[0]._background
+    mo = _lib.DeviceMotifs(ctx, [m._motif_pwm._mat for m in motifs], bg.freqs)
+    for i, m in enumerate(motifs):
+        mo.set_sigma(i, 0, m._motif_sigma)
+        mo.set_sigma(i, 1, m._motif_sigma_rc)
+    plan = _lib.Plan(mo, [m._cutoff for m in motifs], strands=2, skip_ambiguous=True)
+    M = len(motifs)
+    nlen = np.array([size(m._motif_pwm) for m in motifs], dtype=np.int64)
+    nmax = int(nlen.max())
+    names = [m._motif_name for m in motifs]
+    mname_off = np.concatenate([[0], np.cumsum([len(x) for x in names])]).astype(np.int64)
+    mname_buf = b"".join(names)
+    mlen32 = nlen.astype(np.int32)
+    cdf_off = np.concatenate([[0], np.cumsum([m._cdf.xs.size for m in motifs])]).astype(np.int64)
+    cdf_x = np.concatenate([m._cdf.xs for m in motifs])
+    cdf_y = np.concatenate([m._cdf.ps for m in motifs])
+    L = ctx.L
+    p = _lib._ptr
+    results = [] if out is None else None
+    total = 0
+    staging = []                                    # pinned host buffers, reused from chromosome to chromosome
+    for chr_, csize in (getChrSizesOf(genome) if chroms is None else [(c if isinstance(c, bytes) else c.encode(), genome.index[c if isinstance(c, bytes) else c.encode()][1]) for c in chroms]):
+        cstart = genome.index[chr_][0]
+        items = shard.make_items([csize], M, chunk_len)
+        arrays = []
+        for k, it in enumerate(items):
+            lo, hi = shard.chunk_bytes_range(it, csize, nmax)
+            if k >= len(staging) or staging[k].numel() < hi - lo:
+                buf = torch.empty(max(hi - lo, 1), dtype=torch.uint8).pin_memory()
+                if k < len(staging):
+                    staging[k] = buf
+                else:
+                    staging.append(buf)
+            a = staging[k].numpy()[:hi - lo]
+            o = genome.header_size + cstart + lo
+            np.copyto(a, genome.data[o:o + (hi - lo)])              # index file (page cache) -> pinned memory
+            arrays.append(a)
+        hits = plan.scan_host_many(arrays, uppercase=True)
+        if any(h.first_invalid("IUPAC") >= 0 for h in hits):        # fromBS: Left "Bio.Seq.fromBS: unknown character"
+            if warn is not None:
+                print("Warning: no sequence for region: " + repr((chr_.decode("latin1"), 0, csize)), file=warn)
+            continue
+        # chunk c contributes the windows that START in it; its runs of (motif, strand) go behind those of chunk c - 1
+        parts = []
+        for it, h in zip(items, hits):
+            n = len(h)
+            if n == 0:
+                continue
+            own = it[2] - it[1]
+            pos = h.pos32.astype(np.int64)
+            aff = h.affinity(cdf_off, cdf_x, cdf_y)
+            ro = np.asarray(h.run_off)
+            combo = np.repeat(np.arange(2 * M, dtype=np.int64), np.diff(ro))
+            keep = pos < own
+            parts.append((combo[keep], pos[keep] + it[1], aff[keep]))
+        if not parts:
+            continue
+        combo = np.concatenate([q[0] for q in parts])
+        pos = np.concatenate([q[1] for q in parts])
+        aff = np.concatenate([q[2] for q in parts])
+        order = np.argsort(combo, kind="stable")                    # chunks are in position order already
+        combo, pos, aff = combo[order], pos[order], aff[order]
+        mot = (combo >> 1).astype(np.int32)
+        strand = (combo & 1).astype(np.uint8)
+        n = int(pos.size)
+        total += n
+        if out is None:
+            en = pos + nlen[mot]
+            for k in range(n):
+                results.append((chr_, int(pos[k]), int(en[k]), names[mot[k]], int(aff[k]), strand[k] == 0))
+            continue
+        text = C.c_char_p()
+        tlen = C.c_int64(0)
+        seg = np.zeros(n, dtype=np.int32)
+        rchrom = np.zeros(1, dtype=np.int32)
+        starts = np.zeros(1, dtype=np.int64)
+        coff = np.array([0, len(chr_)], dtype=np.int64)
+        rc = L.pwmscan_format_bed6(C.c_int64(n), p(seg), p(mot), p(strand), p(np.ascontiguousarray(pos)), p(np.ascontiguousarray(aff)), p(rchrom), p(starts),
+                                   C.c_char_p(chr_), p(coff), C.c_char_p(mname_buf), p(mname_off), p(mlen32), C.byref(text), C.byref(tlen))
+        if rc != 0:
+            raise _lib.PwmScanError(rc, "pwmscan_format_bed6 failed")
+        out.write(memoryview((C.c_char * tlen.value).from_address(C.cast(text, C.c_void_p).value)))
+        L.pwmscan_free(text)
+    plan.free()
+    mo.free()
+    return total if out is not None else results
+
+
+def getChrSizesOf(genome):
+    return [(k, genome.index[k][1]) for k in genome.order]
+
+
 def streamBed3(path):
     """streamBed ... :: BED3 (Data/Bed.hs:307-309, Types.hs:175-177): first three tab-separated fields."""
     with open(path, "rb") as f:

@@ -4,10 +4,10 @@
 // first from a work counter).  The reference scatters `new[idx] += bg_b * prob` in the order (x ascending, b = A,C,G,T);
 // fp64 addition is not associative, so to be bit-identical every output bin is computed by ONE thread that *gathers* its
 // contributors in exactly that order.  idx is monotone in x for a fixed base, so the contributors of a bin are four
-// contiguous runs of `prev`; their boundaries come from inverting the index function (cdf_core.h: estimate, verified
-// with the exact index function, consecutive boundaries by walking) tile by tile into shared memory.  Per column the
-// kernel reads `prev` and writes `new` — 2 x 1.6 MB — and nothing else: no compaction, no index planes, no atomics
-// (round 1 moved 12.8 MB of workspace per column through L2/HBM).  The prefix sum of toCDF (scanl1 (+)) is
+// contiguous runs of `prev`; their boundaries come from inverting the index function (cdf_core.h: a two-operation
+// approximation with a certified error bound decides, the IEEE expression itself only within that bound of a bin edge).
+// Per column the kernel reads `prev` and writes `new` — 2 x 1.6 MB — and nothing else: no compaction, no index planes,
+// no atomics, no shared-memory staging (round 1 moved 12.8 MB of workspace per column through L2/HBM).  The prefix sum of toCDF (scanl1 (+)) is
 // order-sensitive too and is done sequentially by one thread per motif out of shared memory; the other CTA of the SM
 // keeps the SM busy meanwhile.  All fp64 arithmetic is IEEE (-fmad=false); log' p - log bg_b comes from the host libm.
 #include <algorithm>
@@ -27,14 +27,8 @@ constexpr int kCdfThreads = 512;
 constexpr int kCdfCtasPerSm = 2;
 constexpr int kMaxBin = 200000;        // Motif.hs:305
 constexpr int kScanChunk = 2048;
-constexpr int kTile = 1024;            // output bins per tile
-constexpr int kWalk = 8;               // consecutive boundaries one thread walks: 4 bases x kTile / kWalk = kCdfThreads items per tile
-constexpr int kStartStride = kTile + kTile / kWalk + 2;      // one pad per kWalk entries: conflict-free stores
-static_assert(4 * (kTile / kWalk) == kCdfThreads, "one (base, chunk) item per thread and tile");
 
 constexpr size_t kWorkBytes = (size_t)kMaxBin * 8 * 3 + 256;      // prev / new, compressed P
-
-__device__ __forceinline__ int pad_start(int jj) { return jj + jj / kWalk; }
 
 // exclusive block scan of one int per thread; returns the exclusive prefix, *total = block sum
 __device__ __forceinline__ int block_scan_excl(int v, int* total, int* s_warp /*[33]*/) {
@@ -70,10 +64,10 @@ cdf_kernel(int nwork, int m0, const int32_t* __restrict__ order, unsigned int* n
            unsigned long long* pool, double trunc) {
     __shared__ int s_warp[33];
     __shared__ double s_chunk[kScanChunk];
-    __shared__ int s_start[4 * kStartStride];
     __shared__ int s_nbin, s_skip, s_xlo, s_xhi, s_nlo, s_nhi, s_m;
     __shared__ long long s_off;
-    __shared__ double s_lo, s_step, s_run;
+    __shared__ double s_run;
+    __shared__ CdfExact s_ex;
     const int tid = threadIdx.x, lane = tid & 31;
     double* const buf0 = reinterpret_cast<double*>(work + (size_t)blockIdx.x * kWorkBytes);
     double* const bufs[2] = {buf0, buf0 + kMaxBin};
@@ -96,8 +90,6 @@ cdf_kernel(int nwork, int m0, const int32_t* __restrict__ order, unsigned int* n
         for (int col = 0; col < n; ++col) {
             const double* prev = bufs[cur];
             double* nw = bufs[cur ^ 1];
-            CdfCol c;
-            c.f = f; c.xlo = s_xlo; c.xhi = s_xhi;
             // ---- column scalars (Motif.hs:303-310); lo' / hi' = scores of the first / last non-zero bin of prev
             if (tid == 0) {
                 const double x0 = xa[4 * col], x1 = xa[4 * col + 1], x2 = xa[4 * col + 2], x3 = xa[4 * col + 3];
@@ -105,42 +97,45 @@ cdf_kernel(int nwork, int m0, const int32_t* __restrict__ order, unsigned int* n
                 if (x1 < mn) mn = x1; if (x1 > mx) mx = x1;
                 if (x2 < mn) mn = x2; if (x2 > mx) mx = x2;
                 if (x3 < mn) mn = x3; if (x3 > mx) mx = x3;
-                const double lo = cdf_scfn(f, c.xlo) + mn, hi = cdf_scfn(f, c.xhi) + mx;
+                const double lo = cdf_scfn(f, s_xlo) + mn, hi = cdf_scfn(f, s_xhi) + mx;
                 if (lo < hi) {
                     const double nbd = ceil((hi - lo) / 1e-5);
                     const int nbin = nbd > (double)kMaxBin ? kMaxBin : (int)nbd;
-                    s_nbin = nbin; s_lo = lo; s_step = (hi - lo) / (double)nbin; s_skip = 0;
+                    s_nbin = nbin; s_skip = 0;
+                    s_ex.f = f; s_ex.xb[0] = x0; s_ex.xb[1] = x1; s_ex.xb[2] = x2; s_ex.xb[3] = x3;
+                    s_ex.lo = lo; s_ex.step = (hi - lo) / (double)nbin;
                 } else s_skip = 1;
                 s_nlo = 0x7FFFFFFF; s_nhi = -1;
             }
             __syncthreads();
             if (s_skip) { __syncthreads(); continue; }                 // Motif.hs:299
-            c.nbin = s_nbin; c.lo = s_lo; c.step = s_step;
-            cdf_col_setup(c);
+            CdfFast q;
+            cdf_fast_setup(q, s_ex, bg, s_nbin, s_xlo, s_xhi, plen);
+            const CdfExact* ex = &s_ex;
+            const int last = plen - 1;
             int my_lo = 0x7FFFFFFF, my_hi = -1;
-            const int wb = tid & 3, wj0 = (tid >> 2) * kWalk;          // this thread's boundaries of a tile: base wb, bins wj0 .. wj0 + kWalk
-            const CdfBase cb = cdf_base_setup(c, xa[4 * col + wb]);
-            for (int j0 = 0; j0 < c.nbin; j0 += kTile) {
-                const int tn = min(kTile, c.nbin - j0);
-                if (wj0 <= tn) {
-                    int* st = s_start + wb * kStartStride;
-                    CdfWalk w;
-                    cdf_walk_begin(c, cb, j0 + wj0, w);
-                    st[pad_start(wj0)] = w.x;
+            // ---- gather: a thread owns four adjacent output bins: five run boundaries per base, then the four runs of
+            //      each bin merged in (x, base) order
 #pragma unroll 1
-                    for (int g = 1; g <= kWalk && wj0 + g <= tn; ++g) { cdf_walk_next(c, cb, j0 + wj0 + g, w); st[pad_start(wj0 + g)] = w.x; }
+            for (int j = 4 * tid; j < q.nbin; j += 4 * kCdfThreads) {
+                int B[4][5];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) B[k][g] = cdf_boundary(q, ex, k, j + g);
+                double acc[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    acc[g] = j + g < q.nbin ? cdf_gather_bin(prev, q, last, B[0][g], B[0][g + 1], B[1][g], B[1][g + 1], B[2][g], B[2][g + 1], B[3][g], B[3][g + 1]) : 0.0;
+                if (j + 3 < q.nbin) {
+                    *reinterpret_cast<double2*>(nw + j) = make_double2(acc[0], acc[1]);
+                    *reinterpret_cast<double2*>(nw + j + 2) = make_double2(acc[2], acc[3]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) if (j + g < q.nbin) nw[j + g] = acc[g];
                 }
-                __syncthreads();
-                // ---- gather: one thread per output bin, its four runs merged in (x, base) order
-                for (int jj = tid; jj < tn; jj += kCdfThreads) {
-                    const int a = pad_start(jj), e = pad_start(jj + 1);
-                    const double acc = cdf_gather_bin(prev, bg, s_start[a], s_start[e], s_start[kStartStride + a], s_start[kStartStride + e],
-                                                      s_start[2 * kStartStride + a], s_start[2 * kStartStride + e],
-                                                      s_start[3 * kStartStride + a], s_start[3 * kStartStride + e]);
-                    nw[j0 + jj] = acc;
-                    if (acc != 0.0) { my_lo = min(my_lo, j0 + jj); my_hi = max(my_hi, j0 + jj); }
-                }
-                __syncthreads();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) if (acc[g] != 0.0) { my_lo = min(my_lo, j + g); my_hi = max(my_hi, j + g); }
             }
             my_lo = __reduce_min_sync(0xFFFFFFFFu, my_lo);
             my_hi = __reduce_max_sync(0xFFFFFFFFu, my_hi);
@@ -148,8 +143,8 @@ cdf_kernel(int nwork, int m0, const int32_t* __restrict__ order, unsigned int* n
             __syncthreads();
             if (tid == 0) { s_xlo = s_nlo; s_xhi = s_nhi; }
             cur ^= 1;
-            f.is_const = 0; f.step = c.step; f.lo = c.lo;              // Motif.hs:298
-            plen = c.nbin;
+            f.is_const = 0; f.step = s_ex.step; f.lo = s_ex.lo;        // Motif.hs:298
+            plen = q.nbin;
             __syncthreads();
         }
         // ---- toCDF: sequential scanl1 (+) (Motif.hs:315), in place

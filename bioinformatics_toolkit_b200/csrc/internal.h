@@ -18,7 +18,7 @@ struct KeyLayout { int pb, mb; };
 constexpr int kOrderCap = 4096;        // hits one CTA orders in shared memory (order.cu)
 constexpr int kOrderIdxBits = 12;      // log2(kOrderCap)
 constexpr int kOrderTarget = 8;        // hits per bucket aimed at (a warp orders spans of whole buckets, up to 256 hits, in registers: order.cu)
-constexpr int kMaxLanes = 8;           // scans in flight of pwmscan_scan_many (default: 4 resident items, 5 host items)
+constexpr int kMaxLanes = 8;           // scans in flight of pwmscan_scan_many (default: 6 resident items, 7 host items)
 
 // Everything one in-flight scan needs of its own: streams, events, counters, grow-only scratch.  Lane 0 shares the
 // context's streams and counters (single scans run on it); lanes 1.. are created on demand by pwmscan_scan_many.
@@ -183,6 +183,7 @@ struct pwmscan_hits {
     pwmscan_ctx* ctx = nullptr;
     int64_t count = 0;
     int32_t nseg = 1, M = 0;
+    int64_t first_non_acgt = -1, first_non_iupac = -1;   // fromBS verdict of the bytes a host scan uploaded for this list
     void* buf = nullptr;          // pinned
     size_t buf_bytes = 0;
     const double* score = nullptr;

@@ -418,6 +418,7 @@ km_prefilter_kernel(const uint32_t* __restrict__ seq2, long long anchor0, long l
 //   * blocks whose single table covers every column of every motif (short motifs) skip the middle stage: a surviving
 //     bit already is the whole-window test.
 constexpr int kKm2UnitPos = 2048;
+constexpr int kKm2SmallUnit = 512;               // the last units of every block (and the unit size of short inputs)
 constexpr int kKm2SeqWords = kKmHaloWords + kKm2UnitPos / 16 + 5;
 
 struct Km2Shared {
@@ -652,7 +653,7 @@ __device__ __forceinline__ void km2_unit_plain(const Km2Ctx& c, const DevKmBlock
 }
 
 __global__ void __launch_bounds__(kKmThreads, 1)
-km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long total_units, int unit_pos, int nblocks,
+km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, long long n_big, long long n_small, int unit_pos, int nblocks,
                        const DevKmBlock* __restrict__ blocks, const uint8_t* __restrict__ tables, const uint16_t* __restrict__ q16,
                        const DevCombo* __restrict__ combos, long long len, unsigned long long* __restrict__ cand, unsigned long long cand_cap,
                        unsigned long long* counters, unsigned long long* work_counter) {
@@ -660,7 +661,9 @@ km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, lon
     __shared__ Km2Shared sh;
     uint16_t* s_q16 = reinterpret_cast<uint16_t*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long units_per_block = n_anchor / unit_pos;
+    // Units of a block: n_big of unit_pos positions, then n_small of kKm2SmallUnit covering the block's last stretch — every
+    // change of block is a CTA-wide barrier at which a warp idles for up to one unit, so the last units are short ones.
+    const long long units_per_block = n_big + n_small, total_units = units_per_block * nblocks;
     if (tid == 0) sh.want = 0x7FFFFFFF;
     __syncthreads();
     int cur_blk = -1;
@@ -701,11 +704,13 @@ km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, lon
             cur_blk = nb;
             __syncthreads();
         }
-        const long long U0 = anchor0 + (unit - (long long)blk * units_per_block) * unit_pos;
+        const long long ub = unit - (long long)blk * units_per_block;
+        const int ulen = ub < n_big ? unit_pos : kKm2SmallUnit;
+        const long long U0 = anchor0 + (ub < n_big ? ub * unit_pos : n_big * unit_pos + (ub - n_big) * kKm2SmallUnit);
         uint32_t* sseq = sh.seq[warp];
         {   // stage the unit's 2-bit words (64 bases of history in front; the allocation has one front word)
             const long long w0 = (U0 >> 4) - kKmHaloWords;
-            const int nw = kKmHaloWords + unit_pos / 16 + 5;
+            const int nw = kKmHaloWords + ulen / 16 + 5;
             for (int i = lane; i < nw; i += 32) sseq[i] = (w0 + i >= -1) ? __ldg(seq2 + w0 + i) : 0u;
         }
         __syncwarp();
@@ -713,8 +718,8 @@ km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, lon
         c.sseq = sseq; c.cn = sh.cn; c.q16 = s_q16; c.q = sh.queue[warp]; c.max_n = db.max_n; c.direct = db.direct;
         c.U0 = U0; c.len = len; c.combo_base = (unsigned long long)blk * kKmCombos; c.cand = cand; c.cand_cap = cand_cap; c.counters = counters;
 #define KM2_RUN(NT_) \
-        if (db.bitmap_words > 0) km2_unit_bitmap<NT_>(c, s_bm, db, tables, sh.hitq[warp], unit_pos); \
-        else km2_unit_plain<NT_>(c, db, tables, unit_pos);
+        if (db.bitmap_words > 0) km2_unit_bitmap<NT_>(c, s_bm, db, tables, sh.hitq[warp], ulen); \
+        else km2_unit_plain<NT_>(c, db, tables, ulen);
         switch (db.nt) {
             case 1: KM2_RUN(1) break;
             case 2: KM2_RUN(2) break;
@@ -728,12 +733,15 @@ km_prefilter_kernel_v2(const uint32_t* __restrict__ seq2, long long anchor0, lon
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Third generation (the default): the warp-organised unit code of the second, but NOT persistent.  A CTA is one
-// (block, range of positions) item of the grid: it loads the block's middle-stage rows / bitmap once, its 32 warps draw the
-// units of the range from a counter in shared memory (no global atomic, no block-change barrier) and the CTA retires.
-// Because CTAs retire all the time, the exact replay / ordering kernels of the previous item (high-priority stream) get
-// SMs within microseconds instead of waiting behind a whole persistent first-stage launch, and the next item's CTAs
-// fill the tail of this one (first-stage launches of different lanes are no longer chained).
+// Third generation (PWMSCAN_KM_KERNEL=3; measured and NOT the default): the warp-organised unit code of the second, but not
+// persistent.  A CTA is one (block, range of positions) item of the grid: it loads the block's middle-stage rows / bitmap
+// once, its 32 warps draw the units of the range from a counter in shared memory (no global atomic, no block-change
+// barrier) and the CTA retires, so that the exact replay / ordering kernels of the previous item (high-priority stream) get
+// SMs within microseconds and the next item's CTAs fill the tail of this one (launches of different lanes not chained).
+// Measured on a config-4 chunk: alone 2.5 / 1.75 / 1.68 ms with ranges of 1 Mi / 512 Ki / 256 Ki positions (wave
+// quantisation: 448 CTAs on 148 SMs; warps idle at the end of every CTA) against 1.36 ms for the persistent kernel, and a
+// whole genome 125 / 100 ms against 86 ms: the hardware interleaves the CTAs of the 2-3 launches in flight instead of
+// running them first-in first-out, so the mask tables of several motif blocks compete for L2.
 __global__ void __launch_bounds__(kKmThreads, 1)
 km_prefilter_kernel_v3(const uint32_t* __restrict__ seq2, long long anchor0, long long n_anchor, long long range_pos, int unit_pos, int ranges_per_block,
                        const DevKmBlock* __restrict__ blocks, const uint8_t* __restrict__ tables, const uint16_t* __restrict__ q16,
@@ -821,7 +829,7 @@ int km_build_table(pwmscan_ctx* ctx, const double* d_wdef, const double* d_dsafe
 }
 
 static int km_kernel_choice() {
-    static const int which = std::getenv("PWMSCAN_KM_KERNEL") ? std::atoi(std::getenv("PWMSCAN_KM_KERNEL")) : 3;    // 1, 2 = the persistent kernels (kept as parity-tested variants)
+    static const int which = std::getenv("PWMSCAN_KM_KERNEL") ? std::atoi(std::getenv("PWMSCAN_KM_KERNEL")) : 2;    // 2 = persistent, warp-organised (default); 1 = persistent, CTA-organised; 3 = not persistent
     return which;
 }
 bool km_prefilter_is_persistent() { return km_kernel_choice() != 3; }
@@ -856,9 +864,17 @@ int launch_km_prefilter(pwmscan_ctx* ctx, ScanLane* lane, cudaStream_t stream, c
         // warp-owned units of 2048 positions (512 for short inputs, so that every warp of every SM gets some)
         int unit_pos = kKm2UnitPos;
         while (unit_pos > 512 && (a1 - a0) / unit_pos * nblocks < 4LL * ctx->sm_count * (kKmThreads / 32)) unit_pos >>= 1;
-        const long long units = (a1 - a0) / unit_pos * nblocks;
+        // the last eighth of a block's positions (at most two short units per warp of the device) goes out in short units
+        long long tail_pos = 0;
+        if (unit_pos > kKm2SmallUnit) {
+            static const bool taper = std::getenv("PWMSCAN_KM_NO_TAPER") == nullptr;      // experiments
+            tail_pos = std::min<long long>((a1 - a0) / 8, 2LL * ctx->sm_count * (kKmThreads / 32) * kKm2SmallUnit) / unit_pos * unit_pos;
+            if (!taper) tail_pos = 0;
+        }
+        const long long n_big = (a1 - a0 - tail_pos) / unit_pos, n_small = tail_pos / kKm2SmallUnit;
+        const long long units = (n_big + n_small) * nblocks;
         const int grid = (int)std::min<long long>(ctx->sm_count, (units + kKmThreads / 32 - 1) / (kKmThreads / 32));
-        km_prefilter_kernel_v2<<<grid, kKmThreads, smem_bytes, stream>>>(d_seq2, a0, a1 - a0, units, unit_pos, nblocks, d_blocks, d_tables, d_q16, d_combos,
+        km_prefilter_kernel_v2<<<grid, kKmThreads, smem_bytes, stream>>>(d_seq2, a0, n_big, n_small, unit_pos, nblocks, d_blocks, d_tables, d_q16, d_combos,
                                                                                len, d_cand, cand_cap, lane->d_counters, work_counter);
         PWM_CUDA(cudaGetLastError());
         return PWMSCAN_OK;

@@ -1184,9 +1184,12 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     const pwmscan_plan* pl = j.pl;
     const pwmscan_motifs* mo = pl->motifs;
     cudaStream_t st = lane->stream;
-    // k-mer first stage: counters, packing and the first-stage kernels run on the lane's low-priority stream, everything behind
-    // them (exact replay, ordering, copies) on the high-priority one
-    cudaStream_t pst = pl->mode == PWM_MODE_KMER ? lane->pstream : lane->stream;
+    // pst: the stream of the counters' reset, the packing and the first-stage kernels; st: everything behind them.
+    // Measured (config 4, one B200): with the first stage on its own low-priority stream and the rest on the high-priority one
+    // a genome takes 94 ms, with everything on the lane's one stream 87 ms (the replay grabs SMs at every first-stage boundary
+    // and delays the next persistent launch).  The split is what the non-persistent first stage (PWMSCAN_KM_KERNEL=3) needs.
+    static const bool split = std::getenv("PWMSCAN_SPLIT_STREAMS") != nullptr || !km_prefilter_is_persistent();
+    cudaStream_t pst = (pl->mode == PWM_MODE_KMER && split) ? lane->pstream : lane->stream;
     int rc;
     const int64_t len = seq->len;
     const int64_t n_anchor = round_up(len + kPadFront + 64, kAnchorRound);
@@ -1405,6 +1408,7 @@ int scan_phase_b(pwmscan_ctx* ctx, ScanJob& j) {
     if (!h) return set_err(ctx, PWMSCAN_EINVAL, "out of host memory");
     j.hits = h;
     h->ctx = ctx; h->count = (int64_t)j.nhits; h->nseg = j.seq->nseg; h->M = pl->motifs->M;
+    if (j.host) { h->first_non_acgt = j.up.seq->first_non_acgt; h->first_non_iupac = j.up.seq->first_non_iupac; }
     if (j.nhits == 0) return PWMSCAN_OK;
     const size_t n = (size_t)j.nhits, n8 = (n + 7) & ~(size_t)7;             // keeps every host column 8-byte aligned
     const bool one = h->nseg == 1;
@@ -1525,7 +1529,10 @@ static int scan_many_impl(pwmscan_ctx* ctx, const pwmscan_plan* pl, int32_t n, c
     int rc = ensure_lut(ctx);
     if (rc) return rc;
     const char* env_lanes = std::getenv("PWMSCAN_LANES");                  // read per call: experiments sweep it within one process
-    const int want_lanes = env_lanes ? std::max(1, std::min(kMaxLanes, std::atoi(env_lanes))) : (seqs ? 4 : 5);
+    // An item holds its lane from the start of its first stage until its hit list has landed: its replay / ordering wait for
+    // SMs behind the next item's first stage, then comes the copy — about four first-stage durations.  Six (seven with the
+    // upload in front) keep the next first stage enqueued in time; with fewer the device idles between launches.
+    const int want_lanes = env_lanes ? std::max(1, std::min(kMaxLanes, std::atoi(env_lanes))) : (seqs ? 6 : 7);
     const int K = std::min<int>(want_lanes, n);
     ScanJob jobs[kMaxLanes];
     double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1709,6 +1716,12 @@ int hits_expand_wide(pwmscan_hits* h) {
 }  // namespace pwmscan
 
 extern "C" int64_t pwmscan_hits_count(const pwmscan_hits* h) { return h ? h->count : -1; }
+
+extern "C" int pwmscan_hits_first_invalid(const pwmscan_hits* h, int alphabet, int64_t* pos_out) {
+    if (!h || !pos_out || alphabet < 0 || alphabet > 1) return PWMSCAN_EINVAL;
+    *pos_out = alphabet == 0 ? h->first_non_acgt : h->first_non_iupac;
+    return PWMSCAN_OK;
+}
 
 extern "C" int pwmscan_hits_columns(const pwmscan_hits* h, const int32_t** motif, const uint8_t** strand, const int32_t** segment,
                                     const int64_t** pos, const double** score) {

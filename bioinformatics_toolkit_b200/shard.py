@@ -21,6 +21,14 @@ def make_items(seq_lengths, n_motifs, chunk_len, motif_block=None):
     return items
 
 
+def pick_chunk_len(total_bp, world_size, items_per_rank=24, lo=8_000_000, hi=64_000_000, step=4_000_000):
+    """Chunk length for a whole-genome scan on `world_size` devices: at least ~items_per_rank items per rank, so that the
+    fill and drain of a rank's pipeline (first stage of item i+1 over replay / ordering / hit copy of item i) stay a small
+    part of the job; never above 64 Mbp (buffer sizes) nor below 8 Mbp (per-launch overheads)."""
+    target = total_bp // max(1, items_per_rank * world_size)
+    return int(min(hi, max(lo, target // step * step)))
+
+
 def item_cost(item, motif_cols=None):
     s, st, en, m0, m1 = item
     w = (m1 - m0) if motif_cols is None else float(np.sum(motif_cols[m0:m1]))

@@ -52,6 +52,7 @@ foreign import ccall safe "pwmscan_plan_free"        c_plan_free    :: Ptr Plan 
 foreign import ccall safe "pwmscan_scan"             c_scan         :: Ptr Ctx -> Ptr Seq -> Ptr Plan -> Ptr (Ptr Hits) -> IO CInt
 foreign import ccall safe "pwmscan_scan_host"        c_scan_host    :: Ptr Ctx -> Ptr Plan -> Ptr Word8 -> Ptr Int64 -> Int32 -> CInt -> Ptr (Ptr Hits) -> IO CInt
 foreign import ccall safe "pwmscan_hits_count"       c_hits_count   :: Ptr Hits -> IO Int64
+foreign import ccall safe "pwmscan_hits_first_invalid" c_hits_first_invalid :: Ptr Hits -> CInt -> Ptr Int64 -> IO CInt
 foreign import ccall safe "pwmscan_hits_columns"     c_hits_columns :: Ptr Hits -> Ptr (Ptr Int32) -> Ptr (Ptr Word8) -> Ptr (Ptr Int32) -> Ptr (Ptr Int64) -> Ptr (Ptr Double) -> IO CInt
 foreign import ccall safe "pwmscan_hits_free"        c_hits_free    :: Ptr Hits -> IO ()
 foreign import ccall safe "pwmscan_hits_affinity"    c_hits_affinity :: Ptr Ctx -> Ptr Hits -> Int32 -> Ptr Int64 -> Ptr Double -> Ptr Double -> Ptr Double -> Ptr Int64 -> IO CInt

@@ -141,6 +141,11 @@ int  pwmscan_scan_host_many(pwmscan_ctx* ctx, const pwmscan_plan* plan, int32_t 
 int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
                        const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);
 int64_t pwmscan_hits_count(const pwmscan_hits* hits);
+/* fromBS verdict (Seq.hs:86-95) of the bytes that were uploaded for THIS hit list by pwmscan_scan_host /
+ * pwmscan_scan_host_many (per item, unlike pwmscan_scan_host_first_invalid): offset of the first byte outside the
+ * alphabet (0 = ACGT, 1 = IUPAC), -1 if there is none — also -1 for scans of resident sequences
+ * (ask pwmscan_seq_first_invalid). */
+int  pwmscan_hits_first_invalid(const pwmscan_hits* hits, int alphabet, int64_t* pos_out);
 /* What the device transfers — the compact columns, in the order above: score[n], pos32[n] (window start within
  * its segment) and
  *   - single-segment scans: run_off[2M+1]; the hits of (motif m, strand s) are [run_off[2m+s], run_off[2m+s+1])

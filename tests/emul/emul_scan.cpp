@@ -321,54 +321,45 @@ int emul_km_plan_info(int M, const int* ncol, const double* mats, const double* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// scoreCDF through csrc/cdf_core.h — the gather form cdf_kernel runs (run boundaries by walking the inverted index
-// function, one output bin = its four runs merged by (x, base)), with the kernel's tile / chunk structure executed
-// serially.  Returns the number of compressed CDF points.
+// scoreCDF through csrc/cdf_core.h — the gather form cdf_kernel runs (run boundaries from the inverted index function with
+// its certified fast test, one output bin = its four runs merged by (x, base)), four adjacent bins per "thread" as in
+// the kernel, executed serially.  Returns the number of compressed CDF points.
 #include "../../bioinformatics_toolkit_b200/csrc/cdf_core.h"
 #include <cmath>
 
 extern "C" __attribute__((visibility("default")))
-int64_t emul_score_cdf(const double* bg, int n, const double* mat, double* out_x, double* out_p, int64_t cap, int64_t* stats /* [0] idx evaluations [1] boundaries */) {
-    constexpr int kMaxBin = 200000, kTile = 1024, kG = 8;
+int64_t emul_score_cdf(const double* bg, int n, const double* mat, double* out_x, double* out_p, int64_t cap) {
+    constexpr int kMaxBin = 200000;
     const double m_epsilon = 2.220446049250313e-16;
     std::vector<double> prev(1, 1.0), nw;
     CdfScFn f{1, 0.0, 0.0};
     int xlo = 0, xhi = 0;
     const double lbg[4] = {std::log(bg[0]), std::log(bg[1]), std::log(bg[2]), std::log(bg[3])};
-    int64_t nbound = 0;
     for (int col = 0; col < n; ++col) {
-        CdfCol c;
-        c.f = f; c.xlo = xlo; c.xhi = xhi;
-        double xb[4];
-        for (int b = 0; b < 4; ++b) { const double p = mat[4 * col + b]; xb[b] = (p == 0 ? std::log(0.001) : std::log(p)) - lbg[b]; }
-        double mn = xb[0], mx = xb[0];
-        for (int b = 1; b < 4; ++b) { if (xb[b] < mn) mn = xb[b]; if (xb[b] > mx) mx = xb[b]; }
+        CdfExact ex;
+        ex.f = f;
+        for (int b = 0; b < 4; ++b) { const double p = mat[4 * col + b]; ex.xb[b] = (p == 0 ? std::log(0.001) : std::log(p)) - lbg[b]; }
+        double mn = ex.xb[0], mx = ex.xb[0];
+        for (int b = 0; b < 4; ++b) { if (ex.xb[b] < mn) mn = ex.xb[b]; if (ex.xb[b] > mx) mx = ex.xb[b]; }
         const double lo = cdf_scfn(f, xlo) + mn, hi = cdf_scfn(f, xhi) + mx;
         if (!(lo < hi)) continue;
         const double nbd = std::ceil((hi - lo) / 1e-5);
+        struct { int nbin; double lo, step; } c;
         c.nbin = nbd > (double)kMaxBin ? kMaxBin : (int)nbd;
         c.lo = lo; c.step = (hi - lo) / (double)c.nbin;
-        cdf_col_setup(c);
+        ex.lo = c.lo; ex.step = c.step;
+        CdfFast q;
+        cdf_fast_setup(q, ex, bg, c.nbin, xlo, xhi, (int)prev.size());
         nw.assign((size_t)c.nbin, 0.0);
         int nlo = 0x7FFFFFFF, nhi = -1;
-        std::vector<int> st((size_t)4 * (kTile + 1));
-        for (int j0 = 0; j0 < c.nbin; j0 += kTile) {
-            const int tn = std::min(kTile, c.nbin - j0);
-            for (int item = 0; item < 4 * (kTile / kG); ++item) {            // one item per thread: (base, chunk of kG bins)
-                const int b = item & 3, jj0 = (item >> 2) * kG;
-                if (jj0 > tn) continue;
-                CdfWalk w;
-                const CdfBase cb = cdf_base_setup(c, xb[b]);
-                cdf_walk_begin(c, cb, j0 + jj0, w);
-                st[(size_t)b * (kTile + 1) + jj0] = w.x;
-                for (int g = 1; g <= kG && jj0 + g <= tn; ++g) { cdf_walk_next(c, cb, j0 + jj0 + g, w); st[(size_t)b * (kTile + 1) + jj0 + g] = w.x; ++nbound; }
-            }
-            for (int jj = 0; jj < tn; ++jj) {
-                const int* s0 = &st[0 * (kTile + 1) + jj]; const int* s1 = &st[1 * (kTile + 1) + jj];
-                const int* s2 = &st[2 * (kTile + 1) + jj]; const int* s3 = &st[3 * (kTile + 1) + jj];
-                const double acc = cdf_gather_bin(prev.data(), bg, s0[0], s0[1], s1[0], s1[1], s2[0], s2[1], s3[0], s3[1]);
-                nw[(size_t)j0 + jj] = acc;
-                if (acc != 0.0) { nlo = std::min(nlo, j0 + jj); nhi = std::max(nhi, j0 + jj); }
+        const int last = (int)prev.size() - 1;
+        for (int j = 0; j < c.nbin; j += 4) {
+            int B[4][5];
+            for (int k = 0; k < 4; ++k) for (int g = 0; g < 5; ++g) B[k][g] = cdf_boundary(q, &ex, k, j + g);
+            for (int g = 0; g < 4 && j + g < c.nbin; ++g) {
+                const double acc = cdf_gather_bin(prev.data(), q, last, B[0][g], B[0][g + 1], B[1][g], B[1][g + 1], B[2][g], B[2][g + 1], B[3][g], B[3][g + 1]);
+                nw[(size_t)j + g] = acc;
+                if (acc != 0.0) { nlo = std::min(nlo, j + g); nhi = std::max(nhi, j + g); }
             }
         }
         prev.swap(nw);
@@ -388,6 +379,5 @@ int64_t emul_score_cdf(const double* bg, int n, const double* mat, double* out_x
         }
         if (keep) { if (cnt < cap) { out_x[cnt] = cdf_scfn(f, (int)i); out_p[cnt] = P[(size_t)i]; } ++cnt; }
     }
-    if (stats) { stats[0] = 0; stats[1] = nbound; }
     return cnt;
 }

@@ -26,7 +26,7 @@ def emul_cdf():
         xs, ps = np.zeros(200001), np.zeros(200001)
         vp = C.c_void_p
         n = L.emul_score_cdf(bga.ctypes.data_as(vp), C.c_int(mat.shape[0]), mat.ctypes.data_as(vp), xs.ctypes.data_as(vp), ps.ctypes.data_as(vp),
-                             C.c_int64(200001), None)
+                             C.c_int64(200001))
         return xs[:n], ps[:n]
     return run
 
@@ -47,6 +47,8 @@ def test_synthetic_shapes_and_backgrounds(emul_cdf, oracle):
     mats = synth.synth_pwms(6, 31, nmin=1, nmax=22) + synth.config_c4_motifs(800)[::160]
     mats.append(np.array([[0.25] * 4] * 5))                                   # lo == hi columns are skipped (Motif.hs:299)
     mats.append(np.array([[1.0, 0, 0, 0], [0, 0, 0, 1.0], [0, 0.5, 0.5, 0], [0.97, 0.01, 0.01, 0.01]]))
+    # equal entries in a column: the runs of two bases coincide and must be merged element by element in (x, base) order
+    mats.append(np.array([[0.4, 0.4, 0.1, 0.1], [0.1, 0.2, 0.2, 0.5], [0.3, 0.3, 0.3, 0.1], [0.25, 0.25, 0.3, 0.2]] * 3))
     for bg in ((0.25, 0.25, 0.25, 0.25), (0.3, 0.2, 0.2, 0.3), (0.1, 0.4, 0.15, 0.35)):
         for i, mat in enumerate(mats):
             x, p = emul_cdf(bg, mat)

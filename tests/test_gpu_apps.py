@@ -10,7 +10,7 @@ from bioinformatics_toolkit_b200 import merge as M
 from bioinformatics_toolkit_b200 import motif as Mo
 from bioinformatics_toolkit_b200 import synth
 from bioinformatics_toolkit_b200.alignment import AlignFn, alignment
-from bioinformatics_toolkit_b200.bed_utils import mkCutoffMotifs, scanMotif, streamBed3
+from bioinformatics_toolkit_b200.bed_utils import mkCutoffMotifs, scanGenome, scanMotif, streamBed3
 from bioinformatics_toolkit_b200.seq_io import getChrSizes, getSeq, openGenome, write_genome
 
 pytestmark = pytest.mark.gpu
@@ -63,6 +63,30 @@ def test_scan_motif_app_lines(small_genome, tmp_path):
     exp = app_oracle.scan_motif_lines(chroms, names, mats, beds, p=p)
     assert len(exp) > 50
     assert got == exp
+
+
+def test_scan_genome_whole_chromosomes_from_the_store(small_genome):
+    """scanGenome = scanMotif over [(chr, 0, size)] for every chromosome of the index file, read through pinned staging
+    buffers in small chunks (several chunks + halos per chromosome, pwmscan_scan_host_many): BED6 text byte-identical to
+    the oracle app on whole-chromosome regions; chrW holds a byte outside the IUPAC alphabet and is skipped (fromBS)."""
+    from oracle import app_oracle
+    path, chroms = small_genome
+    mats = synth.synth_pwms(10, 45, nmin=6, nmax=19)
+    names = [b"G%02d" % i for i in range(len(mats))]
+    motifs = [Mo.Motif(nm, Mo.PWM(None, m)) for nm, m in zip(names, mats)]
+    p = 1e-3
+    cms = mkCutoffMotifs(Mo.default_bkgd, p, motifs)
+    g = openGenome(path)
+    beds = [(c, 0, n) for c, n in getChrSizes(g)]
+    exp = app_oracle.scan_motif_lines(chroms, names, mats, beds, p=p)
+    assert len(exp) > 200
+    for chunk_len in (7000, 1 << 20):
+        out = io.BytesIO()
+        n = scanGenome(g, cms, out=out, chunk_len=chunk_len, warn=None)
+        got = out.getvalue().split(b"\n")[:-1] if n else []
+        assert got == exp, chunk_len
+    tuples = scanGenome(g, cms, chroms=[b"chr2"], chunk_len=9000, warn=None)
+    assert len(tuples) == sum(1 for l in exp if l.startswith(b"chr2\t"))
 
 
 def test_iterative_merge_and_tree(oracle):

@@ -115,11 +115,11 @@ def motifs_of(name):
 
 
 def c4_items(world):
-    """The (all motif blocks x 64 Mbp chromosome chunk) items of config 4 and their assignment to the ranks."""
+    """The (all motif blocks x chromosome chunk of <= 64 Mbp) items of config 4 and their assignment to the ranks: equal shares of
+    the genome's concatenated coordinates (shard.partition_contiguous)."""
     from bioinformatics_toolkit_b200 import shard, synth
     lengths = [l for _, l in synth.HG38_CHROM_SIZES]
-    items = shard.make_items(lengths, 800, chunk_len=shard.pick_chunk_len(sum(lengths), world))
-    return lengths, shard.assign(items, world)
+    return lengths, shard.partition_contiguous(lengths, 800, world)
 
 
 def c4_chunk(it, lengths, nmax):

@@ -33,6 +33,10 @@ constexpr size_t kKmSmemBudget = (size_t)194 << 10;     // dynamic shared memory
                                                         // (+ ~32 KB static: staged sequence words and queues of the 32 warps <= 227 KB)
 constexpr double kKmBitmapClk = 0.4;            // clocks per position and SM of the shared-memory bitmap look-up: its wavefronts (~0.11, bank
                                                 // conflicts included) share L1TEX with the gathers, plus index/test instructions — fitted on C2
+// The bitmap path compacts its hits through a per-warp queue, one hit per lane and round; once more than about a fifth of the
+// positions are hits the rounds stop amortising and its cost grows faster than linearly (measured on config-4 chunks, clocks per
+// position and SM: P(hit) 0.05 -> 0.54, 0.20 -> 1.20, 0.34 -> 2.87, against 1.9 - 2.0 for the plain path on the same blocks).
+constexpr double kKmBitmapDenseFrom = 0.2, kKmBitmapDenseClk = 50.0;
 constexpr int kKmQ = 4000;                      // fixed-point budget of the middle stage; entries saturate at 4095 (12 bits)
 
 inline size_t km_table_bytes(int L) { return ((size_t)1 << (2 * L)) * kKmWords * 4; }
@@ -225,9 +229,11 @@ inline void km_build_block(const std::vector<ComboInput>& in, KmBlockPlan& bp, i
                 for (int s = 2; s < cur.nt; ++s) r_bm += pnz[s];
                 for (int s = 1; s < cur.nt; ++s) r_plain += pnz[s];
                 static const int force_bm = std::getenv("PWMSCAN_FORCE_BITMAP") ? std::atoi(std::getenv("PWMSCAN_FORCE_BITMAP")) : -1;   // experiments
-                trial.bitmap = bitmap_fits(trial.order[0]) && (force_bm < 0 ? r_bm + kKmBitmapClk < r_plain : force_bm != 0);
+                const double dense = std::max(0.0, pnz[1] - kKmBitmapDenseFrom);
+                const double bm_clk = kKmBitmapClk + kKmBitmapDenseClk * dense * dense;
+                trial.bitmap = bitmap_fits(trial.order[0]) && (force_bm < 0 ? r_bm + bm_clk < r_plain : force_bm != 0);
                 const double r = trial.bitmap ? r_bm : r_plain;
-                const double cost = r + (trial.bitmap ? kKmBitmapClk : 0.0) + kSurvClk * trial.surv_rate;
+                const double cost = r + (trial.bitmap ? bm_clk : 0.0) + kSurvClk * trial.surv_rate;
                 if (!have_cur || cost < cur.cost) { cur = trial; cur.cost = cost; req = r; have_cur = true; }
                 alpha = std::exp(-tab_sum[first]);
                 if (cur.nt == 1) break;
@@ -303,7 +309,10 @@ inline void build_km_host_plan(const std::vector<MotifHost>& mh, const std::vect
         if (ok) pre.push_back(m);
         else for (int s = 0; s < strands; ++s) hp.generic.emplace_back(m, s);
     }
-    std::stable_sort(pre.begin(), pre.end(), [&](int a, int b) { return mh[a].n < mh[b].n; });
+    // Longest motifs first: the windows of long motifs pass most often, so their blocks are the expensive ones, and the cost of a
+    // block grows less than linearly with its combos (1 - exp(-sum of pass rates)) — the expensive motifs belong together in
+    // full blocks, and the partial last block falls to the shortest motifs, whose blocks cost the bitmap scan and little else.
+    std::stable_sort(pre.begin(), pre.end(), [&](int a, int b) { return mh[a].n > mh[b].n; });
     const int per_block = strands == 2 ? kKmMotifsPerBlock : kKmCombos;        // forward-only: 256 motifs per block
     const int nblocks = (int)((pre.size() + per_block - 1) / per_block);
     hp.blocks.resize(nblocks);

@@ -29,6 +29,42 @@ def pick_chunk_len(total_bp, world_size, items_per_rank=24, lo=8_000_000, hi=64_
     return int(min(hi, max(lo, target // step * step)))
 
 
+def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000, align=32):
+    """Whole-genome scan on `world_size` devices with as few, as large items as possible: the genome's concatenated coordinate
+    space is cut into `world_size` contiguous stretches of equal length (a chunk may start anywhere: every item carries its own
+    halo), each stretch into its pieces of single sequences, each piece into equal chunks of at most `max_chunk` window starts
+    (cut points on multiples of `align`).  Per-launch costs of the first stage (block changes, the tail of every block) are paid
+    per item, so 64 Mbp items cost ~25 % less per base than 16 Mbp ones.  Returns a list (per rank) of items
+    (seq index, start, end, 0, n_motifs); a rank's items run largest first, so that what is left when its last first stage has
+    ended — replay, ordering and the copy of ONE item's hits — is as short as it can be."""
+    total = int(sum(seq_lengths))
+    bounds = [total * r // world_size for r in range(world_size + 1)]
+    out = [[] for _ in range(world_size)]
+    base = 0
+    for s, L in enumerate(seq_lengths):
+        for r in range(world_size):
+            lo, hi = max(bounds[r], base), min(bounds[r + 1], base + L)
+            if hi <= lo:
+                continue
+            lo, hi = lo - base, hi - base
+            # cut points inside a sequence go to multiples of `align` (the next rank starts exactly where this one stops)
+            if lo > 0:
+                lo = min(L, (lo + align - 1) // align * align)
+            if hi < L:
+                hi = min(L, (hi + align - 1) // align * align)
+            if hi <= lo:
+                continue
+            k = max(1, -(-(hi - lo) // max_chunk))
+            cuts = [lo + ((hi - lo) * i // k) // align * align for i in range(k)] + [hi]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                if b > a:
+                    out[r].append((s, a, b, 0, n_motifs))
+        base += L
+    for r in range(world_size):
+        out[r].sort(key=lambda it: (-(it[2] - it[1]), it[0], it[1]))
+    return out
+
+
 def item_cost(item, motif_cols=None):
     s, st, en, m0, m1 = item
     w = (m1 - m0) if motif_cols is None else float(np.sum(motif_cols[m0:m1]))

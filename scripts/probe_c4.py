@@ -7,7 +7,7 @@ BG = (0.25,) * 4
 ctx = _lib.default_context(0)
 mats = synth.config_c4_motifs(800)
 th = np.array([float.fromhex(v) for v in json.load(open("tests/golden/config_thresholds.json"))["c4"]])
-dna = synth.synth_dna(64_000_000, 5, gc=0.41)
+dna = synth.synth_dna(int(os.environ.get("PROBE_BP", "64000000")), 5, gc=0.41)
 mo = _lib.DeviceMotifs(ctx, mats, BG)
 plan = _lib.Plan(mo, th)
 seq = _lib.DeviceSeq(ctx, dna)

@@ -241,9 +241,9 @@ def test_km_planner_decisions(emul):
     assert (nt, l0, bitmap) == (2, 10, 0) and 1.5e6 < sectors < 1.8e6 and surv < 0.06e6 and 1.5e3 < cand < 3e3 and mib == 64
     c4 = plan(synth.config_c4_motifs(800), [float.fromhex(v) for v in th_all["c4"]])
     assert c4.shape[0] == 7                                    # 800 motifs / 128 per block
-    assert c4[:, 2].sum() >= 6                                 # sparse first tables -> bitmap
+    assert c4[:, 2].sum() >= 5                                 # sparse first tables -> bitmap (the block of the longest motifs is dense: plain path)
     assert c4[:, 3].sum() < 2.0e6                              # < 2 sectors per position over all seven blocks
-    assert np.all(np.diff(c4[:, 6]) >= 0)                      # blocks are sorted by motif length
+    assert np.all(np.diff(c4[:, 6]) <= 0)                      # blocks are sorted by motif length, longest first
     one = plan([synth.ctcf_like_pwm()], [float.fromhex(th_all["c1"][0])])
     assert one.shape[0] == 1 and one[0, 3] < 0.05e6            # one motif: almost every position stops at the bitmap
 

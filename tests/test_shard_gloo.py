@@ -30,7 +30,26 @@ def test_items_cover_everything_once():
     assert max(loads) <= 1.5 * (sum(loads) / 3) + 400 * 3
 
 
-def _worker(rank, world, port, q):
+def test_contiguous_partition_covers_everything_once_in_equal_shares():
+    lengths = [l for _, l in synth.HG38_CHROM_SIZES]
+    for world in (1, 2, 3, 8):
+        parts = shard.partition_contiguous(lengths, 800, world, max_chunk=64_000_000)
+        cover = {}
+        for r in parts:
+            assert [it[2] - it[1] for it in r] == sorted((it[2] - it[1] for it in r), reverse=True)       # largest first
+            for (s, st, en, m0, m1) in r:
+                assert (m0, m1) == (0, 800) and 0 < en - st <= 64_000_000 and (st % 32 == 0)
+                cover.setdefault(s, []).append((st, en))
+        for s, L in enumerate(lengths):
+            iv = sorted(cover[s])
+            assert iv[0][0] == 0 and iv[-1][1] == L and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+        loads = [sum(it[2] - it[1] for it in r) for r in parts]
+        assert max(loads) - min(loads) <= 64 * world                                                       # equal up to the alignment of the cuts
+    tiny = shard.partition_contiguous([100, 0, 7], 5, 4, max_chunk=40)
+    assert sorted(sum(tiny, [])) == sorted([(0, 0, 32, 0, 5), (0, 32, 64, 0, 5), (0, 64, 96, 0, 5), (0, 96, 100, 0, 5), (2, 0, 7, 0, 5)])
+
+
+def _worker(rank, world, port, q, contiguous=False):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import oracle as O
@@ -44,6 +63,8 @@ def _worker(rank, world, port, q):
     nmax = max(m.shape[0] for m in mats)
     items = shard.make_items(lengths, len(mats), chunk_len=7000, motif_block=4)
     mine = shard.assign(items, world, np.array([m.shape[0] for m in mats]))[rank]
+    if contiguous:
+        mine = shard.partition_contiguous(lengths, len(mats), world, max_chunk=9000)[rank]
     per_item = []
     for it in mine:
         s, st, en, m0, m1 = it
@@ -66,12 +87,13 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_world_size_2_gloo():
+@pytest.mark.parametrize("contiguous", [False, True])
+def test_world_size_2_gloo(contiguous):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (2000 if contiguous else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, contiguous)) for r in range(2)]
     for p in procs:
         p.start()
     ok = q.get(timeout=180)

@@ -43,6 +43,7 @@ struct pwmscan_ctx {
     bool prefilter_chain_valid = false;          // (lds, mma, kmer kernels 1 and 2) run one after the other; the default one is not chained
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host->device chunks of pwmscan_scan_host
+    cudaStream_t d2h_stream = nullptr;           // hit lists of all lanes to the host
     std::vector<cudaEvent_t> chunk_ev;           // one per in-flight chunk (created on demand)
     std::mutex mu;
     std::string err;

@@ -137,6 +137,27 @@ int  pwmscan_scan_many(pwmscan_ctx* ctx, const pwmscan_plan* plan, int32_t n, co
                        pwmscan_hits_cb cb, void* user);
 int  pwmscan_scan_host_many(pwmscan_ctx* ctx, const pwmscan_plan* plan, int32_t n, const uint8_t* const* ascii,
                             const int64_t* lens, int flags, pwmscan_hits_cb cb, void* user);
+/* ---- the packed genome store ------------------------------------------------------------------------------------
+ * A genome that is scanned again and again need not cross PCIe as one byte per base each time: next to the bytes that
+ * mkIndex writes (Seq/IO.hs:87-106) the index can keep the two planes the device scans — 2 bits per base (16 bases per
+ * uint32, base t at bits 2t..2t+1; A C G T = 0 1 2 3) and 1 bit per base "not A/C/G/T" — 0.375 bytes per base, made ONCE by
+ * pwmscan_pack_host (host, multi-threaded; same codes as the device packer).  Unit: 32 bases = 2 words + 1 word;
+ * units = pwmscan_packed_units(len) = ceil(len / 32); seq2_out holds 2 * units words, mask_out units words.  A slice
+ * that starts at a multiple of 32 bases is a valid packed sequence of its own (seq2 + start / 16, mask + start / 32) —
+ * what the (motif block x chromosome chunk) items of a genome scan pass to pwmscan_scan_packed_many.
+ * first_non_acgt / first_non_iupac: fromBS's verdict (Seq.hs:86-95) of the bytes, -1 if all are inside the alphabet;
+ * flags: PWMSCAN_SEQ_UPPERCASE.  nthreads <= 0: all host cores. */
+int64_t pwmscan_packed_units(int64_t len);
+int  pwmscan_pack_host(const uint8_t* ascii, int64_t len, int flags, uint32_t* seq2_out, uint32_t* mask_out,
+                       int64_t* first_non_acgt, int64_t* first_non_iupac, int nthreads);
+/* getSeq / getChrom from the packed store -> a resident sequence (hits identical to pwmscan_seq_upload of the bytes;
+ * pwmscan_seq_first_invalid answers the `Basic` alphabet from the mask plane and -1 for IUPAC: an index whose bytes are
+ * not IUPAC was rejected when it was packed). */
+int  pwmscan_seq_upload_packed(pwmscan_ctx* ctx, const uint32_t* seq2, const uint32_t* mask, int64_t len, pwmscan_seq** out);
+/* pwmscan_scan_host_many for items given as packed planes (pinned host memory for full PCIe speed); plans made with
+ * skip_ambiguous = 0 need the bytes and are refused. */
+int  pwmscan_scan_packed_many(pwmscan_ctx* ctx, const pwmscan_plan* plan, int32_t n, const uint32_t* const* seq2,
+                              const uint32_t* const* mask, const int64_t* lens, pwmscan_hits_cb cb, void* user);
 /* Convenience: plan_create + scan + plan_free. */
 int  pwmscan_find_tfbs(pwmscan_ctx* ctx, const pwmscan_seq* seq, const pwmscan_motifs* motifs,
                        const double* thres, int strands, int skip_ambiguous, pwmscan_hits** out);

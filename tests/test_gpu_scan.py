@@ -551,3 +551,40 @@ def test_config_c2_slices_on_seams(ctx, oracle):
         assert np.array_equal(h.score[k].view(np.uint64), o[3].view(np.uint64))
         tot += cnt
     assert tot > 1000
+
+
+def test_packed_genome_store_equals_the_bytes(ctx, oracle):
+    """The packed genome store (pwmscan_pack_host -> pwmscan_seq_upload_packed / pwmscan_scan_packed_many): a sequence
+    uploaded as its 2-bit + mask planes gives the hit lists of the same sequence uploaded as bytes — whole sequences
+    (N runs, lower case with the upper-casing flag, lengths around the 32-base unit, empty) and slices that start at a
+    multiple of 32 and end anywhere inside a longer sequence; the oracle confirms one of them."""
+    mats = synth.synth_pwms(90, 8, nmin=6, nmax=21)
+    thres = [0.58 * oracle.optimal_score(BG, m) for m in mats]
+    plan = _lib.Plan(_lib.DeviceMotifs(ctx, mats, BG), thres)
+    lens = [1_500_000, 0, 31, 32, 33, 700_001, 2_000_000]
+    arrays = [synth.synth_dna(L, 500 + i, gc=0.42, n_runs=[(L // 3, 700), (L - 40, 40)] if L > 1000 else ()) for i, L in enumerate(lens)]
+    low = arrays[0].copy()
+    low[1000:200_000] |= 0x20                                     # lower case
+    arrays.append(low)
+    packed = [_lib.PackedSeq(a, uppercase=True, pinned=(i % 2 == 0)) for i, a in enumerate(arrays)]
+    by_bytes = [plan.scan(_lib.DeviceSeq(ctx, a, uppercase=True)) for a in arrays]
+    assert sum(len(h) for h in by_bytes) > 10000
+    for a, p, ref in zip(arrays, packed, by_bytes):
+        seq = _lib.DeviceSeq.from_packed(ctx, p)
+        _same_hits(ref, plan.scan(seq))
+        assert seq.first_invalid("Basic") == _lib.DeviceSeq(ctx, a, uppercase=True).first_invalid("Basic") == p.first_non_acgt
+    many = plan.scan_packed_many([(p, 0, None) for p in packed])
+    for ref, h in zip(by_bytes, many):
+        _same_hits(ref, h)
+    assert_same(many[5], oracle_scan(oracle, mats, thres, arrays[5]))
+    # slices of a longer sequence: what the (motif block x chromosome chunk) items of a genome scan pass
+    big, pbig = arrays[6], packed[6]
+    cuts = [(0, 640_000 + 20), (640_000, 1_280_033), (1_280_000, 2_000_000), (1_999_968, 2_000_000), (666_656, 666_700)]
+    sl = plan.scan_packed_many([(pbig, a, b) for a, b in cuts])
+    for (a, b), h in zip(cuts, sl):
+        _same_hits(plan.scan(_lib.DeviceSeq(ctx, big[a:b])), h)
+        _same_hits(h, plan.scan(_lib.DeviceSeq.from_packed(ctx, pbig, a, b)))
+    # IUPAC-aware plans need the bytes
+    iupac_plan = _lib.Plan(_lib.DeviceMotifs(ctx, mats[:3], BG), thres[:3], skip_ambiguous=False)
+    with pytest.raises(_lib.PwmScanError):
+        iupac_plan.scan_packed_many([(packed[0], 0, None)])

@@ -307,6 +307,8 @@ def main():
     for _ in range(args.steps):
         l2_flush()
         nh = step_resident()
+    torch.cuda.synchronize()
+    t_mine = time.perf_counter()                     # this rank's own finish, before the barrier evens the ranks out
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop()
@@ -318,6 +320,11 @@ def main():
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
         dist.all_reduce(un, op=dist.ReduceOp.SUM)
         dist.all_reduce(hits_all, op=dist.ReduceOp.SUM)
+    per_rank_ms = [1e3 * (t_mine - t0) / args.steps]
+    if world > 1:
+        g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([per_rank_ms[0]], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [float(x.item()) for x in g]
     ms_step = 1e3 * el.item() / args.steps
     value = un.item() / (ms_step / 1e3) / 1e9
 
@@ -421,6 +428,7 @@ def main():
     hit_bytes = res["d2h_bytes"] / args.steps
     phases = {"per_step_rank0_ms": {"first_stage": res["prefilter_ms"] / args.steps, "rescore": res["rescore_ms"] / args.steps,
                                     "order": res["order_ms"] / args.steps},
+              "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms],
               "hit_bytes_to_host_per_step_rank0": hit_bytes, "hit_d2h_gbs_if_serial": hit_bytes / (ms_step / 1e3) / 1e9,
               "note": "CUDA-event time on each item's stream, summed over the items of a step; items overlap (3 in flight), so the sum may exceed ms_per_step"}
 

@@ -18,7 +18,7 @@ struct KeyLayout { int pb, mb; };
 constexpr int kOrderCap = 4096;        // hits one CTA orders in shared memory (order.cu)
 constexpr int kOrderIdxBits = 12;      // log2(kOrderCap)
 constexpr int kOrderTarget = 8;        // hits per bucket aimed at (a warp orders spans of whole buckets, up to 256 hits, in registers: order.cu)
-constexpr int kMaxLanes = 8;           // scans in flight of pwmscan_scan_many (default: 6 resident items, 7 host items)
+constexpr int kMaxLanes = 12;          // scans in flight of pwmscan_scan_many (default: 6 resident items, 7 host items)
 
 // Everything one in-flight scan needs of its own: streams, events, counters, grow-only scratch.  Lane 0 shares the
 // context's streams and counters (single scans run on it); lanes 1.. are created on demand by pwmscan_scan_many.

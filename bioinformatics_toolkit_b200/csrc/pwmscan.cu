@@ -1527,7 +1527,8 @@ int scan_phase_b(pwmscan_ctx* ctx, ScanJob& j) {
     // The hit lists of all lanes leave on ONE device->host stream (the host has seen this item's counters: everything the copies
     // read is final, no event to wait for).  On the lanes' own streams the copies of some lanes completed only together with
     // uploads that had been enqueued ahead on the host->device stream (4.8 instead of 1.2 ms for 25 MB).
-    cudaStream_t ds = ctx->d2h_stream;
+    static const bool d2h_on_lane = std::getenv("PWMSCAN_D2H_LANE") != nullptr;          // experiments
+    cudaStream_t ds = d2h_on_lane ? st : ctx->d2h_stream;
     PWM_CUDA(cudaMemcpyAsync(hb, oc.score, n * 8, cudaMemcpyDeviceToHost, ds));
     PWM_CUDA(cudaMemcpyAsync(hb + n8 * 8, oc.pos32, n * 4, cudaMemcpyDeviceToHost, ds));
     if (one) {

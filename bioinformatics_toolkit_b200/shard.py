@@ -29,14 +29,15 @@ def pick_chunk_len(total_bp, world_size, items_per_rank=24, lo=8_000_000, hi=64_
     return int(min(hi, max(lo, target // step * step)))
 
 
-def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000, align=32):
+def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000, align=32, tail_chunk=16_000_000):
     """Whole-genome scan on `world_size` devices with as few, as large items as possible: the genome's concatenated coordinate
     space is cut into `world_size` contiguous stretches of equal length (a chunk may start anywhere: every item carries its own
     halo), each stretch into its pieces of single sequences, each piece into equal chunks of at most `max_chunk` window starts
     (cut points on multiples of `align`).  Per-launch costs of the first stage (block changes, the tail of every block) are paid
     per item, so 64 Mbp items cost ~25 % less per base than 16 Mbp ones.  Returns a list (per rank) of items
-    (seq index, start, end, 0, n_motifs); a rank's items run largest first, so that what is left when its last first stage has
-    ended — replay, ordering and the copy of ONE item's hits — is as short as it can be."""
+    (seq index, start, end, 0, n_motifs); a rank's items run largest first and its last one is cut into pieces of at most
+    `tail_chunk`, so that what is left when its last first stage has ended — replay, ordering and the copy of ONE item's hits —
+    is as short as it can be."""
     total = int(sum(seq_lengths))
     bounds = [total * r // world_size for r in range(world_size + 1)]
     out = [[] for _ in range(world_size)]
@@ -62,6 +63,13 @@ def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000
         base += L
     for r in range(world_size):
         out[r].sort(key=lambda it: (-(it[2] - it[1]), it[0], it[1]))
+        # the rank's last item goes out in pieces of at most `tail_chunk`: what cannot overlap anything is the replay, ordering
+        # and hit copy of the LAST piece only
+        if tail_chunk and out[r] and out[r][-1][2] - out[r][-1][1] > tail_chunk:
+            s, a, b, m0, m1 = out[r].pop()
+            k = -(-(b - a) // tail_chunk)
+            cuts = [a + ((b - a) * i // k) // align * align for i in range(k)] + [b]
+            out[r] += [(s, x, y, m0, m1) for x, y in zip(cuts[:-1], cuts[1:]) if y > x]
     return out
 
 

@@ -36,7 +36,9 @@ def test_contiguous_partition_covers_everything_once_in_equal_shares():
         parts = shard.partition_contiguous(lengths, 800, world, max_chunk=64_000_000)
         cover = {}
         for r in parts:
-            assert [it[2] - it[1] for it in r] == sorted((it[2] - it[1] for it in r), reverse=True)       # largest first
+            sizes = [it[2] - it[1] for it in r]
+            big = [x for x in sizes if x > 16_000_000]
+            assert big == sorted(big, reverse=True) and sizes[:len(big)] == big                           # largest first, the last item in pieces <= 16 Mbp
             for (s, st, en, m0, m1) in r:
                 assert (m0, m1) == (0, 800) and 0 < en - st <= 64_000_000 and (st % 32 == 0)
                 cover.setdefault(s, []).append((st, en))
@@ -45,7 +47,7 @@ def test_contiguous_partition_covers_everything_once_in_equal_shares():
             assert iv[0][0] == 0 and iv[-1][1] == L and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
         loads = [sum(it[2] - it[1] for it in r) for r in parts]
         assert max(loads) - min(loads) <= 64 * world                                                       # equal up to the alignment of the cuts
-    tiny = shard.partition_contiguous([100, 0, 7], 5, 4, max_chunk=40)
+    tiny = shard.partition_contiguous([100, 0, 7], 5, 4, max_chunk=40, tail_chunk=0)
     assert sorted(sum(tiny, [])) == sorted([(0, 0, 32, 0, 5), (0, 32, 64, 0, 5), (0, 64, 96, 0, 5), (0, 96, 100, 0, 5), (2, 0, 7, 0, 5)])
 
 

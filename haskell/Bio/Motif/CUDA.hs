@@ -17,6 +17,12 @@ module Bio.Motif.CUDA
     , scanChunksGPU
     , hitsAffinityGPU
     , alignAllPairsGPU
+    , PackedDNA (..)
+    , packDNA
+    , scanPackedChunksGPU
+    , mkPlan
+    , getSeqRaw
+    , batchesOf
     ) where
 
 import           Control.Exception        (bracket)
@@ -34,6 +40,7 @@ import           Foreign.C.String
 import           Foreign.C.Types
 import           Data.IORef
 import           System.Environment       (lookupEnv)
+import           System.IO                (Handle, SeekMode (AbsoluteSeek), hSeek)
 import           System.IO.Unsafe         (unsafePerformIO)
 
 import           Bio.Motif                (Bkgd (..), CDF (..), PWM (..), size)
@@ -214,6 +221,37 @@ scanChunksGPU plan nMotif chunks = do
     go chunks [] []
     freeHaskellFunPtr cb
     reverse <$> readIORef acc
+
+-- | The plan `scanMotif` scans with (Bio/Data/Bed/Utils.hs:101-118): every CutoffMotif's PWM on both strands, ambiguous
+-- bases skipped, its stored cutoff.  `parts` = [(pwm, cutoff)] in the order of the motif list (the reverse-complement
+-- tables and both sigma vectors are computed by the library and are bit-identical to `_sigma` / `_sigmaRc`; pass a
+-- CutoffMotif as (_motifPwm m, _cutoff m)).  Lives as long as the process (scanMotif builds it once per motif list).
+mkPlan :: Bkgd -> [(PWM, Double)] -> IO (Ptr Plan)
+mkPlan (BG (a, c, g, t)) parts =
+    S.unsafeWith ncol $ \pn -> S.unsafeWith flat $ \pm -> S.unsafeWith bg $ \pb -> withArray (map snd parts) $ \pt -> do
+        mo <- alloca $ \pp -> c_motifs_create theCtx (fromIntegral $ length parts) pn pm pb pp >>= check theCtx >> peek pp
+        alloca $ \pp -> c_plan_create theCtx mo pt 2 1 pp >>= check theCtx >> peek pp
+  where
+    ncol = S.fromList $ map (fromIntegral . size . fst) parts :: S.Vector Int32
+    flat = S.concat $ map (S.convert . M.flatten . _mat . fst) parts :: S.Vector Double
+    bg   = S.fromList [a, c, g, t]
+
+-- | `getSeq` (Bio/Seq/IO.hs:65-75) without `fromBS`: the bytes of (chr, start, end) as they are in the genome store —
+-- the device upper-cases them and reports fromBS's verdict for the batch (pwmscan_scan_host_first_invalid).
+-- Arguments are the three fields of the reference's `Genome` record (handle, index table lookup, header size).
+getSeqRaw :: Handle -> (B.ByteString -> Maybe (Int, Int)) -> Int -> (B.ByteString, Int, Int) -> IO (Either String B.ByteString)
+getSeqRaw h index headerSize (chr, start, end) = case index chr of
+    Just (chrStart, chrSize)
+        | end > chrSize -> return $ Left $ "Bio.Seq.getSeq: out of index: " ++ show end ++ ">" ++ show chrSize
+        | otherwise     -> do hSeek h AbsoluteSeek $ fromIntegral $ headerSize + chrStart + start
+                              Right <$> B.hGet h (end - start)
+    _ -> return $ Left $ "Bio.Seq.getSeq: Cannot find " ++ show chr
+
+-- | Lists of up to n consecutive elements (the batches of BED records scanMotif hands to the device); plain list version
+-- of what the conduit in INTEGRATION.md does with `Data.Conduit.List.chunksOf`-style buffering.
+batchesOf :: Int -> [a] -> [[a]]
+batchesOf _ [] = []
+batchesOf n xs = let (a, b) = splitAt n xs in a : batchesOf n b
 
 -- | The hits of a single-sequence scan as runs: per (motif, strand) the (position, score) pairs in ascending position.
 hitsRuns :: Int -> Ptr Hits -> IO [((Int, Bool), [(Int, Double)])]

@@ -16,7 +16,8 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(src)))
 h = next(i for i, r in enumerate(rows) if r and r[0] == 'Line No')
 hd = rows[h]
-iL, iS, iI, iT, iW = hd.index('Line No'), hd.index('# Samples'), hd.index('Instructions Executed'), hd.index('Thread Instructions Executed'), hd.index('L1 Wavefronts Shared')
+iL, iS, iI, iT = hd.index('Line No'), hd.index('# Samples'), hd.index('Instructions Executed'), hd.index('Thread Instructions Executed')
+iW = hd.index('L1 Wavefronts Shared') if 'L1 Wavefronts Shared' in hd else None
 agg = collections.defaultdict(lambda: [0, 0, 0, 0]); text = {}; tot = [0, 0, 0]
 def f(x):
     try: return float(x)
@@ -25,7 +26,7 @@ for r in rows[h + 1:]:
     if len(r) < len(hd): continue
     try: ln = int(r[iL])
     except ValueError: continue
-    a = agg[ln]; a[0] += f(r[iS]); a[1] += f(r[iI]); a[2] += f(r[iT]); a[3] += f(r[iW]); text[ln] = r[1]
+    a = agg[ln]; a[0] += f(r[iS]); a[1] += f(r[iI]); a[2] += f(r[iT]); a[3] += (f(r[iW]) if iW is not None else 0.0); text[ln] = r[1]
     tot[0] += f(r[iS]); tot[1] += f(r[iI]); tot[2] += f(r[iT])
 print(f"total: samples {tot[0]:.0f}, warp instructions {tot[1]/1e6:.1f} M, thread instructions {tot[2]/1e9:.2f} G")
 for ln, a in sorted(agg.items()):

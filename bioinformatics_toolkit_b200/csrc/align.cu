@@ -6,12 +6,31 @@
 // reference's tie rules and the distance of those pairs is the reference's bit for bit.
 // Bound: fp64 / SFU (four `log` per column pair); bytes are negligible.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "align_core.h"
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "internal.h"
 
 using namespace pwmscan;
+
+// fn(t) for t in [0, n) on up to 16 host threads (independent iterations; small n stays on the calling thread)
+template <class F>
+static void host_parallel_for(size_t n, F fn) {
+    const size_t nt = std::min<size_t>({(size_t)16, (size_t)std::max(1u, std::thread::hardware_concurrency()), n / 64 + 1});
+    if (nt <= 1) { for (size_t t = 0; t < n; ++t) fn(t); return; }
+    std::atomic<size_t> next(0);
+    auto work = [&]() { for (;;) { const size_t t0 = next.fetch_add(32); if (t0 >= n) return; for (size_t t = t0; t < std::min(n, t0 + 32); ++t) fn(t); } };
+    std::vector<std::thread> th;
+    for (size_t w = 1; w < nt; ++w) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
 
 namespace {
 
@@ -87,8 +106,11 @@ int launch_and_collect(pwmscan_ctx* ctx, const AlignCfg& cfg, const AlignDev& de
     PWM_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    // near-ties: same function, host libm
+    // near-ties: same function, host libm — collected first, then re-evaluated by all host cores (8 942 of the 1 999 000 pairs
+    // of config 5: 49 ms on one core, more than the kernel)
     int64_t namb = 0;
+    struct Redo { int64_t k; int i, j; };
+    std::vector<Redo> todo;
     auto redo = [&](int64_t k, int i, int j) {
         const int n1 = h_n[i], n2 = h_n[j];
         const size_t o1 = 4 * (size_t)col_off[2 * i], o2 = 4 * (size_t)col_off[2 * j], o2r = 4 * (size_t)col_off[2 * j + 1];
@@ -96,14 +118,15 @@ int launch_and_collect(pwmscan_ctx* ctx, const AlignCfg& cfg, const AlignDev& de
         align_pair(cfg, h_mats + o1, h_logs + o1, n1, h_mats + o2, h_logs + o2, h_mats + o2r, h_logs + o2r, n2,
                    h_opti + ((size_t)n1 * (dev.maxc + 1) + n2) * dev.maxc, h_opti + ((size_t)n2 * (dev.maxc + 1) + n1) * dev.maxc, &dd, &sd, &pp, &am);
         dist[k] = dd; same_dir[k] = (uint8_t)sd; pos[k] = pp;
-        ++namb;
     };
     if (all) {
         int64_t k = 0;
-        for (int i = 0; i < M; ++i) for (int j = i + 1; j < M; ++j, ++k) if (h_amb[k]) redo(k, i, j);
+        for (int i = 0; i < M; ++i) for (int j = i + 1; j < M; ++j, ++k) if (h_amb[k]) todo.push_back({k, i, j});
     } else {
-        for (int64_t k = 0; k < npairs; ++k) if (h_amb[k]) redo(k, pa[k], pb[k]);
+        for (int64_t k = 0; k < npairs; ++k) if (h_amb[k]) todo.push_back({k, pa[k], pb[k]});
     }
+    namb = (int64_t)todo.size();
+    host_parallel_for(todo.size(), [&](size_t t) { redo(todo[t].k, todo[t].i, todo[t].j); });
     ctx->timing[10] = ms; ctx->timing[11] = (double)namb;
     return PWMSCAN_OK;
 }
@@ -309,6 +332,62 @@ __global__ void alnmat_refresh_kernel(AlignCfg cfg, AlignDev d, int M, int i, in
     if (i < q) mat_store(cfg, d, M, i, q, D, SD, POS, amb); else mat_store(cfg, d, M, q, i, D, SD, POS, amb);
 }
 
+// The same refresh with ONE WARP per pair.  A merge re-aligns slot i against every live slot — a few thousand pairs, far
+// fewer than the device has threads — so what a merge costs is the LATENCY of one alignment, and a thread that walks all
+// offsets of all four `loop`s alone needs ~0.9 ms for it.  Here the lanes of a warp evaluate the offsets of a loop in
+// parallel (an offset's distance does not depend on the running minimum: aln_offset_value) into shared memory and the
+// decision sequence is replayed in offset order (aln_loop_replay) — the same comparisons on the same numbers.
+constexpr int kRefreshWarps = 4;
+__device__ __forceinline__ void aln_loop_warp(const AlignCfg& c, const double* opti, const double* a, const double* la, int na, const double* b,
+                                              const double* lb, int nb, int n1, int n2, double* dv, double* dmin, int* imin, int* ambiguous) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < nb; i += 32) dv[i] = aln_offset_value(c, a, la, na, b, lb, nb, n1, n2, i);
+    __syncwarp();
+    aln_loop_replay(opti, dv, nb, dmin, imin, ambiguous);       // every lane, same result
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kRefreshWarps)
+alnmat_refresh_warp_kernel(AlignCfg cfg, AlignDev d, int M, int i, int j, const uint8_t* __restrict__ alive, double* D, uint8_t* SD,
+                           int32_t* POS, unsigned long long* amb) {
+    extern __shared__ double s_dv[];                                           // [kRefreshWarps][maxc]
+    const int q = blockIdx.x * kRefreshWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= M) return;
+    const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    if (lane == 0) { D[(size_t)q * M + j] = inf; D[(size_t)j * M + q] = inf; }
+    if (q == i || q == j || !alive[q]) return;
+    const int r = i < q ? i : q, c = i < q ? q : i;
+    double* dv = s_dv + (size_t)(threadIdx.x >> 5) * d.maxc;
+    const int n1 = d.ncol[r], n2 = d.ncol[c];
+    const double *m1 = d.mats + 4 * d.col_off[2 * r], *l1 = d.logs + 4 * d.col_off[2 * r];
+    const double *m2 = d.mats + 4 * d.col_off[2 * c], *l2 = d.logs + 4 * d.col_off[2 * c];
+    const double *m2r = d.mats + 4 * d.col_off[2 * c + 1], *l2r = d.logs + 4 * d.col_off[2 * c + 1];
+    const double* opti1 = d.opti + ((size_t)n1 * (d.maxc + 1) + n2) * d.maxc;
+    const double* opti2 = d.opti + ((size_t)n2 * (d.maxc + 1) + n1) * d.maxc;
+    int am = 0;
+    double df, dr; int pf, pr;
+    {   // align_pair (align_core.h), loop by loop
+        double d1, d2; int i1, i2;
+        aln_loop_warp(cfg, opti2, m2, l2, n2, m1, l1, n1, n1, n2, dv, &d1, &i1, &am);
+        aln_loop_warp(cfg, opti1, m1, l1, n1, m2, l2, n2, n1, n2, dv, &d2, &i2, &am);
+        if (aln_near(d1, d2)) am = 1;
+        if (d1 < d2) { df = d1; pf = i1; } else { df = d2; pf = -i2; }
+    }
+    {
+        double d1, d2; int i1, i2;
+        aln_loop_warp(cfg, opti2, m2r, l2r, n2, m1, l1, n1, n1, n2, dv, &d1, &i1, &am);
+        aln_loop_warp(cfg, opti1, m1, l1, n1, m2r, l2r, n2, n1, n2, dv, &d2, &i2, &am);
+        if (aln_near(d1, d2)) am = 1;
+        if (d1 < d2) { dr = d1; pr = i1; } else { dr = d2; pr = -i2; }
+    }
+    if (aln_near(df, dr)) am = 1;
+    if (lane == 0) {
+        const size_t k = (size_t)r * M + c;
+        if (df <= dr) { D[k] = df; SD[k] = 1; POS[k] = pf; } else { D[k] = dr; SD[k] = 0; POS[k] = pr; }
+        if (am) { const unsigned long long t = atomicAdd(&amb[0], 1ull); amb[1 + t] = (unsigned long long)k; }
+    }
+}
+
 // entries the host re-evaluated (near-ties): k = r * M + c
 __global__ void alnmat_patch_kernel(int n, const unsigned long long* __restrict__ k, const double* __restrict__ dd, const int32_t* __restrict__ pp,
                                     const uint8_t* __restrict__ sd, double* D, uint8_t* SD, int32_t* POS) {
@@ -363,7 +442,7 @@ int alnmat_settle_and_argmin(pwmscan_alnset* a, int32_t* oi, int32_t* oj, double
         std::vector<int32_t> pp((size_t)namb);
         std::vector<uint8_t> sd((size_t)namb);
         const int mc = a->maxc;
-        for (size_t t = 0; t < (size_t)namb; ++t) {
+        host_parallel_for((size_t)namb, [&](size_t t) {
             const int r = (int)(ks[t] / (unsigned long long)M), c = (int)(ks[t] % (unsigned long long)M);
             const int n1 = a->n[r], n2 = a->n[c];
             const size_t o1 = 4 * (size_t)a->col_off[2 * r], o2 = 4 * (size_t)a->col_off[2 * c], o2r = 4 * (size_t)a->col_off[2 * c + 1];
@@ -372,7 +451,7 @@ int alnmat_settle_and_argmin(pwmscan_alnset* a, int32_t* oi, int32_t* oj, double
                        a->logs.data() + o2r, n2, a->opti.data() + ((size_t)n1 * (mc + 1) + n2) * mc, a->opti.data() + ((size_t)n2 * (mc + 1) + n1) * mc,
                        &d, &s, &p, &am);
             dd[t] = d; sd[t] = (uint8_t)s; pp[t] = p;
-        }
+        });
         const size_t nb = (size_t)namb;
         unsigned char* d_p = (unsigned char*)scratch_get(ctx, 1, nb * 24 + 64);
         if (!d_p) return PWMSCAN_ECUDA;
@@ -536,8 +615,13 @@ extern "C" int pwmscan_alnset_merge_step(pwmscan_alnset* a, int32_t i, int32_t j
     a->alive[j] = 0;
     PWM_CUDA(cudaMemsetAsync(a->d_alive + j, 0, 1, ctx->stream));
     PWM_CUDA(cudaMemsetAsync(a->d_amb, 0, 8, ctx->stream));
-    alnmat_refresh_kernel<<<(unsigned)((a->M + 127) / 128), 128, 0, ctx->stream>>>(a->cfg, alnset_dev(a), a->M, i, j, a->d_alive, a->d_D, a->d_SD,
-                                                                                   a->d_POS, a->d_amb);
+    static const bool thread_per_pair = std::getenv("PWMSCAN_ALN_REFRESH_THREAD") != nullptr;       // the round-1 form, for comparison
+    if (thread_per_pair)
+        alnmat_refresh_kernel<<<(unsigned)((a->M + 127) / 128), 128, 0, ctx->stream>>>(a->cfg, alnset_dev(a), a->M, i, j, a->d_alive, a->d_D, a->d_SD,
+                                                                                       a->d_POS, a->d_amb);
+    else
+        alnmat_refresh_warp_kernel<<<(unsigned)((a->M + kRefreshWarps - 1) / kRefreshWarps), 32 * kRefreshWarps, (size_t)kRefreshWarps * a->maxc * 8,
+                                     ctx->stream>>>(a->cfg, alnset_dev(a), a->M, i, j, a->d_alive, a->d_D, a->d_SD, a->d_POS, a->d_amb);
     PWM_CUDA(cudaGetLastError());
     return alnmat_settle_and_argmin(a, ni, nj, d, same_dir, pos);
 }

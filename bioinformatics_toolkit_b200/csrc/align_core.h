@@ -71,6 +71,32 @@ ALN_HD bool aln_near(double a, double b) {
     return fabs(a - b) <= kAmbigRel * m;
 }
 
+// The distance of ONE offset i of `loop` (Alignment.hs:105-111): combFn over zipWith jsd a (drop i b), plus the gap penalty.
+// It does not depend on the running minimum, so offsets can be evaluated in any order (or by different lanes).
+ALN_HD double aln_offset_value(const AlignCfg& c, const double* a, const double* la, int na, const double* b, const double* lb, int nb,
+                               int n1, int n2, int i) {
+    const int nMatch = na < nb - i ? na : nb - i;
+    // combFn over sc = zipWith jsd a (drop i b), streamed
+    double s = 0.0, cc = 0.0, mx = 0.0;
+    for (int k = 0; k < nMatch; ++k) {
+        double v = aln_jsd(a + 4 * k, la + 4 * k, b + 4 * (i + k), lb + 4 * (i + k), c.ln2);
+        if (c.comb_kind == 3) { mx = (k == 0 || v > mx) ? v : mx; continue; }
+        if (c.comb_kind == 1) v = pow(v, 2.0);
+        else if (c.comb_kind == 2) v = pow(v, 3.0);
+        const double s1 = s + v;                               // Kahan-Babuska-Neumaier (Numeric.Sum.kbn)
+        if (fabs(s) >= fabs(v)) cc = cc + ((s - s1) + v); else cc = cc + ((v - s1) + s);
+        s = s1;
+    }
+    double comb;
+    if (c.comb_kind == 3) comb = mx;
+    else {
+        const double mean = (s + cc) / (double)nMatch;
+        comb = c.comb_kind == 0 ? mean : (c.comb_kind == 1 ? sqrt(mean) : pow(mean, 1.0 / 3.0));
+    }
+    const int nGap = n1 + n2 - 2 * nMatch;
+    return comb + aln_penal(c, nGap, nMatch);
+}
+
 // loop opti (1/0,-1) a b 0   (Alignment.hs:103-112); a has na rows, b has nb rows.
 ALN_HD void aln_loop(const AlignCfg& c, const double* opti, const double* a, const double* la, int na, const double* b,
                      const double* lb, int nb, int n1, int n2, double* dmin, int* imin, int* ambiguous) {
@@ -80,26 +106,23 @@ ALN_HD void aln_loop(const AlignCfg& c, const double* opti, const double* a, con
         const double o = opti[i];
         if (aln_near(o, mn)) *ambiguous = 1;
         if (o >= mn) break;                                        // Alignment.hs:104
-        const int nMatch = na < nb - i ? na : nb - i;
-        // combFn over sc = zipWith jsd a (drop i b), streamed
-        double s = 0.0, cc = 0.0, mx = 0.0;
-        for (int k = 0; k < nMatch; ++k) {
-            double v = aln_jsd(a + 4 * k, la + 4 * k, b + 4 * (i + k), lb + 4 * (i + k), c.ln2);
-            if (c.comb_kind == 3) { mx = (k == 0 || v > mx) ? v : mx; continue; }
-            if (c.comb_kind == 1) v = pow(v, 2.0);
-            else if (c.comb_kind == 2) v = pow(v, 3.0);
-            const double s1 = s + v;                               // Kahan-Babuska-Neumaier (Numeric.Sum.kbn)
-            if (fabs(s) >= fabs(v)) cc = cc + ((s - s1) + v); else cc = cc + ((v - s1) + s);
-            s = s1;
-        }
-        double comb;
-        if (c.comb_kind == 3) comb = mx;
-        else {
-            const double mean = (s + cc) / (double)nMatch;
-            comb = c.comb_kind == 0 ? mean : (c.comb_kind == 1 ? sqrt(mean) : pow(mean, 1.0 / 3.0));
-        }
-        const int nGap = n1 + n2 - 2 * nMatch;
-        const double d = comb + aln_penal(c, nGap, nMatch);
+        const double d = aln_offset_value(c, a, la, na, b, lb, nb, n1, n2, i);
+        if (aln_near(d, mn)) *ambiguous = 1;
+        if (d < mn) { mn = d; mi = i; }
+    }
+    *dmin = mn; *imin = mi;
+}
+
+// The decisions of `loop` replayed over offset distances computed beforehand (dv[i], i < nb): same early exit, same strict <,
+// same near-tie flags as aln_loop.
+ALN_HD void aln_loop_replay(const double* opti, const double* dv, int nb, double* dmin, int* imin, int* ambiguous) {
+    double mn = HUGE_VAL;
+    int mi = -1;
+    for (int i = 0; i < nb; ++i) {
+        const double o = opti[i];
+        if (aln_near(o, mn)) *ambiguous = 1;
+        if (o >= mn) break;
+        const double d = dv[i];
         if (aln_near(d, mn)) *ambiguous = 1;
         if (d < mn) { mn = d; mi = i; }
     }

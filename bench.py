@@ -114,12 +114,15 @@ def motifs_of(name):
     return synth.config_c4_motifs(800)
 
 
+C4_WEIGHTS = None        # set by main() after the calibration pass (multi-GPU runs)
+
+
 def c4_items(world):
     """The (all motif blocks x chromosome chunk of <= 64 Mbp) items of config 4 and their assignment to the ranks: equal shares of
     the genome's concatenated coordinates (shard.partition_contiguous)."""
     from bioinformatics_toolkit_b200 import shard, synth
     lengths = [l for _, l in synth.HG38_CHROM_SIZES]
-    return lengths, shard.partition_contiguous(lengths, 800, world)
+    return lengths, shard.partition_contiguous(lengths, 800, world, weights=C4_WEIGHTS if world > 1 else None)
 
 
 def c4_chunk(it, lengths, nmax):
@@ -224,6 +227,7 @@ def main():
     ap.add_argument("--cpu-sample-bp", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="multi-GPU c4: keep equal shares (no calibration pass)")
     args = ap.parse_args()
     big = args.workload == "c4"
     if args.ref_sample_bp is None:
@@ -260,10 +264,44 @@ def main():
     th = mo.pvalue_to_score(1e-5)                    # device scoreCDF + cdf' (Motif.hs:213-214, 252-326)
     plan = _lib.Plan(mo, th)
     M = len(mats)
+
+    def stage(seqs):
+        pinned_ = [torch.from_numpy(a).pin_memory() for _, a, _ in seqs]
+        arrays_ = [p.numpy() for p in pinned_]
+        return pinned_, arrays_, [_lib.DeviceSeq(ctx, a) for a in arrays_]
+
+    pinned, host_arrays, dev_seqs = stage(seqs_host)
+    rebalance = None
+    if big and world > 1 and not args.no_rebalance:
+        # Calibration pass (outside the timed region): the ranks of a box are not equally fast end to end (hit lists into host
+        # memory: 17.4 vs 12.4 ms per step on the two halves of the 8 x B200 box), so every rank times a few steps on equal
+        # shares and the genome is re-cut in proportion to the measured rates (shard.rank_weights / partition_contiguous).
+        global C4_WEIGHTS
+        from bioinformatics_toolkit_b200 import shard
+        history = []
+        shares = [1.0 / world] * world
+        for _round in range(2):                                   # two proportional corrections (a rank's time is not quite linear in its share)
+            for _ in range(2):
+                plan.scan_many(dev_seqs, consume=len)
+            dist.barrier()
+            t0c = time.perf_counter()
+            for _ in range(3):
+                plan.scan_many(dev_seqs, consume=len)
+            torch.cuda.synchronize()
+            mine = torch.tensor([(time.perf_counter() - t0c) / 3], dtype=torch.float64, device="cuda")
+            g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(g, mine)
+            t_r = [float(x.item()) for x in g]
+            history.append([round(1e3 * x, 3) for x in t_r])
+            if max(t_r) <= 1.05 * min(t_r):
+                break
+            shares = [float(x) for x in shard.rank_weights(t_r, shares=shares)]
+            C4_WEIGHTS = shares
+            del dev_seqs, host_arrays, pinned
+            seqs_host, _ = workload(args.workload, rank, world)
+            pinned, host_arrays, dev_seqs = stage(seqs_host)
+        rebalance = {"calibration_ms_by_rank": history, "weights": C4_WEIGHTS and [round(x, 4) for x in C4_WEIGHTS]}
     units = sum(int(own) for _, _, own in seqs_host) * M          # position x motif units of this rank
-    pinned = [torch.from_numpy(a).pin_memory() for _, a, _ in seqs_host]
-    host_arrays = [p.numpy() for p in pinned]
-    dev_seqs = [_lib.DeviceSeq(ctx, a) for a in host_arrays]
     gate = parity_gate(ctx, plan, mats, th, seqs_host) if rank == 0 else {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     t_setup = time.perf_counter() - t_setup
@@ -455,7 +493,9 @@ def main():
             "vs_baseline": None, "dtype": "u8 bit-mask / u16 first stage + f64 re-score", "data": "synthetic",
             "config": {"workload": DESC[args.workload], "items_rank0": len(dev_seqs), "chunk_bp": int(max(a.size for a in host_arrays)), "scans_in_flight": os.environ.get("PWMSCAN_LANES", "6 resident / 7 from host bytes"),
                        "l2": "256 MiB flush write + sync between steps; per step the rank reads %.0f MB of packed genome and %.0f MB of mask tables (> 126 MB L2)" % (0.375 * bp_rank / 1e6, info["table_bytes"] / 1e6),
-                       "thresholds": "device scoreCDF", "hits_per_step": int(hits_all.item()), "setup_s": round(t_setup, 1), **gate},
+                       "thresholds": "device scoreCDF", "hits_per_step": int(hits_all.item()), "setup_s": round(t_setup, 1),
+                       "shares": ("equal" if not rebalance or not rebalance["weights"] else "weighted by each rank's measured rate (calibration pass outside the timed region)"),
+                       "rebalance": rebalance, **gate},
             "e2e": e2e, "gpu_launches": int(res["kernel_launches"]), "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "issue_roofline": issue, "phases": phases, "plan": info, "cpu_baseline": cpu}), flush=True)
     if world > 1:

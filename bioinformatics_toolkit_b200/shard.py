@@ -29,7 +29,7 @@ def pick_chunk_len(total_bp, world_size, items_per_rank=24, lo=8_000_000, hi=64_
     return int(min(hi, max(lo, target // step * step)))
 
 
-def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000, align=32, tail_chunk=16_000_000):
+def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000, align=32, tail_chunk=16_000_000, weights=None):
     """Whole-genome scan on `world_size` devices with as few, as large items as possible: the genome's concatenated coordinate
     space is cut into `world_size` contiguous stretches of equal length (a chunk may start anywhere: every item carries its own
     halo), each stretch into its pieces of single sequences, each piece into equal chunks of at most `max_chunk` window starts
@@ -39,7 +39,17 @@ def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000
     `tail_chunk`, so that what is left when its last first stage has ended — replay, ordering and the copy of ONE item's hits —
     is as short as it can be."""
     total = int(sum(seq_lengths))
-    bounds = [total * r // world_size for r in range(world_size + 1)]
+    if weights is None:
+        bounds = [total * r // world_size for r in range(world_size + 1)]
+    else:
+        # unequal shares (rank_weights): the devices of a box need not be equally fast end to end — e.g. half of the GPUs
+        # of the 8 x B200 box this was measured on move their hit lists into host memory at 60 % of the others' rate
+        w = np.asarray(weights, dtype=np.float64)
+        if w.size != world_size or not np.all(w > 0):
+            raise ValueError("one positive weight per rank expected")
+        cum = np.concatenate([[0.0], np.cumsum(w)]) / float(np.sum(w))
+        bounds = [int(round(total * c)) for c in cum]
+        bounds[0], bounds[-1] = 0, total
     out = [[] for _ in range(world_size)]
     base = 0
     for s, L in enumerate(seq_lengths):
@@ -71,6 +81,19 @@ def partition_contiguous(seq_lengths, n_motifs, world_size, max_chunk=64_000_000
             cuts = [a + ((b - a) * i // k) // align * align for i in range(k)] + [b]
             out[r] += [(s, x, y, m0, m1) for x, y in zip(cuts[:-1], cuts[1:]) if y > x]
     return out
+
+
+def rank_weights(step_seconds, shares=None, damp=1.0):
+    """Shares for `partition_contiguous(weights=...)` from a measured pass: rank r needed step_seconds[r] for its share
+    shares[r] (equal shares if None); the new share is proportional to its rate share / time (damp < 1 moves only part of
+    the way).  Ranks whose times are within a few per cent of each other keep equal shares."""
+    t = np.asarray(step_seconds, dtype=np.float64)
+    s = np.ones_like(t) if shares is None else np.asarray(shares, dtype=np.float64)
+    rate = s / t
+    w = rate / rate.sum()
+    w0 = s / s.sum()
+    w = w0 + damp * (w - w0)
+    return w / w.sum()
 
 
 def item_cost(item, motif_cols=None):

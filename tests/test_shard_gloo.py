@@ -51,6 +51,26 @@ def test_contiguous_partition_covers_everything_once_in_equal_shares():
     assert sorted(sum(tiny, [])) == sorted([(0, 0, 32, 0, 5), (0, 32, 64, 0, 5), (0, 64, 96, 0, 5), (0, 96, 100, 0, 5), (2, 0, 7, 0, 5)])
 
 
+def test_weighted_shares_follow_the_measured_rates():
+    lengths = [l for _, l in synth.HG38_CHROM_SIZES]
+    w = shard.rank_weights([17.4] * 4 + [12.4] * 4)                 # what the two halves of the 8 x B200 box needed on equal shares
+    assert abs(w.sum() - 1) < 1e-12 and abs(w[4] / w[0] - 17.4 / 12.4) < 1e-9
+    half = shard.rank_weights([2.0, 1.0], damp=0.5)                  # only half of the way
+    assert abs(half[0] - (0.5 + 0.5 * (1 / 3 - 0.5))) < 1e-12
+    parts = shard.partition_contiguous(lengths, 800, 8, weights=w)
+    loads = np.array([sum(it[2] - it[1] for it in r) for r in parts], dtype=float)
+    assert loads.sum() == sum(lengths) and np.allclose(loads / loads.sum(), w, atol=1e-6)
+    cover = {}
+    for r in parts:
+        for (s, st, en, _, _) in r:
+            cover.setdefault(s, []).append((st, en))
+    for s, L in enumerate(lengths):
+        iv = sorted(cover[s])
+        assert iv[0][0] == 0 and iv[-1][1] == L and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+    with pytest.raises(ValueError):
+        shard.partition_contiguous(lengths, 800, 8, weights=[1.0] * 7)
+
+
 def _worker(rank, world, port, q, contiguous=False):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -39,6 +39,9 @@ int set_err(pwmscan_ctx* ctx, int code, const std::string& msg) {
 int cuda_fail(pwmscan_ctx* ctx, cudaError_t e, const char* what) {
     std::string m = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
     cudaGetLastError();
+    // Every error path returns through here, often with asynchronous copies into caller / stack / std::vector memory already
+    // enqueued: nothing may still be in flight when that memory goes away.  (Errors are rare; the wait costs nothing that matters.)
+    if (ctx) { cudaDeviceSynchronize(); cudaGetLastError(); }
     return set_err(ctx, PWMSCAN_ECUDA, m);
 }
 

@@ -437,8 +437,11 @@ def main():
     sec = pre_ms_launch / 1e3
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")          # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full captures
+    ncu_facts = None
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("km_prefilter_kernel", {}).get(args.workload)
+        tj = json.load(open(tpath))
+        traffic = tj.get("km_prefilter_kernel", {}).get(args.workload)
+        ncu_facts = tj.get("km_prefilter_kernel_ncu", {}).get(args.workload)
     if info["mode"] == "kmer":
         # governing roof: the L1 gather rate, one 32-byte sector per clock per SM (experiments/masktab/l2gather.cu; profiles/l2gather_*.txt).
         # Algorithmic bytes: the plan's expected mask sectors per position x 32 B (a model; ncu's l1tex sector count agrees within 1 %).
@@ -447,9 +450,11 @@ def main():
         roofline = {"bound": "l1-gather", "achieved": alg_bytes / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peak,
                     "traffic": traffic, "kernel": "km_prefilter_kernel", "ms_per_launch": pre_ms_launch, "launches_per_step": n_launch / args.steps,
                     "peak_source": "148 SMs x one 32-B sector per clk x sm_max_mhz (%s); this repo's micro-benchmark reaches 8.9 TB/s (profiles/l2gather_*.txt); not a MEASURED_PEAKS.json entry" % peaks["source"],
-                    "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "L2-resident k-mer mask tables gathered with 256-bit loads; 'achieved' uses the plan's modelled sectors per position; "
-                            "with many motifs (c4) the kernel is instruction-bound, see issue_roofline and profiles/"}
+                    "algorithmic_bytes_per_launch": alg_bytes, "ncu": ncu_facts,
+                    "note": "L2-resident k-mer mask tables gathered with 256-bit loads; 'achieved' uses the plan's modelled sectors per position "
+                            "(ncu's l1tex sector count agrees within a few per cent); with many motifs (c4: six of seven blocks are a shared-memory bitmap "
+                            "scan with few gathers) the kernel is instruction- and latency-bound rather than gather-bound: see 'ncu' (issue slots, L1TEX) "
+                            "and profiles/README.md; --workload c2 (one dense block) reaches 0.82 of this roof"}
     else:
         smem_bytes = info.get("smem_wavefronts_per_position", 0.0) * 128.0 * bp_launch
         smem_peak = 148 * 128 * clk / 1e9

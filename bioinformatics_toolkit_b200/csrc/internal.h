@@ -97,6 +97,8 @@ struct pwmscan_motifs {
     std::vector<int64_t> tab_off;       // offset of (motif, strand) in d_tab16 (doubles): tab_off[2m+s]
     std::vector<int64_t> col_off;       // offset of (motif, strand) in per-column arrays: col_off[2m+s]
     double* d_tab16 = nullptr;          // all IUPAC tables
+    double* d_tab4 = nullptr;           // the A/C/G/T entries of every column alone, [col_off*4 + 4k + base]: what the exact replay of a
+                                        // skip-ambiguous scan reads (32 B per column, four columns per cache line instead of one)
     double* d_mats = nullptr;           // all probability matrices (strand 0 and 1), n x 4, same order as col_off*4
     int64_t total_cols2 = 0;            // sum over (motif,strand) of n
 };

@@ -609,6 +609,15 @@ extern "C" int pwmscan_motifs_create(pwmscan_ctx* ctx, int32_t M, const int32_t*
     if ((e = cudaMalloc(&mo->d_mats, h_mat.size() * 8)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(mats)"));
     if ((e = cudaMemcpy(mo->d_tab16, h_tab.data(), h_tab.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemcpy(tab16)"));
     if ((e = cudaMemcpy(mo->d_mats, h_mat.data(), h_mat.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemcpy(mats)"));
+    {
+        std::vector<double> h_tab4((size_t)cols * 4);
+        for (int m = 0; m < M; ++m)
+            for (int s = 0; s < 2; ++s)
+                for (int k = 0; k < ncol[m]; ++k)
+                    for (int b = 0; b < 4; ++b) h_tab4[(size_t)(mo->col_off[2 * m + s] + k) * 4 + b] = mo->mh[m].tab16[s][(size_t)16 * k + b];
+        if ((e = cudaMalloc(&mo->d_tab4, h_tab4.size() * 8 + 64)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMalloc(tab4)"));
+        if ((e = cudaMemcpy(mo->d_tab4, h_tab4.data(), h_tab4.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemcpy(tab4)"));
+    }
     *out = mo;
     return PWMSCAN_OK;
 }
@@ -631,6 +640,7 @@ extern "C" void pwmscan_motifs_free(pwmscan_motifs* mo) {
     if (!mo) return;
     if (mo->ctx) cudaSetDevice(mo->ctx->device);
     if (mo->d_tab16) cudaFree(mo->d_tab16);
+    if (mo->d_tab4) cudaFree(mo->d_tab4);
     if (mo->d_mats) cudaFree(mo->d_mats);
     delete mo;
 }
@@ -1036,7 +1046,7 @@ __device__ __forceinline__ void append_hits(bool hit, unsigned long long key, do
 // invalid-base flags fetched up front (three + two 32-bit words for up to 32 columns) instead of one dependent load pair per
 // column; what remains per column are the two independent table reads.  Same additions in the same order.
 __device__ __forceinline__ bool replay_window(const uint32_t* __restrict__ seq2, const uint32_t* __restrict__ mask, int64_t u0, int n,
-                                              const double* __restrict__ tab16, const double* __restrict__ th, double* score) {
+                                              const double* __restrict__ tab16, const double* __restrict__ tab4, const double* __restrict__ th, double* score) {
     if (n > 32) return replay_skip(seq2, mask, u0, n, tab16, th, score);
     const int64_t w = u0 >> 4;
     const int s2 = 2 * (int)(u0 & 15);
@@ -1046,7 +1056,7 @@ __device__ __forceinline__ bool replay_window(const uint32_t* __restrict__ seq2,
     const uint32_t inv = __funnelshift_r(__ldg(mask + mw), __ldg(mask + mw + 1), (int)(u0 & 31));
     double acc = 0.0;
     for (int k = 0; k < n; ++k) {
-        const double sc = ((inv >> k) & 1u) ? PWM_NEG_INF : __ldg(tab16 + 16 * k + (int)((x >> (2 * k)) & 3ull));
+        const double sc = ((inv >> k) & 1u) ? PWM_NEG_INF : __ldg(tab4 + 4 * k + (int)((x >> (2 * k)) & 3ull));      // == tab16[16k + base]
         acc = __dadd_rn(acc, sc);
         if (acc < __ldg(th + k)) return false;
     }
@@ -1057,7 +1067,7 @@ __device__ __forceinline__ bool replay_window(const uint32_t* __restrict__ seq2,
 __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsigned long long cand_cap,
                                const DevCombo* __restrict__ combos, const uint32_t* __restrict__ seq2,
                                const uint32_t* __restrict__ mask, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
-                               const double* __restrict__ tab16, const double* __restrict__ th, HitSink hs, KeyLayout kl) {
+                               const double* __restrict__ tab16, const double* __restrict__ tab4, const double* __restrict__ th, HitSink hs, KeyLayout kl) {
     unsigned long long ncand = hs.counters[0];
     if (ncand > cand_cap) ncand = cand_cap;
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < ncand;
@@ -1073,7 +1083,7 @@ __global__ void rescore_kernel(const unsigned long long* __restrict__ cand, unsi
             if (cb.motif >= 0 && i >= 0 && i + cb.n <= len) {
                 const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
                 if (i + cb.n <= seg_off[seg + 1] &&
-                    replay_window(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, th + cb.th_off, &sc)) {
+                    replay_window(seq2, mask, i + kPadFront, cb.n, tab16 + cb.tab_off, tab4 + 4 * cb.th_off, th + cb.th_off, &sc)) {
                     hit = true;
                     key = hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]);
                 }
@@ -1444,7 +1454,7 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
                                                                       seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
         else
             rescore_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_cand, j.cand_cap, d_combos, seq->d_seq2, seq->d_mask,
-                                                              seq->d_seg_off, seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
+                                                              seq->d_seg_off, seq->nseg, len, mo->d_tab16, mo->d_tab4, pl->d_th, hs, j.kl);
         PWM_CUDA(cudaGetLastError());
         ++j.kernels;
     }

@@ -203,10 +203,26 @@ class DeviceSeq:
             pass
 
 
-class PackedSeq:
+class PackedPlanes:
+    """The two planes of a packed sequence, wherever they live (arrays in memory, a memory-mapped `.packed` sidecar of the
+    genome index): `seq2` uint32[2 * units], `mask` uint32[units], units = ceil(length / 32)."""
+
+    def __init__(self, seq2, mask, length, first_non_acgt=-1, first_non_iupac=-1):
+        self.seq2, self.mask, self.length = seq2, mask, int(length)
+        self.first_non_acgt, self.first_non_iupac = int(first_non_acgt), int(first_non_iupac)
+
+    def slice(self, start=0, end=None):
+        """(seq2 view, mask view, length) of bases [start, end): start must be a multiple of 32."""
+        end = self.length if end is None else min(int(end), self.length)
+        if start % 32 or not (0 <= start <= end):
+            raise ValueError("a packed slice starts at a multiple of 32 bases")
+        return self.seq2[start // 16:], self.mask[start // 32:], end - start
+
+
+class PackedSeq(PackedPlanes):
     """The packed genome store of one sequence in HOST memory (pwmscan_pack_host): 2 bits per base + 1 invalid-base bit per
-    base, 0.375 bytes per base, made once (mkIndex time) and uploaded instead of the bytes.  `seq2`: uint32[2 * units],
-    `mask`: uint32[units], units = ceil(length / 32).  Pure host code — works without a GPU."""
+    base, 0.375 bytes per base, made once (mkIndex time) and uploaded instead of the bytes.  Pure host code — works
+    without a GPU."""
 
     def __init__(self, data, uppercase=False, nthreads=0, pinned=False):
         L = load()
@@ -229,13 +245,6 @@ class PackedSeq:
         if rc != OK:
             raise PwmScanError(rc, "pwmscan_pack_host: bad argument")
         self.first_non_acgt, self.first_non_iupac = a.value, i.value
-
-    def slice(self, start=0, end=None):
-        """(seq2 view, mask view, length) of bases [start, end): start must be a multiple of 32."""
-        end = self.length if end is None else min(int(end), self.length)
-        if start % 32 or not (0 <= start <= end):
-            raise ValueError("a packed slice starts at a multiple of 32 bases")
-        return self.seq2[start // 16:], self.mask[start // 32:], end - start
 
 
 class DeviceMotifs:

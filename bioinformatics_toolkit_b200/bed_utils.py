@@ -216,7 +216,7 @@ def scanMotif(genome, motifs, beds, out=None, batch_bases=192 << 20, warn=sys.st
     return total if out is not None else results
 
 
-def scanGenome(genome, motifs, out=None, chroms=None, chunk_len=64_000_000, warn=sys.stderr, ctx=None):
+def scanGenome(genome, motifs, out=None, chroms=None, chunk_len=64_000_000, warn=sys.stderr, ctx=None, packed=None):
     """scanMotif over WHOLE chromosomes straight from the genome store — the result of
     `scanMotif genome motifs [(chr, 0, size) | (chr, size) <- getChrSizes genome]` (Utils.hs:101-124 with getChrom,
     Seq/IO.hs:77-84), produced chromosome by chromosome: the bytes of a chromosome are read from the index file in
@@ -225,6 +225,9 @@ def scanGenome(genome, motifs, out=None, chroms=None, chunk_len=64_000_000, warn
     per-hit BED score comes from the device (pwmscan_hits_affinity) and the chunks' (motif, strand) runs are stitched
     into the reference's order (motif, strand, ascending position over the whole chromosome).  A chromosome with a byte
     outside the IUPAC alphabet is a Left in the reference (fromBS): warned about and skipped.
+    With `packed` (a seq_io.PackedGenome: the `.packed` sidecar of the index, `mkindex --packed`) the chunks are slices of
+    the chromosome's 2-bit + mask planes instead (0.375 bytes per base through the staging buffers and over PCIe,
+    pwmscan_scan_packed_many; chunk_len is rounded down to a multiple of 32) — same output.
     Yields / writes BED6 like scanMotif; returns the hit count when `out` is given."""
     import ctypes as C
     import torch
@@ -255,9 +258,31 @@ def scanGenome(genome, motifs, out=None, chroms=None, chunk_len=64_000_000, warn
     staging = []                                    # pinned host buffers, reused from chromosome to chromosome
     for chr_, csize in (getChrSizesOf(genome) if chroms is None else [(c if isinstance(c, bytes) else c.encode(), genome.index[c if isinstance(c, bytes) else c.encode()][1]) for c in chroms]):
         cstart = genome.index[chr_][0]
-        items = shard.make_items([csize], M, chunk_len)
+        if packed is not None:
+            pl = packed.planes(chr_)
+            if pl.first_non_iupac >= 0:                                 # fromBS's verdict, taken when the store was packed
+                if warn is not None:
+                    print("Warning: no sequence for region: " + repr((chr_.decode("latin1"), 0, csize)), file=warn)
+                continue
+            items = shard.make_items([csize], M, max(32, chunk_len // 32 * 32))
+            pitems = []
+            for k, it in enumerate(items):
+                lo, hi = shard.chunk_bytes_range(it, csize, nmax)
+                s2, mk, n = pl.slice(lo, hi)
+                units = (n + 31) // 32
+                while len(staging) <= k:
+                    staging.append(None)
+                if staging[k] is None or not isinstance(staging[k], tuple) or staging[k][0].numel() < 2 * units:
+                    staging[k] = (torch.empty(max(2 * units, 2), dtype=torch.int32).pin_memory(), torch.empty(max(units, 1), dtype=torch.int32).pin_memory())
+                a2 = staging[k][0].numpy().view(np.uint32)[:2 * units]
+                am = staging[k][1].numpy().view(np.uint32)[:units]
+                np.copyto(a2, s2[:2 * units])                           # sidecar (page cache) -> pinned memory
+                np.copyto(am, mk[:units])
+                pitems.append((_lib.PackedPlanes(a2, am, n), 0, None))
+            hits = plan.scan_packed_many(pitems)
+        items = items if packed is not None else shard.make_items([csize], M, chunk_len)
         arrays = []
-        for k, it in enumerate(items):
+        for k, it in enumerate(items if packed is None else []):
             lo, hi = shard.chunk_bytes_range(it, csize, nmax)
             if k >= len(staging) or staging[k].numel() < hi - lo:
                 buf = torch.empty(max(hi - lo, 1), dtype=torch.uint8).pin_memory()
@@ -269,8 +294,9 @@ def scanGenome(genome, motifs, out=None, chroms=None, chunk_len=64_000_000, warn
             o = genome.header_size + cstart + lo
             np.copyto(a, genome.data[o:o + (hi - lo)])              # index file (page cache) -> pinned memory
             arrays.append(a)
-        hits = plan.scan_host_many(arrays, uppercase=True)
-        if any(h.first_invalid("IUPAC") >= 0 for h in hits):        # fromBS: Left "Bio.Seq.fromBS: unknown character"
+        if packed is None:
+            hits = plan.scan_host_many(arrays, uppercase=True)
+        if packed is None and any(h.first_invalid("IUPAC") >= 0 for h in hits):        # fromBS: Left "Bio.Seq.fromBS: unknown character"
             if warn is not None:
                 print("Warning: no sequence for region: " + repr((chr_.decode("latin1"), 0, csize)), file=warn)
             continue

@@ -140,3 +140,63 @@ def write_genome(chroms, out_path):
         f.write(MAGIC + b"\n" + b" ".join(hdr) + b"\n")
         for _, arr in chroms:
             f.write(np.ascontiguousarray(arr, dtype=np.uint8).tobytes())
+
+
+# ---- the packed genome store next to the index file -------------------------------------------------------------------
+# `<genome>.packed`: the 2-bit + invalid-base planes of every chromosome (csrc/hostpack.cu, 0.375 bytes per base), made
+# ONCE at index time (upper-cased like fromBS, Seq.hs:86-95) so that whole-genome scans upload those instead of the bytes.
+# Layout: magic line, one JSON line [{name, length, first_non_acgt, first_non_iupac, seq2_off, mask_off}] (offsets in bytes
+# from the start of the data section, 64-byte aligned), then the uint32 planes.
+PACKED_MAGIC = b"<PWMSCAN_PACKED_GENOME_V1>"
+
+
+def mkPackedIndex(genome, out_path=None, nthreads=0):
+    """Writes `<genome.path>.packed` (or out_path) from an open Genome.  Returns the path."""
+    import json
+    from . import _lib
+    out_path = out_path or genome.path + ".packed"
+    meta, planes, off = [], [], 0
+    for name in genome.order:
+        cstart, csize = genome.index[name]
+        o = genome.header_size + cstart
+        p = _lib.PackedSeq(genome.data[o:o + csize], uppercase=True, nthreads=nthreads)
+        rec = {"name": name.decode("latin1"), "length": csize, "first_non_acgt": p.first_non_acgt, "first_non_iupac": p.first_non_iupac}
+        for key, arr in (("seq2_off", p.seq2), ("mask_off", p.mask)):
+            rec[key] = off
+            planes.append(arr)
+            off += (arr.nbytes + 63) // 64 * 64
+        meta.append(rec)
+    with open(out_path, "wb") as f:
+        f.write(PACKED_MAGIC + b"\n" + json.dumps(meta).encode() + b"\n")
+        for arr in planes:
+            f.write(arr.tobytes())
+            f.write(b"\0" * ((-arr.nbytes) % 64))
+    return out_path
+
+
+class PackedGenome:
+    """The `.packed` sidecar, memory-mapped: `planes(chr)` -> _lib.PackedPlanes of a chromosome (views into the file)."""
+
+    def __init__(self, path):
+        import json
+        from . import _lib
+        with open(path, "rb") as f:
+            if f.readline().rstrip(b"\n") != PACKED_MAGIC:
+                raise ValueError("not a packed genome store: " + path)
+            meta = json.loads(f.readline())
+            base = f.tell()
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        data = self._mm.view(np.ndarray)
+        self.chroms = {}
+        for rec in meta:
+            units = (rec["length"] + 31) // 32
+            s2 = data[base + rec["seq2_off"]: base + rec["seq2_off"] + 8 * units].view(np.uint32)
+            mk = data[base + rec["mask_off"]: base + rec["mask_off"] + 4 * units].view(np.uint32)
+            self.chroms[rec["name"].encode("latin1")] = _lib.PackedPlanes(s2, mk, rec["length"], rec["first_non_acgt"], rec["first_non_iupac"])
+
+    def planes(self, chr_):
+        return self.chroms[chr_ if isinstance(chr_, bytes) else chr_.encode()]
+
+    def close(self):
+        self.chroms = {}
+        self._mm = None

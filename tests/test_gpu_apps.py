@@ -87,6 +87,14 @@ def test_scan_genome_whole_chromosomes_from_the_store(small_genome):
         assert got == exp, chunk_len
     tuples = scanGenome(g, cms, chroms=[b"chr2"], chunk_len=9000, warn=None)
     assert len(tuples) == sum(1 for l in exp if l.startswith(b"chr2\t"))
+    # the same from the packed sidecar of the index (mkindex --packed): slices of the 2-bit + mask planes instead of bytes
+    from bioinformatics_toolkit_b200.seq_io import PackedGenome, mkPackedIndex
+    pg = PackedGenome(mkPackedIndex(g))
+    for chunk_len in (7000, 1 << 20):
+        out = io.BytesIO()
+        n = scanGenome(g, cms, out=out, chunk_len=chunk_len, warn=None, packed=pg)
+        got = out.getvalue().split(b"\n")[:-1] if n else []
+        assert got == exp, ("packed", chunk_len)
 
 
 def test_iterative_merge_and_tree(oracle):

@@ -55,3 +55,28 @@ def test_pack_host_threads_agree_and_invalid_bytes_are_reported():
     assert length == 936 and s2[0] == one.seq2[4] and mk[0] == one.mask[2]
     with pytest.raises(ValueError):
         one.slice(33, 100)
+
+
+def test_packed_sidecar_of_the_genome_index_roundtrip(tmp_path):
+    """seq_io.mkPackedIndex / PackedGenome: the `.packed` file next to the index holds, per chromosome, exactly the planes
+    pwmscan_pack_host makes of its upper-cased bytes, plus fromBS's verdict; slices are views into the mapped file."""
+    from bioinformatics_toolkit_b200 import seq_io
+    chroms = [(b"chr1", synth.synth_dna(100_003, 1, n_runs=[(5000, 100)])), (b"chr2", synth.synth_dna(33, 2)), (b"chrE", np.zeros(0, np.uint8)),
+              (b"chrW", synth.synth_dna(5000, 3))]
+    chroms[0][1][7:20] |= 0x20                       # lower case
+    chroms[3][1][1234] = ord("!")                    # outside the IUPAC alphabet
+    path = str(tmp_path / "g.idx")
+    seq_io.write_genome(chroms, path)
+    with seq_io.Genome(path) as g:
+        pth = seq_io.mkPackedIndex(g)
+    assert pth == path + ".packed"
+    pg = seq_io.PackedGenome(pth)
+    for nm, arr in chroms:
+        pl, ref = pg.planes(nm), _lib.PackedSeq(arr, uppercase=True)
+        assert pl.length == arr.size and np.array_equal(pl.seq2, ref.seq2) and np.array_equal(pl.mask, ref.mask)
+        assert (pl.first_non_acgt, pl.first_non_iupac) == (ref.first_non_acgt, ref.first_non_iupac)
+    assert pg.planes(b"chr1").first_non_acgt == 5000 and pg.planes(b"chrW").first_non_iupac == 1234 and pg.planes("chr2").first_non_acgt == -1
+    s2, mk, n = pg.planes(b"chr1").slice(64, 1000)
+    assert n == 936 and s2[0] == pg.planes(b"chr1").seq2[4]
+    with pytest.raises(ValueError):
+        seq_io.PackedGenome(path)                    # the index file itself is not a packed store

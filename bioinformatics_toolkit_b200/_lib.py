@@ -99,6 +99,25 @@ class Context:
         if rc != 0:
             raise PwmScanError(rc, (self.L.pwmscan_last_error(None) or b"").decode())
         self.device = device
+        # Handles made from this context (sequences, motif sets, plans, hit lists, alignment sets) hand buffers back to ITS pools
+        # when they are freed, so the C context must outlive them all.  Reference counts alone do not guarantee that: the
+        # cyclic garbage collector (module globals captured by lambdas, interpreter shutdown) runs the finalisers of a
+        # cycle in arbitrary order.  The context therefore counts its live handles and is destroyed by whoever goes last.
+        self._live = 0
+        self._closing = False
+
+    def _retain(self):
+        self._live += 1
+
+    def _release(self):
+        self._live -= 1
+        if self._closing and self._live <= 0:
+            self._destroy()
+
+    def _destroy(self):
+        if self.h:
+            self.L.pwmscan_ctx_destroy(self.h)
+            self.h = _vp()
 
     def check(self, rc):
         if rc == 0:
@@ -126,9 +145,10 @@ class Context:
         return int(pos.value)
 
     def close(self):
-        if self.h:
-            self.L.pwmscan_ctx_destroy(self.h)
-            self.h = _vp()
+        """Destroys the context — at once if nothing made from it is alive, else when its last handle is freed."""
+        self._closing = True
+        if self._live <= 0:
+            self._destroy()
 
     def __del__(self):
         try:
@@ -171,6 +191,7 @@ class DeviceSeq:
             self.seg_off = so
             rc = ctx.L.pwmscan_seq_upload_segments(ctx.h, _ptr(data), _ptr(so), C.c_int32(self.nseg), C.c_int(flags), C.byref(self.h))
         ctx.check(rc)
+        ctx._retain()
 
     @classmethod
     def from_packed(cls, ctx, packed, start=0, end=None):
@@ -184,6 +205,7 @@ class DeviceSeq:
         self.nseg = 1
         self.seg_off = np.array([0, n], dtype=np.int64)
         ctx.check(ctx.L.pwmscan_seq_upload_packed(ctx.h, _ptr(seq2), _ptr(mask), C.c_int64(n), C.byref(self.h)))
+        ctx._retain()
         return self
 
     def first_invalid(self, alphabet="IUPAC"):
@@ -195,6 +217,7 @@ class DeviceSeq:
         if self.h:
             self.ctx.L.pwmscan_seq_free(self.h)
             self.h = _vp()
+            self.ctx._release()
 
     def __del__(self):
         try:
@@ -259,6 +282,7 @@ class DeviceMotifs:
         self.bg = _arr(bg, np.float64)
         self.h = _vp()
         ctx.check(ctx.L.pwmscan_motifs_create(ctx.h, C.c_int32(self.M), _ptr(self.ncol), _ptr(flat), _ptr(self.bg), C.byref(self.h)))
+        ctx._retain()
 
     def set_sigma(self, m, strand, sigma):
         s = _arr(sigma, np.float64)
@@ -326,6 +350,7 @@ class DeviceMotifs:
         if self.h:
             self.ctx.L.pwmscan_motifs_free(self.h)
             self.h = _vp()
+            self.ctx._release()
 
     def __del__(self):
         try:
@@ -372,6 +397,7 @@ class AlignSet:
         self.h = _vp()
         ctx.check(ctx.L.pwmscan_alnset_create(ctx.h, C.c_int32(self.M), _ptr(ncol), _ptr(flat), C.c_int(PENAL[penal]),
                                               C.c_double(gap), C.c_int(COMB[comb]), C.byref(self.h)))
+        ctx._retain()
 
     def update(self, slot, mat):
         m = _arr(mat, np.float64).reshape(-1, 4)
@@ -411,6 +437,7 @@ class AlignSet:
         if self.h:
             self.ctx.L.pwmscan_alnset_free(self.h)
             self.h = _vp()
+            self.ctx._release()
 
     def __del__(self):
         try:
@@ -425,12 +452,14 @@ class _HitsHandle:
     def __init__(self, ctx, h):
         self.ctx, self.L, self.h = ctx, ctx.L, h        # the hit buffer goes back to the context's pool: keep the context alive
         self.M = 0
+        ctx._retain()
 
     def __del__(self):
         try:
             if self.h:
                 self.L.pwmscan_hits_free(self.h)
                 self.h = None
+                self.ctx._release()
         except Exception:
             pass
 
@@ -566,6 +595,7 @@ class Plan:
         self.h = _vp()
         self.ctx.check(self.ctx.L.pwmscan_plan_create(self.ctx.h, motifs.h, _ptr(th), C.c_int(strands),
                                                       C.c_int(1 if skip_ambiguous else 0), C.byref(self.h)))
+        self.ctx._retain()
 
     def info(self):
         out = np.zeros(8)
@@ -648,6 +678,7 @@ class Plan:
         if self.h:
             self.ctx.L.pwmscan_plan_free(self.h)
             self.h = _vp()
+            self.ctx._release()
 
     def __del__(self):
         try:

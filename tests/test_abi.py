@@ -113,3 +113,31 @@ def test_haskell_shim_binds_every_entry_point():
     hs = open(os.path.join(root, "haskell", "Bio", "Motif", "CUDA.hs")).read()
     missing = [n for n in _lib.exported_symbols() if ('"%s"' % n) not in hs]
     assert missing == []
+
+
+def test_context_outlives_its_handles_whatever_the_finaliser_order():
+    """The cyclic garbage collector runs finalisers in arbitrary order (module globals captured by lambdas, interpreter
+    shutdown): a Context whose __del__ comes first must not destroy the C context under the handles that still hand
+    buffers back to its pools — it is destroyed by whoever goes last (seen as an abort at exit under MALLOC_PERTURB_)."""
+    calls = []
+
+    class FakeL:
+        def pwmscan_ctx_destroy(self, h):
+            calls.append("ctx")
+
+    ctx = _lib.Context.__new__(_lib.Context)
+    ctx.L, ctx.h, ctx._live, ctx._closing = FakeL(), _lib._vp(1), 0, False
+    ctx._retain()
+    ctx._retain()
+    ctx.close()                      # e.g. Context.__del__ called first by the collector
+    assert calls == []
+    ctx._release()
+    assert calls == []
+    ctx._release()                   # the last handle
+    assert calls == ["ctx"] and not ctx.h
+    ctx.close()
+    assert calls == ["ctx"]          # idempotent
+    idle = _lib.Context.__new__(_lib.Context)
+    idle.L, idle.h, idle._live, idle._closing = FakeL(), _lib._vp(1), 0, False
+    idle.close()
+    assert calls == ["ctx", "ctx"]   # nothing alive: destroyed at once

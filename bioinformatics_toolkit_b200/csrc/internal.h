@@ -169,6 +169,9 @@ struct pwmscan_plan {
     size_t km_smem_bytes = 0;          // dynamic shared memory the prefilter kernel needs (largest block)
     std::vector<pwmscan::KmBlockPlan> km_blocks;
     std::vector<DevCombo> km_generic;
+    std::vector<DevCombo> km_ambig;              // skip == 0: every prefiltered combo, for the pass over windows with a non-ACGT letter
+    DevCombo* d_km_ambig = nullptr;
+    int km_ambig_max_n = 0;
     DevKmBlock* d_km_blocks = nullptr;
     DevCombo* d_km_combos = nullptr;   // km_nblocks * 256
     DevCombo* d_km_generic = nullptr;

@@ -285,6 +285,9 @@ struct KmHostPlan {
     std::vector<double> th;
     std::vector<KmBlockPlan> blocks;
     std::vector<std::pair<int, int>> generic;
+    // skip == 0 (IUPAC-aware lookAheadSearch): the combos of the blocks once more — their windows that hold a letter other
+    // than A/C/G/T are not the first stage's business (it sees 2-bit codes) and get an exact pass of their own
+    std::vector<std::pair<int, int>> ambig;
     double cand_rate = 0, surv_rate = 0, req_rate = 0;
     int max_n = 0;
 };
@@ -300,14 +303,18 @@ inline void build_km_host_plan(const std::vector<MotifHost>& mh, const std::vect
         }
     std::vector<int> pre;
     for (int m = 0; m < M; ++m) {
-        bool ok = skip != 0;
+        bool ok = true;
         for (int s = 0; s < strands && ok; ++s) {
             if (!std::isfinite(hp.th[(size_t)col_off[2 * m + s] + mh[m].n - 1])) ok = false;
             for (int k = 0; k < mh[m].n && ok; ++k)
                 for (int b = 0; b < 4; ++b) if (!std::isfinite(mh[m].tab16[s][16 * k + b])) ok = false;
         }
-        if (ok) pre.push_back(m);
-        else for (int s = 0; s < strands; ++s) hp.generic.emplace_back(m, s);
+        if (ok) {
+            pre.push_back(m);
+            if (!skip) for (int s = 0; s < strands; ++s) hp.ambig.emplace_back(m, s);
+        } else {
+            for (int s = 0; s < strands; ++s) hp.generic.emplace_back(m, s);
+        }
     }
     // Longest motifs first: the windows of long motifs pass most often, so their blocks are the expensive ones, and the cost of a
     // block grows less than linearly with its combos (1 - exp(-sum of pass rates)) — the expensive motifs belong together in

@@ -692,6 +692,7 @@ extern "C" void pwmscan_plan_free(pwmscan_plan* pl) {
     if (pl->d_km_blocks) cudaFree(pl->d_km_blocks);
     if (pl->d_km_combos) cudaFree(pl->d_km_combos);
     if (pl->d_km_generic) cudaFree(pl->d_km_generic);
+    if (pl->d_km_ambig) cudaFree(pl->d_km_ambig);
     if (pl->d_km_tables) { if (pl->ctx) dev_pool_put(pl->ctx, pl->d_km_tables, pl->km_tables_cap); else cudaFree(pl->d_km_tables); }
     if (pl->d_km_q16) cudaFree(pl->d_km_q16);
     delete pl;
@@ -823,6 +824,7 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
         pl->km_cand_rate = kp.cand_rate; pl->km_surv_rate = kp.surv_rate; pl->km_req_rate = kp.req_rate;
         pl->cand_rate = kp.cand_rate;
         for (auto& g : kp.generic) pl->km_generic.push_back(dev_combo(g.first, g.second));
+        for (auto& g : kp.ambig) { pl->km_ambig.push_back(dev_combo(g.first, g.second)); pl->km_ambig_max_n = std::max(pl->km_ambig_max_n, (int)mo->mh[g.first].n); }
         std::vector<DevKmBlock> hb(pl->km_nblocks);
         std::vector<DevCombo> hc((size_t)pl->km_nblocks * kKmCombos);
         std::vector<uint16_t> hq;
@@ -870,6 +872,7 @@ extern "C" int pwmscan_plan_create(pwmscan_ctx* ctx, const pwmscan_motifs* mo, c
         if ((rc = up((void**)&pl->d_km_blocks, hb.data(), hb.size() * sizeof(DevKmBlock), "upload kmer blocks"))) return bail(rc);
         if ((rc = up((void**)&pl->d_km_combos, hc.data(), hc.size() * sizeof(DevCombo), "upload kmer combos"))) return bail(rc);
         if ((rc = up((void**)&pl->d_km_generic, pl->km_generic.data(), pl->km_generic.size() * sizeof(DevCombo), "upload kmer generic"))) return bail(rc);
+        if ((rc = up((void**)&pl->d_km_ambig, pl->km_ambig.data(), pl->km_ambig.size() * sizeof(DevCombo), "upload kmer ambig"))) return bail(rc);
         if ((rc = up((void**)&pl->d_km_q16, hq.data(), hq.size() * 2, "upload q16"))) return bail(rc);
         if (pl->km_nblocks > 0) {
             // the mask tables are computed on the device from the per-window deficits
@@ -1162,6 +1165,45 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
         if (hit) sink_store(hs, atomicAdd(&counters[1], 1ull), hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]), sc);
     }
   }
+}
+
+// IUPAC-aware search (skip == 0) next to the first stage: the k-mer masks and the replay of their candidates cover the
+// windows made of A/C/G/T only (lookAheadSearch and lookAheadSearch' agree on those); this kernel takes the rest — every
+// window that holds at least one other letter (a set bit of the mask plane among its n positions) — through the literal
+// lookAheadSearch loop on the bytes (Search.hs:133-157: IUPAC letters score their expected log-odds, an invalid letter THAT
+// THE LOOK-AHEAD VISITS is the reference's `error`).  One thread per window start; the mask bits of the next 64 positions
+// decide at once whether any motif has to be looked at.
+__global__ void ambig_kernel(const DevCombo* __restrict__ combos, int ncombo, int max_n, const uint32_t* __restrict__ mask,
+                             const uint8_t* __restrict__ ascii, const int64_t* __restrict__ seg_off, int nseg, int64_t len,
+                             const double* __restrict__ tab16, const double* __restrict__ th, HitSink hs, KeyLayout kl) {
+    unsigned long long* counters = hs.counters;
+    const unsigned long long all_n = max_n >= 64 ? ~0ull : ((1ull << max_n) - 1ull);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = i + kPadFront, mw = u >> 5;
+        const int sh = (int)(u & 31);
+        const uint32_t m0 = __ldg(mask + mw), m1 = __ldg(mask + mw + 1), m2 = __ldg(mask + mw + 2);
+        const unsigned long long inv = (unsigned long long)__funnelshift_r(m0, m1, sh) | ((unsigned long long)__funnelshift_r(m1, m2, sh) << 32);
+        if ((inv & all_n) == 0ull) continue;                                   // 64 positions of A/C/G/T ahead: nothing for this pass
+        const int seg = nseg == 1 ? 0 : find_segment(seg_off, nseg, i);
+        const int64_t seg_end = seg_off[seg + 1];
+        for (int ci = 0; ci < ncombo; ++ci) {
+            const DevCombo cb = combos[ci];
+            if (i + cb.n > seg_end) continue;
+            const unsigned long long mine = cb.n >= 64 ? ~0ull : ((1ull << cb.n) - 1ull);
+            if ((inv & mine) == 0ull) continue;                                // this motif's window is all A/C/G/T: the first stage has it
+            const double* tb = tab16 + cb.tab_off;
+            const double* tk = th + cb.th_off;
+            double sc = 0.0;
+            bool hit = true;
+            for (int k = 0; k < cb.n; ++k) {
+                const unsigned code = c_iupac_lut[ascii[i + k]];
+                if (code == 15u) { atomicOr(&counters[2], 1ull); hit = false; break; }
+                sc = __dadd_rn(sc, tb[16 * k + code]);
+                if (sc < tk[k]) { hit = false; break; }
+            }
+            if (hit) sink_store(hs, atomicAdd(&counters[1], 1ull), hit_key(kl, seg, cb.motif, cb.strand, i - seg_off[seg]), sc);
+        }
+    }
 }
 
 }  // namespace
@@ -1464,6 +1506,14 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         dim3 grid((unsigned)gx, (unsigned)std::min<size_t>(generic.size(), 65535));
         exact_kernel<<<grid, bs, 0, st>>>(d_generic, (int)generic.size(), pl->skip, seq->d_seq2, seq->d_mask, seq->d_ascii, seq->d_seg_off,
                                           seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
+        PWM_CUDA(cudaGetLastError());
+        ++j.kernels;
+    }
+    if (use_km && !pl->skip && !pl->km_ambig.empty() && len > 0) {
+        const int bs = 256;
+        const long long gx = std::min<long long>((len + bs - 1) / bs, (long long)ctx->sm_count * 64);
+        ambig_kernel<<<(unsigned)gx, bs, 0, st>>>(pl->d_km_ambig, (int)pl->km_ambig.size(), pl->km_ambig_max_n, seq->d_mask, seq->d_ascii, seq->d_seg_off,
+                                                  seq->nseg, len, mo->d_tab16, pl->d_th, hs, j.kl);
         PWM_CUDA(cudaGetLastError());
         ++j.kernels;
     }

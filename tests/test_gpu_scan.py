@@ -588,3 +588,34 @@ def test_packed_genome_store_equals_the_bytes(ctx, oracle):
     iupac_plan = _lib.Plan(_lib.DeviceMotifs(ctx, mats[:3], BG), thres[:3], skip_ambiguous=False)
     with pytest.raises(_lib.PwmScanError):
         iupac_plan.scan_packed_many([(packed[0], 0, None)])
+
+
+def test_iupac_aware_search_through_the_first_stage(ctx, oracle):
+    """skip_ambiguous = False on a sequence that is mostly A/C/G/T: the k-mer first stage finds the hits of the pure windows,
+    ambig_kernel replays the windows that hold another letter (N runs, scattered IUPAC letters, the two ends of every run,
+    several segments) — together exactly lookAheadSearch over every window (the oracle), and exactly the skip = True hits
+    plus the ones that contain such a letter."""
+    mats = synth.synth_pwms(30, 21, nmin=6, nmax=22)
+    thres = [0.45 * oracle.optimal_score(BG, m) for m in mats]
+    d = synth.synth_dna(300_000, 9, gc=0.45, n_runs=[(0, 70), (100_000, 3000), (299_990, 10)])
+    rng = np.random.default_rng(3)
+    for p in rng.integers(200, 299_000, 400):
+        d[p] = rng.choice(np.frombuffer(b"NVHDBMKWSYR", dtype=np.uint8))
+    h = gpu_scan(ctx, mats, thres, d, skip=False)
+    o = oracle_scan(oracle, mats, thres, d, skip=False)
+    assert len(h) > 5000
+    assert_same(h, o)
+    hs = gpu_scan(ctx, mats, thres, d, skip=True)
+    assert len(hs) < len(h)
+    key = lambda x: set(zip(x.motif.tolist(), x.strand.tolist(), x.pos.tolist()))
+    assert key(hs) <= key(h)
+    # segments: windows never span two of them, ambiguous letters right at the seams
+    seg_off = [0, 50_000, 50_007, 180_000, 300_000]
+    d[49_995:50_012] = ord("N")
+    hseg = gpu_scan(ctx, mats, thres, d, skip=False, seg_off=seg_off)
+    parts = [oracle_scan(oracle, mats, thres, d[a:b], skip=False) for a, b in zip(seg_off[:-1], seg_off[1:])]
+    assert len(hseg) == sum(q[0].size for q in parts)
+    for g, q in enumerate(parts):
+        sel = hseg.select(segment=g)
+        assert np.array_equal(sel.motif, q[0]) and np.array_equal(sel.strand, q[1]) and np.array_equal(sel.pos, q[2])
+        assert np.array_equal(sel.score.view(np.uint64), q[3].view(np.uint64))

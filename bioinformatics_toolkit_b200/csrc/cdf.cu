@@ -255,7 +255,8 @@ int run_cdf(pwmscan_ctx* ctx, const pwmscan_motifs* mo, int m0, int mcount, doub
                 h_xat[(size_t)(h_off[m] + k) * 4 + b] = (p == 0 ? std::log(0.001) : std::log(p)) - lbg[b];
             }
     for (double v : h_xat) if (!std::isfinite(v)) return set_err(ctx, PWMSCAN_EDOMAIN, "scoreCDF: a background frequency or matrix entry gives a non-finite log-odds score");
-    const int grid = std::min(mcount, kCdfCtasPerSm * ctx->sm_count);
+    static const int grid_env = std::getenv("PWMSCAN_CDF_CTAS") ? std::max(1, std::atoi(std::getenv("PWMSCAN_CDF_CTAS"))) : 0;     // experiments
+    const int grid = std::min(mcount, grid_env ? std::min(grid_env, kCdfCtasPerSm * ctx->sm_count) : kCdfCtasPerSm * ctx->sm_count);
     auto al = [](size_t b) { return (b + 63) & ~(size_t)63; };
     const size_t b_xat = al(h_xat.size() * 8), b_off = al((size_t)M * 8), b_n = al((size_t)M * 4), b_th = al((size_t)M * 8), b_st = al((size_t)M * 4);
     const size_t b_ord = al((size_t)mcount * 4), b_cnt = al((size_t)mcount * 8);

@@ -619,3 +619,28 @@ def test_iupac_aware_search_through_the_first_stage(ctx, oracle):
         sel = hseg.select(segment=g)
         assert np.array_equal(sel.motif, q[0]) and np.array_equal(sel.strand, q[1]) and np.array_equal(sel.pos, q[2])
         assert np.array_equal(sel.score.view(np.uint64), q[3].view(np.uint64))
+
+
+def test_max_match_sc_pruned_equals_the_maximum_of_the_dense_scores(ctx, oracle, ref_motifs):
+    """maxMatchSc prunes windows against the running maximum like the reference (Search.hs:98-109) behind a first stretch of
+    65 536 windows: the result is still the maximum of the exact fp64 window sums (the dense `scores` of the same sequence,
+    bit for bit), for motifs of every length, with IUPAC letters and N runs in the sequence; the oracle confirms a slice."""
+    mats = [m for _, m in ref_motifs][:6] + synth.synth_pwms(6, 33, nmin=5, nmax=30)
+    d = synth.synth_dna(3_000_000, 21, gc=0.43, n_runs=[(1_000_000, 5000)])
+    rng = np.random.default_rng(5)
+    for p in rng.integers(0, d.size, 300):
+        d[p] = rng.choice(np.frombuffer(b"NVHDBMKWSYR", dtype=np.uint8))
+    seq = _lib.DeviceSeq(ctx, d, keep_ascii=True)
+    mo = _lib.DeviceMotifs(ctx, mats, BG)
+    mx = _lib.max_match_sc(seq, mo)
+    for m in range(len(mats)):
+        dense = _lib.scores(seq, mo, m, 0)
+        assert mx[m] == dense.max() and np.float64(mx[m]).view(np.uint64) == dense.max().view(np.uint64)
+    sl = bytes(d[900_000:1_200_000])
+    mxs = _lib.max_match_sc(_lib.DeviceSeq(ctx, sl, keep_ascii=True), mo)
+    for m in (0, 5, len(mats) - 1):
+        assert mxs[m] == oracle.max_match_sc(BG, mats[m], sl)
+    bad = d.copy()
+    bad[2_999_990] = ord("!")                      # an invalid letter is still the reference's `error`
+    with pytest.raises(_lib.InvalidNucleotide):
+        _lib.max_match_sc(_lib.DeviceSeq(ctx, bad, keep_ascii=True), mo)

@@ -39,8 +39,31 @@ extern "C" int pwmscan_pack_host(const uint8_t* ascii, int64_t len, int flags, u
     auto work = [&](int w) {
         const int64_t t0 = units * w / nt, t1 = units * (w + 1) / nt;
         int64_t ba = -1, bi = -1;
+        const uint32_t fold = upper ? 0xDFDFDFDFu : 0xFFFFFFFFu;
+        // four ASCII bytes -> their 2-bit codes in 8 bits + "not one of ACGT" flags, without a table (pack_kernel's pack4)
+        auto pack4 = [fold](uint32_t w, uint32_t* bad) -> uint32_t {
+            const uint32_t v = w & fold;
+            const uint32_t x = (v >> 1) & 0x03030303u;
+            const uint32_t m = (x >> 1) & ~x & 0x01010101u;
+            const uint32_t expect = 0x41414141u + (x << 1) + (m << 4) - m;
+            const uint32_t d = v ^ expect;
+            *bad |= (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+            const uint32_t code = x ^ ((x >> 1) & 0x01010101u);
+            return (code * 0x01041040u) >> 24;
+        };
         for (int64_t t = t0; t < t1; ++t) {
             const int64_t p0 = t * 32;
+            if (p0 + 32 <= len) {                                  // fast path: 32 bytes that are all A/C/G/T
+                uint32_t w[8], bad = 0, c[8];
+                std::memcpy(w, ascii + p0, 32);
+                for (int q = 0; q < 8; ++q) c[q] = pack4(w[q], &bad);
+                if (bad == 0u) {
+                    seq2_out[2 * t] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+                    seq2_out[2 * t + 1] = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
+                    mask_out[t] = 0u;
+                    continue;
+                }
+            }
             uint32_t w0 = 0, w1 = 0, mk = 0;
             const int lim = (int)std::min<int64_t>(32, len - p0);
             for (int k = 0; k < 32; ++k) {

@@ -71,9 +71,12 @@ __global__ void __launch_bounds__(256) bucket_tile_sum_kernel(const unsigned int
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) bucket_tile_scan_kernel(unsigned long long* __restrict__ tile_sum, unsigned long long ntiles) {
+// (also zeroes the two queue counters of the sorting kernels: a cudaMemsetAsync in the middle of the chain is a copy-engine
+//  operation and waits behind whatever hit-list copies of other items that engine is busy with)
+__global__ void __launch_bounds__(1024) bucket_tile_scan_kernel(unsigned long long* __restrict__ tile_sum, unsigned long long ntiles,
+                                                                unsigned long long* __restrict__ zero_a, unsigned long long* __restrict__ zero_b) {
     __shared__ unsigned long long s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) { s_carry = 0; *zero_a = 0ull; *zero_b = 0ull; }
     __syncthreads();
     for (unsigned long long t0 = 0; t0 < ntiles; t0 += 1024) {
         const unsigned long long t = t0 + threadIdx.x;
@@ -366,14 +369,12 @@ int order_finish(pwmscan_ctx* ctx, cudaStream_t st, const unsigned long long* d_
     const int sm = ctx->sm_count;
     const unsigned long long ntiles = (w.nb + kScanTile - 1) / kScanTile;
     bucket_tile_sum_kernel<<<(unsigned)ntiles, 256, 0, st>>>(w.cnt, w.nb, w.tiles);
-    bucket_tile_scan_kernel<<<1, 1024, 0, st>>>(w.tiles, ntiles);
+    bucket_tile_scan_kernel<<<1, 1024, 0, st>>>(w.tiles, ntiles, w.big, w.med);
     bucket_tile_apply_kernel<<<(unsigned)ntiles, 256, 0, st>>>(w.cnt, w.nb, w.tiles, w.start, w.cursor);
     const unsigned grid_n = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((n_est + 255) / 256, (unsigned long long)sm * 16));
     bucket_scatter_kernel<<<grid_n, 256, 0, st>>>(d_keys, d_sc, w.start + w.nb, shift, w.cursor, d_tkeys, d_tsc);
     SortOut so{d_tsc, d_skeys, d_score, d_pos32, d_seg32, d_ms16, kl, nseg > 1 ? 1 : 0};
-    PWM_CUDA(cudaMemsetAsync(w.big, 0, 8, st));
     const unsigned grid_b = (unsigned)std::max<size_t>(1, std::min<size_t>((w.nb + 255) / 256, (size_t)sm * 8));      // 8 warps = 8 groups of 32 buckets per CTA
-    PWM_CUDA(cudaMemsetAsync(w.med, 0, 8, st));
     bucket_sort_kernel<<<grid_b, 256, 0, st>>>(w.start, w.nb, shift, d_tkeys, so, w.med, w.med_cap, w.big, w.big_cap, d_flags);
     bucket_sort_medium_kernel<<<sm * 4, 256, 0, st>>>(w.start, shift, d_tkeys, so, w.med, w.med_cap);
     bucket_sort_big_kernel<<<sm * 6, kSortThreads, 0, st>>>(w.start, shift, d_tkeys, so, w.big, w.big_cap, d_flags);

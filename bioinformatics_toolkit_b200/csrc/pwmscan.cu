@@ -1167,6 +1167,14 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
   }
 }
 
+// Start of a scan on a lane: counters [0, 4) and [6, nwords) and the ordering's bucket counters to zero ([4, 6) hold the fromBS
+// verdict of the upload that may just have been packed on this lane).
+__global__ void scan_reset_kernel(unsigned long long* __restrict__ counters, int nwords, unsigned int* __restrict__ cnt, size_t nb) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = t; i < (size_t)nwords; i += step) if (i < 4 || i >= 6) counters[i] = 0ull;
+    for (size_t i = t; i < nb; i += step) cnt[i] = 0u;
+}
+
 // IUPAC-aware search (skip == 0) next to the first stage: the k-mer masks and the replay of their candidates cover the
 // windows made of A/C/G/T only (lookAheadSearch and lookAheadSearch' agree on those); this kernel takes the rest — every
 // window that holds at least one other letter (a set bit of the mask plane among its n positions) — through the literal
@@ -1402,9 +1410,10 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
         PWM_CUDA(cudaEventRecord(lane->ev[EV_GATE], st));
         PWM_CUDA(cudaStreamWaitEvent(pst, lane->ev[EV_GATE], 0));
     }
-    PWM_CUDA(cudaMemsetAsync(lane->d_counters, 0, 4 * sizeof(unsigned long long), pst));
-    PWM_CUDA(cudaMemsetAsync(lane->d_counters + 6, 0, (kCounterWords - 6) * sizeof(unsigned long long), pst));
-    PWM_CUDA(cudaMemsetAsync(ow.cnt, 0, ow.nb * 4, pst));
+    // (a kernel, not three cudaMemsetAsync: memsets are copy-engine operations and wait behind the hit-list copies of the items
+    //  before this one — at eight GPUs, where those copies are slow, that delayed every item's first stage and ordering)
+    scan_reset_kernel<<<std::max(1u, std::min(64u, (unsigned)((ow.nb + 1023) / 1024))), 256, 0, pst>>>(lane->d_counters, kCounterWords, ow.cnt, ow.nb);
+    PWM_CUDA(cudaGetLastError());
     if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, j.cand_cap * 8, pst));     // sentinel: warps reserve whole chunks
     if (j.host && j.attempt == 0 && j.up.h_seq2) {
         // packed planes from the host: two copies (0.375 bytes per base), padding on the device, one first-stage launch

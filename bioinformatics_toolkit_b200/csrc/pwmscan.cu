@@ -433,7 +433,8 @@ static int seq_alloc(pwmscan_ctx* ctx, ScanLane* lane, const int64_t* seg_off, i
         *d_raw_out = (uint8_t*)lane_scratch_get(ctx, lane, 0, (size_t)len + 64);
         if (!*d_raw_out) return bail(PWMSCAN_ECUDA);
     }
-    if ((e = cudaMemsetAsync(lane->d_counters + 4, 0xFF, 16, lane->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
+    // (the fromBS verdict words: for the sequence of a scan job the job's reset kernel sets them — no copy-engine operation on its chain)
+    if (!lane_owned && (e = cudaMemsetAsync(lane->d_counters + 4, 0xFF, 16, lane->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
     *out = s;
     return PWMSCAN_OK;
 }
@@ -1169,9 +1170,12 @@ __global__ void exact_kernel(const DevCombo* __restrict__ combos, int ncombo, in
 
 // Start of a scan on a lane: counters [0, 4) and [6, nwords) and the ordering's bucket counters to zero ([4, 6) hold the fromBS
 // verdict of the upload that may just have been packed on this lane).
-__global__ void scan_reset_kernel(unsigned long long* __restrict__ counters, int nwords, unsigned int* __restrict__ cnt, size_t nb) {
+__global__ void scan_reset_kernel(unsigned long long* __restrict__ counters, int nwords, unsigned int* __restrict__ cnt, size_t nb, int new_upload) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = t; i < (size_t)nwords; i += step) if (i < 4 || i >= 6) counters[i] = 0ull;
+    for (size_t i = t; i < (size_t)nwords; i += step) {
+        if (i < 4 || i >= 6) counters[i] = 0ull;
+        else if (new_upload) counters[i] = ~0ull;            // "no byte outside the alphabet yet": the pack kernels of this job take the minimum
+    }
     for (size_t i = t; i < nb; i += step) cnt[i] = 0u;
 }
 
@@ -1412,7 +1416,8 @@ int scan_phase_a(pwmscan_ctx* ctx, ScanJob& j) {
     }
     // (a kernel, not three cudaMemsetAsync: memsets are copy-engine operations and wait behind the hit-list copies of the items
     //  before this one — at eight GPUs, where those copies are slow, that delayed every item's first stage and ordering)
-    scan_reset_kernel<<<std::max(1u, std::min(64u, (unsigned)((ow.nb + 1023) / 1024))), 256, 0, pst>>>(lane->d_counters, kCounterWords, ow.cnt, ow.nb);
+    scan_reset_kernel<<<std::max(1u, std::min(64u, (unsigned)((ow.nb + 1023) / 1024))), 256, 0, pst>>>(lane->d_counters, kCounterWords, ow.cnt, ow.nb,
+                                                                                                       (j.host && j.attempt == 0) ? 1 : 0);
     PWM_CUDA(cudaGetLastError());
     if (use_mma) PWM_CUDA(cudaMemsetAsync(d_cand, 0xFF, j.cand_cap * 8, pst));     // sentinel: warps reserve whole chunks
     if (j.host && j.attempt == 0 && j.up.h_seq2) {
